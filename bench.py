@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- Gcell-updates/s of the Margolus block update at 16384^2 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size S] [--impl ours|reference]
+  N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Definitions (DESIGN.md "Measurement"):
+  step      one Margolus step (one `Simulation::run`, simulation.rs:195) over the whole S x S grid
+  value     S*S*K / t, t = CUDA-event time of K steps issued through ONE se_sim_step(K) call, inputs resident in
+            HBM, max over ranks; default rule set (data/materials.yaml), lighting off, no modifications,
+            counter-hash initial grid seed 3, frames 2.. after W warm-up steps
+  e2e       the same K steps through the public per-frame API with HOST buffers, every step: push the frame's
+            modification record(s) from host memory (H2D), Simulation.run(), read the step's result -- the
+            per-material census (256 x u64) -- back to the host (D2H); wall clock around the loop (sync both sides)
+  roofline  algorithmic bytes = 8 B per cell-update (packed u32 in + out) / average launch duration of the
+            dominant kernel, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the C restatement of the reference shader (oracle/, "port": the GLSL cannot run in this image)
+            timed on the host cores over a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+if str(REPO) not in sys.path:
+    sys.path.insert(0, str(REPO))
+
+SEED = 3
+METRIC = "Gcell-updates/s at 16384^2 (Margolus block update, default rule set, lighting off)"
+UNIT = "Gcell-updates/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--size", type=int, default=16384)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--halo", type=int, default=32)
+    ap.add_argument("--temporal-block", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def cpu_port_rate(size_sample: int, budget_s: float, seed: int = SEED):
+    """Oracle (C restatement of the shader, OpenMP over all host cores) on a bounded sample of the workload."""
+    import numpy as np
+
+    from oracle.build_oracle import load_oracle
+    from sandengine_b200.grids import synthetic_grid
+
+    orc = load_oracle()
+    g = synthetic_grid(size_sample, size_sample, seed)
+    cores = len(os.sched_getaffinity(0))
+    frame = orc.run_blocks(g, 1, 2)   # warm-up (page-in, thread pool)
+    steps, t0 = 0, time.perf_counter()
+    while True:
+        frame = orc.run_blocks(g, frame, 4)
+        steps += 4
+        dt = time.perf_counter() - t0
+        if dt >= budget_s or steps >= 4000:
+            break
+    rate = size_sample * size_sample * steps / dt / 1e9
+    return {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{size_sample}x{size_sample} crop-sized grid of the same generator (seed {seed}), {steps} steps in {dt:.1f} s, "
+                      f"C restatement of the reference shader (per-block form), gcc -O2 -fopenmp, {cores} threads; "
+                      "llvmpipe GL 4.3 is not available in this image"}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own algorithm on the host cores (oracle port; no GL in this image)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = min(args.size, 4096)
+    # each "step" of this arm is one Margolus step over the bounded sample; K + W of them
+    import numpy as np
+
+    from oracle.build_oracle import load_oracle
+    from sandengine_b200.grids import synthetic_grid
+
+    orc = load_oracle()
+    g = synthetic_grid(sample, sample, SEED)
+    cores = len(os.sched_getaffinity(0))
+    K = max(1, min(args.steps, 400))
+    Wm = max(0, min(args.warmup, 20))
+    frame = orc.run_blocks(g, 1, Wm) if Wm else 1
+    t0 = time.perf_counter()
+    frame = orc.run_blocks(g, frame, K)
+    dt = time.perf_counter() - t0
+    rate = sample * sample * K / dt / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(rate, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": Wm,
+        "ms_per_step": round(dt / K * 1e3, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": f"bounded sample of the {args.size}^2 workload: {sample}x{sample} grid, same generator (seed {SEED}), "
+                               "default rule set, lighting off, no modifications", "rules": "data/materials.yaml"},
+        "cpu_baseline": {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample}x{sample}, {K} steps; C restatement of the reference shader (oracle/), gcc -O2 -fopenmp, {cores} threads; "
+                                   "the reference's GLSL needs GL 4.3 (llvmpipe) which this image does not have"},
+        "e2e": {"value": round(rate, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: sandengine_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.gpus != world and rank == 0:
+        print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+
+    import sandengine_b200 as se
+    from sandengine_b200.distributed import StripSimulation
+    from sandengine_b200.grids import synthetic_grid
+
+    S = args.size
+    K, Wm = args.steps, max(args.warmup, 3)
+    rules = se.parse_path(REPO / "data" / "materials.yaml")
+    strip = StripSimulation(rules, (S, S), halo_rows=args.halo, device=local_rank, temporal_block=args.temporal_block)
+    sim = strip.sim
+    stream = torch.cuda.current_stream()
+    sim.set_stream(stream.cuda_stream)
+
+    rows = strip.row_end - strip.row_begin
+    host = torch.empty((rows, S), dtype=torch.int32).pin_memory()
+    host_np = host.numpy().view(np.uint32)
+    synthetic_grid(S, S, SEED, row_begin=strip.row_begin, row_end=strip.row_end, out=host_np)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reset():
+        strip.upload_cells(host_np)
+        sim.params.frame = 1
+
+    # ---------------- device-resident timing (value) ----------------
+    reset()
+    strip.step(Wm)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = sim.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    strip.step(K)
+    ev1.record(stream)
+    barrier()
+    t_dev = ev0.elapsed_time(ev1) / 1e3
+    launches = sim.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([t_dev], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_dev = float(t.item())
+    value = S * S * K / t_dev / 1e9
+
+    # ---------------- end to end through the per-frame API with host buffers ----------------
+    reset()
+    strip.step(Wm)
+    terminator = np.zeros(1, dtype=se.MOD_DTYPE)   # the frame's modification UBO: "no modifications" (mod_size == 0)
+    census_host = np.zeros(256, np.uint64)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        sim.push_modifications(terminator)           # H2D of the step's input (32 B per record)
+        strip.step(1)                                # Simulation.run()
+        census_host = sim.census()                   # D2H of the step's result (256 x u64), synchronises
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    t_e2e = float(te.item())
+    e2e_value = S * S * K / t_e2e / 1e9
+
+    # whole job from a host grid to a host grid (upload + K steps + download), reported beside e2e
+    barrier()
+    t0 = time.perf_counter()
+    sim.upload_cells_ptr(host.data_ptr())
+    if world > 1:
+        strip.exchange()
+    sim.params.frame = 1
+    strip.step(K)
+    out_host = torch.empty_like(host).pin_memory() if False else host   # download in place of the pinned upload buffer
+    sim.download_cells_ptr(out_host.data_ptr())
+    barrier()
+    t_job = time.perf_counter() - t0
+    tj = torch.tensor([t_job], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tj, op=dist.ReduceOp.MAX)
+    t_job = float(tj.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        cells_per_launch = rows_local_cells = S * (sim.owned_shape[0] + sum(strip.plan.ghosts(rank)))
+        per_launch_s = t_dev / max(launches, 1)
+        achieved = 8.0 * cells_per_launch / per_launch_s / 1e9
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": round(t_dev / K * 1e3, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"{S}x{S} grid, default rule set (data/materials.yaml), lighting off, no modifications, "
+                                   f"counter-hash initial grid seed {SEED}, frames {2 + Wm}..{1 + Wm + K}",
+                       "parallelism": f"strips{world}" + (f" halo{args.halo}" if world > 1 else ""),
+                       "l2": "inputs larger than L2 (1 GiB cell buffer at 16384^2); no explicit flush" if S * S * 4 > 2 * 126e6 else
+                             "L2-RESIDENT workload: the cell buffer fits the 126 MB L2",
+                       "cells_bytes": S * S * 4},
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         "traffic": None, "kernel": "se_step_inplace", "peak_source": peak_src,
+                         "algorithmic_bytes_per_cell_update": 8, "launches_timed": launches,
+                         "avg_launch_us": round(per_launch_s * 1e6, 2)},
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": 32, "d2h_bytes_per_step": 2048,
+                    "what": "per frame: push modification record (H2D) + Simulation.run() + per-material census (D2H)",
+                    "job_roundtrip": {"value": round(S * S * K / t_job / 1e9, 2), "unit": UNIT,
+                                      "what": f"upload grid from pinned host memory + {K} steps + download grid",
+                                      "h2d_bytes": S * rows * 4, "d2h_bytes": S * rows * 4}},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_port_rate(min(S, 4096), args.cpu_seconds)
+            except Exception as e:   # the baseline is a reported number, never a dependency of the GPU path
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": len(os.sched_getaffinity(0)), "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    strip.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,134 @@
+/* sandengine_b200 -- C ABI of the B200-native falling-sand simulation core.
+ *
+ * This is the drop-in boundary for the ONE hot path of ARez2/sandengine: the Margolus 2x2 block update
+ * generated from materials.yaml, with its two riders (modification override, flood-fill lighting).
+ * The reference has no FFI; its seam is two in-process Rust APIs.  Each entry point below names the
+ * reference interface it replaces (file:line under /root/reference).  A Rust `extern "C"` binding
+ * and the `Simulation` shim that would sit on top of it are shown in INTEGRATION.md.
+ *
+ * Conventions: every function returns 0 (SE_OK) or a negative se_status; no exceptions or panics
+ * cross the ABI; se_last_error() returns a thread-local message for the last failure.  Plain pointers
+ * and sizes only.  A se_sim is single-owner and not thread-safe (mirrors the GL-context rule of the
+ * reference, simulation.rs:97-126); distinct sims are independent.  se_sim_step() is asynchronous on
+ * the sim's stream; uploads/downloads synchronise that stream.
+ *
+ * There is NO CPU fallback: without a CUDA device se_sim_create() fails with SE_ERR_CUDA.
+ * se_rules_compile_yaml() needs only NVRTC (no device) and so also works on a build host.
+ */
+#ifndef SANDENGINE_B200_H
+#define SANDENGINE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum se_status {
+    SE_OK = 0,
+    SE_ERR_YAML = -1,            /* serde_yaml error surfaced by parse_string, parser.rs:95-98 */
+    SE_ERR_MISSING_FIELD = -2,   /* ParsingErr::MissingField   parser.rs:46-50 */
+    SE_ERR_INVALID_TYPE = -3,    /* ParsingErr::InvalidType    parser.rs:53-58 */
+    SE_ERR_NOT_FOUND = -4,       /* ParsingErr::NotFound       parser.rs:61-65 */
+    SE_ERR_NOT_RECOGNIZED = -5,  /* ParsingErr::NotRecognized  parser.rs:68-72 */
+    SE_ERR_UNSUPPORTED = -6,     /* valid in the reference's grammar but outside this build's limits */
+    SE_ERR_COMPILE = -7,         /* NVRTC failure (the reference panics on a GLSL compile error, simulation.rs:133-137) */
+    SE_ERR_CUDA = -8,
+    SE_ERR_INVALID_ARG = -9
+} se_status;
+
+typedef struct se_rules se_rules;   /* parsed rule set + generated CUDA C + sm_100a cubin */
+typedef struct se_sim se_sim;       /* opaque; owns device buffers of one grid (or one strip of it) */
+
+/* == simulation.rs:45-56 `SimModification` (std140 stride 32 B of the shader's UBO, falling_sand.glsl:43-55) */
+typedef struct se_modification {
+    int32_t position[2];
+    int32_t mod_shape;   /* SE_MODSHAPE_* */
+    int32_t mod_size;
+    int32_t mod_matID;
+    int32_t _pad4[3];
+} se_modification;
+#define SE_MODSHAPE_CIRCLE 0     /* simulation.rs:41 */
+#define SE_MODSHAPE_SQUARE 1     /* simulation.rs:42 */
+#define SE_MAX_MODIFICATIONS 256 /* simulation.rs:43 */
+
+#define SE_FLAG_LIGHTING 1u      /* evaluate the lighting relaxation every step (operations.glsl:114-169) */
+
+typedef struct se_create_params {
+    uint32_t width;          /* simSize.x */
+    uint32_t height;         /* simSize.y of the WHOLE grid */
+    uint32_t flags;          /* SE_FLAG_* */
+    int32_t device;          /* CUDA device ordinal */
+    /* Strip decomposition (multi-GPU): this sim owns global rows [row_begin, row_end) and keeps
+     * `halo_rows` ghost rows towards each neighbour.  Single GPU: row_begin = 0, row_end = 0 (= height),
+     * halo_rows = 0.  row_begin/row_end must be even (Margolus blocks are 2 rows). */
+    uint32_t row_begin, row_end, halo_rows;
+    uint32_t temporal_block; /* Margolus steps fused per launch by the tiled kernel; 0 = library default */
+} se_create_params;
+
+/* ---- codegen seam: replaces sandengine_lang::parse_string + create_glsl_from_parser ------------
+ * (parser.rs:93, sandengine-lang/src/lib.rs:17).  Parses the YAML rule language, generates CUDA C and
+ * compiles it for sm_100a.  Parser errors map 1:1 onto the four ParsingErr classes. */
+int se_rules_compile_yaml(const char* yaml, size_t len, se_rules** out);
+int se_rules_parse_only(const char* yaml, size_t len, se_rules** out);   /* front end only: no NVRTC */
+int se_rules_destroy(se_rules* r);
+/* Known-answer text: what the reference's emitter writes to gen/materials.glsl (which=0) and
+ * gen/rules.glsl (which=1); which=2: the generated CUDA header; which=3: NVRTC log. Pointer valid until destroy. */
+int se_rules_text(const se_rules* r, int which, const char** text, size_t* len);
+int se_rules_cubin(const se_rules* r, const void** data, size_t* len);
+int se_rules_counts(const se_rules* r, int32_t* n_rules, int32_t* n_types, int32_t* n_materials);
+/* ParsingResult.materials[i]: id == index (materials.rs:91,196). color/emission: 4 floats each. */
+int se_rules_material(const se_rules* r, int32_t id, const char** name, const char** type_name, float* density,
+                      float* color4, float* emission4, int32_t* selectable);
+int se_rules_material_id(const se_rules* r, const char* name, int32_t* id);
+/* ParsingResult.rules[i] (rules.rs:25-44): kind 0 Mirrored / 1 Left / 2 Right as this build executes it. */
+int se_rules_rule(const se_rules* r, int32_t index, const char** name, int32_t* used, int32_t* kind, const char** precondition);
+
+/* ---- simulation seam: replaces sandengine_core::simulation::Simulation ---------------------- */
+int se_sim_create(const se_rules* rules, const se_create_params* params, se_sim** out);   /* Simulation::new, simulation.rs:128-192 */
+int se_sim_destroy(se_sim* s);
+/* One call == n_steps calls of Simulation::run (simulation.rs:195-253): frame += 1 before each step;
+ * pending modifications are consumed by the FIRST step only and then cleared (:246-252). */
+int se_sim_step(se_sim* s, uint32_t n_steps);
+/* sim.modifications.push(..) (sandengine-core/src/lib.rs:59-67).  Appends; only the first 256 pending
+ * entries are used by the next step (simulation.rs:205), like the reference. */
+int se_sim_push_modifications(se_sim* s, const se_modification* mods, uint32_t n);
+int se_sim_set_frame(se_sim* s, int32_t frame);     /* params.frame, simulation.rs:78 */
+int se_sim_get_frame(const se_sim* s, int32_t* frame);
+/* Cell state (the reference's input_data texture, .r channel): packed uint32 material ids, row-major,
+ * y down, OWNED rows only: width * (row_end - row_begin) entries. */
+int se_sim_upload_cells(se_sim* s, const uint32_t* host_cells);
+int se_sim_download_cells(se_sim* s, uint32_t* host_cells);
+/* Light state (input_light texture): 4 floats per cell, owned rows.  Needs SE_FLAG_LIGHTING. */
+int se_sim_upload_light(se_sim* s, const float* host_rgba);
+int se_sim_download_light(se_sim* s, float* host_rgba);
+/* Device pointer of the current cell buffer's first OWNED row (for CUDA-GL interop / zero-copy readers);
+ * pitch in bytes.  Valid until the next se_sim_step. */
+int se_sim_device_cells(se_sim* s, void** dptr, size_t* pitch_bytes);
+/* Per-material population of the owned rows (256 bins), computed on the device. */
+int se_sim_census(se_sim* s, uint64_t* counts256);
+/* Run on a caller-provided CUDA stream (cudaStream_t as void*); NULL restores the sim's own stream. */
+int se_sim_set_stream(se_sim* s, void* cuda_stream);
+int se_sim_synchronize(se_sim* s);
+/* Number of kernel launches issued by this sim so far (for the bench's gpu_launches claim). */
+int se_sim_launch_count(const se_sim* s, uint64_t* n);
+
+/* ---- strips: ghost-row exchange between neighbouring sims ---------------------- */
+/* Export a CUDA IPC handle (64 bytes) for each of this sim's two cell buffers so that a neighbour
+ * process can map them; buffer geometry is returned alongside. */
+int se_sim_ipc_export(se_sim* s, void* handles_2x64, uint64_t* local_rows, uint64_t* ghost_top, uint64_t* ghost_bottom);
+/* Attach a neighbour (which: 0 = the strip above, 1 = the strip below) from its exported handles.
+ * same_process != 0: `handles` holds two raw device pointers instead (peer access must be enabled). */
+int se_sim_ipc_attach(se_sim* s, int which, const void* handles_2x64, int same_process, uint64_t nb_local_rows,
+                      uint64_t nb_ghost_top, uint64_t nb_ghost_bottom);
+/* Push this sim's boundary rows into the attached neighbours' ghost rows (device-to-device over NVLink). */
+int se_sim_halo_push(se_sim* s);
+
+const char* se_last_error(void);
+const char* se_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SANDENGINE_B200_H */

@@ -663,14 +663,14 @@ def emit_c_rules(res: ParsingResult) -> str:
         second, fourth = ("left", "downleft") if et == "Left" else ("right", "downright")
         pre = "" if r.precondition is None else f"    if (!({_to_c(r.precondition)})) {{ return; }}\n"
         body = _to_c(SandRule._func_logic(list(r.if_conds), list(r.do_actions), list(r.probabilities), 1))
-        o.append(f"static void rule_{r.name}(Cell* p_self, Cell* p_second, Cell* p_down, Cell* p_fourth, const float* rand4, const int* pos) {{\n"
+        o.append(f"static void rule_{r.name}(Cell* p_self, Cell* p_second, Cell* p_down, Cell* p_fourth, const float* rand4, ivec2 pos) {{\n"
                  f"#define self (*p_self)\n#define {second} (*p_second)\n#define down (*p_down)\n#define {fourth} (*p_fourth)\n"
                  f"    const struct {{ float x, y, z, w; }} rand = {{ rand4[0], rand4[1], rand4[2], rand4[3] }}; (void)rand;\n"
                  f"{pre}{body}\n"
                  f"#undef self\n#undef {second}\n#undef down\n#undef {fourth}\n}}\n\n")
         call = f"    rule_{r.name}(self, right, down, downright, rand, pos);\n"
         (mir if et == "Mirrored" else left if et == "Left" else right).append(call)
-    sig = "(Cell* self, Cell* right, Cell* down, Cell* downright, const float* rand, const int* pos)"
+    sig = "(Cell* self, Cell* right, Cell* down, Cell* downright, const float* rand, ivec2 pos)"
     o.append(f"static void applyMirroredRules{sig} {{\n{''.join(mir)}    (void)self; (void)right; (void)down; (void)downright; (void)rand; (void)pos;\n}}\n")
     o.append(f"/* Left rules: called in the MIRRORED view (see oracle_lang.py docstring, SURVEY 8a P3). */\n"
              f"static void applyLeftRules{sig} {{\n{''.join(left)}    (void)self; (void)right; (void)down; (void)downright; (void)rand; (void)pos;\n}}\n")

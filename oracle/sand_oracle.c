@@ -30,9 +30,11 @@ typedef struct {            /* falling_sand.glsl:211-218 */
     int type;
 } Material;
 
+typedef struct { int x, y; } ivec2;
+
 typedef struct {            /* falling_sand.glsl:221-224 */
     Material mat;
-    int pos[2];
+    ivec2 pos;
 } Cell;
 
 typedef struct {            /* falling_sand.glsl:346-351; std140 stride 32 B == simulation.rs:45-56 */
@@ -47,8 +49,8 @@ typedef struct {            /* falling_sand.glsl:346-351; std140 stride 32 B == 
 #define MODSHAPE_SQUARE 1
 #define MAX_MODIFICATIONS 256   /* simulation.rs:43; falling_sand.glsl:354 */
 
-static inline Cell newCell(Material mat, const int* pos) {   /* falling_sand.glsl:226-228 */
-    Cell c; c.mat = mat; c.pos[0] = pos[0]; c.pos[1] = pos[1]; return c;
+static inline Cell newCell(Material mat, ivec2 pos) {   /* falling_sand.glsl:226-228 */
+    Cell c; c.mat = mat; c.pos = pos; return c;
 }
 
 static void swap_cells(Cell* a, Cell* b);
@@ -114,7 +116,7 @@ static inline void getMargolusOffset(int frame, int off[2]) {   /* :380-389 */
 }
 
 static inline Cell getCell(const Ctx* c, int x, int y) {   /* :400-412, SCREEN_IS_BORDER defined (:4) */
-    int pos[2] = {x, y};
+    ivec2 pos = {x, y};
     if (outOfBounds(c, x, y)) return newCell(MAT_WALL, pos);
     int matID = (int)c->input_data[(size_t)y * c->W + x];
     return newCell(getMaterialFromID(matID), pos);
@@ -130,12 +132,12 @@ static inline int isLightObstacle(const Cell* cell) {   /* :423-425 */
 /* Margolus block transition shared by the per-cell and per-block drivers: falling_sand.glsl:692-718.
  * cells = self,right,down,downright at pos_rounded+{(0,0),(1,0),(0,1),(1,1)}.  Returns 0 on the
  * all-EMPTY early-out (:692-694), in which case the caller's result is MAT_EMPTY. */
-static inline int block_transition(Cell* self, Cell* right, Cell* down, Cell* downright, const int* pos_rounded, int frame) {
+static inline int block_transition(Cell* self, Cell* right, Cell* down, Cell* downright, ivec2 pos_rounded, int frame) {
     if (self->mat.id == MAT_EMPTY.id && right->mat.id == MAT_EMPTY.id && down->mat.id == MAT_EMPTY.id && downright->mat.id == MAT_EMPTY.id) {
         return 0;
     }
     float rand[4]; uint32_t lanes[4];
-    hash43(pos_rounded[0], pos_rounded[1], frame, rand, lanes);   /* :698 (rand2, up, upright are unused) */
+    hash43(pos_rounded.x, pos_rounded.y, frame, rand, lanes);   /* :698 (rand2, up, upright are unused) */
     int shouldMirror = rand[0] < 0.5f;                            /* :701 */
     if (shouldMirror) { swap_cells(self, right); swap_cells(down, downright); }   /* :702-705 */
     applyMirroredRules(self, right, down, downright, rand, pos_rounded);           /* :707 */
@@ -152,14 +154,14 @@ static inline int block_transition(Cell* self, Cell* right, Cell* down, Cell* do
 static Cell simulate(const Ctx* c, int gx, int gy) {
     int off[2]; getMargolusOffset(c->frame, off);
     int pos[2] = {gx + off[0], gy + off[1]};
-    int pos_rounded[2] = {(pos[0] / 2) * 2, (pos[1] / 2) * 2};
+    ivec2 pos_rounded = {(pos[0] / 2) * 2, (pos[1] / 2) * 2};
     int marg_idx = (pos[0] & 1) + (pos[1] & 1) * 2;
-    pos_rounded[0] -= off[0]; pos_rounded[1] -= off[1];
+    pos_rounded.x -= off[0]; pos_rounded.y -= off[1];
 
-    Cell self = getCell(c, pos_rounded[0], pos_rounded[1]);
-    Cell right = getCell(c, pos_rounded[0] + 1, pos_rounded[1]);
-    Cell down = getCell(c, pos_rounded[0], pos_rounded[1] + 1);
-    Cell downright = getCell(c, pos_rounded[0] + 1, pos_rounded[1] + 1);
+    Cell self = getCell(c, pos_rounded.x, pos_rounded.y);
+    Cell right = getCell(c, pos_rounded.x + 1, pos_rounded.y);
+    Cell down = getCell(c, pos_rounded.x, pos_rounded.y + 1);
+    Cell downright = getCell(c, pos_rounded.x + 1, pos_rounded.y + 1);
 
     if (!block_transition(&self, &right, &down, &downright, pos_rounded, c->frame)) {
         return newCell(MAT_EMPTY, pos_rounded);
@@ -332,13 +334,13 @@ void so_step_blocks_inplace(uint32_t* cells, int W, int H, int frame) {
 #pragma omp parallel for schedule(static)
     for (int by = 0; by < nby; by++) {
         for (int bx = 0; bx < nbx; bx++) {
-            int pr[2] = {bx * 2 - off[0], by * 2 - off[1]};
+            ivec2 pr = {bx * 2 - off[0], by * 2 - off[1]};
             Cell q[4];
-            q[0] = getCell(&c, pr[0], pr[1]);     q[1] = getCell(&c, pr[0] + 1, pr[1]);
-            q[2] = getCell(&c, pr[0], pr[1] + 1); q[3] = getCell(&c, pr[0] + 1, pr[1] + 1);
+            q[0] = getCell(&c, pr.x, pr.y);     q[1] = getCell(&c, pr.x + 1, pr.y);
+            q[2] = getCell(&c, pr.x, pr.y + 1); q[3] = getCell(&c, pr.x + 1, pr.y + 1);
             if (!block_transition(&q[0], &q[1], &q[2], &q[3], pr, frame)) continue;   /* all EMPTY stays EMPTY */
             for (int k = 0; k < 4; k++) {
-                int x = pr[0] + (k & 1), y = pr[1] + (k >> 1);
+                int x = pr.x + (k & 1), y = pr.y + (k >> 1);
                 if (!outOfBounds(&c, x, y)) cells[(size_t)y * W + x] = (uint32_t)q[k].mat.id;
             }
         }

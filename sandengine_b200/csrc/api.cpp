@@ -1,0 +1,651 @@
+// C ABI implementation (include/sandengine_b200.h): rule compilation (front end + NVRTC) and the
+// simulation host that replaces sandengine-core's `Simulation` (/root/reference/sandengine-core/src/simulation.rs).
+//
+// Device work is launched through the CUDA driver API on functions loaded from the NVRTC-built cubin;
+// the driver entry points are resolved with cudaGetDriverEntryPoint so the library does not link
+// libcuda and can be loaded (and can compile rules) on a host without a GPU.
+#include "../../include/sandengine_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "lang/codegen.h"
+#include "lang/lang.h"
+#include "static_kernels.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+int map_kind(se::ErrKind k) {
+    switch (k) {
+        case se::ErrKind::Yaml: return SE_ERR_YAML;
+        case se::ErrKind::MissingField: return SE_ERR_MISSING_FIELD;
+        case se::ErrKind::InvalidType: return SE_ERR_INVALID_TYPE;
+        case se::ErrKind::NotFound: return SE_ERR_NOT_FOUND;
+        case se::ErrKind::NotRecognized: return SE_ERR_NOT_RECOGNIZED;
+        case se::ErrKind::Unsupported: return SE_ERR_UNSUPPORTED;
+    }
+    return SE_ERR_INVALID_ARG;
+}
+
+const char* const KERNEL_SOURCE =
+#include "_gen/sand_kernels_embed.inc"
+    ;
+
+// ---- driver API through the runtime (no libcuda link dependency) -----------------------------
+struct Driver {
+    decltype(&cuModuleLoadData) ModuleLoadData = nullptr;
+    decltype(&cuModuleUnload) ModuleUnload = nullptr;
+    decltype(&cuModuleGetFunction) ModuleGetFunction = nullptr;
+    decltype(&cuLaunchKernel) LaunchKernel = nullptr;
+    decltype(&cuFuncSetAttribute) FuncSetAttribute = nullptr;
+    decltype(&cuGetErrorString) GetErrorString = nullptr;
+    bool ok = false;
+    std::string why;
+};
+
+Driver& driver() {
+    static Driver d;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        auto get = [&](const char* name, void** fn) {
+            cudaDriverEntryPointQueryResult q;
+            cudaError_t e = cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q);
+            if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !*fn) {
+                d.why = std::string("cudaGetDriverEntryPoint(") + name + ") failed: " + cudaGetErrorString(e);
+                (void)cudaGetLastError();
+                return false;
+            }
+            return true;
+        };
+        d.ok = get("cuModuleLoadData", (void**)&d.ModuleLoadData) && get("cuModuleUnload", (void**)&d.ModuleUnload) &&
+               get("cuModuleGetFunction", (void**)&d.ModuleGetFunction) && get("cuLaunchKernel", (void**)&d.LaunchKernel) &&
+               get("cuFuncSetAttribute", (void**)&d.FuncSetAttribute) && get("cuGetErrorString", (void**)&d.GetErrorString);
+    });
+    return d;
+}
+
+std::string cu_err(CUresult r) {
+    const char* s = nullptr;
+    if (driver().GetErrorString) driver().GetErrorString(r, &s);
+    return s ? s : ("CUresult " + std::to_string((int)r));
+}
+
+#define SE_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) return fail(SE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+#define SE_CU(call)                                                                   \
+    do {                                                                              \
+        CUresult r_ = (call);                                                         \
+        if (r_ != CUDA_SUCCESS) return fail(SE_ERR_CUDA, std::string(#call) + ": " + cu_err(r_)); \
+    } while (0)
+
+// mirrors the device structs of kernels/sand_kernels.cuh
+struct SeMod { int px, py, shape, size, mat, pad0, pad1, pad2; };
+struct SeStepParams {
+    const unsigned* in;
+    unsigned* out;
+    int W, Hl, gy0, Hg;
+    int frame;
+    int n_mods;
+    const SeMod* mods;
+};
+struct SeLightParams {
+    const unsigned* old_cells;
+    const unsigned* new_cells;
+    const float4* light_in;
+    float4* light_out;
+    int W, Hl, gy0, Hg;
+};
+
+}  // namespace
+
+struct se_rules {
+    se::CompiledRules cr;
+    std::string glsl_materials, glsl_rules;
+    std::vector<char> cubin;
+    std::string nvrtc_log;
+    bool compiled = false;
+};
+
+struct Neighbour {
+    bool attached = false;
+    bool ipc = false;
+    unsigned* cells[2] = {nullptr, nullptr};
+    uint64_t local_rows = 0, ghost_top = 0, ghost_bottom = 0;
+};
+
+struct se_sim {
+    const se_rules* rules = nullptr;
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    CUmodule mod = nullptr;
+    CUfunction f_inplace = nullptr, f_inplace_mods = nullptr, f_pingpong = nullptr, f_pingpong_mods = nullptr, f_light = nullptr, f_fill = nullptr;
+    int W = 0, Hg = 0;
+    int row_begin = 0, row_end = 0, ghost_top = 0, ghost_bottom = 0;
+    int gy0 = 0, Hl = 0;   // local buffer: rows [gy0, gy0 + Hl) of the global grid
+    bool lighting = false;
+    unsigned* cells[2] = {nullptr, nullptr};
+    int cur = 0;
+    float4* light[2] = {nullptr, nullptr};
+    int lcur = 0;
+    SeMod* d_mods = nullptr;
+    SeMod* h_mods = nullptr;   // pinned staging, SE_MAX_MODIFICATIONS entries
+    std::vector<se_modification> pending;
+    int frame = 0;
+    uint64_t launches = 0;
+    unsigned long long* d_census = nullptr;
+    Neighbour nb[2];
+    size_t cells_bytes() const { return (size_t)W * Hl * sizeof(unsigned); }
+    size_t owned_offset() const { return (size_t)ghost_top * W; }
+    size_t owned_cells() const { return (size_t)W * (row_end - row_begin); }
+};
+
+namespace {
+
+int compile_front(const char* yaml, size_t len, se_rules** out, bool with_nvrtc) {
+    if (!yaml || !out) return fail(SE_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    se_rules* r = new se_rules();
+    try {
+        se::ParsingResult pr = se::parse_string(std::string(yaml, len));
+        r->glsl_materials = se::emit_glsl_materials(pr);
+        r->glsl_rules = se::emit_glsl_rules(pr);
+        if (with_nvrtc) r->cr = se::compile_rules(pr);   // typed expression check + CUDA C emission
+        else r->cr.parsed = pr;                          // parse_string only, like the reference crate
+    } catch (const se::ParseError& e) {
+        int code = map_kind(e.kind);
+        std::string msg = e.what();
+        delete r;
+        return fail(code, msg);
+    } catch (const std::exception& e) {
+        std::string msg = e.what();
+        delete r;
+        return fail(SE_ERR_INVALID_ARG, msg);
+    }
+    if (with_nvrtc) {
+        nvrtcProgram prog;
+        const char* hdr_src[1] = {r->cr.cuda_header.c_str()};
+        const char* hdr_name[1] = {"rules_gen.cuh"};
+        if (nvrtcCreateProgram(&prog, KERNEL_SOURCE, "sand_kernels.cu", 1, hdr_src, hdr_name) != NVRTC_SUCCESS) {
+            delete r;
+            return fail(SE_ERR_COMPILE, "nvrtcCreateProgram failed");
+        }
+        // -fmad=false: the lighting sums and any float arithmetic in rule conditions are evaluated as
+        // written (no FMA contraction), matching the reference expression tree.
+        const char* opts[] = {"-arch=sm_100a", "-std=c++17", "-lineinfo", "-fmad=false"};
+        nvrtcResult res = nvrtcCompileProgram(prog, 4, opts);
+        size_t log_size = 0;
+        nvrtcGetProgramLogSize(prog, &log_size);
+        r->nvrtc_log.resize(log_size ? log_size - 1 : 0);
+        if (log_size > 1) {
+            std::vector<char> log(log_size);
+            nvrtcGetProgramLog(prog, log.data());
+            r->nvrtc_log.assign(log.data());
+        }
+        if (res != NVRTC_SUCCESS) {
+            std::string msg = "NVRTC: " + std::string(nvrtcGetErrorString(res)) + "\n" + r->nvrtc_log;
+            nvrtcDestroyProgram(&prog);
+            delete r;
+            return fail(SE_ERR_COMPILE, msg);
+        }
+        size_t cubin_size = 0;
+        if (nvrtcGetCUBINSize(prog, &cubin_size) != NVRTC_SUCCESS || cubin_size == 0) {
+            nvrtcDestroyProgram(&prog);
+            delete r;
+            return fail(SE_ERR_COMPILE, "NVRTC produced no cubin");
+        }
+        r->cubin.resize(cubin_size);
+        nvrtcGetCUBIN(prog, r->cubin.data());
+        nvrtcDestroyProgram(&prog);
+        r->compiled = true;
+    }
+    *out = r;
+    return SE_OK;
+}
+
+int launch(se_sim* s, CUfunction f, dim3 grid, dim3 block, void** args, unsigned smem = 0) {
+    SE_CU(driver().LaunchKernel(f, grid.x, grid.y, grid.z, block.x, block.y, block.z, smem, (CUstream)s->stream, args, nullptr));
+    s->launches++;
+    return SE_OK;
+}
+
+int one_step(se_sim* s, bool use_mods, int n_mods) {
+    s->frame += 1;
+    const int frame = s->frame;
+    const int ox = ((frame & 3) == 1 || (frame & 3) == 3) ? 1 : 0;
+    const int oy = ((frame & 3) == 1 || (frame & 3) == 2) ? 1 : 0;
+    if (frame == 1) {
+        // falling_sand.glsl:743-746: every cell becomes EMPTY; modifications are ignored this frame.
+        size_t n = (size_t)s->W * s->Hl;
+        unsigned zero = 0;
+        if (!s->lighting) {
+            unsigned* buf = s->cells[s->cur];
+            void* args[] = {&buf, &n, &zero};
+            return launch(s, s->f_fill, dim3(148 * 8), dim3(256), args);
+        }
+        unsigned* outb = s->cells[s->cur ^ 1];
+        void* args[] = {&outb, &n, &zero};
+        int rc = launch(s, s->f_fill, dim3(148 * 8), dim3(256), args);
+        if (rc) return rc;
+        SeLightParams lp{s->cells[s->cur], outb, s->light[s->lcur], s->light[s->lcur ^ 1], s->W, s->Hl, s->gy0, s->Hg};
+        void* largs[] = {&lp};
+        rc = launch(s, s->f_light, dim3((s->W + 63) / 64, (s->Hl + 3) / 4), dim3(64, 4), largs);
+        if (rc) return rc;
+        s->cur ^= 1;
+        s->lcur ^= 1;
+        return SE_OK;
+    }
+    const int jb0 = (s->gy0 + oy) >> 1;
+    const int y_end = std::min(s->Hg, s->gy0 + s->Hl);
+    const int nby = ((y_end + oy + 1) >> 1) - jb0;
+    const int nbx = (s->W + ox + 1) >> 1;
+    dim3 block(64, 4), grid((nbx + 63) / 64, (nby + 3) / 4);
+    SeStepParams p;
+    p.W = s->W; p.Hl = s->Hl; p.gy0 = s->gy0; p.Hg = s->Hg; p.frame = frame;
+    p.n_mods = use_mods ? n_mods : 0;
+    p.mods = s->d_mods;
+    void* args[] = {&p};
+    if (!s->lighting) {
+        p.in = s->cells[s->cur];
+        p.out = s->cells[s->cur];
+        return launch(s, p.n_mods ? s->f_inplace_mods : s->f_inplace, grid, block, args);
+    }
+    p.in = s->cells[s->cur];
+    p.out = s->cells[s->cur ^ 1];
+    int rc = launch(s, p.n_mods ? s->f_pingpong_mods : s->f_pingpong, grid, block, args);
+    if (rc) return rc;
+    SeLightParams lp{p.in, p.out, s->light[s->lcur], s->light[s->lcur ^ 1], s->W, s->Hl, s->gy0, s->Hg};
+    void* largs[] = {&lp};
+    rc = launch(s, s->f_light, dim3((s->W + 63) / 64, (s->Hl + 3) / 4), dim3(64, 4), largs);
+    if (rc) return rc;
+    s->cur ^= 1;
+    s->lcur ^= 1;
+    return SE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* se_last_error(void) { return g_err.c_str(); }
+const char* se_version(void) { return "sandengine_b200 0.1 (sm_100a)"; }
+
+int se_rules_compile_yaml(const char* yaml, size_t len, se_rules** out) { return compile_front(yaml, len, out, true); }
+int se_rules_parse_only(const char* yaml, size_t len, se_rules** out) { return compile_front(yaml, len, out, false); }
+
+int se_rules_destroy(se_rules* r) {
+    delete r;
+    return SE_OK;
+}
+
+int se_rules_text(const se_rules* r, int which, const char** text, size_t* len) {
+    if (!r || !text || !len) return fail(SE_ERR_INVALID_ARG, "null argument");
+    const std::string* s = nullptr;
+    switch (which) {
+        case 0: s = &r->glsl_materials; break;
+        case 1: s = &r->glsl_rules; break;
+        case 2: s = &r->cr.cuda_header; break;
+        case 3: s = &r->nvrtc_log; break;
+        default: return fail(SE_ERR_INVALID_ARG, "which must be 0..3");
+    }
+    *text = s->c_str();
+    *len = s->size();
+    return SE_OK;
+}
+
+int se_rules_cubin(const se_rules* r, const void** data, size_t* len) {
+    if (!r || !data || !len) return fail(SE_ERR_INVALID_ARG, "null argument");
+    if (!r->compiled) return fail(SE_ERR_INVALID_ARG, "rules were parsed without NVRTC compilation");
+    *data = r->cubin.data();
+    *len = r->cubin.size();
+    return SE_OK;
+}
+
+int se_rules_counts(const se_rules* r, int32_t* n_rules, int32_t* n_types, int32_t* n_materials) {
+    if (!r) return fail(SE_ERR_INVALID_ARG, "null argument");
+    if (n_rules) *n_rules = (int32_t)r->cr.parsed.rules.size();
+    if (n_types) *n_types = (int32_t)r->cr.parsed.types.size();
+    if (n_materials) *n_materials = (int32_t)r->cr.parsed.materials.size();
+    return SE_OK;
+}
+
+int se_rules_material(const se_rules* r, int32_t id, const char** name, const char** type_name, float* density, float* color4,
+                      float* emission4, int32_t* selectable) {
+    if (!r) return fail(SE_ERR_INVALID_ARG, "null argument");
+    if (id < 0 || id >= (int32_t)r->cr.parsed.materials.size()) return fail(SE_ERR_INVALID_ARG, "material id out of range");
+    const se::SandMaterial& m = r->cr.parsed.materials[id];
+    if (name) *name = m.name.c_str();
+    if (type_name) *type_name = m.mattype.c_str();
+    if (density) *density = m.density;
+    if (color4) std::memcpy(color4, m.color, sizeof m.color);
+    if (emission4) std::memcpy(emission4, m.emission, sizeof m.emission);
+    if (selectable) *selectable = m.selectable ? 1 : 0;
+    return SE_OK;
+}
+
+int se_rules_material_id(const se_rules* r, const char* name, int32_t* id) {
+    if (!r || !name || !id) return fail(SE_ERR_INVALID_ARG, "null argument");
+    for (auto& m : r->cr.parsed.materials)
+        if (m.name == name) { *id = m.id; return SE_OK; }
+    return fail(SE_ERR_NOT_FOUND, std::string("(NotFound) material '") + name + "'");
+}
+
+int se_rules_rule(const se_rules* r, int32_t index, const char** name, int32_t* used, int32_t* kind, const char** precondition) {
+    if (!r) return fail(SE_ERR_INVALID_ARG, "null argument");
+    if (index < 0 || index >= (int32_t)r->cr.parsed.rules.size()) return fail(SE_ERR_INVALID_ARG, "rule index out of range");
+    const se::SandRule& ru = r->cr.parsed.rules[index];
+    if (name) *name = ru.name.c_str();
+    if (used) *used = ru.used ? 1 : 0;
+    if (kind) *kind = ru.effective_type() == se::SandRuleType::Mirrored ? 0 : ru.effective_type() == se::SandRuleType::Left ? 1 : 2;
+    if (precondition) *precondition = ru.has_precondition ? ru.precondition.c_str() : nullptr;
+    return SE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int se_sim_destroy(se_sim* s) {
+    if (!s) return SE_OK;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (int w = 0; w < 2; ++w) {
+        if (s->nb[w].attached && s->nb[w].ipc)
+            for (int b = 0; b < 2; ++b)
+                if (s->nb[w].cells[b]) cudaIpcCloseMemHandle(s->nb[w].cells[b]);
+    }
+    for (int b = 0; b < 2; ++b) {
+        if (s->cells[b]) cudaFree(s->cells[b]);
+        if (s->light[b]) cudaFree(s->light[b]);
+    }
+    if (s->d_mods) cudaFree(s->d_mods);
+    if (s->h_mods) cudaFreeHost(s->h_mods);
+    if (s->d_census) cudaFree(s->d_census);
+    if (s->mod && driver().ok) driver().ModuleUnload(s->mod);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    delete s;
+    return SE_OK;
+}
+
+int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** out) {
+    if (!rules || !prm || !out) return fail(SE_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (!rules->compiled) return fail(SE_ERR_INVALID_ARG, "rules were not compiled (use se_rules_compile_yaml)");
+    if (prm->width == 0 || prm->height == 0 || prm->width > (1u << 30) || prm->height > (1u << 30))
+        return fail(SE_ERR_INVALID_ARG, "bad grid size");
+    uint32_t rb = prm->row_begin, re = prm->row_end ? prm->row_end : prm->height;
+    if (rb >= re || re > prm->height) return fail(SE_ERR_INVALID_ARG, "bad row range");
+    if ((rb & 1u) || ((re & 1u) && re != prm->height)) return fail(SE_ERR_INVALID_ARG, "strip boundaries must be even rows");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        return fail(SE_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e));
+    }
+    if (prm->device < 0 || prm->device >= ndev) return fail(SE_ERR_INVALID_ARG, "bad device ordinal");
+    SE_CUDA(cudaSetDevice(prm->device));
+    SE_CUDA(cudaFree(nullptr));   // make sure the primary context exists
+    if (!driver().ok) return fail(SE_ERR_CUDA, driver().why);
+
+    se_sim* s = new se_sim();
+    s->rules = rules;
+    s->device = prm->device;
+    s->W = (int)prm->width;
+    s->Hg = (int)prm->height;
+    s->row_begin = (int)rb;
+    s->row_end = (int)re;
+    s->ghost_top = rb > 0 ? (int)prm->halo_rows : 0;
+    s->ghost_bottom = re < prm->height ? (int)prm->halo_rows : 0;
+    s->ghost_top = std::min(s->ghost_top, s->row_begin);
+    s->ghost_bottom = std::min(s->ghost_bottom, s->Hg - s->row_end);
+    s->gy0 = s->row_begin - s->ghost_top;
+    s->Hl = (s->row_end - s->row_begin) + s->ghost_top + s->ghost_bottom;
+    s->lighting = (prm->flags & SE_FLAG_LIGHTING) != 0;
+
+    auto bail = [&](int code) { se_sim_destroy(s); return code; };
+#define SE_TRY(expr) do { int rc_ = (expr); if (rc_ != SE_OK) return bail(rc_); } while (0)
+#define SE_CUDA_S(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(SE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); return bail(SE_ERR_CUDA); } } while (0)
+#define SE_CU_S(call) do { CUresult r_ = (call); if (r_ != CUDA_SUCCESS) { fail(SE_ERR_CUDA, std::string(#call) + ": " + cu_err(r_)); return bail(SE_ERR_CUDA); } } while (0)
+
+    SE_CUDA_S(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    s->stream = s->own_stream;
+    SE_CU_S(driver().ModuleLoadData(&s->mod, rules->cubin.data()));
+    SE_CU_S(driver().ModuleGetFunction(&s->f_inplace, s->mod, "se_step_inplace"));
+    SE_CU_S(driver().ModuleGetFunction(&s->f_inplace_mods, s->mod, "se_step_inplace_mods"));
+    SE_CU_S(driver().ModuleGetFunction(&s->f_pingpong, s->mod, "se_step_pingpong"));
+    SE_CU_S(driver().ModuleGetFunction(&s->f_pingpong_mods, s->mod, "se_step_pingpong_mods"));
+    SE_CU_S(driver().ModuleGetFunction(&s->f_light, s->mod, "se_light"));
+    SE_CU_S(driver().ModuleGetFunction(&s->f_fill, s->mod, "se_fill_cells"));
+
+    // Simulation::new allocates zero-filled textures (simulation.rs:145,177-181)
+    const bool two = s->lighting;
+    SE_CUDA_S(cudaMalloc(&s->cells[0], s->cells_bytes()));
+    SE_CUDA_S(cudaMemsetAsync(s->cells[0], 0, s->cells_bytes(), s->stream));
+    if (two) {
+        SE_CUDA_S(cudaMalloc(&s->cells[1], s->cells_bytes()));
+        SE_CUDA_S(cudaMemsetAsync(s->cells[1], 0, s->cells_bytes(), s->stream));
+        for (int b = 0; b < 2; ++b) {
+            SE_CUDA_S(cudaMalloc(&s->light[b], (size_t)s->W * s->Hl * sizeof(float4)));
+            SE_CUDA_S(cudaMemsetAsync(s->light[b], 0, (size_t)s->W * s->Hl * sizeof(float4), s->stream));
+        }
+    }
+    SE_CUDA_S(cudaMalloc(&s->d_mods, SE_MAX_MODIFICATIONS * sizeof(SeMod)));
+    SE_CUDA_S(cudaMallocHost(&s->h_mods, SE_MAX_MODIFICATIONS * sizeof(SeMod)));
+    SE_CUDA_S(cudaMalloc(&s->d_census, 256 * sizeof(unsigned long long)));
+    SE_CUDA_S(cudaStreamSynchronize(s->stream));
+    *out = s;
+    return SE_OK;
+}
+
+int se_sim_step(se_sim* s, uint32_t n_steps) {
+    if (!s) return fail(SE_ERR_INVALID_ARG, "null sim");
+    if (n_steps == 0) return SE_OK;
+    SE_CUDA(cudaSetDevice(s->device));
+    // simulation.rs:203-208: the first min(len, 256) pending modifications go into the UBO; the shader
+    // stops at the first entry with mod_size == 0 (falling_sand.glsl:754-756).
+    int n_mods = 0, n_staged = 0;
+    if (!s->pending.empty()) {
+        // Stage the UBO the way the host of the reference does (all of the first min(len, 256) records are
+        // copied, simulation.rs:205-207); the kernels scan only up to the first mod_size == 0 record.
+        n_staged = (int)std::min<size_t>(s->pending.size(), SE_MAX_MODIFICATIONS);
+        bool open = true;
+        for (int i = 0; i < n_staged; ++i) {
+            const se_modification& m = s->pending[i];
+            if (m.mod_size == 0) open = false;
+            SeMod d;
+            d.px = m.position[0]; d.py = m.position[1]; d.shape = m.mod_shape; d.size = m.mod_size;
+            // getMaterialFromID: unknown id => MAT_NULL (id 1), gen/materials.glsl:79-86
+            d.mat = (m.mod_matID >= 0 && m.mod_matID < s->rules->cr.tables.n_materials) ? m.mod_matID : 1;
+            d.pad0 = d.pad1 = d.pad2 = 0;
+            s->h_mods[i] = d;
+            if (open) n_mods = i + 1;
+        }
+        SE_CUDA(cudaMemcpyAsync(s->d_mods, s->h_mods, (size_t)n_staged * sizeof(SeMod), cudaMemcpyHostToDevice, s->stream));
+    }
+    for (uint32_t k = 0; k < n_steps; ++k) {
+        int rc = one_step(s, k == 0, n_mods);
+        if (rc) return rc;
+    }
+    if (n_staged > 0) {
+        // h_mods is reused by the next call: the async copy must have been consumed
+        SE_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    s->pending.clear();   // simulation.rs:252
+    return SE_OK;
+}
+
+int se_sim_push_modifications(se_sim* s, const se_modification* mods, uint32_t n) {
+    if (!s || (!mods && n)) return fail(SE_ERR_INVALID_ARG, "null argument");
+    s->pending.insert(s->pending.end(), mods, mods + n);
+    return SE_OK;
+}
+
+int se_sim_set_frame(se_sim* s, int32_t frame) {
+    if (!s) return fail(SE_ERR_INVALID_ARG, "null sim");
+    if (frame < 0) return fail(SE_ERR_INVALID_ARG, "frame must be >= 0");
+    s->frame = frame;
+    return SE_OK;
+}
+
+int se_sim_get_frame(const se_sim* s, int32_t* frame) {
+    if (!s || !frame) return fail(SE_ERR_INVALID_ARG, "null argument");
+    *frame = s->frame;
+    return SE_OK;
+}
+
+int se_sim_upload_cells(se_sim* s, const uint32_t* host) {
+    if (!s || !host) return fail(SE_ERR_INVALID_ARG, "null argument");
+    SE_CUDA(cudaSetDevice(s->device));
+    SE_CUDA(cudaMemcpyAsync(s->cells[s->cur] + s->owned_offset(), host, s->owned_cells() * sizeof(unsigned), cudaMemcpyHostToDevice, s->stream));
+    SE_CUDA(cudaStreamSynchronize(s->stream));
+    return SE_OK;
+}
+
+int se_sim_download_cells(se_sim* s, uint32_t* host) {
+    if (!s || !host) return fail(SE_ERR_INVALID_ARG, "null argument");
+    SE_CUDA(cudaSetDevice(s->device));
+    SE_CUDA(cudaMemcpyAsync(host, s->cells[s->cur] + s->owned_offset(), s->owned_cells() * sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
+    SE_CUDA(cudaStreamSynchronize(s->stream));
+    return SE_OK;
+}
+
+int se_sim_upload_light(se_sim* s, const float* host) {
+    if (!s || !host) return fail(SE_ERR_INVALID_ARG, "null argument");
+    if (!s->lighting) return fail(SE_ERR_INVALID_ARG, "sim was created without SE_FLAG_LIGHTING");
+    SE_CUDA(cudaSetDevice(s->device));
+    SE_CUDA(cudaMemcpyAsync(s->light[s->lcur] + s->owned_offset(), host, s->owned_cells() * sizeof(float4), cudaMemcpyHostToDevice, s->stream));
+    SE_CUDA(cudaStreamSynchronize(s->stream));
+    return SE_OK;
+}
+
+int se_sim_download_light(se_sim* s, float* host) {
+    if (!s || !host) return fail(SE_ERR_INVALID_ARG, "null argument");
+    if (!s->lighting) return fail(SE_ERR_INVALID_ARG, "sim was created without SE_FLAG_LIGHTING");
+    SE_CUDA(cudaSetDevice(s->device));
+    SE_CUDA(cudaMemcpyAsync(host, s->light[s->lcur] + s->owned_offset(), s->owned_cells() * sizeof(float4), cudaMemcpyDeviceToHost, s->stream));
+    SE_CUDA(cudaStreamSynchronize(s->stream));
+    return SE_OK;
+}
+
+int se_sim_device_cells(se_sim* s, void** dptr, size_t* pitch) {
+    if (!s || !dptr) return fail(SE_ERR_INVALID_ARG, "null argument");
+    *dptr = s->cells[s->cur] + s->owned_offset();
+    if (pitch) *pitch = (size_t)s->W * sizeof(unsigned);
+    return SE_OK;
+}
+
+int se_sim_census(se_sim* s, uint64_t* counts256) {
+    if (!s || !counts256) return fail(SE_ERR_INVALID_ARG, "null argument");
+    SE_CUDA(cudaSetDevice(s->device));
+    SE_CUDA(cudaMemsetAsync(s->d_census, 0, 256 * sizeof(unsigned long long), s->stream));
+    se_static::launch_census(s->cells[s->cur] + s->owned_offset(), s->owned_cells(), s->d_census, s->stream);
+    s->launches++;
+    SE_CUDA(cudaGetLastError());
+    SE_CUDA(cudaMemcpyAsync(counts256, s->d_census, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    SE_CUDA(cudaStreamSynchronize(s->stream));
+    return SE_OK;
+}
+
+int se_sim_set_stream(se_sim* s, void* stream) {
+    if (!s) return fail(SE_ERR_INVALID_ARG, "null sim");
+    SE_CUDA(cudaSetDevice(s->device));
+    SE_CUDA(cudaStreamSynchronize(s->stream));
+    s->stream = stream ? (cudaStream_t)stream : s->own_stream;
+    return SE_OK;
+}
+
+int se_sim_synchronize(se_sim* s) {
+    if (!s) return fail(SE_ERR_INVALID_ARG, "null sim");
+    SE_CUDA(cudaSetDevice(s->device));
+    SE_CUDA(cudaStreamSynchronize(s->stream));
+    return SE_OK;
+}
+
+int se_sim_launch_count(const se_sim* s, uint64_t* n) {
+    if (!s || !n) return fail(SE_ERR_INVALID_ARG, "null argument");
+    *n = s->launches;
+    return SE_OK;
+}
+
+// ---- strips ----------------------------------------------------------------------------------
+int se_sim_ipc_export(se_sim* s, void* handles, uint64_t* local_rows, uint64_t* ghost_top, uint64_t* ghost_bottom) {
+    if (!s || !handles) return fail(SE_ERR_INVALID_ARG, "null argument");
+    SE_CUDA(cudaSetDevice(s->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    std::memset(handles, 0, 128);
+    for (int b = 0; b < 2; ++b) {
+        if (!s->cells[b]) continue;
+        cudaIpcMemHandle_t h;
+        SE_CUDA(cudaIpcGetMemHandle(&h, s->cells[b]));
+        std::memcpy((char*)handles + 64 * b, &h, 64);
+    }
+    if (local_rows) *local_rows = (uint64_t)s->Hl;
+    if (ghost_top) *ghost_top = (uint64_t)s->ghost_top;
+    if (ghost_bottom) *ghost_bottom = (uint64_t)s->ghost_bottom;
+    return SE_OK;
+}
+
+int se_sim_ipc_attach(se_sim* s, int which, const void* handles, int same_process, uint64_t nb_local_rows, uint64_t nb_ghost_top,
+                      uint64_t nb_ghost_bottom) {
+    if (!s || !handles || which < 0 || which > 1) return fail(SE_ERR_INVALID_ARG, "bad argument");
+    SE_CUDA(cudaSetDevice(s->device));
+    Neighbour& nb = s->nb[which];
+    nb.local_rows = nb_local_rows;
+    nb.ghost_top = nb_ghost_top;
+    nb.ghost_bottom = nb_ghost_bottom;
+    nb.ipc = !same_process;
+    for (int b = 0; b < 2; ++b) {
+        if (!s->cells[b]) continue;
+        if (same_process) {
+            void* p;
+            std::memcpy(&p, (const char*)handles + 8 * b, sizeof p);
+            nb.cells[b] = (unsigned*)p;
+        } else {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, (const char*)handles + 64 * b, 64);
+            void* p = nullptr;
+            SE_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            nb.cells[b] = (unsigned*)p;
+        }
+    }
+    nb.attached = true;
+    return SE_OK;
+}
+
+int se_sim_halo_push(se_sim* s) {
+    if (!s) return fail(SE_ERR_INVALID_ARG, "null sim");
+    SE_CUDA(cudaSetDevice(s->device));
+    const size_t rowb = (size_t)s->W * sizeof(unsigned);
+    // strip above (which = 0): my first `nb.ghost_bottom` owned rows become its bottom ghost rows
+    if (s->nb[0].attached && s->nb[0].ghost_bottom > 0) {
+        const Neighbour& nb = s->nb[0];
+        const unsigned* src = s->cells[s->cur] + s->owned_offset();
+        unsigned* dst = nb.cells[s->cur] + (size_t)(nb.local_rows - nb.ghost_bottom) * s->W;
+        SE_CUDA(cudaMemcpyAsync(dst, src, rowb * nb.ghost_bottom, cudaMemcpyDeviceToDevice, s->stream));
+    }
+    // strip below (which = 1): my last `nb.ghost_top` owned rows become its top ghost rows
+    if (s->nb[1].attached && s->nb[1].ghost_top > 0) {
+        const Neighbour& nb = s->nb[1];
+        const unsigned* src = s->cells[s->cur] + s->owned_offset() + (size_t)(s->row_end - s->row_begin - (int)nb.ghost_top) * s->W;
+        unsigned* dst = nb.cells[s->cur];
+        SE_CUDA(cudaMemcpyAsync(dst, src, rowb * nb.ghost_top, cudaMemcpyDeviceToDevice, s->stream));
+    }
+    return SE_OK;
+}
+
+}  // extern "C"

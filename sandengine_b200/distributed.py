@@ -1,0 +1,116 @@
+"""Strip sharding of one grid over the GPUs of a node: one process per GPU,
+`torch.distributed` for the plumbing (rendezvous, IPC-handle exchange, barriers), ghost rows pushed
+device-to-device over NVLink by the native library (se_sim_halo_push) -- no data-path collective.
+
+The grid is cut into horizontal strips on EVEN rows.  A strip keeps `halo_rows` ghost rows towards each
+neighbour and re-computes them redundantly: the Margolus update is block-local and its RAND depends
+only on (block position, frame) (falling_sand.glsl:698), so both neighbours compute identical values
+for the rows they share.  One step can invalidate at most the outermost still-valid ghost row (its
+block may be cut by the buffer edge), hence G ghost rows are good for G steps; then the owners push
+fresh copies.  `StripPlan` holds that arithmetic and is shared by the GPU path and by the CPU (gloo)
+emulation the tests use.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Tuple
+
+
+@dataclass(frozen=True)
+class StripPlan:
+    width: int
+    height: int
+    world: int
+    halo_rows: int
+
+    def __post_init__(self):
+        if self.halo_rows % 2:
+            raise ValueError("halo_rows must be even (strip buffers must start on even rows)")
+        if self.world > 1 and self.halo_rows < 2:
+            raise ValueError("need at least 2 ghost rows to shard")
+        if self.world > 1 and self.height < 2 * self.world:
+            raise ValueError("grid too small to shard")
+        if self.world > 1:
+            smallest = min(e - b for b, e in (self.rows(r) for r in range(self.world)))
+            if smallest < self.halo_rows:
+                raise ValueError("halo_rows exceeds a strip's own rows")
+
+    def rows(self, rank: int) -> Tuple[int, int]:
+        """Owned global rows [begin, end) of `rank`; boundaries are even."""
+        blocks = (self.height + 1) // 2
+        b0 = (blocks * rank) // self.world
+        b1 = (blocks * (rank + 1)) // self.world
+        return 2 * b0, min(self.height, 2 * b1)
+
+    def ghosts(self, rank: int) -> Tuple[int, int]:
+        b, e = self.rows(rank)
+        return (min(self.halo_rows, b) if rank > 0 else 0), (min(self.halo_rows, self.height - e) if rank < self.world - 1 else 0)
+
+    def chunks(self, n_steps: int) -> List[int]:
+        """Step counts between ghost exchanges."""
+        if self.world == 1:
+            return [n_steps] if n_steps else []
+        g = self.halo_rows
+        return [g] * (n_steps // g) + ([n_steps % g] if n_steps % g else [])
+
+
+class StripSimulation:
+    """One rank's strip of a sharded `Simulation` (lighting off)."""
+
+    def __init__(self, rules, size, halo_rows: int = 32, device=None, temporal_block: int = 0):
+        import torch
+        import torch.distributed as dist
+
+        from .simulation import Simulation
+
+        self.dist = dist
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.plan = StripPlan(int(size[0]), int(size[1]), self.world, int(halo_rows) if self.world > 1 else 0)
+        self.row_begin, self.row_end = self.plan.rows(self.rank)
+        dev = torch.cuda.current_device() if device is None else device
+        self.sim = Simulation(rules, size, lighting=False, device=dev, row_begin=self.row_begin, row_end=self.row_end,
+                              halo_rows=self.plan.halo_rows, temporal_block=temporal_block)
+        if self.world > 1:
+            mine = self.sim.ipc_export()
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, mine)
+            if self.rank > 0:
+                h, lr, gt, gb = everyone[self.rank - 1]
+                self.sim.ipc_attach(0, h, lr, gt, gb)
+            if self.rank < self.world - 1:
+                h, lr, gt, gb = everyone[self.rank + 1]
+                self.sim.ipc_attach(1, h, lr, gt, gb)
+            dist.barrier()
+
+    @property
+    def params(self):
+        return self.sim.params
+
+    def upload_cells(self, owned_rows) -> None:
+        self.sim.upload_cells(owned_rows)
+        self.exchange()
+
+    def download_cells(self, out=None):
+        return self.sim.download_cells(out)
+
+    def exchange(self) -> None:
+        """Everyone has finished computing -> push boundary rows into the neighbours' ghosts -> everyone has landed."""
+        if self.world == 1:
+            return
+        self.sim.synchronize()
+        self.dist.barrier()
+        self.sim.halo_push()
+        self.sim.synchronize()
+        self.dist.barrier()
+
+    def step(self, n_steps: int) -> None:
+        for k in self.plan.chunks(int(n_steps)):
+            self.sim.step(k)
+            self.exchange()
+
+    def census(self):
+        return self.sim.census()
+
+    def close(self):
+        self.sim.close()

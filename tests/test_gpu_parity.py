@@ -1,0 +1,230 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle -- the gate for every kernel.
+Bit-exact for cell state; light within 1e-6 absolute (f32, same expression order, no FMA)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import yaml_cases as Y
+from conftest import DEFAULT_YAML
+from sandengine_b200.grids import kat_grid, synthetic_grid
+
+pytestmark = pytest.mark.gpu
+
+LIGHT_ATOL = 1e-6   # recommended tolerance for the f32 lighting values
+
+
+def sha16(g):
+    return hashlib.sha256(g.astype(np.uint8).tobytes()).hexdigest()[:16]
+
+
+@pytest.fixture(scope="module")
+def se(native_lib):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import sandengine_b200
+    return sandengine_b200
+
+
+@pytest.fixture(scope="module")
+def rich(se):
+    from oracle.build_oracle import load_oracle
+    return se.parse_string(Y.RICH_YAML), load_oracle(Y.RICH_YAML)
+
+
+def run_gpu(se, rules, grid, n_steps, frame0=1, lighting=False, light0=None, mods_per_step=None, chunk=None):
+    H, W = grid.shape
+    sim = se.Simulation(rules, (W, H), lighting=lighting)
+    sim.upload_cells(grid)
+    if lighting and light0 is not None:
+        sim.upload_light(light0)
+    sim.params.frame = frame0
+    if mods_per_step is None:
+        if chunk is None:
+            sim.step(n_steps)
+        else:
+            done = 0
+            while done < n_steps:
+                k = min(chunk, n_steps - done)
+                sim.step(k)
+                done += k
+    else:
+        for s in range(n_steps):
+            if mods_per_step[s] is not None and len(mods_per_step[s]):
+                sim.push_modifications(mods_per_step[s])
+            sim.run()
+    out = sim.download_cells()
+    light = sim.download_light() if lighting else None
+    frame = sim.params.frame
+    sim.close()
+    return out, light, frame
+
+
+def test_survey_state_kats(se, default_rules):
+    for n, steps, final in [(16, 40, "e4ab9d8c55d01623"), (32, 100, "d2f2ab20d7d3a8bc"), (20, 60, "298014800d6a9b1b")]:
+        c, _, f = run_gpu(se, default_rules, kat_grid(n), steps)
+        assert f == 1 + steps and sha16(c) == final
+
+
+@pytest.mark.parametrize("w,h,seed,steps", [(256, 256, 1, 1000), (64, 48, 2, 200), (33, 21, 7, 120), (1, 9, 3, 40), (9, 1, 4, 40),
+                                            (2, 2, 5, 16), (130, 66, 11, 257), (515, 77, 13, 64)])
+def test_default_rules_vs_oracle(se, default_rules, oracle, w, h, seed, steps):
+    """configs[0]: 256x256, default rule set, 1000 steps, fixed seed -- plus ragged / degenerate sizes."""
+    g = synthetic_grid(w, h, seed)
+    ref, _, _ = oracle.run(g, 1, steps, blocks=True)
+    got, _, _ = run_gpu(se, default_rules, g, steps)
+    assert np.array_equal(got, ref)
+
+
+def test_every_intermediate_step_256(se, default_rules, oracle):
+    g = synthetic_grid(256, 256, 1)
+    sim = se.Simulation(default_rules, (256, 256))
+    sim.upload_cells(g)
+    sim.params.frame = 1
+    ref = g.copy()
+    frame = 1
+    for k in range(100):
+        sim.run()
+        frame = oracle.run_blocks(ref, frame, 1)
+        assert np.array_equal(sim.download_cells(), ref), f"diverged at step {k + 1}"
+    sim.close()
+
+
+def test_frame_phase_alignment(se, default_rules, oracle):
+    """Start frames covering all four Margolus offsets, and a large frame number."""
+    g = synthetic_grid(96, 80, 21)
+    for f0 in (1, 2, 3, 4, 5, 1000, 1_000_003):
+        ref, _, _ = oracle.run(g, f0, 9, blocks=True)
+        got, _, f = run_gpu(se, default_rules, g, 9, frame0=f0)
+        assert f == f0 + 9 and np.array_equal(got, ref)
+
+
+def test_frame1_clears(se, default_rules, oracle):
+    g = synthetic_grid(64, 64, 3)
+    got, _, f = run_gpu(se, default_rules, g, 1, frame0=0)
+    assert f == 1 and not got.any()
+    got, _, f = run_gpu(se, default_rules, g, 5, frame0=0)
+    assert f == 5 and not got.any()
+
+
+def test_unknown_ids(se, default_rules, oracle):
+    g = synthetic_grid(64, 64, 5)
+    g[10, 10] = 11; g[11, 20] = 200; g[30, 31] = 255; g[40, 40] = 70000; g[41, 41] = 0xFFFFFFFF
+    ref, _, _ = oracle.run(g, 1, 20)
+    got, _, _ = run_gpu(se, default_rules, g, 20)
+    assert np.array_equal(got, ref)
+
+
+def test_rich_rules_left_right_vs_oracle(se, rich):
+    rules, orc = rich
+    for (w, h, seed, steps) in [(128, 96, 5, 300), (61, 47, 6, 150)]:
+        g = synthetic_grid(w, h, seed, mix=Y.RICH_MIX, ids=Y.RICH_IDS)
+        ref, _, _ = orc.run(g, 1, steps, blocks=True)
+        got, _, _ = run_gpu(se, rules, g, steps)
+        assert np.array_equal(got, ref)
+        assert len(np.unique(ref)) > 5
+
+
+def make_mods(se, frame, n_mats, w, h, rng):
+    from sandengine_b200 import MOD_DTYPE
+    k = int(rng.integers(0, 7))
+    m = np.zeros(k, MOD_DTYPE)
+    for i in range(k):
+        m[i]["position"] = (int(rng.integers(-4, w + 4)), int(rng.integers(-4, h + 4)))
+        m[i]["mod_shape"] = int(rng.integers(0, 2))
+        m[i]["mod_size"] = int(rng.integers(1, 12))
+        m[i]["mod_matID"] = int(rng.integers(0, n_mats))
+    return m
+
+
+def test_modifications_vs_oracle(se, default_rules, oracle):
+    """configs[3] semantics at small size: stamps + explosions every frame, incl. size-0 terminator and unknown ids."""
+    from sandengine_b200 import MOD_DTYPE
+    rng = np.random.default_rng(42)
+    w, h, steps = 96, 72, 60
+    g = synthetic_grid(w, h, 4)
+    mods = [make_mods(se, s, 11, w, h, rng) for s in range(steps)]
+    mods[3] = np.zeros(4, MOD_DTYPE)
+    mods[3][0] = ((20, 20), 0, 6, 3, (0, 0, 0)); mods[3][1] = ((30, 30), 1, 0, 4, (0, 0, 0)); mods[3][2] = ((40, 40), 1, 5, 4, (0, 0, 0))
+    mods[5] = np.zeros(2, MOD_DTYPE)
+    mods[5][0] = ((50, 20), 0, 6, 4, (0, 0, 0)); mods[5][1] = ((50, 20), 0, 3, 77, (0, 0, 0))   # unknown id cancels the centre
+    mods[7] = np.zeros(300, MOD_DTYPE)   # more than 256: extras silently dropped (simulation.rs:205)
+    for i in range(300):
+        mods[7][i] = ((i % w, (i * 7) % h), i % 2, 1, 3 + (i % 8), (0, 0, 0))
+    ref, _, _ = oracle.run(g, 1, steps, mods_per_step=mods)
+    got, _, _ = run_gpu(se, default_rules, g, steps, mods_per_step=mods)
+    assert np.array_equal(got, ref)
+
+
+def test_lighting_vs_oracle(se, default_rules, oracle):
+    g = kat_grid(16); g[5][5] = 6; g[9][12] = 8
+    ref, refL, _ = oracle.run(g, 1, 40, light=np.zeros((16, 16, 4), np.float32))
+    got, gotL, _ = run_gpu(se, default_rules, g, 40, lighting=True, light0=np.zeros((16, 16, 4), np.float32))
+    assert sha16(got) == "ca0e8b7d36edd6b2" and np.array_equal(got, ref)
+    assert np.abs(gotL - refL).max() <= LIGHT_ATOL
+    # larger, random light, with modifications
+    rng = np.random.default_rng(7)
+    w, h, steps = 80, 64, 50
+    g = synthetic_grid(w, h, 9)
+    L0 = rng.random((h, w, 4), dtype=np.float32)
+    mods = [make_mods(se, s, 11, w, h, rng) for s in range(steps)]
+    ref, refL, _ = oracle.run(g, 1, steps, light=L0, mods_per_step=mods)
+    got, gotL, _ = run_gpu(se, default_rules, g, steps, lighting=True, light0=L0, mods_per_step=mods)
+    assert np.array_equal(got, ref)
+    err = np.abs(gotL - refL).max()
+    assert err <= LIGHT_ATOL, err
+
+
+def test_lighting_frame1(se, default_rules, oracle):
+    g = synthetic_grid(32, 32, 2)
+    L0 = np.random.default_rng(1).random((32, 32, 4), dtype=np.float32)
+    ref, refL, _ = oracle.run(g, 0, 3, light=L0)
+    got, gotL, _ = run_gpu(se, default_rules, g, 3, frame0=0, lighting=True, light0=L0)
+    assert np.array_equal(got, ref) and np.abs(gotL - refL).max() <= LIGHT_ATOL
+
+
+def test_4096_short_horizon_vs_oracle(se, default_rules, oracle):
+    """configs[1] size (4096^2): oracle comparison at steps 1..5 and 32."""
+    g = synthetic_grid(4096, 4096, 2)
+    sim = se.Simulation(default_rules, (4096, 4096))
+    sim.upload_cells(g)
+    sim.params.frame = 1
+    ref = g.copy()
+    frame = 1
+    for target in (1, 2, 3, 4, 5, 32):
+        k = target - (frame - 1)
+        sim.step(k)
+        frame = oracle.run_blocks(ref, frame, k)
+        assert np.array_equal(sim.download_cells(), ref), f"step {target}"
+    sim.close()
+
+
+def test_census_and_conservation_properties(se, default_rules):
+    """Size-independent properties at a BASELINE-size grid (16384 x 2048 strip-sized): census equals a host
+    bincount, and materials that no rule creates or destroys (rock, radioactive, toxic_sludge, sand, dirt, water) are conserved."""
+    w, h = 16384, 2048
+    g = synthetic_grid(w, h, 3)
+    sim = se.Simulation(default_rules, (w, h))
+    sim.upload_cells(g)
+    sim.params.frame = 1
+    c0 = sim.census()
+    assert np.array_equal(c0[:11], np.bincount(g.ravel(), minlength=11).astype(np.uint64))
+    sim.step(200)
+    c1 = sim.census()
+    out = sim.download_cells()
+    assert np.array_equal(c1[:11], np.bincount(out.ravel(), minlength=11).astype(np.uint64))
+    assert c1.sum() == w * h
+    for mat in (4, 6, 8, 5, 10):       # rock, radioactive, toxic_sludge, water, dirt: only ever swapped
+        assert c1[mat] == c0[mat]
+    assert c1[3] == c0[3]               # sand
+    assert c1[1] == 0 and c1[2] == 0    # no NULL / WALL leaks into the grid
+    assert c1[7] <= c0[7]               # smoke only dissolves
+    sim.close()
+
+
+def test_step_chunking_is_equivalent(se, default_rules):
+    g = synthetic_grid(300, 200, 8)
+    a, _, _ = run_gpu(se, default_rules, g, 64)
+    b, _, _ = run_gpu(se, default_rules, g, 64, chunk=1)
+    c, _, _ = run_gpu(se, default_rules, g, 64, chunk=7)
+    assert np.array_equal(a, b) and np.array_equal(a, c)
