@@ -197,7 +197,8 @@ def run_ours(args):
     rules = se.parse_path(REPO / "data" / "materials.yaml")
     strip = StripSimulation(rules, (S, S), halo_rows=args.halo, device=local_rank, temporal_block=args.temporal_block)
     sim = strip.sim
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-legacy) stream: events below are recorded on the launching stream
+    torch.cuda.set_stream(stream)
     sim.set_stream(stream.cuda_stream)
 
     rows = strip.row_end - strip.row_begin

@@ -118,10 +118,13 @@ int se_sim_launch_count(const se_sim* s, uint64_t* n);
 /* Export a CUDA IPC handle (64 bytes) for each of this sim's two cell buffers so that a neighbour
  * process can map them; buffer geometry is returned alongside. */
 int se_sim_ipc_export(se_sim* s, void* handles_2x64, uint64_t* local_rows, uint64_t* ghost_top, uint64_t* ghost_bottom);
-/* Attach a neighbour (which: 0 = the strip above, 1 = the strip below) from its exported handles.
- * same_process != 0: `handles` holds two raw device pointers instead (peer access must be enabled). */
-int se_sim_ipc_attach(se_sim* s, int which, const void* handles_2x64, int same_process, uint64_t nb_local_rows,
+/* Attach a neighbour living in ANOTHER process (which: 0 = the strip above, 1 = the strip below) from its
+ * exported handles. */
+int se_sim_ipc_attach(se_sim* s, int which, const void* handles_2x64, uint64_t nb_local_rows,
                       uint64_t nb_ghost_top, uint64_t nb_ghost_bottom);
+/* Attach a neighbour that lives in THIS process (one process driving several strips / devices, the
+ * reference's single-process model); peer access is enabled when the devices differ. */
+int se_sim_attach_local(se_sim* s, int which, se_sim* neighbour);
 /* Push this sim's boundary rows into the attached neighbours' ghost rows (device-to-device over NVLink). */
 int se_sim_halo_push(se_sim* s);
 

@@ -106,6 +106,15 @@ struct SeStepParams {
     int n_mods;
     const SeMod* mods;
 };
+struct SeTileParams {
+    const unsigned* in;
+    unsigned* out;
+    int W, Hl, gy0, Hg;
+    int frame0, nsub, T, HX, PH;
+    int tiles_x, tiles_y;
+    int lut_words, pool_offset, tile_offset;
+    const unsigned* lut;
+};
 struct SeLightParams {
     const unsigned* old_cells;
     const unsigned* new_cells;
@@ -152,6 +161,11 @@ struct se_sim {
     int frame = 0;
     uint64_t launches = 0;
     unsigned long long* d_census = nullptr;
+    // transition-table tile kernel (K1b)
+    bool tiled = false;
+    CUfunction f_tiles = nullptr, f_build_lut = nullptr;
+    unsigned* d_lut = nullptr;
+    int T = 0, HX = 0, PH = 0, tiles_x = 0, tiles_y = 0, lut_words = 0, pool_offset = 0, tile_offset = 0, tile_smem = 0, tile_grid = 0;
     Neighbour nb[2];
     size_t cells_bytes() const { return (size_t)W * Hl * sizeof(unsigned); }
     size_t owned_offset() const { return (size_t)ghost_top * W; }
@@ -376,6 +390,7 @@ int se_sim_destroy(se_sim* s) {
     if (s->d_mods) cudaFree(s->d_mods);
     if (s->h_mods) cudaFreeHost(s->h_mods);
     if (s->d_census) cudaFree(s->d_census);
+    if (s->d_lut) cudaFree(s->d_lut);
     if (s->mod && driver().ok) driver().ModuleUnload(s->mod);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
@@ -447,6 +462,64 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
     SE_CUDA_S(cudaMalloc(&s->d_mods, SE_MAX_MODIFICATIONS * sizeof(SeMod)));
     SE_CUDA_S(cudaMallocHost(&s->h_mods, SE_MAX_MODIFICATIONS * sizeof(SeMod)));
     SE_CUDA_S(cudaMalloc(&s->d_census, 256 * sizeof(unsigned long long)));
+
+    // ---- K1b: transition table + shared-memory tiles with temporal blocking -------------------------
+    // Used for runs of steps without modifications when lighting is off, the rule set is table-eligible
+    // (codegen.h) and rows are 16-byte aligned.  temporal_block == 1 forces the per-step kernel K1a.
+    if (rules->cr.lut_eligible && !s->lighting && (s->W % 4) == 0 && prm->temporal_block != 1) {
+        const int N = rules->cr.tables.n_materials, NCLS = (int)rules->cr.lut_thresholds.size() + 1;
+        const int N4 = N * N * N * N;
+        const int POOL_MAX = 4095;
+        (void)NCLS;
+        const size_t pool_off = ((size_t)N4 * 2 + 7) / 8 * 8;     // pool entries are 8 bytes {thr, A, B}
+        const size_t lut_cap = pool_off + (size_t)POOL_MAX * 8 + 16;
+        unsigned* d_counter = nullptr;
+        SE_CU_S(driver().ModuleGetFunction(&s->f_tiles, s->mod, "se_step_tiles"));
+        SE_CU_S(driver().ModuleGetFunction(&s->f_build_lut, s->mod, "se_build_lut"));
+        SE_CUDA_S(cudaMalloc(&s->d_lut, lut_cap));
+        SE_CUDA_S(cudaMalloc(&d_counter, sizeof(unsigned)));
+        SE_CUDA_S(cudaMemsetAsync(s->d_lut, 0, lut_cap, s->stream));
+        SE_CUDA_S(cudaMemsetAsync(d_counter, 0, sizeof(unsigned), s->stream));
+        unsigned short* base = reinterpret_cast<unsigned short*>(s->d_lut);
+        void* pool = reinterpret_cast<char*>(s->d_lut) + pool_off;
+        void* bargs[] = {&base, &pool, &d_counter};
+        SE_TRY(launch(s, s->f_build_lut, dim3((N4 + 255) / 256), dim3(256), bargs));
+        unsigned n_pool = 0;
+        SE_CUDA_S(cudaMemcpyAsync(&n_pool, d_counter, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
+        SE_CUDA_S(cudaStreamSynchronize(s->stream));
+        cudaFree(d_counter);
+        int smem_sm = 0, smem_optin = 0;
+        SE_CUDA_S(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, s->device));
+        SE_CUDA_S(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
+        if ((int)n_pool <= POOL_MAX) {
+            const size_t lut_bytes = pool_off + (size_t)n_pool * 8;
+            s->pool_offset = (int)pool_off;
+            s->lut_words = (int)((lut_bytes + 3) / 4);
+            s->tile_offset = (int)((lut_bytes + 15) / 16 * 16);
+            // two CTAs per SM: each gets half of the SM's shared memory minus the per-CTA reservation (1 KB)
+            // and the kernel's static shared memory (1 KB fat table)
+            const int budget = std::min(smem_optin, smem_sm / 2 - 2048 - 256);
+            int T = prm->temporal_block ? (int)prm->temporal_block : 4;
+            T = std::max(2, T + (T & 1));
+            int PH = ((budget - s->tile_offset) / 256) & ~1;
+            PH = std::min(PH, 256);
+            if (PH >= 4 * T + 16) {
+                s->T = T;
+                s->HX = (T + 3) & ~3;
+                s->PH = PH;
+                s->tile_smem = s->tile_offset + 256 * PH;
+                s->tiles_x = (s->W + (256 - 2 * s->HX) - 1) / (256 - 2 * s->HX);
+                s->tiles_y = (s->Hl + (PH - 2 * T) - 1) / (PH - 2 * T);
+                int n_sm = 0;
+                SE_CUDA_S(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device));
+                s->tile_grid = std::min(2 * n_sm, s->tiles_x * s->tiles_y);
+                SE_CU_S(driver().FuncSetAttribute(s->f_tiles, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->tile_smem));
+                SE_CUDA_S(cudaMalloc(&s->cells[1], s->cells_bytes()));
+                SE_CUDA_S(cudaMemsetAsync(s->cells[1], 0, s->cells_bytes(), s->stream));
+                s->tiled = true;
+            }
+        }
+    }
     SE_CUDA_S(cudaStreamSynchronize(s->stream));
     *out = s;
     return SE_OK;
@@ -477,9 +550,28 @@ int se_sim_step(se_sim* s, uint32_t n_steps) {
         }
         SE_CUDA(cudaMemcpyAsync(s->d_mods, s->h_mods, (size_t)n_staged * sizeof(SeMod), cudaMemcpyHostToDevice, s->stream));
     }
-    for (uint32_t k = 0; k < n_steps; ++k) {
+    for (uint32_t k = 0; k < n_steps;) {
+        const bool mods_now = (k == 0 && n_mods > 0);
+        if (s->tiled && !mods_now && s->frame + 1 != 1) {
+            // a run of plain steps: fuse up to T of them per launch (ping-pong buffers)
+            const int nsub = (int)std::min<uint32_t>((uint32_t)s->T, n_steps - k);
+            SeTileParams tp;
+            tp.in = s->cells[s->cur]; tp.out = s->cells[s->cur ^ 1];
+            tp.W = s->W; tp.Hl = s->Hl; tp.gy0 = s->gy0; tp.Hg = s->Hg;
+            tp.frame0 = s->frame + 1; tp.nsub = nsub; tp.T = s->T; tp.HX = s->HX; tp.PH = s->PH;
+            tp.tiles_x = s->tiles_x; tp.tiles_y = s->tiles_y; tp.lut_words = s->lut_words; tp.pool_offset = s->pool_offset; tp.tile_offset = s->tile_offset;
+            tp.lut = s->d_lut;
+            void* targs[] = {&tp};
+            int rc = launch(s, s->f_tiles, dim3(s->tile_grid), dim3(512), targs, (unsigned)s->tile_smem);
+            if (rc) return rc;
+            s->frame += nsub;
+            s->cur ^= 1;
+            k += (uint32_t)nsub;
+            continue;
+        }
         int rc = one_step(s, k == 0, n_mods);
         if (rc) return rc;
+        ++k;
     }
     if (n_staged > 0) {
         // h_mods is reused by the next call: the async copy must have been consumed
@@ -600,29 +692,45 @@ int se_sim_ipc_export(se_sim* s, void* handles, uint64_t* local_rows, uint64_t* 
     return SE_OK;
 }
 
-int se_sim_ipc_attach(se_sim* s, int which, const void* handles, int same_process, uint64_t nb_local_rows, uint64_t nb_ghost_top,
-                      uint64_t nb_ghost_bottom) {
+int se_sim_ipc_attach(se_sim* s, int which, const void* handles, uint64_t nb_local_rows, uint64_t nb_ghost_top, uint64_t nb_ghost_bottom) {
     if (!s || !handles || which < 0 || which > 1) return fail(SE_ERR_INVALID_ARG, "bad argument");
     SE_CUDA(cudaSetDevice(s->device));
     Neighbour& nb = s->nb[which];
     nb.local_rows = nb_local_rows;
     nb.ghost_top = nb_ghost_top;
     nb.ghost_bottom = nb_ghost_bottom;
-    nb.ipc = !same_process;
+    nb.ipc = true;
     for (int b = 0; b < 2; ++b) {
         if (!s->cells[b]) continue;
-        if (same_process) {
-            void* p;
-            std::memcpy(&p, (const char*)handles + 8 * b, sizeof p);
-            nb.cells[b] = (unsigned*)p;
-        } else {
-            cudaIpcMemHandle_t h;
-            std::memcpy(&h, (const char*)handles + 64 * b, 64);
-            void* p = nullptr;
-            SE_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-            nb.cells[b] = (unsigned*)p;
-        }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, (const char*)handles + 64 * b, 64);
+        void* p = nullptr;
+        SE_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        nb.cells[b] = (unsigned*)p;
     }
+    nb.attached = true;
+    return SE_OK;
+}
+
+int se_sim_attach_local(se_sim* s, int which, se_sim* other) {
+    if (!s || !other || which < 0 || which > 1) return fail(SE_ERR_INVALID_ARG, "bad argument");
+    if (s->W != other->W || s->Hg != other->Hg) return fail(SE_ERR_INVALID_ARG, "neighbour belongs to a different grid");
+    SE_CUDA(cudaSetDevice(s->device));
+    if (other->device != s->device) {
+        int can = 0;
+        SE_CUDA(cudaDeviceCanAccessPeer(&can, s->device, other->device));
+        if (!can) return fail(SE_ERR_CUDA, "devices cannot access each other's memory");
+        cudaError_t e = cudaDeviceEnablePeerAccess(other->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(SE_ERR_CUDA, cudaGetErrorString(e));
+        (void)cudaGetLastError();
+    }
+    Neighbour& nb = s->nb[which];
+    nb.local_rows = (uint64_t)other->Hl;
+    nb.ghost_top = (uint64_t)other->ghost_top;
+    nb.ghost_bottom = (uint64_t)other->ghost_bottom;
+    nb.ipc = false;
+    nb.cells[0] = other->cells[0];
+    nb.cells[1] = other->cells[1];
     nb.attached = true;
     return SE_OK;
 }

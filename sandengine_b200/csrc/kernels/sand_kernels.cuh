@@ -71,10 +71,8 @@ static __device__ __forceinline__ void se_hash43(int px, int py, int frame, SeRa
     rnd.u[3] = (SE_RAND_LANES & 8u) ? se_hashi(x * 213132u) : 0u;
 }
 
-// falling_sand.glsl:698-718.  The caller has already taken the all-EMPTY early-out (:692-694).
-static __device__ __forceinline__ void se_block(unsigned& s, unsigned& r, unsigned& d, unsigned& dr, int px, int py, int frame) {
-    SeRand rnd;
-    se_hash43(px, py, frame, rnd);
+// falling_sand.glsl:701-718 for a given RAND.  The caller has already taken the all-EMPTY early-out (:692-694).
+static __device__ __forceinline__ void se_block_with_rand(unsigned& s, unsigned& r, unsigned& d, unsigned& dr, const SeRand& rnd, int px, int py, int frame) {
     const bool mirror = rnd.u[0] <= SE_MIRROR_UMAX;   // rand.x < 0.5
     if (mirror) { SE_SWAP(s, r); SE_SWAP(d, dr); }
     se_apply_mirrored(s, r, d, dr, rnd, px, py, frame);
@@ -85,6 +83,13 @@ static __device__ __forceinline__ void se_block(unsigned& s, unsigned& r, unsign
 #if SE_HAVE_RIGHT_RULES
     if (!mirror) se_apply_right(s, r, d, dr, rnd, px, py, frame);
 #endif
+}
+
+// falling_sand.glsl:698-718
+static __device__ __forceinline__ void se_block(unsigned& s, unsigned& r, unsigned& d, unsigned& dr, int px, int py, int frame) {
+    SeRand rnd;
+    se_hash43(px, py, frame, rnd);
+    se_block_with_rand(s, r, d, dr, rnd, px, py, frame);
 }
 
 static __device__ __forceinline__ void se_margolus_offset(int frame, int& ox, int& oy) {   // operations.glsl:25-34
@@ -115,6 +120,7 @@ static __device__ __forceinline__ bool se_mod_lookup(const SeMod* __restrict__ m
     return got && fin != 1;
 }
 
+#ifndef SE_HOST_EMU   // kernels (the pure device functions above are also compiled on the host by tests/emu)
 // ---------------------------------------------------------------------------------------------
 // K1a: one Margolus step, one thread per 2x2 block, straight from/to global memory.
 //   IN_PLACE : out == in, only cells whose id changed are stored (blocks partition the grid, so the
@@ -257,3 +263,295 @@ extern "C" __global__ void __launch_bounds__(256) se_fill_cells(unsigned* cells,
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) cells[i] = value;
 }
+
+
+#endif  // SE_HOST_EMU
+
+// =============================================================================================
+// K1b: transition-table kernel with shared-memory tiles and temporal blocking.
+//
+// Eligible rule sets (SE_LUT_ELIGIBLE, decided by the code generator): the block transition is a pure
+// function of (4 material ids, mirror bit, rand.y) with rand.y used only against literal thresholds --
+// no pos/frame/other rand use -- there are no non-mirrored rules and N = SE_N_MATERIALS <= 12.  Then
+//     T0[idx],  idx = ((a*N + b)*N + c)*N + d            (N^4 entries, 16 bit)
+// holds the UNMIRRORED transition of every block state, nibble-packed (a | b<<4 | c<<8 | d<<12), built on
+// the device by se_build_lut from the very rule code generated for the generic path.  Entry kinds:
+//     0x0000..0xEFFF  the result (ids < 15)
+//     0xF000 | k      result depends on rand.y: pool[k] = {thr, A, B}: result = (u1 <= thr) ? A : B, where A/B
+//                     are again entries (B may chain to another pool entry for states with several thresholds)
+//     0xFFFF          the state or its result holds WALL / NULL (guarded swaps, operations.glsl:16-23):
+//                     take the generic path (same generated code as K1a)
+// The mirrored transition is  swap_pairs(T0[swap_pairs(state)])  -- exact when no cell of the block
+// refuses to swap, which is precisely when the table is used.
+//
+// One persistent CTA loops over tiles: load (uint4 global -> u8 shared), nsub Margolus sub-steps in
+// shared memory with a halo of T cells, store the interior (u8 shared -> uint4 global, ping-pong buffer).
+// HBM traffic per cell-update ~ (4 * tile/interior + 4) / T bytes instead of 8.
+// =============================================================================================
+#if SE_LUT_ELIGIBLE
+#define SE_N4 (SE_N_MATERIALS * SE_N_MATERIALS * SE_N_MATERIALS * SE_N_MATERIALS)
+#define SE_TILE_PW 256          // tile width in cells (= bytes); 64 words per row
+#define SE_LUT_POOL_MAX 4095
+#define SE_LUT_SLOW 0xFFFFu
+
+struct SePoolEntry { unsigned thr; unsigned short a, b; };   // 8 bytes
+
+// one block state: evaluate every rand.y class with the generated rule code, then encode
+static __device__ __forceinline__ void se_build_lut_entry(int idx, unsigned short* __restrict__ base, SePoolEntry* __restrict__ pool,
+                                                          unsigned* __restrict__ counter) {
+    const int N = SE_N_MATERIALS;
+    const unsigned ia = idx / (N * N * N), ib = (idx / (N * N)) % N, ic = (idx / N) % N, id = idx % N;
+    unsigned short res[SE_LUT_NCLS];
+    // class c <=> rand.y hash lane u1 in (U_{c-1}, U_c]  (U_{-1} = -1, U_{NCLS-1} = 2^32-1)
+    bool noswap = ((se_fat_table[ia] | se_fat_table[ib] | se_fat_table[ic] | se_fat_table[id]) & SE_F_NOSWAP) != 0u;
+#pragma unroll
+    for (int cls = 0; cls < SE_LUT_NCLS; ++cls) {
+        unsigned s = se_fat_table[ia], r = se_fat_table[ib], d = se_fat_table[ic], dr = se_fat_table[id];
+        if (idx != 0) {
+            SeRand rnd;
+            rnd.u[0] = 0xFFFFFFFFu;                                       // rand.x >= 0.5: unmirrored view
+            rnd.u[1] = cls == 0 ? 0u : se_lut_thresholds[cls - 1] + 1u;  // representative of the class
+            rnd.u[2] = 0u; rnd.u[3] = 0u;
+            se_block_with_rand(s, r, d, dr, rnd, 0, 0, 0);
+        }
+        if ((s | r | d | dr) & SE_F_NOSWAP) noswap = true;
+        res[cls] = (unsigned short)(SE_ID(s) | (SE_ID(r) << 4) | (SE_ID(d) << 8) | (SE_ID(dr) << 12));
+    }
+    if (noswap) { base[idx] = SE_LUT_SLOW; return; }
+    int n_breaks = 0;
+#pragma unroll
+    for (int cls = 1; cls < SE_LUT_NCLS; ++cls) n_breaks += (res[cls] != res[cls - 1]) ? 1 : 0;
+    if (n_breaks == 0) { base[idx] = res[0]; return; }
+    const unsigned k0 = atomicAdd(counter, (unsigned)n_breaks);
+    if (k0 + n_breaks > SE_LUT_POOL_MAX) { base[idx] = SE_LUT_SLOW; return; }   // overflow: the host refuses the table
+    base[idx] = (unsigned short)(0xF000u | k0);
+    unsigned k = k0;
+    int left = n_breaks;
+    for (int cls = 1; cls < SE_LUT_NCLS; ++cls) {
+        if (res[cls] != res[cls - 1]) {
+            --left;
+            SePoolEntry e;
+            e.thr = se_lut_thresholds[cls - 1];            // u1 <= U_{cls-1}  <=>  class < cls
+            e.a = res[cls - 1];
+            e.b = left ? (unsigned short)(0xF000u | (k + 1)) : res[cls];
+            pool[k] = e;
+            ++k;
+        }
+    }
+}
+
+#ifndef SE_HOST_EMU
+extern "C" __global__ void __launch_bounds__(256) se_build_lut(unsigned short* __restrict__ base, SePoolEntry* __restrict__ pool,
+                                                               unsigned* __restrict__ counter) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < SE_N4) se_build_lut_entry(idx, base, pool, counter);
+}
+#endif
+
+struct SeTileParams {
+    const unsigned* in;     // local buffer (row 0 == global row gy0)
+    unsigned* out;          // the other ping-pong buffer
+    int W, Hl, gy0, Hg;
+    int frame0;             // frame number of the first sub-step of this launch
+    int nsub;               // sub-steps in this launch, 1..T
+    int T;                  // halo depth in rows (even)
+    int HX;                 // halo depth in columns (multiple of 4, >= T)
+    int PH;                 // tile height in cells (even)
+    int tiles_x, tiles_y;
+    int lut_words;          // 32-bit words of (base + pad + pool) to stage in shared memory
+    int pool_offset;        // byte offset of the pool inside the staged table (8-aligned)
+    int tile_offset;        // byte offset of the tile inside dynamic shared memory (16-aligned)
+    const unsigned* lut;
+};
+
+static __device__ __forceinline__ unsigned se_pack_ids(uint4 v) {
+    const unsigned a = v.x < SE_N_MATERIALS ? v.x : 1u, b = v.y < SE_N_MATERIALS ? v.y : 1u;
+    const unsigned c = v.z < SE_N_MATERIALS ? v.z : 1u, d = v.w < SE_N_MATERIALS ? v.w : 1u;
+    return a | (b << 8) | (c << 16) | (d << 24);
+}
+
+static __device__ __forceinline__ unsigned se_nibbles_to_bytes(unsigned e) {
+    unsigned x = (e | (e << 8)) & 0x00FF00FFu;
+    return (x | (x << 4)) & 0x0F0F0F0Fu;
+}
+
+// Table access: on the device the table lives in shared memory and is addressed with 32-bit shared
+// addresses (explicit ld.shared keeps the compiler from re-deriving the shared window base per access);
+// the host emulation reads the same layout through plain pointers.
+#ifdef SE_HOST_EMU
+typedef const unsigned char* se_tab_t;
+static inline unsigned se_tab_u16(se_tab_t t, unsigned byte_off) { unsigned short v; std::memcpy(&v, t + byte_off, 2); return v; }
+static inline void se_tab_pool(se_tab_t t, unsigned byte_off, unsigned& thr, unsigned& ab) { std::memcpy(&thr, t + byte_off, 4); std::memcpy(&ab, t + byte_off + 4, 4); }
+static inline unsigned se_idx4(unsigned vv) {
+    return (((vv & 0xFFu) * SE_N_MATERIALS + ((vv >> 8) & 0xFFu)) * SE_N_MATERIALS + ((vv >> 16) & 0xFFu)) * SE_N_MATERIALS + (vv >> 24);
+}
+#else
+typedef unsigned se_tab_t;   // shared-space address
+static __device__ __forceinline__ unsigned se_lds_u8(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+static __device__ __forceinline__ unsigned se_lds_u16(unsigned a) { unsigned v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+static __device__ __forceinline__ unsigned se_lds_u32(unsigned a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+static __device__ __forceinline__ void se_sts_u8(unsigned a, unsigned v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+static __device__ __forceinline__ void se_sts_u16(unsigned a, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+static __device__ __forceinline__ void se_sts_u32(unsigned a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+static __device__ __forceinline__ unsigned se_tab_u16(se_tab_t t, unsigned byte_off) { return se_lds_u16(t + byte_off); }
+static __device__ __forceinline__ void se_tab_pool(se_tab_t t, unsigned byte_off, unsigned& thr, unsigned& ab) {
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(thr), "=r"(ab) : "r"(t + byte_off));
+}
+// idx = ((a*N + b)*N + c)*N + d from the four id bytes: one dp4a for a*N^2 + b*N + c
+static __device__ __forceinline__ unsigned se_idx4(unsigned vv) {
+    return __dp4a(vv, (unsigned)(SE_N_MATERIALS * SE_N_MATERIALS) | ((unsigned)SE_N_MATERIALS << 8) | (1u << 16), 0u) * SE_N_MATERIALS + (vv >> 24);
+}
+#endif
+
+// one block: v = a | b<<8 | c<<16 | d<<24 (material ids), returns the new ids in the same packing
+static __device__ __forceinline__ unsigned se_block_lut(unsigned v, unsigned seed, int px, int py, int frame,
+                                                        se_tab_t tab, unsigned pool_off, const unsigned* __restrict__ fat_sm) {
+    const unsigned u0 = se_hashi(seed * 213u);
+    const bool mirror = u0 <= SE_MIRROR_UMAX;
+    const unsigned vv = mirror ? __byte_perm(v, 0u, 0x2301) : v;
+    unsigned e = se_tab_u16(tab, se_idx4(vv) * 2u);
+    if (e >= 0xF000u) {
+        if (e != SE_LUT_SLOW) {
+            const unsigned u1 = se_hashi(seed * 2131u);
+            do {
+                unsigned thr, ab;
+                se_tab_pool(tab, pool_off + (e & 0xFFFu) * 8u, thr, ab);
+                e = (u1 <= thr) ? (ab & 0xFFFFu) : (ab >> 16);
+            } while (e >= 0xF000u);
+        } else {
+            // generic path (the block touches WALL / NULL): same generated code as K1a
+            unsigned s = fat_sm[v & 0xFFu], r = fat_sm[(v >> 8) & 0xFFu], d = fat_sm[(v >> 16) & 0xFFu], dr = fat_sm[v >> 24];
+            SeRand rnd;
+            rnd.u[0] = u0;
+            rnd.u[1] = (SE_RAND_LANES & 2u) ? se_hashi(seed * 2131u) : 0u;
+            rnd.u[2] = 0u; rnd.u[3] = 0u;
+            se_block_with_rand(s, r, d, dr, rnd, px, py, frame);
+            return SE_ID(s) | (SE_ID(r) << 8) | (SE_ID(d) << 16) | (SE_ID(dr) << 24);
+        }
+    }
+    const unsigned rr = se_nibbles_to_bytes(e);
+    return mirror ? __byte_perm(rr, 0u, 0x2301) : rr;
+}
+
+#ifndef SE_HOST_EMU
+// one Margolus sub-step over the whole tile; OX (column phase) is a template parameter so that the
+// aligned 16-bit and the byte access variants are separate straight-line loops
+template <int OX>
+static __device__ __forceinline__ void se_tile_substep(unsigned tile_sa, se_tab_t tab, unsigned pool_off, const unsigned* __restrict__ fat_sm,
+                                                       int PH, int oy, int frame, int gx_org, int gy_org, int warp, int nwarps, int lane) {
+    const int PW = SE_TILE_PW;
+    const int nbx = (PW - OX) >> 1, nby = (PH - oy) >> 1;
+    const unsigned fterm = (unsigned)frame * (2131u * 2131u) + (unsigned)(gx_org + OX) * 461u;
+    for (int j = warp; j < nby; j += nwarps) {
+        const int ly = 2 * j + oy;
+        const unsigned rowseed = (unsigned)(gy_org + ly) * 2131u + fterm;
+        const unsigned row_sa = tile_sa + (unsigned)(ly * PW + OX);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = lane + 32 * k;
+            if (OX == 0 || i < nbx) {
+                const unsigned c0 = row_sa + 2u * (unsigned)i;
+                unsigned v;
+                if (OX == 0) v = se_lds_u16(c0) | (se_lds_u16(c0 + PW) << 16);
+                else v = se_lds_u8(c0) | (se_lds_u8(c0 + 1) << 8) | (se_lds_u8(c0 + PW) << 16) | (se_lds_u8(c0 + PW + 1) << 24);
+                if (v != 0u) {                     // all-EMPTY early-out (falling_sand.glsl:692-694)
+                    const unsigned seed = rowseed + (unsigned)(2 * i) * 461u;
+                    const unsigned nv = se_block_lut(v, seed, gx_org + OX + 2 * i, gy_org + ly, frame, tab, pool_off, fat_sm);
+                    if (nv != v) {
+                        if (OX == 0) {
+                            se_sts_u16(c0, nv & 0xFFFFu);
+                            se_sts_u16(c0 + PW, nv >> 16);
+                        } else {
+                            se_sts_u8(c0, nv & 0xFFu); se_sts_u8(c0 + 1, (nv >> 8) & 0xFFu);
+                            se_sts_u8(c0 + PW, (nv >> 16) & 0xFFu); se_sts_u8(c0 + PW + 1, nv >> 24);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(512, 2) se_step_tiles(const SeTileParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ unsigned fat_sm[256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    unsigned smem_sa;   // laundered through asm so the compiler keeps it in a register instead of re-deriving it (S2R) per access
+    asm volatile("mov.u32 %0, %1;" : "=r"(smem_sa) : "r"((unsigned)__cvta_generic_to_shared(smem)));
+    const se_tab_t tab = smem_sa;
+    const unsigned pool_off = (unsigned)p.pool_offset;
+    const unsigned tile_sa = smem_sa + (unsigned)p.tile_offset;
+
+    for (int i = tid; i < p.lut_words; i += blockDim.x) se_sts_u32(smem_sa + 4u * i, __ldg(p.lut + i));
+    if (tid < 256) fat_sm[tid] = se_fat_table[tid];
+    __syncthreads();
+
+    const int PW = SE_TILE_PW, PH = p.PH;
+    const int TWo = PW - 2 * p.HX, THo = PH - 2 * p.T;
+    const int n_tiles = p.tiles_x * p.tiles_y;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+        const int gx_org = tx * TWo - p.HX;              // global x of tile column 0 (multiple of 4)
+        const int gy_org = p.gy0 + ty * THo - p.T;       // global y of tile row 0 (even)
+        const bool border = gx_org < 0 || gx_org + PW > p.W || gy_org < 0 || gy_org + PH > p.Hg;
+
+        // ---- load: uint4 of packed-u32 cells -> 4 id bytes ----
+        for (int r = warp; r < PH; r += nwarps) {
+            const int gy = gy_org + r, lr = gy - p.gy0;
+            const bool row_ok = gy >= 0 && gy < p.Hg && lr >= 0 && lr < p.Hl;
+            const uint4* src = reinterpret_cast<const uint4*>(p.in + (size_t)(row_ok ? lr : 0) * p.W);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int q = lane + 32 * h;
+                const int gx = gx_org + 4 * q;
+                unsigned w = 0x02020202u;               // WALL outside the grid (operations.glsl:45-51)
+                if (row_ok && gx >= 0 && gx < p.W) w = se_pack_ids(__ldg(src + (gx >> 2)));
+                se_sts_u32(tile_sa + 4u * (unsigned)(r * (PW / 4) + q), w);
+            }
+        }
+        __syncthreads();
+
+        // ---- nsub Margolus sub-steps in shared memory ----
+        for (int sub = 0; sub < p.nsub; ++sub) {
+            const int frame = p.frame0 + sub;
+            int ox, oy;
+            se_margolus_offset(frame, ox, oy);
+            if (ox == 0) se_tile_substep<0>(tile_sa, tab, pool_off, fat_sm, PH, oy, frame, gx_org, gy_org, warp, nwarps, lane);
+            else se_tile_substep<1>(tile_sa, tab, pool_off, fat_sm, PH, oy, frame, gx_org, gy_org, warp, nwarps, lane);
+            __syncthreads();
+            if (border) {
+                // cells outside the grid are WALL at every step, whatever a SET wrote into them
+                for (int r = warp; r < PH; r += nwarps) {
+                    const int gy = gy_org + r;
+                    const bool row_out = gy < 0 || gy >= p.Hg;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int q = lane + 32 * h;
+                        const int gx = gx_org + 4 * q;
+                        if (row_out || gx < 0 || gx >= p.W) se_sts_u32(tile_sa + 4u * (unsigned)(r * (PW / 4) + q), 0x02020202u);
+                    }
+                }
+                __syncthreads();
+            }
+        }
+
+        // ---- store the interior: 4 id bytes -> uint4 of packed-u32 cells ----
+        for (int r = p.T + warp; r < PH - p.T; r += nwarps) {
+            const int gy = gy_org + r, lr = gy - p.gy0;
+            if (gy >= p.Hg || lr >= p.Hl) break;
+            uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)lr * p.W);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int q = lane + 32 * h;
+                const int gx = gx_org + 4 * q;
+                if (4 * q >= p.HX && 4 * q < PW - p.HX && gx < p.W) {
+                    const unsigned w = se_lds_u32(tile_sa + 4u * (unsigned)(r * (PW / 4) + q));
+                    dst[gx >> 2] = make_uint4(w & 0xFFu, (w >> 8) & 0xFFu, (w >> 16) & 0xFFu, w >> 24);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+#endif  // SE_HOST_EMU
+#endif  // SE_LUT_ELIGIBLE

@@ -62,6 +62,8 @@ struct Ctx {
     bool left_view;                          // rule is a Left rule: `left`/`downleft` bind to r/dr
     std::string where;                       // for messages
     uint32_t* rand_lanes;
+    std::vector<uint32_t>* y_thresholds;     // integer thresholds taken on hash lane 1 (rand.y)
+    bool* lut_ok;                            // cleared by anything a transition table cannot capture
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -118,7 +120,10 @@ struct Parser {
     static Val mk_ilit(long long i) { Val v = mk_int(std::to_string(i)); v.is_lit = true; v.lit = (double)i; return v; }
 
     std::string as_float_code(const Val& v) {
-        if (v.type == VT::Float) return v.code;
+        if (v.type == VT::Float) {
+            if (v.is_rand) *cx.lut_ok = false;   // rand used as a plain float, not against a literal threshold
+            return v.code;
+        }
         if (v.type == VT::Int) {
             if (v.is_lit) return f32_lit((float)v.lit);
             return "((float)(" + v.code + "))";
@@ -196,11 +201,14 @@ struct Parser {
         bool negate = (op == ">" || op == ">=");
         bool strict = (op == "<" || op == ">=");   // x >= p  ==  !(x < p)
         if (op == "==" || op == "!=") {
+            *cx.lut_ok = false;
             return mk_bool("(SE_RANDF(" + std::to_string(lane) + ") " + op + " " + f32_lit(lit) + ")");
         }
         uint32_t U;
         bool all;
         bool any = rand_threshold(lit, strict, &U, &all);
+        if (lane != 1) *cx.lut_ok = false;
+        else if (any && !all) cx.y_thresholds->push_back(U);
         std::string base;
         if (!any) base = "false";
         else if (all) base = "true";
@@ -353,6 +361,7 @@ struct Parser {
             return r;
         }
         if (v.type == VT::PosVec) {
+            *cx.lut_ok = false;
             if (m == "x") return mk_int("px");
             if (m == "y") return mk_int("py");
             bad("unknown component of pos");
@@ -397,7 +406,7 @@ struct Parser {
             if (id == "true" || id == "false") return mk_bool(id);
             if (id == "rand") { Val v; v.type = VT::RandVec; return v; }
             if (id == "pos") { Val v; v.type = VT::PosVec; return v; }
-            if (id == "frame") return mk_int("frame");
+            if (id == "frame") { *cx.lut_ok = false; return mk_int("frame"); }
             std::string reg = cell_reg(id);
             if (!reg.empty()) { Val v; v.type = VT::Cell; v.code = reg; return v; }
             if (id.rfind("MAT_", 0) == 0) {
@@ -498,13 +507,13 @@ std::string emit_rule(const SandRule& r, Ctx& cx) {
         std::string act = compile_actions(r.do_actions[k], cx);
         if (k < n_if) {
             cx.where = "rules/" + r.name + "/if[" + std::to_string(k) + "]";
-            std::string cond = compile_condition(r.if_conds[k], cx);
+            // The reference pastes the probability test in front of the condition WITHOUT parentheses
+            // (rules.rs:56-68: "rand.y <= {p} && {cond}"), so with a top-level `||` in the condition the
+            // probability only guards the first disjunct.  Compile the very same text to keep that.
             float p = r.probabilities[k];
-            if (p != 1.0f) {
-                Parser pp("rand.y <= p", cx);
-                Val pv = pp.rand_vs_lit(1, "<=", p);
-                cond = "(" + pv.code + " && " + cond + ")";
-            }
+            std::string text = r.if_conds[k];
+            if (p != 1.0f) text = "rand.y <= " + f32_display(p) + " && " + text;
+            std::string cond = compile_condition(text, cx);
             o << indent << "if (" << cond << ") { " << act << "} else {\n";
             indent += "    ";
             ++depth;
@@ -603,10 +612,12 @@ CompiledRules compile_rules(const ParsingResult& parsed) {
     // ---- rule functions ----
     std::ostringstream fn, mir, left, right;
     out.rand_lanes = 1;   // lane x: mirror decision (falling_sand.glsl:86)
+    bool lut_ok = true;
+    std::vector<uint32_t> y_thr;
     for (auto& r : parsed.rules) {
         if (!r.used) continue;
         SandRuleType et = r.effective_type();
-        Ctx cx{tb, parsed, ranks, et == SandRuleType::Left, "rules/" + r.name, &out.rand_lanes};
+        Ctx cx{tb, parsed, ranks, et == SandRuleType::Left, "rules/" + r.name, &out.rand_lanes, &y_thr, &lut_ok};
         fn << emit_rule(r, cx);
         std::string call = "    se_rule_" + r.name + "(s, r, d, dr, rnd, px, py, frame);\n";
         if (et == SandRuleType::Mirrored) mir << call;
@@ -615,8 +626,23 @@ CompiledRules compile_rules(const ParsingResult& parsed) {
         ++out.n_used_rules;
     }
 
+    std::sort(y_thr.begin(), y_thr.end());
+    y_thr.erase(std::unique(y_thr.begin(), y_thr.end()), y_thr.end());
+    // table budget: 2 mirror variants x N^4 states x 2 B must leave room for a tile in shared memory
+    out.lut_eligible = lut_ok && tb.n_materials <= 12 && y_thr.size() <= 15 && !out.have_left && !out.have_right;
+    out.lut_thresholds = y_thr;
+
     std::ostringstream h;
     h << "// GENERATED by sandengine_b200 (CUDA C back end of the rule language). Do not edit.\n";
+    h << "#define SE_LUT_ELIGIBLE " << (out.lut_eligible ? 1 : 0) << "\n";
+    h << "#define SE_LUT_NCLS " << (y_thr.size() + 1) << "\n";
+    h << "// class c of a block = number of thresholds its rand.y hash lane exceeds (u1 > U_i)\n";
+    h << "#define SE_LUT_CLASS(u1) (0u";
+    for (uint32_t t : y_thr) h << " + ((u1) > " << hex32(t) << " ? 1u : 0u)";
+    h << ")\n";
+    h << "__device__ const unsigned se_lut_thresholds[16] = {";
+    for (size_t k = 0; k < 16; ++k) h << (k < y_thr.size() ? hex32(y_thr[k]) : std::string("0xffffffffu")) << (k < 15 ? ", " : "");
+    h << "};\n";
     h << "#define SE_N_MATERIALS " << tb.n_materials << "\n#define SE_N_TYPES " << tb.n_types << "\n";
     h << "#define SE_RAND_LANES " << out.rand_lanes << "u\n";
     h << "#define SE_HAVE_LEFT_RULES " << (out.have_left ? 1 : 0) << "\n#define SE_HAVE_RIGHT_RULES " << (out.have_right ? 1 : 0) << "\n";

@@ -47,6 +47,11 @@ struct CompiledRules {
     uint32_t rand_lanes = 1;     // bit k: hash lane k (x,y,z,w) is consumed by the rule set (bit 0: mirror)
     bool have_left = false, have_right = false;
     int n_used_rules = 0;
+    // Transition-table (LUT) mode: possible when the block transition is a pure function of
+    // (4 material ids, mirror bit, which of the sorted rand.y thresholds the hash lane clears):
+    // no pos / frame / other rand lanes / generic float use of rand, and few enough materials.
+    bool lut_eligible = false;
+    std::vector<uint32_t> lut_thresholds;   // sorted distinct U: condition i is `u1 <= U_i`
 };
 
 // Largest u in [0, 2^32) with  float_rn(u) / 2^32 <op> p  (op is "<=" or "<"); returns false when no u

@@ -171,9 +171,13 @@ class Simulation:
         _capi.check(_capi.lib().se_sim_ipc_export(self._h, buf, C.byref(lr), C.byref(gt), C.byref(gb)))
         return bytes(buf), lr.value, gt.value, gb.value
 
-    def ipc_attach(self, which: int, handles: bytes, local_rows: int, ghost_top: int, ghost_bottom: int, same_process: bool = False):
+    def ipc_attach(self, which: int, handles: bytes, local_rows: int, ghost_top: int, ghost_bottom: int):
         buf = (C.c_ubyte * 128).from_buffer_copy(handles.ljust(128, b"\0"))
-        _capi.check(_capi.lib().se_sim_ipc_attach(self._h, which, buf, 1 if same_process else 0, local_rows, ghost_top, ghost_bottom))
+        _capi.check(_capi.lib().se_sim_ipc_attach(self._h, which, buf, local_rows, ghost_top, ghost_bottom))
+
+    def attach_local(self, which: int, neighbour: "Simulation"):
+        """Neighbour strip owned by this process (0 = above, 1 = below)."""
+        _capi.check(_capi.lib().se_sim_attach_local(self._h, which, neighbour._h))
 
     def halo_push(self) -> None:
         _capi.check(_capi.lib().se_sim_halo_push(self._h))

@@ -1,0 +1,102 @@
+// Test infrastructure: compiles the GENERATED CUDA rule header (rules_gen.cuh) and the pure device
+// functions of kernels/sand_kernels.cuh (hash, block transition, transition-table build + lookup) on the
+// HOST (g++), so that code-generation and table bugs can be found without a GPU.  Device intrinsics
+// are shimmed with their exact host equivalents; the __global__ kernels are compiled out (SE_HOST_EMU).
+// This is not a product path and not the oracle; tests/test_codegen_host_emulation.py compares it with
+// the oracle.
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#define SE_HOST_EMU 1
+#define __device__
+#define __forceinline__ inline
+#define __restrict__
+struct uint4 { unsigned x, y, z, w; };
+static inline float __uint2float_rn(unsigned u) { return (float)u; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fsqrt_rn(float a) { return std::sqrt(a); }
+static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
+    unsigned long long v = ((unsigned long long)b << 32) | a;
+    unsigned r = 0;
+    for (int k = 0; k < 4; ++k) r |= (unsigned)((v >> (8 * ((sel >> (4 * k)) & 7))) & 0xFF) << (8 * k);
+    return r;
+}
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p += v; return o; }
+using std::abs;
+
+#include "sand_kernels.cuh"
+
+// one in-place Margolus step with the generic (generated-code) block transition
+extern "C" void emu_step_inplace(uint32_t* cells, int W, int H, int frame) {
+    int ox, oy;
+    se_margolus_offset(frame, ox, oy);
+    for (int y0 = -oy; y0 < H; y0 += 2)
+        for (int x0 = -ox; x0 < W; x0 += 2) {
+            unsigned raw[4];
+            for (int k = 0; k < 4; ++k) {
+                int x = x0 + (k & 1), y = y0 + (k >> 1);
+                raw[k] = (x < 0 || x >= W || y < 0 || y >= H) ? 2u : cells[(size_t)y * W + x];
+            }
+            unsigned q[4];
+            for (int k = 0; k < 4; ++k) q[k] = se_fat_table[raw[k] < 255u ? raw[k] : 255u];
+            if ((raw[0] | raw[1] | raw[2] | raw[3]) != 0u) se_block(q[0], q[1], q[2], q[3], x0, y0, frame);
+            for (int k = 0; k < 4; ++k) {
+                int x = x0 + (k & 1), y = y0 + (k >> 1);
+                if (!(x < 0 || x >= W || y < 0 || y >= H)) cells[(size_t)y * W + x] = SE_ID(q[k]);
+            }
+        }
+}
+
+extern "C" int emu_lut_eligible(void) { return SE_LUT_ELIGIBLE; }
+
+#if SE_LUT_ELIGIBLE
+// table image exactly as the kernel stages it: base[N^4] u16, padding to 8 bytes, pool[] of 8-byte entries
+static std::vector<unsigned char> g_table;
+static unsigned g_pool_off = 0, g_pool_entries = 0;
+
+// returns the number of pool entries, or -1 on pool overflow
+extern "C" int emu_build_lut(void) {
+    g_pool_off = ((unsigned)SE_N4 * 2u + 7u) / 8u * 8u;
+    g_table.assign(g_pool_off + (size_t)SE_LUT_POOL_MAX * 8, 0);
+    g_pool_entries = 0;
+    unsigned short* base = reinterpret_cast<unsigned short*>(g_table.data());
+    SePoolEntry* pool = reinterpret_cast<SePoolEntry*>(g_table.data() + g_pool_off);
+    for (int idx = 0; idx < SE_N4; ++idx) se_build_lut_entry(idx, base, pool, &g_pool_entries);
+    return g_pool_entries > SE_LUT_POOL_MAX ? -1 : (int)g_pool_entries;
+}
+
+// one in-place Margolus step through the transition table (se_block_lut), ids packed as in the tile kernel
+extern "C" void emu_step_lut_inplace(uint32_t* cells, int W, int H, int frame) {
+    int ox, oy;
+    se_margolus_offset(frame, ox, oy);
+    for (int y0 = -oy; y0 < H; y0 += 2)
+        for (int x0 = -ox; x0 < W; x0 += 2) {
+            unsigned v = 0;
+            for (int k = 0; k < 4; ++k) {
+                int x = x0 + (k & 1), y = y0 + (k >> 1);
+                unsigned id = (x < 0 || x >= W || y < 0 || y >= H) ? 2u : cells[(size_t)y * W + x];
+                if (id >= SE_N_MATERIALS) id = 1u;
+                v |= id << (8 * k);
+            }
+            unsigned nv = v;
+            if (v != 0u) {
+                const unsigned seed = (unsigned)x0 * 461u + (unsigned)y0 * 2131u + (unsigned)frame * (2131u * 2131u);
+                nv = se_block_lut(v, seed, x0, y0, frame, g_table.data(), g_pool_off, se_fat_table);
+            }
+            for (int k = 0; k < 4; ++k) {
+                int x = x0 + (k & 1), y = y0 + (k >> 1);
+                if (!(x < 0 || x >= W || y < 0 || y >= H)) cells[(size_t)y * W + x] = (nv >> (8 * k)) & 0xFFu;
+            }
+        }
+}
+#else
+extern "C" int emu_build_lut(void) { return -2; }
+extern "C" void emu_step_lut_inplace(uint32_t*, int, int, int) {}
+#endif

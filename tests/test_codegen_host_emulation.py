@@ -1,0 +1,95 @@
+"""The GENERATED CUDA rule code, compiled for the host (tests/emu/host_emu.cpp shims the device intrinsics)
+and stepped on the CPU, must reproduce the oracle bit for bit.  This checks the typed expression compiler,
+the fat-cell tables, the integer RAND thresholds, Left/Right routing and operator precedence of the CUDA
+back end without a GPU; the kernels around it are covered by the -m gpu parity tests."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import yaml_cases as Y
+from conftest import DEFAULT_YAML, REPO
+from sandengine_b200.grids import DEFAULT_IDS, DEFAULT_MIX, synthetic_grid
+
+
+def build_emu(tmp_path_factory, tag, rules):
+    d = tmp_path_factory.mktemp(f"emu_{tag}")
+    (d / "rules_gen.cuh").write_text(rules.cuda_header)
+    so = d / "emu.so"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-I", str(d),
+                           "-I", str(REPO / "sandengine_b200" / "csrc" / "kernels"),
+                           str(REPO / "tests" / "emu" / "host_emu.cpp"), "-o", str(so)])
+    lib = C.CDLL(str(so))
+    lib.emu_step_inplace.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.emu_step_lut_inplace.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    return lib
+
+
+def compare(lib, orc, g, steps, frame=1, lut=False):
+    a, b = g.copy(), g.copy()
+    step = lib.emu_step_lut_inplace if lut else lib.emu_step_inplace
+    for s in range(steps):
+        frame += 1
+        orc.step_blocks_inplace(a, frame)
+        step(b.ctypes.data, g.shape[1], g.shape[0], frame)
+        assert np.array_equal(a, b), f"generated code diverges from the oracle at step {s + 1} (frame {frame})"
+    return a
+
+
+def test_default_rules(native_lib, tmp_path_factory, default_rules, oracle):
+    lib = build_emu(tmp_path_factory, "default", default_rules)
+    for (w, h, seed, steps) in [(96, 64, 1, 300), (33, 17, 2, 100), (2, 2, 3, 20)]:
+        compare(lib, oracle, synthetic_grid(w, h, seed), steps)
+
+
+def test_transition_table_default_rules(native_lib, tmp_path_factory, default_rules, oracle):
+    """The transition table (built from the generated rule code) + its lookup with mirror folding, rand.y
+    classes and the WALL/NULL slow path reproduces the oracle -- incl. grids with WALL / NULL / unknown ids."""
+    lib = build_emu(tmp_path_factory, "default_lut", default_rules)
+    assert lib.emu_lut_eligible() == 1
+    n_sens = lib.emu_build_lut()
+    assert 0 < n_sens <= 4095
+    for (w, h, seed, steps) in [(96, 64, 1, 300), (33, 17, 2, 100), (2, 2, 3, 20), (128, 128, 3, 400)]:
+        compare(lib, oracle, synthetic_grid(w, h, seed), steps, lut=True)
+    g = synthetic_grid(64, 64, 9)
+    rng = np.random.default_rng(3)
+    g[rng.integers(0, 64, 60), rng.integers(0, 64, 60)] = 2      # WALL cells inside the grid
+    g[rng.integers(0, 64, 20), rng.integers(0, 64, 20)] = 1      # NULL
+    g[rng.integers(0, 64, 20), rng.integers(0, 64, 20)] = 9      # vine
+    g[5, 5] = 77; g[6, 9] = 4000000000                           # unknown ids read as NULL
+    compare(lib, oracle, g, 200, lut=True)
+
+
+def test_rich_rules_left_right_precedence(native_lib, tmp_path_factory):
+    import sandengine_b200 as se
+    from oracle.build_oracle import load_oracle
+    rules = se.parse_string(Y.RICH_YAML)
+    lib = build_emu(tmp_path_factory, "rich", rules)
+    assert lib.emu_lut_eligible() == 0      # uses pos.y, rand.x and non-mirrored rules
+    orc = load_oracle(Y.RICH_YAML)
+    out = compare(lib, orc, synthetic_grid(128, 96, 5, mix=Y.RICH_MIX, ids=Y.RICH_IDS), 300)
+    assert len(np.unique(out)) > 5
+    compare(lib, orc, synthetic_grid(61, 47, 6, mix=Y.RICH_MIX, ids=Y.RICH_IDS), 150, frame=1001)
+
+
+def test_synthetic_64_material_rule_set(native_lib, tmp_path_factory):
+    """configs[4] rule set (deep isType_* inheritance, non-mirrored LEFT rules) at crop size."""
+    import sandengine_b200 as se
+    from oracle.build_oracle import load_oracle
+    from oracle import oracle_lang as L
+    from sandengine_b200.synth_rules import synthetic_rule_set
+    text, ids, mix = synthetic_rule_set(64, 28, seed=5)
+    rules = se.parse_string(text)
+    o = L.parse_string(text)
+    assert len(rules.materials) == 64 and rules.glsl_rules == L.emit_glsl_rules(o) and rules.glsl_materials == L.emit_glsl_materials(o)
+    kinds = [r.ruletype for r in rules.rules if r.used]
+    assert kinds.count("Left") >= 4 and kinds.count("Right") >= 4 and kinds.count("Mirrored") >= 8 and len(kinds) >= 24
+    depth = lambda t: 0 if not t.inherits else 1 + depth(next(x for x in o.types if x.name == t.inherits))
+    assert max(depth(t) for t in o.types) >= 5
+    lib = build_emu(tmp_path_factory, "synth64", rules)
+    orc = load_oracle(text)
+    g = synthetic_grid(160, 128, 5, mix=mix, ids=ids)
+    out = compare(lib, orc, g, 200)
+    assert not np.array_equal(out, g)

@@ -32,9 +32,9 @@ def rich(se):
     return se.parse_string(Y.RICH_YAML), load_oracle(Y.RICH_YAML)
 
 
-def run_gpu(se, rules, grid, n_steps, frame0=1, lighting=False, light0=None, mods_per_step=None, chunk=None):
+def run_gpu(se, rules, grid, n_steps, frame0=1, lighting=False, light0=None, mods_per_step=None, chunk=None, temporal_block=0):
     H, W = grid.shape
-    sim = se.Simulation(rules, (W, H), lighting=lighting)
+    sim = se.Simulation(rules, (W, H), lighting=lighting, temporal_block=temporal_block)
     sim.upload_cells(grid)
     if lighting and light0 is not None:
         sim.upload_light(light0)
@@ -227,4 +227,106 @@ def test_step_chunking_is_equivalent(se, default_rules):
     a, _, _ = run_gpu(se, default_rules, g, 64)
     b, _, _ = run_gpu(se, default_rules, g, 64, chunk=1)
     c, _, _ = run_gpu(se, default_rules, g, 64, chunk=7)
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+def test_synthetic_64_material_rules_1024(se):
+    """configs[4] rule set at crop size (1024^2): 64 materials, deep inheritance, LEFT and RIGHT rules."""
+    from oracle.build_oracle import load_oracle
+    from sandengine_b200.synth_rules import synthetic_rule_set
+    text, ids, mix = synthetic_rule_set(64, 28, seed=5)
+    rules = se.parse_string(text)
+    orc = load_oracle(text)
+    g = synthetic_grid(1024, 1024, 5, mix=mix, ids=ids)
+    ref, _, _ = orc.run(g, 1, 100, blocks=True)
+    got, _, _ = run_gpu(se, rules, g, 100)
+    assert np.array_equal(got, ref) and not np.array_equal(got, g)
+
+
+def _strip_pair_run(se, rules, g, steps, halo, n_strips):
+    """n strips of one grid on ONE device in ONE process (se_sim_attach_local): exercises ghost rows, the
+    missing-row logic and se_sim_halo_push without torch.distributed."""
+    from sandengine_b200.distributed import StripPlan
+    H, W = g.shape
+    plan = StripPlan(W, H, n_strips, halo)
+    sims = []
+    for r in range(n_strips):
+        b, e = plan.rows(r)
+        s = se.Simulation(rules, (W, H), row_begin=b, row_end=e, halo_rows=halo)
+        s.upload_cells(g[b:e])
+        s.params.frame = 1
+        sims.append(s)
+    for r, s in enumerate(sims):
+        if r > 0:
+            s.attach_local(0, sims[r - 1])
+        if r < n_strips - 1:
+            s.attach_local(1, sims[r + 1])
+
+    def exchange():
+        for s in sims: s.synchronize()
+        for s in sims: s.halo_push()
+        for s in sims: s.synchronize()
+    exchange()
+    for k in plan.chunks(steps):
+        for s in sims: s.step(k)
+        exchange()
+    out = np.concatenate([s.download_cells() for s in sims], axis=0)
+    for s in sims: s.close()
+    return out
+
+
+@pytest.mark.parametrize("n_strips,halo,h", [(2, 4, 64), (3, 8, 100), (4, 2, 64), (2, 16, 130)])
+def test_strips_equal_single_grid(se, default_rules, oracle, n_strips, halo, h):
+    g = synthetic_grid(96, h, 17)
+    steps = 45
+    ref, _, _ = oracle.run(g, 1, steps, blocks=True)
+    got = _strip_pair_run(se, default_rules, g, steps, halo, n_strips)
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("T", [1, 2, 4, 6, 8, 16])
+def test_tiled_table_kernel_vs_oracle(se, default_rules, oracle, T):
+    """K1b (transition table + shared-memory tiles, T fused steps per launch) against the oracle; T = 1 is K1a.
+    Sizes straddle tile boundaries (tile 256 wide) and include WALL / NULL cells (slow path inside tiles)."""
+    for (w, h, seed, steps) in [(512, 300, 31, 97), (260, 1000, 32, 50), (1024, 64, 33, 64)]:
+        g = synthetic_grid(w, h, seed)
+        rng = np.random.default_rng(seed)
+        g[rng.integers(0, h, 200), rng.integers(0, w, 200)] = 2
+        g[rng.integers(0, h, 50), rng.integers(0, w, 50)] = 1
+        g[rng.integers(0, h, 50), rng.integers(0, w, 50)] = 9
+        ref, _, _ = oracle.run(g, 1, steps, blocks=True)
+        got, _, f = run_gpu(se, default_rules, g, steps, temporal_block=T)
+        assert f == 1 + steps
+        assert np.array_equal(got, ref), f"T={T} size {w}x{h}"
+
+
+def test_tiled_with_modifications_interleaved(se, default_rules, oracle):
+    """Steps with modifications fall back to K1a for that step and return to the tiled kernel afterwards."""
+    rng = np.random.default_rng(5)
+    w, h, steps = 512, 256, 40
+    g = synthetic_grid(w, h, 12)
+    mods = [make_mods(se, s, 11, w, h, rng) if s % 3 == 0 else None for s in range(steps)]
+    ref, _, _ = oracle.run(g, 1, steps, mods_per_step=[m if m is not None else np.zeros(0, se.MOD_DTYPE) for m in mods])
+    sim = se.Simulation(default_rules, (w, h))
+    sim.upload_cells(g)
+    sim.params.frame = 1
+    s = 0
+    while s < steps:
+        if mods[s] is not None and len(mods[s]):
+            sim.push_modifications(mods[s])
+        run = 1
+        while s + run < steps and mods[s + run] is None:
+            run += 1
+        sim.step(run)      # first step consumes the modifications, the rest are plain (tiled)
+        s += run
+    assert np.array_equal(sim.download_cells(), ref)
+    sim.close()
+
+
+def test_tiled_4096_vs_per_step_kernel(se, default_rules):
+    """configs[1] size: the tiled kernel and the per-step kernel agree bit for bit after 256 steps at 4096^2."""
+    g = synthetic_grid(4096, 4096, 2)
+    a, _, _ = run_gpu(se, default_rules, g, 256, temporal_block=1)
+    b, _, _ = run_gpu(se, default_rules, g, 256, temporal_block=4)
+    c, _, _ = run_gpu(se, default_rules, g, 256, temporal_block=8, chunk=37)
     assert np.array_equal(a, b) and np.array_equal(a, c)
