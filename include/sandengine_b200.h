@@ -125,8 +125,15 @@ int se_sim_ipc_attach(se_sim* s, int which, const void* handles_2x64, uint64_t n
 /* Attach a neighbour that lives in THIS process (one process driving several strips / devices, the
  * reference's single-process model); peer access is enabled when the devices differ. */
 int se_sim_attach_local(se_sim* s, int which, se_sim* neighbour);
-/* Push this sim's boundary rows into the attached neighbours' ghost rows (device-to-device over NVLink). */
+/* Push this sim's boundary rows into the attached neighbours' ghost rows (device-to-device over NVLink).
+ * The caller is responsible for ordering against the neighbours' kernels (host barriers). */
 int se_sim_halo_push(se_sim* s);
+/* The same exchange with the ordering done ON THE DEVICE, no host synchronisation: stream-ordered flag
+ * writes / waits on peer-mapped words (cuStreamWriteValue32 / cuStreamWaitValue32):
+ *   signal "done computing" -> wait for the neighbours' "done" -> push rows -> signal "delivered" ->
+ *   make this stream wait for the neighbours' "delivered".
+ * Every strip must call it the same number of times (lock-step epochs). */
+int se_sim_halo_exchange_async(se_sim* s);
 
 const char* se_last_error(void);
 const char* se_version(void);

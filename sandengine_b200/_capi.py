@@ -30,7 +30,7 @@ EXPORTS = [
     "se_sim_create", "se_sim_destroy", "se_sim_step", "se_sim_push_modifications", "se_sim_set_frame", "se_sim_get_frame",
     "se_sim_upload_cells", "se_sim_download_cells", "se_sim_upload_light", "se_sim_download_light", "se_sim_device_cells",
     "se_sim_census", "se_sim_set_stream", "se_sim_synchronize", "se_sim_launch_count",
-    "se_sim_ipc_export", "se_sim_ipc_attach", "se_sim_attach_local", "se_sim_halo_push", "se_last_error", "se_version",
+    "se_sim_ipc_export", "se_sim_ipc_attach", "se_sim_attach_local", "se_sim_halo_push", "se_sim_halo_exchange_async", "se_last_error", "se_version",
 ]
 
 
@@ -88,6 +88,7 @@ def lib() -> C.CDLL:
     L.se_sim_ipc_attach.argtypes = [vp, C.c_int, vp, C.c_uint64, C.c_uint64, C.c_uint64]
     L.se_sim_attach_local.argtypes = [vp, C.c_int, vp]
     L.se_sim_halo_push.argtypes = [vp]
+    L.se_sim_halo_exchange_async.argtypes = [vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("se_last_error", "se_version"):

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -54,6 +55,8 @@ struct Driver {
     decltype(&cuLaunchKernel) LaunchKernel = nullptr;
     decltype(&cuFuncSetAttribute) FuncSetAttribute = nullptr;
     decltype(&cuGetErrorString) GetErrorString = nullptr;
+    decltype(&cuStreamWriteValue32) StreamWriteValue32 = nullptr;
+    decltype(&cuStreamWaitValue32) StreamWaitValue32 = nullptr;
     bool ok = false;
     std::string why;
 };
@@ -74,7 +77,8 @@ Driver& driver() {
         };
         d.ok = get("cuModuleLoadData", (void**)&d.ModuleLoadData) && get("cuModuleUnload", (void**)&d.ModuleUnload) &&
                get("cuModuleGetFunction", (void**)&d.ModuleGetFunction) && get("cuLaunchKernel", (void**)&d.LaunchKernel) &&
-               get("cuFuncSetAttribute", (void**)&d.FuncSetAttribute) && get("cuGetErrorString", (void**)&d.GetErrorString);
+               get("cuFuncSetAttribute", (void**)&d.FuncSetAttribute) && get("cuGetErrorString", (void**)&d.GetErrorString) &&
+               get("cuStreamWriteValue32", (void**)&d.StreamWriteValue32) && get("cuStreamWaitValue32", (void**)&d.StreamWaitValue32);
     });
     return d;
 }
@@ -131,12 +135,14 @@ struct se_rules {
     std::vector<char> cubin;
     std::string nvrtc_log;
     bool compiled = false;
+    int tile_threads = 1024;   // CTA size of the tile kernel (compile-time launch bound; tunable: env SE_TILE_THREADS)
 };
 
 struct Neighbour {
     bool attached = false;
     bool ipc = false;
     unsigned* cells[2] = {nullptr, nullptr};
+    unsigned* flags = nullptr;   // the neighbour's flag words (inside its cells[0] allocation)
     uint64_t local_rows = 0, ghost_top = 0, ghost_bottom = 0;
 };
 
@@ -167,6 +173,12 @@ struct se_sim {
     unsigned* d_lut = nullptr;
     int T = 0, HX = 0, PH = 0, tiles_x = 0, tiles_y = 0, lut_words = 0, pool_offset = 0, tile_offset = 0, tile_smem = 0, tile_grid = 0;
     Neighbour nb[2];
+    // Device-side exchange protocol: 4 flag words live right behind cells[0] (same allocation, so that one
+    // IPC handle maps both): [0]/[1] = "done computing" epoch of the strip above/below, [2]/[3] = "ghost rows
+    // delivered" epoch from above/below.  Written by the neighbours, waited on by this sim's stream.
+    unsigned* flags = nullptr;
+    unsigned epoch = 0;
+    static size_t flags_offset(size_t W_, size_t Hl_) { return ((W_ * Hl_ * sizeof(unsigned)) + 255) / 256 * 256; }
     size_t cells_bytes() const { return (size_t)W * Hl * sizeof(unsigned); }
     size_t owned_offset() const { return (size_t)ghost_top * W; }
     size_t owned_cells() const { return (size_t)W * (row_end - row_begin); }
@@ -204,8 +216,13 @@ int compile_front(const char* yaml, size_t len, se_rules** out, bool with_nvrtc)
         }
         // -fmad=false: the lighting sums and any float arithmetic in rule conditions are evaluated as
         // written (no FMA contraction), matching the reference expression tree.
-        const char* opts[] = {"-arch=sm_100a", "-std=c++17", "-lineinfo", "-fmad=false"};
-        nvrtcResult res = nvrtcCompileProgram(prog, 4, opts);
+        if (const char* tt = std::getenv("SE_TILE_THREADS")) {
+            int v = std::atoi(tt);
+            if (v == 256 || v == 512 || v == 768 || v == 1024) r->tile_threads = v;
+        }
+        const std::string def_threads = "-DSE_TILE_THREADS=" + std::to_string(r->tile_threads);
+        const char* opts[] = {"-arch=sm_100a", "-std=c++17", "-lineinfo", "-fmad=false", def_threads.c_str()};
+        nvrtcResult res = nvrtcCompileProgram(prog, 5, opts);
         size_t log_size = 0;
         nvrtcGetProgramLogSize(prog, &log_size);
         r->nvrtc_log.resize(log_size ? log_size - 1 : 0);
@@ -449,8 +466,10 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
 
     // Simulation::new allocates zero-filled textures (simulation.rs:145,177-181)
     const bool two = s->lighting;
-    SE_CUDA_S(cudaMalloc(&s->cells[0], s->cells_bytes()));
-    SE_CUDA_S(cudaMemsetAsync(s->cells[0], 0, s->cells_bytes(), s->stream));
+    const size_t flags_off = se_sim::flags_offset((size_t)s->W, (size_t)s->Hl);
+    SE_CUDA_S(cudaMalloc(&s->cells[0], flags_off + 256));
+    SE_CUDA_S(cudaMemsetAsync(s->cells[0], 0, flags_off + 256, s->stream));
+    s->flags = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(s->cells[0]) + flags_off);
     if (two) {
         SE_CUDA_S(cudaMalloc(&s->cells[1], s->cells_bytes()));
         SE_CUDA_S(cudaMemsetAsync(s->cells[1], 0, s->cells_bytes(), s->stream));
@@ -499,20 +518,35 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
             // two CTAs per SM: each gets half of the SM's shared memory minus the per-CTA reservation (1 KB)
             // and the kernel's static shared memory (1 KB fat table)
             const int budget = std::min(smem_optin, smem_sm / 2 - 2048 - 256);
-            int T = prm->temporal_block ? (int)prm->temporal_block : 4;
+            int T = prm->temporal_block ? (int)prm->temporal_block : 8;
             T = std::max(2, T + (T & 1));
-            int PH = ((budget - s->tile_offset) / 256) & ~1;
-            PH = std::min(PH, 256);
-            if (PH >= 4 * T + 16) {
-                s->T = T;
-                s->HX = (T + 3) & ~3;
-                s->PH = PH;
-                s->tile_smem = s->tile_offset + 256 * PH;
-                s->tiles_x = (s->W + (256 - 2 * s->HX) - 1) / (256 - 2 * s->HX);
-                s->tiles_y = (s->Hl + (PH - 2 * T) - 1) / (PH - 2 * T);
+            int PH_max = ((budget - s->tile_offset) / 256) & ~1;
+            PH_max = std::min(PH_max, 256);
+            if (PH_max >= 4 * T + 16) {
                 int n_sm = 0;
                 SE_CUDA_S(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device));
-                s->tile_grid = std::min(2 * n_sm, s->tiles_x * s->tiles_y);
+                const int grid_max = 2 * n_sm;                       // persistent: 2 CTAs per SM
+                s->T = T;
+                s->HX = (T + 3) & ~3;
+                s->tiles_x = (s->W + (256 - 2 * s->HX) - 1) / (256 - 2 * s->HX);
+                // Tile height: every CTA processes ceil(tiles / grid) tiles of PH rows, so the launch costs
+                // rounds * (PH + c).  Pick the PH that minimises it (avoids a nearly empty last round: at
+                // 16384 x 2176 rows per GPU a fixed PH = 256 would spend 3 rounds on 2.3 rounds of work).
+                long best_cost = -1;
+                int best_PH = PH_max;
+                for (int PH = PH_max; PH >= 4 * T + 16; PH -= 2) {
+                    const int ty = (s->Hl + (PH - 2 * T) - 1) / (PH - 2 * T);
+                    const long tiles = (long)s->tiles_x * ty;
+                    const long rounds = (tiles + grid_max - 1) / grid_max;
+                    // useful rows per tile shrink with PH: account for the halo rows recomputed by every tile
+                    const long cost = rounds * (PH + 6);
+                    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_PH = PH; }
+                }
+                const int PH = best_PH;
+                s->PH = PH;
+                s->tile_smem = s->tile_offset + 256 * PH;
+                s->tiles_y = (s->Hl + (PH - 2 * T) - 1) / (PH - 2 * T);
+                s->tile_grid = std::min(grid_max, s->tiles_x * s->tiles_y);
                 SE_CU_S(driver().FuncSetAttribute(s->f_tiles, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->tile_smem));
                 SE_CUDA_S(cudaMalloc(&s->cells[1], s->cells_bytes()));
                 SE_CUDA_S(cudaMemsetAsync(s->cells[1], 0, s->cells_bytes(), s->stream));
@@ -562,7 +596,7 @@ int se_sim_step(se_sim* s, uint32_t n_steps) {
             tp.tiles_x = s->tiles_x; tp.tiles_y = s->tiles_y; tp.lut_words = s->lut_words; tp.pool_offset = s->pool_offset; tp.tile_offset = s->tile_offset;
             tp.lut = s->d_lut;
             void* targs[] = {&tp};
-            int rc = launch(s, s->f_tiles, dim3(s->tile_grid), dim3(512), targs, (unsigned)s->tile_smem);
+            int rc = launch(s, s->f_tiles, dim3(s->tile_grid), dim3(s->rules->tile_threads), targs, (unsigned)s->tile_smem);
             if (rc) return rc;
             s->frame += nsub;
             s->cur ^= 1;
@@ -708,6 +742,7 @@ int se_sim_ipc_attach(se_sim* s, int which, const void* handles, uint64_t nb_loc
         SE_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
         nb.cells[b] = (unsigned*)p;
     }
+    nb.flags = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(nb.cells[0]) + se_sim::flags_offset((size_t)s->W, (size_t)nb_local_rows));
     nb.attached = true;
     return SE_OK;
 }
@@ -731,6 +766,7 @@ int se_sim_attach_local(se_sim* s, int which, se_sim* other) {
     nb.ipc = false;
     nb.cells[0] = other->cells[0];
     nb.cells[1] = other->cells[1];
+    nb.flags = other->flags;
     nb.attached = true;
     return SE_OK;
 }
@@ -753,6 +789,30 @@ int se_sim_halo_push(se_sim* s) {
         unsigned* dst = nb.cells[s->cur];
         SE_CUDA(cudaMemcpyAsync(dst, src, rowb * nb.ghost_top, cudaMemcpyDeviceToDevice, s->stream));
     }
+    return SE_OK;
+}
+
+int se_sim_halo_exchange_async(se_sim* s) {
+    if (!s) return fail(SE_ERR_INVALID_ARG, "null sim");
+    SE_CUDA(cudaSetDevice(s->device));
+    if (!driver().ok) return fail(SE_ERR_CUDA, driver().why);
+    const unsigned e = ++s->epoch;
+    CUstream st = (CUstream)s->stream;
+    // (a) tell both neighbours that this strip has finished every step enqueued so far
+    for (int w = 0; w < 2; ++w)
+        if (s->nb[w].attached) SE_CU(driver().StreamWriteValue32(st, (CUdeviceptr)(s->nb[w].flags + (w == 0 ? 1 : 0)), e, CU_STREAM_WRITE_VALUE_DEFAULT));
+    // (b) wait until the neighbours have finished theirs: only then may their ghost rows be overwritten
+    for (int w = 0; w < 2; ++w)
+        if (s->nb[w].attached) SE_CU(driver().StreamWaitValue32(st, (CUdeviceptr)(s->flags + (w == 0 ? 0 : 1)), e, CU_STREAM_WAIT_VALUE_GEQ));
+    // (c) push boundary rows over NVLink
+    int rc = se_sim_halo_push(s);
+    if (rc) return rc;
+    // (d) publish "delivered"
+    for (int w = 0; w < 2; ++w)
+        if (s->nb[w].attached) SE_CU(driver().StreamWriteValue32(st, (CUdeviceptr)(s->nb[w].flags + (w == 0 ? 3 : 2)), e, CU_STREAM_WRITE_VALUE_DEFAULT));
+    // (e) later work of this stream starts once this strip's own ghost rows have been delivered
+    for (int w = 0; w < 2; ++w)
+        if (s->nb[w].attached) SE_CU(driver().StreamWaitValue32(st, (CUdeviceptr)(s->flags + (w == 0 ? 2 : 3)), e, CU_STREAM_WAIT_VALUE_GEQ));
     return SE_OK;
 }
 

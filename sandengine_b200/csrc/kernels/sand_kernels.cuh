@@ -62,6 +62,18 @@ static __device__ __forceinline__ unsigned se_hashi(unsigned x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
     return x;
 }
+// Same function with the right shifts written as high multiplies (x >> k == umulhi(x, 2^(32-k))): they
+// issue on the FMA pipe (IMAD.HI) instead of the ALU pipe, which the table kernel saturates (ncu:
+// sm__pipe_alu_cycles_active 69 % vs fma 16 %).  Bit-identical by construction.  MEASURED SLOWER on B200
+// (931 -> 851 Gcell/s at 16384^2, T=8: IMAD.HI issues at a lower rate than SHF), so it is not used.
+static __device__ __forceinline__ unsigned se_hashi_fma(unsigned x) {
+#ifdef SE_HOST_EMU
+    return se_hashi(x);
+#else
+    x ^= __umulhi(x, 1u << 16); x *= 0x7feb352dU; x ^= __umulhi(x, 1u << 17); x *= 0x846ca68bU; x ^= __umulhi(x, 1u << 16);
+    return x;
+#endif
+}
 // hash43(uvec3(pos_rounded, frame)) -- only the lanes the rule set consumes are evaluated
 static __device__ __forceinline__ void se_hash43(int px, int py, int frame, SeRand& rnd) {
     const unsigned x = (unsigned)px * 461u + (unsigned)py * 2131u + (unsigned)frame * (2131u * 2131u);
@@ -293,6 +305,9 @@ extern "C" __global__ void __launch_bounds__(256) se_fill_cells(unsigned* cells,
 #define SE_TILE_PW 256          // tile width in cells (= bytes); 64 words per row
 #define SE_LUT_POOL_MAX 4095
 #define SE_LUT_SLOW 0xFFFFu
+#ifndef SE_TILE_THREADS
+#define SE_TILE_THREADS 512
+#endif
 
 struct SePoolEntry { unsigned thr; unsigned short a, b; };   // 8 bytes
 
@@ -454,7 +469,9 @@ static __device__ __forceinline__ void se_tile_substep(unsigned tile_sa, se_tab_
                 unsigned v;
                 if (OX == 0) v = se_lds_u16(c0) | (se_lds_u16(c0 + PW) << 16);
                 else v = se_lds_u8(c0) | (se_lds_u8(c0 + 1) << 8) | (se_lds_u8(c0 + PW) << 16) | (se_lds_u8(c0 + PW + 1) << 24);
-                if (v != 0u) {                     // all-EMPTY early-out (falling_sand.glsl:692-694)
+                // No branch for the all-EMPTY early-out (falling_sand.glsl:692-694): T0[0] == 0 by construction
+                // (se_build_lut_entry skips the rules for state 0), so an empty block maps to itself.
+                {
                     const unsigned seed = rowseed + (unsigned)(2 * i) * 461u;
                     const unsigned nv = se_block_lut(v, seed, gx_org + OX + 2 * i, gy_org + ly, frame, tab, pool_off, fat_sm);
                     if (nv != v) {
@@ -472,7 +489,7 @@ static __device__ __forceinline__ void se_tile_substep(unsigned tile_sa, se_tab_
     }
 }
 
-extern "C" __global__ void __launch_bounds__(512, 2) se_step_tiles(const SeTileParams p) {
+extern "C" __global__ void __launch_bounds__(SE_TILE_THREADS, 2) se_step_tiles(const SeTileParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned fat_sm[256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;

@@ -57,13 +57,14 @@ class StripPlan:
 class StripSimulation:
     """One rank's strip of a sharded `Simulation` (lighting off)."""
 
-    def __init__(self, rules, size, halo_rows: int = 32, device=None, temporal_block: int = 0):
+    def __init__(self, rules, size, halo_rows: int = 32, device=None, temporal_block: int = 0, device_sync: bool = True):
         import torch
         import torch.distributed as dist
 
         from .simulation import Simulation
 
         self.dist = dist
+        self.device_sync = device_sync
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.plan = StripPlan(int(size[0]), int(size[1]), self.world, int(halo_rows) if self.world > 1 else 0)
@@ -95,8 +96,13 @@ class StripSimulation:
         return self.sim.download_cells(out)
 
     def exchange(self) -> None:
-        """Everyone has finished computing -> push boundary rows into the neighbours' ghosts -> everyone has landed."""
+        """Everyone has finished computing -> push boundary rows into the neighbours' ghosts -> everyone has landed.
+        device_sync: the ordering is enforced by stream-ordered flag writes/waits on peer memory (no host in
+        the loop); otherwise by two host barriers."""
         if self.world == 1:
+            return
+        if self.device_sync:
+            self.sim.halo_exchange_async()
             return
         self.sim.synchronize()
         self.dist.barrier()

@@ -182,6 +182,10 @@ class Simulation:
     def halo_push(self) -> None:
         _capi.check(_capi.lib().se_sim_halo_push(self._h))
 
+    def halo_exchange_async(self) -> None:
+        """Device-ordered ghost-row exchange (no host synchronisation); lock-step on every strip."""
+        _capi.check(_capi.lib().se_sim_halo_exchange_async(self._h))
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             _capi.lib().se_sim_destroy(self._h)

@@ -86,7 +86,7 @@ extern "C" void emu_step_lut_inplace(uint32_t* cells, int W, int H, int frame) {
                 v |= id << (8 * k);
             }
             unsigned nv = v;
-            if (v != 0u) {
+            {   // like the tile kernel: no all-EMPTY branch, T0[0] == 0
                 const unsigned seed = (unsigned)x0 * 461u + (unsigned)y0 * 2131u + (unsigned)frame * (2131u * 2131u);
                 nv = se_block_lut(v, seed, x0, y0, frame, g_table.data(), g_pool_off, se_fat_table);
             }

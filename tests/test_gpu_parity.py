@@ -243,7 +243,7 @@ def test_synthetic_64_material_rules_1024(se):
     assert np.array_equal(got, ref) and not np.array_equal(got, g)
 
 
-def _strip_pair_run(se, rules, g, steps, halo, n_strips):
+def _strip_pair_run(se, rules, g, steps, halo, n_strips, device_sync=False):
     """n strips of one grid on ONE device in ONE process (se_sim_attach_local): exercises ghost rows, the
     missing-row logic and se_sim_halo_push without torch.distributed."""
     from sandengine_b200.distributed import StripPlan
@@ -263,6 +263,9 @@ def _strip_pair_run(se, rules, g, steps, halo, n_strips):
             s.attach_local(1, sims[r + 1])
 
     def exchange():
+        if device_sync:      # stream-ordered flags on (here: same-device) peer memory, no host synchronisation
+            for s in sims: s.halo_exchange_async()
+            return
         for s in sims: s.synchronize()
         for s in sims: s.halo_push()
         for s in sims: s.synchronize()
@@ -281,6 +284,8 @@ def test_strips_equal_single_grid(se, default_rules, oracle, n_strips, halo, h):
     steps = 45
     ref, _, _ = oracle.run(g, 1, steps, blocks=True)
     got = _strip_pair_run(se, default_rules, g, steps, halo, n_strips)
+    assert np.array_equal(got, ref)
+    got = _strip_pair_run(se, default_rules, g, steps, halo, n_strips, device_sync=True)
     assert np.array_equal(got, ref)
 
 
