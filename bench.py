@@ -40,8 +40,8 @@ UNIT = "Gcell-updates/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=64)
     ap.add_argument("--size", type=int, default=16384)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--halo", type=int, default=64)
@@ -64,18 +64,22 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  nvidia-smi needs
+    ~100 ms to produce its first row, so sampling starts before the warm-up and every row is time-stamped; the
+    rows inside [mark_begin, mark_end] are the ones reported (the same kernel runs during the warm-up, whose rows
+    are used if the timed region was too short to catch one)."""
 
     def __init__(self, index: int):
         self.index = index
         self.rows = []
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -84,33 +88,47 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            parts = [p.strip() for p in r.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
-                "reasons": sorted(reasons)}
+
+        def digest(rows):
+            sm, mx, pw, reasons = [], [], [], set()
+            for _, r in rows:
+                parts = [p.strip() for p in r.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, parts[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            sm.sort()
+            return sm, mx, pw, reasons
+        inside = [r for r in self.rows if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or 1e30)]
+        window = "timed region"
+        if not inside:
+            inside, window = [r for r in self.rows if self.t1 is None or r[0] <= self.t1 + 0.05][-10:], "warm-up + timed region (timed region shorter than one sample)"
+        sm, mx, pw, reasons = digest(inside)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def cpu_port_rate(size_sample: int, budget_s: float, seed: int = SEED):
@@ -221,19 +239,21 @@ def run_ours(args):
         sim.params.frame = 1
 
     # ---------------- device-resident timing (value) ----------------
-    reset()
-    strip.step(Wm)
     sampler = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
         sampler.start()
+    reset()
+    strip.step(Wm)
+    barrier()
     l0 = sim.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     ev0.record(stream)
     strip.step(K)
     ev1.record(stream)
     barrier()
+    sampler.mark_end()
     t_dev = ev0.elapsed_time(ev1) / 1e3
     print(f"[bench] rank {rank}: device time {t_dev * 1e3:.3f} ms for {K} steps, rows {strip.row_begin}..{strip.row_end}", file=sys.stderr, flush=True)
     launches = sim.launch_count - l0
@@ -287,6 +307,9 @@ def run_ours(args):
         local_cells = S * (sim.owned_shape[0] + sum(strip.plan.ghosts(rank)))
         per_launch_s = t_dev / max(launches, 1)
         achieved = 8.0 * local_cells * K / t_dev / 1e9
+        # physical DRAM bytes of one se_step_tiles launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full,
+        # profiles/r1_k1b_ncu_full.txt): captured for exactly this configuration, null otherwise
+        traffic = 1.116995e9 + 1.023260e9 if (S == 16384 and world == 1 and launches * 8 == K) else None
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": round(t_dev / K * 1e3, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -298,7 +321,8 @@ def run_ours(args):
                              "L2-RESIDENT workload: the cell buffer fits the 126 MB L2",
                        "cells_bytes": S * S * 4},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": None, "kernel": "se_step_tiles" if launches < K else "se_step_inplace", "peak_source": peak_src,
+                         "traffic": traffic, "traffic_unit": "bytes per launch (8 fused steps; algorithmic bytes per launch = 8 B x 268435456 cells x 8 steps = 1.718e10)",
+                         "kernel": "se_step_tiles" if launches < K else "se_step_inplace", "peak_source": peak_src,
                          "algorithmic_bytes_per_cell_update": 8, "launches_timed": launches,
                          "steps_per_launch": round(K / max(launches, 1), 2), "avg_launch_us": round(per_launch_s * 1e6, 2),
                          "note": "temporal blocking: physical DRAM bytes per launch are ~8/T per cell-update (see profiles/), "

@@ -69,6 +69,8 @@ class Oracle:
         self.lib.so_step_cells.restype = None
         self.lib.so_step_blocks_inplace.argtypes = [u32p, C.c_int, C.c_int, C.c_int]
         self.lib.so_step_blocks_inplace.restype = None
+        self.lib.so_step_blocks_strip.argtypes = [u32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        self.lib.so_step_blocks_strip.restype = None
         self.lib.so_run_blocks.argtypes = [u32p, C.c_int, C.c_int, C.c_int, C.c_int]
         self.lib.so_run_blocks.restype = C.c_int
         self.lib.so_hash43.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32 * 4),
@@ -113,6 +115,12 @@ class Oracle:
         assert cells.dtype == np.uint32 and cells.flags.c_contiguous
         H, W = cells.shape
         self.lib.so_step_blocks_inplace(cells, W, H, int(frame))
+
+    def step_blocks_strip(self, cells, gy0, Hg, frame):
+        """Local rows [gy0, gy0 + len(cells)) of a grid of Hg rows (ghost-row schedule emulation only)."""
+        assert cells.dtype == np.uint32 and cells.flags.c_contiguous
+        Hl, W = cells.shape
+        self.lib.so_step_blocks_strip(cells, W, Hl, int(gy0), int(Hg), int(frame))
 
     def run_blocks(self, cells, frame, n_steps):
         """In-place, lighting off, no modifications. Returns the final frame."""

@@ -358,4 +358,38 @@ int so_run_blocks(uint32_t* cells, int W, int H, int frame, int n_steps) {
     return frame;
 }
 
+/* Strip form of the per-block update, used ONLY by the CPU (gloo) emulation of the multi-GPU ghost-row
+ * schedule (tests/test_distributed_gloo.py): `cells` holds local rows [gy0, gy0 + Hl) of a grid of Hg rows.
+ * Rows outside the global grid read as WALL; a block that needs a row inside the grid but outside the
+ * local buffer is skipped (its in-buffer row goes stale -- exactly what the ghost-row schedule accounts for).
+ * Positions fed to the hash are GLOBAL (falling_sand.glsl:698). */
+void so_step_blocks_strip(uint32_t* cells, int W, int Hl, int gy0, int Hg, int frame) {
+    int off[2]; getMargolusOffset(frame, off);
+    int jb0 = (gy0 + off[1]) / 2;
+    int y_end = (gy0 + Hl < Hg) ? gy0 + Hl : Hg;
+    int nby = (y_end + off[1] + 1) / 2 - jb0, nbx = (W + off[0] + 1) / 2;
+#pragma omp parallel for schedule(static)
+    for (int jl = 0; jl < nby; jl++) {
+        int y0 = 2 * (jb0 + jl) - off[1], y1 = y0 + 1;
+        int st0 = (y0 < 0) ? 1 : (y0 < gy0 ? 2 : 0);
+        int st1 = (y1 >= Hg) ? 1 : (y1 >= gy0 + Hl ? 2 : 0);
+        if (st0 == 2 || st1 == 2 || y0 >= y_end) continue;
+        for (int bx = 0; bx < nbx; bx++) {
+            ivec2 pr = {bx * 2 - off[0], y0};
+            Cell q[4];
+            for (int k = 0; k < 4; k++) {
+                int x = pr.x + (k & 1), y = pr.y + (k >> 1);
+                ivec2 pos = {x, y};
+                if (x < 0 || x >= W || y < 0 || y >= Hg) q[k] = newCell(MAT_WALL, pos);
+                else q[k] = newCell(getMaterialFromID((int)cells[(size_t)(y - gy0) * W + x]), pos);
+            }
+            if (!block_transition(&q[0], &q[1], &q[2], &q[3], pr, frame)) continue;
+            for (int k = 0; k < 4; k++) {
+                int x = pr.x + (k & 1), y = pr.y + (k >> 1);
+                if (!(x < 0 || x >= W || y < 0 || y >= Hg)) cells[(size_t)(y - gy0) * W + x] = (uint32_t)q[k].mat.id;
+            }
+        }
+    }
+}
+
 int so_n_materials(void) { return N_MATERIALS; }
