@@ -108,6 +108,12 @@ int se_sim_download_light(se_sim* s, float* host_rgba);
 int se_sim_device_cells(se_sim* s, void** dptr, size_t* pitch_bytes);
 /* Per-material population of the owned rows (256 bins), computed on the device. */
 int se_sim_census(se_sim* s, uint64_t* counts256);
+/* Asynchronous census: enqueued after everything issued so far, runs on the sim's side stream CONCURRENTLY with
+ * later steps (a later step that would overwrite the buffer being counted waits for it on the device).
+ * host_counts256 (256 x uint64; pinned memory for a truly asynchronous copy) is valid after
+ * se_sim_census_wait().  Up to 4 censuses may be in flight. */
+int se_sim_census_async(se_sim* s, uint64_t* host_counts256);
+int se_sim_census_wait(se_sim* s);
 /* Run on a caller-provided CUDA stream (cudaStream_t as void*); NULL restores the sim's own stream. */
 int se_sim_set_stream(se_sim* s, void* cuda_stream);
 int se_sim_synchronize(se_sim* s);

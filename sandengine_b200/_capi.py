@@ -29,7 +29,7 @@ EXPORTS = [
     "se_rules_material", "se_rules_material_id", "se_rules_rule",
     "se_sim_create", "se_sim_destroy", "se_sim_step", "se_sim_push_modifications", "se_sim_set_frame", "se_sim_get_frame",
     "se_sim_upload_cells", "se_sim_download_cells", "se_sim_upload_light", "se_sim_download_light", "se_sim_device_cells",
-    "se_sim_census", "se_sim_set_stream", "se_sim_synchronize", "se_sim_launch_count",
+    "se_sim_census", "se_sim_census_async", "se_sim_census_wait", "se_sim_set_stream", "se_sim_synchronize", "se_sim_launch_count",
     "se_sim_ipc_export", "se_sim_ipc_attach", "se_sim_attach_local", "se_sim_halo_push", "se_sim_halo_exchange_async", "se_last_error", "se_version",
 ]
 
@@ -81,6 +81,8 @@ def lib() -> C.CDLL:
     L.se_sim_download_light.argtypes = [vp, vp]
     L.se_sim_device_cells.argtypes = [vp, P(vp), P(sz)]
     L.se_sim_census.argtypes = [vp, vp]
+    L.se_sim_census_async.argtypes = [vp, vp]
+    L.se_sim_census_wait.argtypes = [vp]
     L.se_sim_set_stream.argtypes = [vp, vp]
     L.se_sim_synchronize.argtypes = [vp]
     L.se_sim_launch_count.argtypes = [vp, P(C.c_uint64)]

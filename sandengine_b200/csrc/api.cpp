@@ -114,9 +114,16 @@ struct SeTileParams {
     const unsigned* in;
     unsigned* out;
     int W, Hl, gy0, Hg;
-    int frame0, nsub, T, HX, PH;
+    int frame0, nsub, HY, HX, PH;
     int tiles_x, tiles_y;
     int lut_words, pool_offset, tile_offset;
+    const unsigned* lut;
+};
+struct SeLutStepParams {
+    unsigned* cells;
+    int W, Hl, gy0, Hg;
+    int frame;
+    int lut_words, pool_offset;
     const unsigned* lut;
 };
 struct SeLightParams {
@@ -162,16 +169,26 @@ struct se_sim {
     float4* light[2] = {nullptr, nullptr};
     int lcur = 0;
     SeMod* d_mods = nullptr;
-    SeMod* h_mods = nullptr;   // pinned staging, SE_MAX_MODIFICATIONS entries
+    // pinned staging ring for the modification UBO: SE_MOD_SLOTS x SE_MAX_MODIFICATIONS records.  A slot is
+    // reused only after the async copy that read it has completed (event per slot), so se_sim_step never
+    // has to synchronise the stream.
+    SeMod* h_mods = nullptr;
+    cudaEvent_t mod_events[16] = {};
+    unsigned mod_slot = 0;
     std::vector<se_modification> pending;
     int frame = 0;
     uint64_t launches = 0;
-    unsigned long long* d_census = nullptr;
+    unsigned long long* d_census = nullptr;   // 4 slots of 256 bins (slot 0 is also used by the synchronous census)
+    // asynchronous census: side stream + events; census_done[b] guards cell buffer b against being overwritten
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_main = nullptr, census_done[2] = {nullptr, nullptr};
+    bool census_pending[2] = {false, false};
+    unsigned census_slot = 0;
     // transition-table tile kernel (K1b)
     bool tiled = false;
-    CUfunction f_tiles = nullptr, f_build_lut = nullptr;
+    CUfunction f_tiles = nullptr, f_build_lut = nullptr, f_lut_global = nullptr;
     unsigned* d_lut = nullptr;
-    int T = 0, HX = 0, PH = 0, tiles_x = 0, tiles_y = 0, lut_words = 0, pool_offset = 0, tile_offset = 0, tile_smem = 0, tile_grid = 0;
+    int T = 0, HY = 0, HX = 0, PH = 0, tiles_x = 0, tiles_y = 0, lut_words = 0, pool_offset = 0, tile_offset = 0, tile_smem = 0, tile_grid = 0, tile_grid_max = 0;
     Neighbour nb[2];
     // Device-side exchange protocol: 4 flag words live right behind cells[0] (same allocation, so that one
     // IPC handle maps both): [0]/[1] = "done computing" epoch of the strip above/below, [2]/[3] = "ghost rows
@@ -252,6 +269,16 @@ int compile_front(const char* yaml, size_t len, se_rules** out, bool with_nvrtc)
     return SE_OK;
 }
 
+// A cell buffer that an asynchronous census is still reading must not be overwritten: make the main stream
+// wait (on the device) for that census before the next writer of the buffer.
+int guard_buffer_write(se_sim* s, int buf) {
+    if (s->census_pending[buf]) {
+        SE_CUDA(cudaStreamWaitEvent(s->stream, s->census_done[buf], 0));
+        s->census_pending[buf] = false;
+    }
+    return SE_OK;
+}
+
 int launch(se_sim* s, CUfunction f, dim3 grid, dim3 block, void** args, unsigned smem = 0) {
     SE_CU(driver().LaunchKernel(f, grid.x, grid.y, grid.z, block.x, block.y, block.z, smem, (CUstream)s->stream, args, nullptr));
     s->launches++;
@@ -259,6 +286,7 @@ int launch(se_sim* s, CUfunction f, dim3 grid, dim3 block, void** args, unsigned
 }
 
 int one_step(se_sim* s, bool use_mods, int n_mods) {
+    { int rc = guard_buffer_write(s, 0); if (rc) return rc; rc = guard_buffer_write(s, 1); if (rc) return rc; }
     s->frame += 1;
     const int frame = s->frame;
     const int ox = ((frame & 3) == 1 || (frame & 3) == 3) ? 1 : 0;
@@ -278,7 +306,7 @@ int one_step(se_sim* s, bool use_mods, int n_mods) {
         if (rc) return rc;
         SeLightParams lp{s->cells[s->cur], outb, s->light[s->lcur], s->light[s->lcur ^ 1], s->W, s->Hl, s->gy0, s->Hg};
         void* largs[] = {&lp};
-        rc = launch(s, s->f_light, dim3((s->W + 63) / 64, (s->Hl + 3) / 4), dim3(64, 4), largs);
+        rc = launch(s, s->f_light, dim3((s->W + 31) / 32, (s->Hl + 7) / 8), dim3(32, 8), largs);
         if (rc) return rc;
         s->cur ^= 1;
         s->lcur ^= 1;
@@ -305,7 +333,7 @@ int one_step(se_sim* s, bool use_mods, int n_mods) {
     if (rc) return rc;
     SeLightParams lp{p.in, p.out, s->light[s->lcur], s->light[s->lcur ^ 1], s->W, s->Hl, s->gy0, s->Hg};
     void* largs[] = {&lp};
-    rc = launch(s, s->f_light, dim3((s->W + 63) / 64, (s->Hl + 3) / 4), dim3(64, 4), largs);
+    rc = launch(s, s->f_light, dim3((s->W + 31) / 32, (s->Hl + 7) / 8), dim3(32, 8), largs);
     if (rc) return rc;
     s->cur ^= 1;
     s->lcur ^= 1;
@@ -406,7 +434,11 @@ int se_sim_destroy(se_sim* s) {
     }
     if (s->d_mods) cudaFree(s->d_mods);
     if (s->h_mods) cudaFreeHost(s->h_mods);
+    for (auto& ev : s->mod_events) if (ev) cudaEventDestroy(ev);
     if (s->d_census) cudaFree(s->d_census);
+    if (s->aux_stream) { cudaStreamSynchronize(s->aux_stream); cudaStreamDestroy(s->aux_stream); }
+    if (s->ev_main) cudaEventDestroy(s->ev_main);
+    for (auto& ev : s->census_done) if (ev) cudaEventDestroy(ev);
     if (s->d_lut) cudaFree(s->d_lut);
     if (s->mod && driver().ok) driver().ModuleUnload(s->mod);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
@@ -479,8 +511,12 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
         }
     }
     SE_CUDA_S(cudaMalloc(&s->d_mods, SE_MAX_MODIFICATIONS * sizeof(SeMod)));
-    SE_CUDA_S(cudaMallocHost(&s->h_mods, SE_MAX_MODIFICATIONS * sizeof(SeMod)));
-    SE_CUDA_S(cudaMalloc(&s->d_census, 256 * sizeof(unsigned long long)));
+    SE_CUDA_S(cudaMallocHost(&s->h_mods, 16 * SE_MAX_MODIFICATIONS * sizeof(SeMod)));
+    for (auto& ev : s->mod_events) SE_CUDA_S(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    SE_CUDA_S(cudaMalloc(&s->d_census, 4 * 256 * sizeof(unsigned long long)));
+    SE_CUDA_S(cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
+    SE_CUDA_S(cudaEventCreateWithFlags(&s->ev_main, cudaEventDisableTiming));
+    for (auto& ev : s->census_done) SE_CUDA_S(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 
     // ---- K1b: transition table + shared-memory tiles with temporal blocking -------------------------
     // Used for runs of steps without modifications when lighting is off, the rule set is table-eligible
@@ -495,6 +531,7 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
         unsigned* d_counter = nullptr;
         SE_CU_S(driver().ModuleGetFunction(&s->f_tiles, s->mod, "se_step_tiles"));
         SE_CU_S(driver().ModuleGetFunction(&s->f_build_lut, s->mod, "se_build_lut"));
+        SE_CU_S(driver().ModuleGetFunction(&s->f_lut_global, s->mod, "se_step_lut_global"));
         SE_CUDA_S(cudaMalloc(&s->d_lut, lut_cap));
         SE_CUDA_S(cudaMalloc(&d_counter, sizeof(unsigned)));
         SE_CUDA_S(cudaMemsetAsync(s->d_lut, 0, lut_cap, s->stream));
@@ -522,11 +559,14 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
             T = std::max(2, T + (T & 1));
             int PH_max = ((budget - s->tile_offset) / 256) & ~1;
             PH_max = std::min(PH_max, 256);
+            // rows: the Margolus row offset changes every other frame, so T fused steps need only T/2+1 halo rows
+            const int HY = ((T / 2 + 1) + 1) & ~1;
             if (PH_max >= 4 * T + 16) {
                 int n_sm = 0;
                 SE_CUDA_S(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device));
                 const int grid_max = 2 * n_sm;                       // persistent: 2 CTAs per SM
                 s->T = T;
+                s->HY = HY;
                 s->HX = (T + 3) & ~3;
                 s->tiles_x = (s->W + (256 - 2 * s->HX) - 1) / (256 - 2 * s->HX);
                 // Tile height: every CTA processes ceil(tiles / grid) tiles of PH rows, so the launch costs
@@ -535,7 +575,7 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
                 long best_cost = -1;
                 int best_PH = PH_max;
                 for (int PH = PH_max; PH >= 4 * T + 16; PH -= 2) {
-                    const int ty = (s->Hl + (PH - 2 * T) - 1) / (PH - 2 * T);
+                    const int ty = (s->Hl + (PH - 2 * HY) - 1) / (PH - 2 * HY);
                     const long tiles = (long)s->tiles_x * ty;
                     const long rounds = (tiles + grid_max - 1) / grid_max;
                     // useful rows per tile shrink with PH: account for the halo rows recomputed by every tile
@@ -545,9 +585,11 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
                 const int PH = best_PH;
                 s->PH = PH;
                 s->tile_smem = s->tile_offset + 256 * PH;
-                s->tiles_y = (s->Hl + (PH - 2 * T) - 1) / (PH - 2 * T);
+                s->tiles_y = (s->Hl + (PH - 2 * HY) - 1) / (PH - 2 * HY);
                 s->tile_grid = std::min(grid_max, s->tiles_x * s->tiles_y);
+                s->tile_grid_max = grid_max;
                 SE_CU_S(driver().FuncSetAttribute(s->f_tiles, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->tile_smem));
+                SE_CU_S(driver().FuncSetAttribute(s->f_lut_global, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->tile_offset));
                 SE_CUDA_S(cudaMalloc(&s->cells[1], s->cells_bytes()));
                 SE_CUDA_S(cudaMemsetAsync(s->cells[1], 0, s->cells_bytes(), s->stream));
                 s->tiled = true;
@@ -570,6 +612,9 @@ int se_sim_step(se_sim* s, uint32_t n_steps) {
         // Stage the UBO the way the host of the reference does (all of the first min(len, 256) records are
         // copied, simulation.rs:205-207); the kernels scan only up to the first mod_size == 0 record.
         n_staged = (int)std::min<size_t>(s->pending.size(), SE_MAX_MODIFICATIONS);
+        const unsigned slot = s->mod_slot++ % 16u;
+        SE_CUDA(cudaEventSynchronize(s->mod_events[slot]));   // returns at once unless 16 steps are still in flight
+        SeMod* stage = s->h_mods + (size_t)slot * SE_MAX_MODIFICATIONS;
         bool open = true;
         for (int i = 0; i < n_staged; ++i) {
             const se_modification& m = s->pending[i];
@@ -579,20 +624,37 @@ int se_sim_step(se_sim* s, uint32_t n_steps) {
             // getMaterialFromID: unknown id => MAT_NULL (id 1), gen/materials.glsl:79-86
             d.mat = (m.mod_matID >= 0 && m.mod_matID < s->rules->cr.tables.n_materials) ? m.mod_matID : 1;
             d.pad0 = d.pad1 = d.pad2 = 0;
-            s->h_mods[i] = d;
+            stage[i] = d;
             if (open) n_mods = i + 1;
         }
-        SE_CUDA(cudaMemcpyAsync(s->d_mods, s->h_mods, (size_t)n_staged * sizeof(SeMod), cudaMemcpyHostToDevice, s->stream));
+        SE_CUDA(cudaMemcpyAsync(s->d_mods, stage, (size_t)n_staged * sizeof(SeMod), cudaMemcpyHostToDevice, s->stream));
+        SE_CUDA(cudaEventRecord(s->mod_events[slot], s->stream));
     }
     for (uint32_t k = 0; k < n_steps;) {
         const bool mods_now = (k == 0 && n_mods > 0);
         if (s->tiled && !mods_now && s->frame + 1 != 1) {
             // a run of plain steps: fuse up to T of them per launch (ping-pong buffers)
             const int nsub = (int)std::min<uint32_t>((uint32_t)s->T, n_steps - k);
+            if (nsub == 1) {
+                // a lone step (the per-frame path): K1c, table transitions straight from global memory, in place
+                { int rc = guard_buffer_write(s, s->cur); if (rc) return rc; }
+                SeLutStepParams lp;
+                lp.cells = s->cells[s->cur];
+                lp.W = s->W; lp.Hl = s->Hl; lp.gy0 = s->gy0; lp.Hg = s->Hg; lp.frame = s->frame + 1;
+                lp.lut_words = s->lut_words; lp.pool_offset = s->pool_offset; lp.lut = s->d_lut;
+                void* largs[] = {&lp};
+                int n_sm = s->tile_grid_max;
+                int rc = launch(s, s->f_lut_global, dim3(n_sm), dim3(512), largs, (unsigned)s->tile_offset);   // SE_K1C_THREADS
+                if (rc) return rc;
+                s->frame += 1;
+                k += 1;
+                continue;
+            }
+            { int rc = guard_buffer_write(s, s->cur ^ 1); if (rc) return rc; }
             SeTileParams tp;
             tp.in = s->cells[s->cur]; tp.out = s->cells[s->cur ^ 1];
             tp.W = s->W; tp.Hl = s->Hl; tp.gy0 = s->gy0; tp.Hg = s->Hg;
-            tp.frame0 = s->frame + 1; tp.nsub = nsub; tp.T = s->T; tp.HX = s->HX; tp.PH = s->PH;
+            tp.frame0 = s->frame + 1; tp.nsub = nsub; tp.HY = s->HY; tp.HX = s->HX; tp.PH = s->PH;
             tp.tiles_x = s->tiles_x; tp.tiles_y = s->tiles_y; tp.lut_words = s->lut_words; tp.pool_offset = s->pool_offset; tp.tile_offset = s->tile_offset;
             tp.lut = s->d_lut;
             void* targs[] = {&tp};
@@ -606,10 +668,6 @@ int se_sim_step(se_sim* s, uint32_t n_steps) {
         int rc = one_step(s, k == 0, n_mods);
         if (rc) return rc;
         ++k;
-    }
-    if (n_staged > 0) {
-        // h_mods is reused by the next call: the async copy must have been consumed
-        SE_CUDA(cudaStreamSynchronize(s->stream));
     }
     s->pending.clear();   // simulation.rs:252
     return SE_OK;
@@ -637,6 +695,7 @@ int se_sim_get_frame(const se_sim* s, int32_t* frame) {
 int se_sim_upload_cells(se_sim* s, const uint32_t* host) {
     if (!s || !host) return fail(SE_ERR_INVALID_ARG, "null argument");
     SE_CUDA(cudaSetDevice(s->device));
+    { int rc = guard_buffer_write(s, s->cur); if (rc) return rc; }
     SE_CUDA(cudaMemcpyAsync(s->cells[s->cur] + s->owned_offset(), host, s->owned_cells() * sizeof(unsigned), cudaMemcpyHostToDevice, s->stream));
     SE_CUDA(cudaStreamSynchronize(s->stream));
     return SE_OK;
@@ -684,6 +743,35 @@ int se_sim_census(se_sim* s, uint64_t* counts256) {
     SE_CUDA(cudaGetLastError());
     SE_CUDA(cudaMemcpyAsync(counts256, s->d_census, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
     SE_CUDA(cudaStreamSynchronize(s->stream));
+    return SE_OK;
+}
+
+int se_sim_census_async(se_sim* s, uint64_t* host_counts256) {
+    if (!s || !host_counts256) return fail(SE_ERR_INVALID_ARG, "null argument");
+    SE_CUDA(cudaSetDevice(s->device));
+    const int buf = s->cur;
+    if (s->census_pending[buf]) {
+        // the previous census of this buffer is still being tracked by the same event: finish it first
+        SE_CUDA(cudaEventSynchronize(s->census_done[buf]));
+        s->census_pending[buf] = false;
+    }
+    unsigned long long* slot = s->d_census + 256 * (size_t)(s->census_slot++ % 4u);
+    SE_CUDA(cudaEventRecord(s->ev_main, s->stream));
+    SE_CUDA(cudaStreamWaitEvent(s->aux_stream, s->ev_main, 0));
+    SE_CUDA(cudaMemsetAsync(slot, 0, 256 * sizeof(unsigned long long), s->aux_stream));
+    se_static::launch_census(s->cells[buf] + s->owned_offset(), s->owned_cells(), slot, s->aux_stream);
+    s->launches++;
+    SE_CUDA(cudaGetLastError());
+    SE_CUDA(cudaMemcpyAsync(host_counts256, slot, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->aux_stream));
+    SE_CUDA(cudaEventRecord(s->census_done[buf], s->aux_stream));
+    s->census_pending[buf] = true;
+    return SE_OK;
+}
+
+int se_sim_census_wait(se_sim* s) {
+    if (!s) return fail(SE_ERR_INVALID_ARG, "null sim");
+    SE_CUDA(cudaSetDevice(s->device));
+    SE_CUDA(cudaStreamSynchronize(s->aux_stream));
     return SE_OK;
 }
 

@@ -188,13 +188,45 @@ static __device__ __forceinline__ void se_step_global_impl(const SeStepParams& p
     }
 }
 
+// Modifications are culled per CTA: thread t tests record t against the CTA's cell rectangle (+ the
+// record's size) and the survivors are compacted IN ORDER (last match wins, falling_sand.glsl:764-773)
+// into shared memory, so the per-cell scan only walks the records that can touch this CTA.
+static __device__ __forceinline__ int se_cull_mods(const SeStepParams& p, SeMod* mods_sm, int* warp_counts) {
+    int ox, oy;
+    se_margolus_offset(p.frame, ox, oy);
+    const int t = threadIdx.y * blockDim.x + threadIdx.x;
+    const int x_lo = 2 * (int)(blockIdx.x * blockDim.x) - ox, x_hi = x_lo + 2 * (int)blockDim.x - 1;
+    const int jb0 = (p.gy0 + oy) >> 1;
+    const int y_lo = 2 * (jb0 + (int)(blockIdx.y * blockDim.y)) - oy, y_hi = y_lo + 2 * (int)blockDim.y - 1;
+    bool keep = false;
+    SeMod m;
+    if (t < p.n_mods) {
+        m = p.mods[t];
+        // both shapes are contained in the square |dx| <= size, |dy| <= size (negative sizes never match)
+        keep = m.size >= 0 && m.px + m.size >= x_lo && m.px - m.size <= x_hi && m.py + m.size >= y_lo && m.py - m.size <= y_hi;
+    }
+    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
+    const int warp = t >> 5, lane = t & 31;
+    if (lane == 0) warp_counts[warp] = __popc(ballot);
+    __syncthreads();
+    int base = 0, total = 0;
+    for (int w = 0; w < 8; ++w) { if (w < warp) base += warp_counts[w]; total += warp_counts[w]; }
+    if (keep) mods_sm[base + __popc(ballot & ((1u << lane) - 1u))] = m;
+    __syncthreads();
+    return total;
+}
+
 #define SE_DEFINE_STEP_GLOBAL(NAME, IN_PLACE, HAS_MODS)                                  \
     extern "C" __global__ void __launch_bounds__(256) NAME(const SeStepParams p) {        \
         __shared__ unsigned fat_sm[256];                                                  \
+        __shared__ SeMod mods_sm[HAS_MODS ? 256 : 1];                                     \
+        __shared__ int warp_counts[8];                                                    \
         const int t = threadIdx.y * blockDim.x + threadIdx.x;                             \
         if (t < 256) fat_sm[t] = se_fat_table[t];                                         \
+        SeStepParams q = p;                                                               \
+        if (HAS_MODS) { q.n_mods = se_cull_mods(p, mods_sm, warp_counts); q.mods = mods_sm; } \
         __syncthreads();                                                                  \
-        se_step_global_impl<IN_PLACE, HAS_MODS>(p, fat_sm);                               \
+        se_step_global_impl<IN_PLACE, HAS_MODS>(q, fat_sm);                               \
     }
 SE_DEFINE_STEP_GLOBAL(se_step_inplace, true, false)
 SE_DEFINE_STEP_GLOBAL(se_step_inplace_mods, true, true)
@@ -216,15 +248,39 @@ struct SeLightParams {
     int W, Hl, gy0, Hg;
 };
 
+// The per-neighbour term (rgb * keep * a, a) does not depend on which cell reads it, so each CTA computes it
+// ONCE per cell of its 32 x 8 tile (+ a one-cell ring) into shared memory -- one id load, one float4 load and
+// one table lookup per cell instead of eight -- and every cell then combines its 8 neighbours from shared
+// memory in the shader's order with the shader's arithmetic (the reader-dependent part is only
+// `falloff = (a == 0) ? max_falloff : a`).
 extern "C" __global__ void __launch_bounds__(256) se_light(const SeLightParams p) {
     __shared__ unsigned fat_sm[256];
-    {
-        const int t = threadIdx.y * blockDim.x + threadIdx.x;
-        if (t < 256) fat_sm[t] = se_fat_table[t];
+    __shared__ float4 term[10][34];      // (vr, vg, vb, a) of cell (tile_x0 - 1 + j, tile_y0 - 1 + i)
+    __shared__ unsigned char ok[10][36]; // 1 = neighbour exists (inside the grid and the local buffer)
+    const int t = threadIdx.y * blockDim.x + threadIdx.x;
+    if (t < 256) fat_sm[t] = se_fat_table[t];
+    __syncthreads();
+    const int x0 = blockIdx.x * 32 - 1, yl0 = blockIdx.y * 8 - 1;
+    for (int e = t; e < 10 * 34; e += 256) {
+        const int i = e / 34, j = e - i * 34;
+        const int nx = x0 + j, nyl = yl0 + i, ny = p.gy0 + nyl;
+        unsigned char valid = 0;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nx >= 0 && nx < p.W && ny >= 0 && ny < p.Hg && nyl >= 0 && nyl < p.Hl) {   // outOfBounds, :139-141
+            const size_t nidx = (size_t)nyl * p.W + nx;
+            const unsigned nf = fat_sm[min(p.old_cells[nidx], 255u)];
+            const float keep = (nf & SE_F_OBSTACLE) ? 0.0f : 1.0f;
+            const float4 li = p.light_in[nidx];
+            const float la = li.w * 1.0f;
+            v = make_float4((li.x * keep) * la, (li.y * keep) * la, (li.z * keep) * la, la);
+            valid = 1;
+        }
+        term[i][j] = v;
+        ok[i][j] = valid;
     }
     __syncthreads();
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int yl = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int yl = blockIdx.y * 8 + threadIdx.y;
     if (x >= p.W || yl >= p.Hl) return;
     const int y = p.gy0 + yl;                     // global row
     const size_t idx = (size_t)yl * p.W + x;
@@ -235,28 +291,22 @@ extern "C" __global__ void __launch_bounds__(256) se_light(const SeLightParams p
     } else if (y == 0) {                          // :128-129
         light = make_float4(1.0f, 1.0f, 1.0f, 0.999999f);
     } else {
+        // neighbour order DOWN, UP, DOWNLEFT, UPLEFT, DOWNRIGHT, UPRIGHT, RIGHT, LEFT (math.glsl:154-166)
         const int NX[8] = {0, 0, -1, -1, 1, 1, 1, -1};
         const int NY[8] = {1, -1, 1, -1, 1, -1, 0, 0};
         float4 avg = make_float4(0.f, 0.f, 0.f, 0.f), mx = make_float4(0.f, 0.f, 0.f, 0.f);
         float max_falloff = 0.0f;
         int num = 0;
+        const int ci = threadIdx.y + 1, cj = threadIdx.x + 1;
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-            const int nx = x + NX[n], ny = y + NY[n];
-            if (nx < 0 || nx >= p.W || ny < 0 || ny >= p.Hg) continue;          // outOfBounds, :139-141
-            const int nyl = ny - p.gy0;
-            if (nyl < 0 || nyl >= p.Hl) continue;   // missing ghost row: result row is stale by schedule
-            const size_t nidx = (size_t)nyl * p.W + nx;
-            const unsigned nf = fat_sm[min(p.old_cells[nidx], 255u)];
-            const float keep = (nf & SE_F_OBSTACLE) ? 0.0f : 1.0f;
-            const float4 t = p.light_in[nidx];
-            const float lr = t.x * keep, lg = t.y * keep, lb = t.z * keep, la = t.w * 1.0f;
-            const float falloff = (la == 0.0f) ? max_falloff : la;
-            const float vr = lr * la, vg = lg * la, vb = lb * la;
-            avg.x += vr; avg.y += vg; avg.z += vb; avg.w += falloff;
+            if (!ok[ci + NY[n]][cj + NX[n]]) continue;
+            const float4 v = term[ci + NY[n]][cj + NX[n]];
+            const float falloff = (v.w == 0.0f) ? max_falloff : v.w;
+            avg.x += v.x; avg.y += v.y; avg.z += v.z; avg.w += falloff;
             max_falloff = fmaxf(falloff, max_falloff);
             num += 1;
-            mx.x = fmaxf(mx.x, vr); mx.y = fmaxf(mx.y, vg); mx.z = fmaxf(mx.z, vb); mx.w = fmaxf(mx.w, falloff);
+            mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, falloff);
         }
         if (num > 0) {
             const float dn = (float)num;
@@ -297,7 +347,7 @@ extern "C" __global__ void __launch_bounds__(256) se_fill_cells(unsigned* cells,
 // refuses to swap, which is precisely when the table is used.
 //
 // One persistent CTA loops over tiles: load (uint4 global -> u8 shared), nsub Margolus sub-steps in
-// shared memory with a halo of T cells, store the interior (u8 shared -> uint4 global, ping-pong buffer).
+// shared memory with a halo of T columns / T/2+1 rows, store the interior (u8 shared -> uint4 global, ping-pong buffer).
 // HBM traffic per cell-update ~ (4 * tile/interior + 4) / T bytes instead of 8.
 // =============================================================================================
 #if SE_LUT_ELIGIBLE
@@ -369,8 +419,9 @@ struct SeTileParams {
     int W, Hl, gy0, Hg;
     int frame0;             // frame number of the first sub-step of this launch
     int nsub;               // sub-steps in this launch, 1..T
-    int T;                  // halo depth in rows (even)
-    int HX;                 // halo depth in columns (multiple of 4, >= T)
+    int HY;                 // halo depth in rows (even, >= nsub/2 + 1: the row offset changes every OTHER frame,
+                            // operations.glsl:25-34, so validity shrinks by at most floor(n/2)+1 rows in n steps)
+    int HX;                 // halo depth in columns (multiple of 4, >= nsub: the column offset alternates every frame)
     int PH;                 // tile height in cells (even)
     int tiles_x, tiles_y;
     int lut_words;          // 32-bit words of (base + pad + pool) to stage in shared memory
@@ -499,17 +550,25 @@ extern "C" __global__ void __launch_bounds__(SE_TILE_THREADS, 2) se_step_tiles(c
     const unsigned pool_off = (unsigned)p.pool_offset;
     const unsigned tile_sa = smem_sa + (unsigned)p.tile_offset;
 
-    for (int i = tid; i < p.lut_words; i += blockDim.x) se_sts_u32(smem_sa + 4u * i, __ldg(p.lut + i));
+    // stage the table with 16-byte loads (it is re-read by every CTA of every launch: keep this prologue short)
+    {
+        const uint4* lut4 = reinterpret_cast<const uint4*>(p.lut);
+        const int n4 = (p.lut_words + 3) >> 2;           // the device buffer is padded to a multiple of 16 bytes
+        for (int i = tid; i < n4; i += blockDim.x) {
+            const uint4 v = __ldg(lut4 + i);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(smem_sa + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        }
+    }
     if (tid < 256) fat_sm[tid] = se_fat_table[tid];
     __syncthreads();
 
     const int PW = SE_TILE_PW, PH = p.PH;
-    const int TWo = PW - 2 * p.HX, THo = PH - 2 * p.T;
+    const int TWo = PW - 2 * p.HX, THo = PH - 2 * p.HY;
     const int n_tiles = p.tiles_x * p.tiles_y;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
         const int gx_org = tx * TWo - p.HX;              // global x of tile column 0 (multiple of 4)
-        const int gy_org = p.gy0 + ty * THo - p.T;       // global y of tile row 0 (even)
+        const int gy_org = p.gy0 + ty * THo - p.HY;      // global y of tile row 0 (even)
         const bool border = gx_org < 0 || gx_org + PW > p.W || gy_org < 0 || gy_org + PH > p.Hg;
 
         // ---- load: uint4 of packed-u32 cells -> 4 id bytes ----
@@ -553,7 +612,7 @@ extern "C" __global__ void __launch_bounds__(SE_TILE_THREADS, 2) se_step_tiles(c
         }
 
         // ---- store the interior: 4 id bytes -> uint4 of packed-u32 cells ----
-        for (int r = p.T + warp; r < PH - p.T; r += nwarps) {
+        for (int r = p.HY + warp; r < PH - p.HY; r += nwarps) {
             const int gy = gy_org + r, lr = gy - p.gy0;
             if (gy >= p.Hg || lr >= p.Hl) break;
             uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)lr * p.W);
@@ -568,6 +627,115 @@ extern "C" __global__ void __launch_bounds__(SE_TILE_THREADS, 2) se_step_tiles(c
             }
         }
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1c: ONE Margolus step with the transition table, straight from/to global memory, in place.
+// This is the per-frame path (`Simulation::run()` called once per frame): a single step cannot amortise the
+// tile load/store of K1b, so blocks are read directly (two 8-byte loads per block when the column phase is
+// even, four 4-byte loads otherwise), pushed through se_block_lut and only the cells that changed are
+// written back.  Persistent CTAs keep the table in shared memory; a warp walks 32 consecutive blocks of
+// one block row, a CTA walks block rows grid-stride.  HBM-bound: ~4 B read + (changed fraction) x 4 B
+// written per cell.
+// ---------------------------------------------------------------------------------------------
+struct SeLutStepParams {
+    unsigned* cells;        // local buffer, updated in place
+    int W, Hl, gy0, Hg;
+    int frame;
+    int lut_words, pool_offset;
+    const unsigned* lut;
+};
+
+#define SE_K1C_THREADS 512
+#define SE_K1C_SPAN 8           // a work item = one block row x SPAN chunks of 32 blocks (amortises the row set-up)
+#define SE_K1C_BATCH 2          // chunks whose loads are issued together (the update is in place, so the compiler
+                                // cannot hoist loads over the previous chunk's stores by itself)
+
+extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, 2) se_step_lut_global(const SeLutStepParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ unsigned fat_sm[256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    unsigned smem_sa;
+    asm volatile("mov.u32 %0, %1;" : "=r"(smem_sa) : "r"((unsigned)__cvta_generic_to_shared(smem)));
+    {
+        const uint4* lut4 = reinterpret_cast<const uint4*>(p.lut);
+        const int n4 = (p.lut_words + 3) >> 2;
+        for (int i = tid; i < n4; i += blockDim.x) {
+            const uint4 v = __ldg(lut4 + i);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(smem_sa + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        }
+    }
+    if (tid < 256) fat_sm[tid] = se_fat_table[tid];
+    __syncthreads();
+    const se_tab_t tab = smem_sa;
+    const unsigned pool_off = (unsigned)p.pool_offset;
+
+    int ox, oy;
+    se_margolus_offset(p.frame, ox, oy);
+    const int jb0 = (p.gy0 + oy) >> 1;
+    const int y_end = min(p.Hg, p.gy0 + p.Hl);
+    const unsigned nby = (unsigned)(((y_end + oy + 1) >> 1) - jb0);
+    const int nbx = (p.W + ox + 1) >> 1;
+    const unsigned chunks_x = (unsigned)((nbx + 31) >> 5);                 // 32 blocks per warp-iteration
+    const unsigned spans_x = (chunks_x + SE_K1C_SPAN - 1) / SE_K1C_SPAN;
+    const unsigned n_items = nby * spans_x;
+    const unsigned fterm = (unsigned)p.frame * (2131u * 2131u);
+    const bool vec_ok = (ox == 0) && ((p.W & 1) == 0);                     // 8-byte aligned pairs
+    for (unsigned item = blockIdx.x * nwarps + warp; item < n_items; item += gridDim.x * nwarps) {
+        const unsigned jl = item / spans_x, sp = item - jl * spans_x;
+        const int y0 = 2 * (jb0 + (int)jl) - oy, y1 = y0 + 1;
+        const int st0 = (y0 < 0) ? 1 : (y0 < p.gy0 ? 2 : 0);
+        const int st1 = (y1 >= p.Hg) ? 1 : (y1 >= p.gy0 + p.Hl ? 2 : 0);
+        if (st0 == 2 || st1 == 2) continue;                                // missing ghost row: block row skipped (see K1a)
+        unsigned* base0 = p.cells + (size_t)(st0 == 0 ? y0 - p.gy0 : 0) * (size_t)p.W;
+        unsigned* base1 = p.cells + (size_t)(st1 == 0 ? y1 - p.gy0 : 0) * (size_t)p.W;
+        const unsigned rowseed = (unsigned)y0 * 2131u + fterm;
+        const int c_begin = (int)sp * SE_K1C_SPAN, c_end = min((int)chunks_x, c_begin + SE_K1C_SPAN);
+        for (int cb = c_begin; cb < c_end; cb += SE_K1C_BATCH) {
+            unsigned a[SE_K1C_BATCH], b[SE_K1C_BATCH], c[SE_K1C_BATCH], d[SE_K1C_BATCH];
+#pragma unroll
+            for (int u = 0; u < SE_K1C_BATCH; ++u) {                       // ---- loads of the whole batch first
+                const int bx = (cb + u) * 32 + lane;
+                const int x0 = 2 * bx - ox;
+                a[u] = b[u] = c[u] = d[u] = 2u;                            // WALL outside the grid
+                if (cb + u < c_end && bx < nbx) {
+                    if (vec_ok) {
+                        if (st0 == 0) { const uint2 t = *reinterpret_cast<const uint2*>(base0 + x0); a[u] = t.x; b[u] = t.y; }
+                        if (st1 == 0) { const uint2 t = *reinterpret_cast<const uint2*>(base1 + x0); c[u] = t.x; d[u] = t.y; }
+                    } else {
+                        const bool cx0 = x0 >= 0, cx1 = (x0 + 1) < p.W;
+                        if (st0 == 0 && cx0) a[u] = base0[x0];
+                        if (st0 == 0 && cx1) b[u] = base0[x0 + 1];
+                        if (st1 == 0 && cx0) c[u] = base1[x0];
+                        if (st1 == 0 && cx1) d[u] = base1[x0 + 1];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < SE_K1C_BATCH; ++u) {                       // ---- transitions + write-back
+                const int bx = (cb + u) * 32 + lane;
+                const int x0 = 2 * bx - ox;
+                if (cb + u < c_end && bx < nbx) {
+                    const unsigned ia = a[u] < SE_N_MATERIALS ? a[u] : 1u, ib = b[u] < SE_N_MATERIALS ? b[u] : 1u;
+                    const unsigned ic = c[u] < SE_N_MATERIALS ? c[u] : 1u, id = d[u] < SE_N_MATERIALS ? d[u] : 1u;
+                    const unsigned v = ia | (ib << 8) | (ic << 16) | (id << 24);
+                    const unsigned seed = (unsigned)x0 * 461u + rowseed;
+                    const unsigned nv = se_block_lut(v, seed, x0, y0, p.frame, tab, pool_off, fat_sm);
+                    const unsigned na = nv & 0xFFu, nb = (nv >> 8) & 0xFFu, nc = (nv >> 16) & 0xFFu, nd = nv >> 24;
+                    if (vec_ok) {
+                        if (st0 == 0 && (na != a[u] || nb != b[u])) *reinterpret_cast<uint2*>(base0 + x0) = make_uint2(na, nb);
+                        if (st1 == 0 && (nc != c[u] || nd != d[u])) *reinterpret_cast<uint2*>(base1 + x0) = make_uint2(nc, nd);
+                    } else {
+                        const bool cx0 = x0 >= 0, cx1 = (x0 + 1) < p.W;
+                        if (st0 == 0 && cx0 && na != a[u]) base0[x0] = na;
+                        if (st0 == 0 && cx1 && nb != b[u]) base0[x0 + 1] = nb;
+                        if (st1 == 0 && cx0 && nc != c[u]) base1[x0] = nc;
+                        if (st1 == 0 && cx1 && nd != d[u]) base1[x0 + 1] = nd;
+                    }
+                }
+            }
+        }
     }
 }
 #endif  // SE_HOST_EMU

@@ -5,9 +5,10 @@ device-to-device over NVLink by the native library (se_sim_halo_push) -- no data
 The grid is cut into horizontal strips on EVEN rows.  A strip keeps `halo_rows` ghost rows towards each
 neighbour and re-computes them redundantly: the Margolus update is block-local and its RAND depends
 only on (block position, frame) (falling_sand.glsl:698), so both neighbours compute identical values
-for the rows they share.  One step can invalidate at most the outermost still-valid ghost row (its
-block may be cut by the buffer edge), hence G ghost rows are good for G steps; then the owners push
-fresh copies.  `StripPlan` holds that arithmetic and is shared by the GPU path and by the CPU (gloo)
+for the rows they share.  A step invalidates the outermost still-valid ghost row only when its block is cut
+by the buffer edge, and the Margolus ROW offset changes every other frame (operations.glsl:25-34:
+frame%4 -> 1,1,0,0), so n steps invalidate at most floor(n/2)+1 rows: G ghost rows are good for 2(G-1)
+steps; then the owners push fresh copies.  `StripPlan` holds that arithmetic and is shared by the GPU path and by the CPU (gloo)
 emulation the tests use.
 """
 from __future__ import annotations
@@ -46,11 +47,17 @@ class StripPlan:
         b, e = self.rows(rank)
         return (min(self.halo_rows, b) if rank > 0 else 0), (min(self.halo_rows, self.height - e) if rank < self.world - 1 else 0)
 
+    @property
+    def steps_per_exchange(self) -> int:
+        """n with floor(n/2) + 1 <= halo_rows, rounded down to a multiple of 8 (whole fused launches) when possible."""
+        n = 2 * (self.halo_rows - 1)
+        return n // 8 * 8 if n >= 8 else n
+
     def chunks(self, n_steps: int) -> List[int]:
         """Step counts between ghost exchanges."""
         if self.world == 1:
             return [n_steps] if n_steps else []
-        g = self.halo_rows
+        g = self.steps_per_exchange
         return [g] * (n_steps // g) + ([n_steps % g] if n_steps % g else [])
 
 

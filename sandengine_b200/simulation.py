@@ -152,6 +152,14 @@ class Simulation:
         _capi.check(_capi.lib().se_sim_census(self._h, out.ctypes.data))
         return out
 
+    def census_async(self, host_ptr: int) -> None:
+        """Enqueue a census whose 256 x uint64 result lands at `host_ptr` (pinned memory) after census_wait();
+        it runs on a side stream concurrently with later steps."""
+        _capi.check(_capi.lib().se_sim_census_async(self._h, C.c_void_p(host_ptr)))
+
+    def census_wait(self) -> None:
+        _capi.check(_capi.lib().se_sim_census_wait(self._h))
+
     def set_stream(self, cuda_stream: int) -> None:
         _capi.check(_capi.lib().se_sim_set_stream(self._h, C.c_void_p(cuda_stream)))
 

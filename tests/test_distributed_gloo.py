@@ -83,7 +83,8 @@ def test_strip_plan_arithmetic():
     p = StripPlan(16384, 16384, 8, 64)
     assert [p.rows(r) for r in range(8)] == [(2048 * r, 2048 * (r + 1)) for r in range(8)]
     assert p.ghosts(0) == (0, 64) and p.ghosts(3) == (64, 64) and p.ghosts(7) == (64, 0)
-    assert p.chunks(200) == [64, 64, 64, 8] and p.chunks(0) == []
+    assert p.steps_per_exchange == 120 and p.chunks(200) == [120, 80] and p.chunks(0) == []
+    assert StripPlan(16384, 16384, 8, 34).steps_per_exchange == 64 and StripPlan(64, 64, 2, 2).steps_per_exchange == 2 and StripPlan(64, 64, 2, 4).steps_per_exchange == 6
     q = StripPlan(100, 50, 3, 4)      # ragged: even boundaries, last strip takes the odd tail
     rows = [q.rows(r) for r in range(3)]
     assert rows[0][0] == 0 and rows[-1][1] == 50 and all(b % 2 == 0 for b, _ in rows) and all(rows[i][1] == rows[i + 1][0] for i in range(2))

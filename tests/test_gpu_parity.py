@@ -243,7 +243,7 @@ def test_synthetic_64_material_rules_1024(se):
     assert np.array_equal(got, ref) and not np.array_equal(got, g)
 
 
-def _strip_pair_run(se, rules, g, steps, halo, n_strips, device_sync=False):
+def _strip_pair_run(se, rules, g, steps, halo, n_strips, device_sync=False, per_step=False):
     """n strips of one grid on ONE device in ONE process (se_sim_attach_local): exercises ghost rows, the
     missing-row logic and se_sim_halo_push without torch.distributed."""
     from sandengine_b200.distributed import StripPlan
@@ -271,7 +271,11 @@ def _strip_pair_run(se, rules, g, steps, halo, n_strips, device_sync=False):
         for s in sims: s.synchronize()
     exchange()
     for k in plan.chunks(steps):
-        for s in sims: s.step(k)
+        for s in sims:
+            if per_step:            # one se_sim_step(1) per frame: the K1c (single-step table kernel) path
+                for _ in range(k): s.step(1)
+            else:
+                s.step(k)
         exchange()
     out = np.concatenate([s.download_cells() for s in sims], axis=0)
     for s in sims: s.close()
@@ -286,6 +290,8 @@ def test_strips_equal_single_grid(se, default_rules, oracle, n_strips, halo, h):
     got = _strip_pair_run(se, default_rules, g, steps, halo, n_strips)
     assert np.array_equal(got, ref)
     got = _strip_pair_run(se, default_rules, g, steps, halo, n_strips, device_sync=True)
+    assert np.array_equal(got, ref)
+    got = _strip_pair_run(se, default_rules, g, steps, halo, n_strips, device_sync=True, per_step=True)
     assert np.array_equal(got, ref)
 
 
@@ -335,3 +341,39 @@ def test_tiled_4096_vs_per_step_kernel(se, default_rules):
     b, _, _ = run_gpu(se, default_rules, g, 256, temporal_block=4)
     c, _, _ = run_gpu(se, default_rules, g, 256, temporal_block=8, chunk=37)
     assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+def test_census_async_overlaps_steps(se, default_rules):
+    """se_sim_census_async: results equal a host bincount of the state at the time of the call, also when later
+    steps (which ping-pong / overwrite buffers) are enqueued before the wait."""
+    import torch
+    w, h = 1024, 768
+    g = synthetic_grid(w, h, 19)
+    for T in (0, 1):      # tiled (ping-pong) and per-step in-place kernels
+        sim = se.Simulation(default_rules, (w, h), temporal_block=T)
+        sim.upload_cells(g); sim.params.frame = 1
+        ring = torch.zeros((4, 256), dtype=torch.int64).pin_memory()
+        expect = []
+        for k in range(4):
+            sim.step(3)
+            expect.append(np.bincount(sim.download_cells().ravel(), minlength=256))
+            sim.census_async(ring[k].data_ptr())
+            sim.step(2)                      # enqueued before the census is consumed
+            sim.step(1)
+        sim.census_wait()
+        for k in range(4):
+            assert np.array_equal(ring[k].numpy(), expect[k]), (T, k)
+        sim.close()
+
+
+def test_single_step_table_kernel_k1c(se, default_rules, oracle):
+    """K1c (se_step_lut_global): every frame issued as its own se_sim_step(1), incl. odd widths that disable the
+    8-byte path, WALL/NULL cells and all four Margolus phases."""
+    for (w, h, seed, steps) in [(516, 130, 41, 41), (1024, 64, 42, 24), (260, 258, 43, 19)]:
+        g = synthetic_grid(w, h, seed)
+        rng = np.random.default_rng(seed)
+        g[rng.integers(0, h, 100), rng.integers(0, w, 100)] = 2
+        g[rng.integers(0, h, 30), rng.integers(0, w, 30)] = 1
+        ref, _, _ = oracle.run(g, 1, steps, blocks=True)
+        got, _, _ = run_gpu(se, default_rules, g, steps, chunk=1)
+        assert np.array_equal(got, ref), (w, h)
