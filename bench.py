@@ -125,7 +125,8 @@ class ClockSampler:
         inside = [r for r in self.rows if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or 1e30)]
         window = "timed region"
         if not inside:
-            inside, window = [r for r in self.rows if self.t1 is None or r[0] <= self.t1 + 0.05][-10:], "warm-up + timed region (timed region shorter than one sample)"
+            inside = [r for r in self.rows if self.t1 is None or r[0] <= self.t1 + 0.05][-10:] or self.rows[-10:]
+            window = "warm-up + timed region (timed region shorter than one sample)"
         sm, mx, pw, reasons = digest(inside)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
                 "samples": len(sm), "window": window, "reasons": sorted(reasons)}

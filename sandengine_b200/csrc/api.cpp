@@ -558,7 +558,7 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
             int T = prm->temporal_block ? (int)prm->temporal_block : 8;
             T = std::max(2, T + (T & 1));
             int PH_max = ((budget - s->tile_offset) / 256) & ~1;
-            PH_max = std::min(PH_max, 256);
+            PH_max = std::min(PH_max, 256);   // measured: taller tiles (up to the 276 rows that fit) are slower (less load/compute overlap)
             // rows: the Margolus row offset changes every other frame, so T fused steps need only T/2+1 halo rows
             const int HY = ((T / 2 + 1) + 1) & ~1;
             if (PH_max >= 4 * T + 16) {
@@ -579,10 +579,16 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
                     const long tiles = (long)s->tiles_x * ty;
                     const long rounds = (tiles + grid_max - 1) / grid_max;
                     // useful rows per tile shrink with PH: account for the halo rows recomputed by every tile
-                    const long cost = rounds * (PH + 6);
+                    // + 24: per-tile fixed work (table/phase set-up, barriers, exposed load/store) expressed in rows;
+                    // fitted on B200 (16384 x 2116 rows: 3 rounds of PH 190 beat 4 rounds of PH 138)
+                    const long cost = rounds * (PH + 24);
                     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_PH = PH; }
                 }
-                const int PH = best_PH;
+                int PH = best_PH;
+                if (const char* ov = std::getenv("SE_TILE_PH")) {      // experiments only: override the search
+                    const int v = std::atoi(ov) & ~1;
+                    if (v >= 4 * T + 16 && v <= PH_max) PH = v;
+                }
                 s->PH = PH;
                 s->tile_smem = s->tile_offset + 256 * PH;
                 s->tiles_y = (s->Hl + (PH - 2 * HY) - 1) / (PH - 2 * HY);
