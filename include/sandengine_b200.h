@@ -103,6 +103,10 @@ int se_sim_download_cells(se_sim* s, uint32_t* host_cells);
 /* Light state (input_light texture): 4 floats per cell, owned rows.  Needs SE_FLAG_LIGHTING. */
 int se_sim_upload_light(se_sim* s, const float* host_rgba);
 int se_sim_download_light(se_sim* s, float* host_rgba);
+/* Colour shading of the owned rows on the device (the reference's output_color texture, operations.glsl:100-108,170:
+ * material colour minus simplex noise of the position, clamped).  host_rgba_f32: width*rows*4 floats, or NULL;
+ * host_rgba8: width*rows packed R|G<<8|B<<16|A<<24 bytes for headless readback, or NULL. */
+int se_sim_download_color(se_sim* s, float* host_rgba_f32, uint32_t* host_rgba8);
 /* Device pointer of the current cell buffer's first OWNED row (for CUDA-GL interop / zero-copy readers);
  * pitch in bytes.  Valid until the next se_sim_step. */
 int se_sim_device_cells(se_sim* s, void** dptr, size_t* pitch_bytes);

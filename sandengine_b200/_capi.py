@@ -28,7 +28,7 @@ EXPORTS = [
     "se_rules_compile_yaml", "se_rules_parse_only", "se_rules_destroy", "se_rules_text", "se_rules_cubin", "se_rules_counts",
     "se_rules_material", "se_rules_material_id", "se_rules_rule",
     "se_sim_create", "se_sim_destroy", "se_sim_step", "se_sim_push_modifications", "se_sim_set_frame", "se_sim_get_frame",
-    "se_sim_upload_cells", "se_sim_download_cells", "se_sim_upload_light", "se_sim_download_light", "se_sim_device_cells",
+    "se_sim_upload_cells", "se_sim_download_cells", "se_sim_upload_light", "se_sim_download_light", "se_sim_download_color", "se_sim_device_cells",
     "se_sim_census", "se_sim_census_async", "se_sim_census_wait", "se_sim_set_stream", "se_sim_synchronize", "se_sim_launch_count",
     "se_sim_ipc_export", "se_sim_ipc_attach", "se_sim_attach_local", "se_sim_halo_push", "se_sim_halo_exchange_async", "se_last_error", "se_version",
 ]
@@ -79,6 +79,7 @@ def lib() -> C.CDLL:
     L.se_sim_download_cells.argtypes = [vp, vp]
     L.se_sim_upload_light.argtypes = [vp, vp]
     L.se_sim_download_light.argtypes = [vp, vp]
+    L.se_sim_download_color.argtypes = [vp, vp, vp]
     L.se_sim_device_cells.argtypes = [vp, P(vp), P(sz)]
     L.se_sim_census.argtypes = [vp, vp]
     L.se_sim_census_async.argtypes = [vp, vp]

@@ -119,6 +119,12 @@ struct SeTileParams {
     int lut_words, pool_offset, tile_offset;
     const unsigned* lut;
 };
+struct SeShadeParams {
+    const unsigned* cells;
+    float4* rgba_f32;
+    unsigned* rgba8;
+    int W, rows, y0;
+};
 struct SeLutStepParams {
     unsigned* cells;
     int W, Hl, gy0, Hg;
@@ -159,7 +165,7 @@ struct se_sim {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     CUmodule mod = nullptr;
-    CUfunction f_inplace = nullptr, f_inplace_mods = nullptr, f_pingpong = nullptr, f_pingpong_mods = nullptr, f_light = nullptr, f_fill = nullptr;
+    CUfunction f_inplace = nullptr, f_inplace_mods = nullptr, f_pingpong = nullptr, f_pingpong_mods = nullptr, f_light = nullptr, f_fill = nullptr, f_shade = nullptr;
     int W = 0, Hg = 0;
     int row_begin = 0, row_end = 0, ghost_top = 0, ghost_bottom = 0;
     int gy0 = 0, Hl = 0;   // local buffer: rows [gy0, gy0 + Hl) of the global grid
@@ -495,6 +501,7 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
     SE_CU_S(driver().ModuleGetFunction(&s->f_pingpong_mods, s->mod, "se_step_pingpong_mods"));
     SE_CU_S(driver().ModuleGetFunction(&s->f_light, s->mod, "se_light"));
     SE_CU_S(driver().ModuleGetFunction(&s->f_fill, s->mod, "se_fill_cells"));
+    SE_CU_S(driver().ModuleGetFunction(&s->f_shade, s->mod, "se_shade"));
 
     // Simulation::new allocates zero-filled textures (simulation.rs:145,177-181)
     const bool two = s->lighting;
@@ -730,6 +737,29 @@ int se_sim_download_light(se_sim* s, float* host) {
     SE_CUDA(cudaSetDevice(s->device));
     SE_CUDA(cudaMemcpyAsync(host, s->light[s->lcur] + s->owned_offset(), s->owned_cells() * sizeof(float4), cudaMemcpyDeviceToHost, s->stream));
     SE_CUDA(cudaStreamSynchronize(s->stream));
+    return SE_OK;
+}
+
+int se_sim_download_color(se_sim* s, float* host_f32, uint32_t* host_rgba8) {
+    if (!s || (!host_f32 && !host_rgba8)) return fail(SE_ERR_INVALID_ARG, "null argument");
+    SE_CUDA(cudaSetDevice(s->device));
+    const int rows = s->row_end - s->row_begin;
+    const size_t n = (size_t)s->W * rows;
+    float4* d_f32 = nullptr;
+    unsigned* d_u8 = nullptr;
+    if (host_f32) SE_CUDA(cudaMalloc(&d_f32, n * sizeof(float4)));
+    if (host_rgba8) { cudaError_t e = cudaMalloc(&d_u8, n * sizeof(unsigned)); if (e != cudaSuccess) { cudaFree(d_f32); return fail(SE_ERR_CUDA, cudaGetErrorString(e)); } }
+    SeShadeParams sp{s->cells[s->cur] + s->owned_offset(), d_f32, d_u8, s->W, rows, s->row_begin};
+    void* args[] = {&sp};
+    int rc = launch(s, s->f_shade, dim3((s->W + 63) / 64, (rows + 3) / 4), dim3(64, 4), args);
+    cudaError_t e = cudaSuccess;
+    if (rc == SE_OK && host_f32) e = cudaMemcpyAsync(host_f32, d_f32, n * sizeof(float4), cudaMemcpyDeviceToHost, s->stream);
+    if (rc == SE_OK && e == cudaSuccess && host_rgba8) e = cudaMemcpyAsync(host_rgba8, d_u8, n * sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_f32);
+    cudaFree(d_u8);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(SE_ERR_CUDA, cudaGetErrorString(e));
     return SE_OK;
 }
 

@@ -318,6 +318,75 @@ extern "C" __global__ void __launch_bounds__(256) se_light(const SeLightParams p
     p.light_out[idx] = light;
 }
 
+// ---------------------------------------------------------------------------------------------
+// K5: colour shading (operations.glsl:100-108, math.glsl:82-111) -- the render product of `setCell`:
+// colour = material colour, and for non-EMPTY cells rgb -= 0.25 * noise(pos, 3 octaves, lacunarity 2, freq 0.25),
+// clamped to [0,1].  A pure function of (material id, position), so it is evaluated on demand from the
+// id buffer instead of being stored every step like the reference's output_color texture.
+// Uses sinf (not __sinf); the hash `fract(sin(p) * 43758.5453)` amplifies last-bit differences of sin, so
+// parity with the CPU restatement is a tolerance statement (tests/test_gpu_parity.py::test_colour_shading).
+// ---------------------------------------------------------------------------------------------
+#ifndef SE_HOST_EMU
+static __device__ __forceinline__ float se_fract(float x) { return x - floorf(x); }
+static __device__ __forceinline__ float2 se_old_hash2(float px, float py) {   // math.glsl:40-44
+    const float a = px * 127.1f + py * 311.7f;
+    const float b = px * 269.5f + py * 183.3f;
+    return make_float2(-1.0f + 2.0f * se_fract(sinf(a) * 43758.5453123f), -1.0f + 2.0f * se_fract(sinf(b) * 43758.5453123f));
+}
+static __device__ float se_simplex(float px, float py) {                      // math.glsl:82-96
+    const float K1 = 0.366025404f, K2 = 0.211324865f;
+    const float sk = (px + py) * K1;
+    const float ix = floorf(px + sk), iy = floorf(py + sk);
+    const float t = (ix + iy) * K2;
+    const float ax = px - ix + t, ay = py - iy + t;
+    const float m = (ax < ay) ? 0.0f : 1.0f;                                   // step(a.y, a.x)
+    const float ox = m, oy = 1.0f - m;
+    const float bx = ax - ox + K2, by = ay - oy + K2;
+    const float cx = ax - 1.0f + 2.0f * K2, cy = ay - 1.0f + 2.0f * K2;
+    const float h0 = fmaxf(0.5f - (ax * ax + ay * ay), 0.0f);
+    const float h1 = fmaxf(0.5f - (bx * bx + by * by), 0.0f);
+    const float h2 = fmaxf(0.5f - (cx * cx + cy * cy), 0.0f);
+    const float2 g0 = se_old_hash2(ix + 0.0f, iy + 0.0f), g1 = se_old_hash2(ix + ox, iy + oy), g2 = se_old_hash2(ix + 1.0f, iy + 1.0f);
+    const float n0 = h0 * h0 * h0 * h0 * (ax * g0.x + ay * g0.y);
+    const float n1 = h1 * h1 * h1 * h1 * (bx * g1.x + by * g1.y);
+    const float n2 = h2 * h2 * h2 * h2 * (cx * g2.x + cy * g2.y);
+    return 0.25f + 0.5f * (n0 * 70.0f + n1 * 70.0f + n2 * 70.0f);
+}
+
+struct SeShadeParams {
+    const unsigned* cells;   // first OWNED row
+    float4* rgba_f32;        // or nullptr
+    unsigned* rgba8;         // or nullptr: packed R | G<<8 | B<<16 | A<<24, round-to-nearest of clamp(c)*255
+    int W, rows, y0;         // y0 = global row of the first owned row (positions feed the noise)
+};
+
+extern "C" __global__ void __launch_bounds__(256) se_shade(const SeShadeParams p) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yl = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= p.W || yl >= p.rows) return;
+    const size_t idx = (size_t)yl * p.W + x;
+    const unsigned id = min(p.cells[idx], 255u);
+    float4 col = make_float4(se_color_table[id * 4 + 0], se_color_table[id * 4 + 1], se_color_table[id * 4 + 2], se_color_table[id * 4 + 3]);
+    if (id != 0u) {                                                            // cell.mat != MAT_EMPTY
+        float fx = (float)x, fy = (float)(p.y0 + yl), f = 0.0f;
+        for (int o = 1; o < 4; ++o) {                                          // noise(pos, 3, 2.0, 0.25), math.glsl:98-107
+            f += 1.0f / (float)o * se_simplex(fx * 0.25f, fy * 0.25f);
+            fx *= 2.0f; fy *= 2.0f;
+        }
+        const float rnd = f * 0.25f;
+        col.x = fminf(fmaxf(col.x - rnd, 0.0f), 1.0f);
+        col.y = fminf(fmaxf(col.y - rnd, 0.0f), 1.0f);
+        col.z = fminf(fmaxf(col.z - rnd, 0.0f), 1.0f);
+    }
+    if (p.rgba_f32) p.rgba_f32[idx] = col;
+    if (p.rgba8) {
+        const unsigned r = (unsigned)__float2int_rn(fminf(fmaxf(col.x, 0.f), 1.f) * 255.0f), g = (unsigned)__float2int_rn(fminf(fmaxf(col.y, 0.f), 1.f) * 255.0f);
+        const unsigned b = (unsigned)__float2int_rn(fminf(fmaxf(col.z, 0.f), 1.f) * 255.0f), a = (unsigned)__float2int_rn(fminf(fmaxf(col.w, 0.f), 1.f) * 255.0f);
+        p.rgba8[idx] = r | (g << 8) | (b << 16) | (a << 24);
+    }
+}
+#endif  // SE_HOST_EMU
+
 // frame == 1: every cell becomes EMPTY (falling_sand.glsl:743-746); lighting (if on) then runs with
 // new_cells == all-EMPTY through se_light.
 extern "C" __global__ void __launch_bounds__(256) se_fill_cells(unsigned* cells, size_t n, unsigned value) {

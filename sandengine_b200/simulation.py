@@ -136,6 +136,17 @@ class Simulation:
         _capi.check(_capi.lib().se_sim_download_light(self._h, out.ctypes.data))
         return out
 
+    def download_color(self, rgba8: bool = False) -> np.ndarray:
+        """The reference's `output_color` (operations.glsl:100-108) shaded on demand from the id buffer:
+        float32 (rows, width, 4), or packed RGBA8 uint32 (rows, width) for headless readback."""
+        if rgba8:
+            out = np.empty(self.owned_shape, np.uint32)
+            _capi.check(_capi.lib().se_sim_download_color(self._h, None, out.ctypes.data))
+        else:
+            out = np.empty(self.owned_shape + (4,), np.float32)
+            _capi.check(_capi.lib().se_sim_download_color(self._h, out.ctypes.data, None))
+        return out
+
     def upload_cells_ptr(self, host_ptr: int) -> None:
         _capi.check(_capi.lib().se_sim_upload_cells(self._h, C.c_void_p(host_ptr)))
 

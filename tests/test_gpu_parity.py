@@ -377,3 +377,52 @@ def test_single_step_table_kernel_k1c(se, default_rules, oracle):
         ref, _, _ = oracle.run(g, 1, steps, blocks=True)
         got, _, _ = run_gpu(se, default_rules, g, steps, chunk=1)
         assert np.array_equal(got, ref), (w, h)
+
+
+def test_colour_shading(se, default_rules, oracle):
+    """K5 (next row L3): colour = f(material, position) with simplex noise built on fract(sin(p) * 43758.5453).
+    That hash amplifies last-bit differences between CUDA sinf and glibc sinf by ~4e4 and is discontinuous, so parity
+    is stated as a tolerance on the distribution: EMPTY cells exact, >= 99 % of channels within 2e-3 of the CPU
+    restatement, alpha exact (noise never touches it)."""
+    w, h = 192, 160
+    g = synthetic_grid(w, h, 23)
+    _, _, ref = oracle.step_cells(g, 2, want_color=True)          # colour of the cells AFTER frame 2
+    after, _, _ = oracle.run(g, 1, 1)
+    sim = se.Simulation(default_rules, (w, h))
+    sim.upload_cells(g); sim.params.frame = 1
+    sim.run()
+    assert np.array_equal(sim.download_cells(), after)
+    col = sim.download_color()
+    err = np.abs(col - ref)
+    assert np.array_equal(col[..., 3], ref[..., 3])
+    assert err[after == 0].max() == 0.0
+    frac_ok = float((err[..., :3] <= 2e-3).mean())
+    assert frac_ok >= 0.99, (frac_ok, float(err.max()), float(np.median(err)))
+    rgba8 = sim.download_color(rgba8=True)
+    expect8 = np.rint(np.clip(col, 0, 1) * 255).astype(np.uint32)
+    packed = expect8[..., 0] | (expect8[..., 1] << 8) | (expect8[..., 2] << 16) | (expect8[..., 3] << 24)
+    assert np.array_equal(rgba8, packed)
+    sim.close()
+
+
+def test_snapshot_resume_is_bit_identical(se, default_rules, tmp_path):
+    from sandengine_b200 import snapshot
+    g = synthetic_grid(256, 128, 29)
+    L0 = np.random.default_rng(2).random((128, 256, 4), dtype=np.float32)
+    for lighting in (False, True):
+        a = se.Simulation(default_rules, (256, 128), lighting=lighting)
+        a.upload_cells(g); a.params.frame = 1
+        if lighting: a.upload_light(L0)
+        a.step(23)
+        snapshot.save(a, tmp_path / "s.npz")
+        a.step(40)
+        b = snapshot.load(default_rules, tmp_path / "s.npz")
+        assert b.params.frame == 24
+        b.step(40)
+        assert np.array_equal(a.download_cells(), b.download_cells())
+        if lighting:
+            assert np.array_equal(a.download_light(), b.download_light())
+        a.close(); b.close()
+    other = se.parse_string(Y.RICH_YAML)
+    with pytest.raises(ValueError):
+        snapshot.load(other, tmp_path / "s.npz")
