@@ -213,6 +213,9 @@ def run_ours(args):
     from sandengine_b200.distributed import StripSimulation
     from sandengine_b200.grids import synthetic_grid
 
+    sampler = ClockSampler(local_rank)     # started early: nvidia-smi takes a few 100 ms to deliver its first row
+    if rank == 0:
+        sampler.start()
     S = args.size
     K, Wm = args.steps, max(args.warmup, 3)
     rules = se.parse_path(REPO / "data" / "materials.yaml")
@@ -240,9 +243,6 @@ def run_ours(args):
         sim.params.frame = 1
 
     # ---------------- device-resident timing (value) ----------------
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     reset()
     strip.step(Wm)
     barrier()
