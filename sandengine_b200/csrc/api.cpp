@@ -194,7 +194,7 @@ struct se_sim {
     bool tiled = false;
     CUfunction f_tiles = nullptr, f_build_lut = nullptr, f_lut_global = nullptr;
     unsigned* d_lut = nullptr;
-    int T = 0, HY = 0, HX = 0, PH = 0, tiles_x = 0, tiles_y = 0, lut_words = 0, pool_offset = 0, tile_offset = 0, tile_smem = 0, tile_grid = 0, tile_grid_max = 0;
+    int T = 0, HY = 0, HX = 0, PH = 0, tiles_x = 0, tiles_y = 0, lut_words = 0, pool_offset = 0, tile_offset = 0, tile_smem = 0, tile_grid = 0, tile_grid_max = 0, k1c_grid = 0;
     Neighbour nb[2];
     // Device-side exchange protocol: 4 flag words live right behind cells[0] (same allocation, so that one
     // IPC handle maps both): [0]/[1] = "done computing" epoch of the strip above/below, [2]/[3] = "ghost rows
@@ -244,8 +244,17 @@ int compile_front(const char* yaml, size_t len, se_rules** out, bool with_nvrtc)
             if (v == 256 || v == 512 || v == 768 || v == 1024) r->tile_threads = v;
         }
         const std::string def_threads = "-DSE_TILE_THREADS=" + std::to_string(r->tile_threads);
-        const char* opts[] = {"-arch=sm_100a", "-std=c++17", "-lineinfo", "-fmad=false", def_threads.c_str()};
-        nvrtcResult res = nvrtcCompileProgram(prog, 5, opts);
+        std::vector<std::string> extra;                       // experiments only: SE_NVRTC_DEFS="-DX=1 -DY=2"
+        if (const char* defs = std::getenv("SE_NVRTC_DEFS")) {
+            std::string d(defs), tok;
+            for (size_t i = 0; i <= d.size(); ++i) {
+                if (i == d.size() || d[i] == ' ') { if (!tok.empty()) extra.push_back(tok); tok.clear(); }
+                else tok.push_back(d[i]);
+            }
+        }
+        std::vector<const char*> opts = {"-arch=sm_100a", "-std=c++17", "-lineinfo", "-fmad=false", def_threads.c_str()};
+        for (auto& e : extra) opts.push_back(e.c_str());
+        nvrtcResult res = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
         size_t log_size = 0;
         nvrtcGetProgramLogSize(prog, &log_size);
         r->nvrtc_log.resize(log_size ? log_size - 1 : 0);
@@ -601,6 +610,8 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
                 s->tiles_y = (s->Hl + (PH - 2 * HY) - 1) / (PH - 2 * HY);
                 s->tile_grid = std::min(grid_max, s->tiles_x * s->tiles_y);
                 s->tile_grid_max = grid_max;
+                s->k1c_grid = grid_max;
+                if (const char* kg = std::getenv("SE_K1C_GRID")) s->k1c_grid = std::max(1, std::atoi(kg));   // experiments only
                 SE_CU_S(driver().FuncSetAttribute(s->f_tiles, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->tile_smem));
                 SE_CU_S(driver().FuncSetAttribute(s->f_lut_global, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->tile_offset));
                 SE_CUDA_S(cudaMalloc(&s->cells[1], s->cells_bytes()));
@@ -656,8 +667,7 @@ int se_sim_step(se_sim* s, uint32_t n_steps) {
                 lp.W = s->W; lp.Hl = s->Hl; lp.gy0 = s->gy0; lp.Hg = s->Hg; lp.frame = s->frame + 1;
                 lp.lut_words = s->lut_words; lp.pool_offset = s->pool_offset; lp.lut = s->d_lut;
                 void* largs[] = {&lp};
-                int n_sm = s->tile_grid_max;
-                int rc = launch(s, s->f_lut_global, dim3(n_sm), dim3(512), largs, (unsigned)s->tile_offset);   // SE_K1C_THREADS
+                int rc = launch(s, s->f_lut_global, dim3(s->k1c_grid), dim3(512), largs, (unsigned)s->tile_offset);   // SE_K1C_THREADS
                 if (rc) return rc;
                 s->frame += 1;
                 k += 1;

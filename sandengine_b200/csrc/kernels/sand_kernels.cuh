@@ -62,18 +62,8 @@ static __device__ __forceinline__ unsigned se_hashi(unsigned x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
     return x;
 }
-// Same function with the right shifts written as high multiplies (x >> k == umulhi(x, 2^(32-k))): they
-// issue on the FMA pipe (IMAD.HI) instead of the ALU pipe, which the table kernel saturates (ncu:
-// sm__pipe_alu_cycles_active 69 % vs fma 16 %).  Bit-identical by construction.  MEASURED SLOWER on B200
-// (931 -> 851 Gcell/s at 16384^2, T=8: IMAD.HI issues at a lower rate than SHF), so it is not used.
-static __device__ __forceinline__ unsigned se_hashi_fma(unsigned x) {
-#ifdef SE_HOST_EMU
-    return se_hashi(x);
-#else
-    x ^= __umulhi(x, 1u << 16); x *= 0x7feb352dU; x ^= __umulhi(x, 1u << 17); x *= 0x846ca68bU; x ^= __umulhi(x, 1u << 16);
-    return x;
-#endif
-}
+// (Writing the shifts as high multiplies -- x >> k == umulhi(x, 2^(32-k)) -- to move them from the saturated ALU
+// pipe to the FMA pipe was measured SLOWER on B200: 931 -> 851 Gcell/s; IMAD.HI issues at a lower rate.)
 // hash43(uvec3(pos_rounded, frame)) -- only the lanes the rule set consumes are evaluated
 static __device__ __forceinline__ void se_hash43(int px, int py, int frame, SeRand& rnd) {
     const unsigned x = (unsigned)px * 461u + (unsigned)py * 2131u + (unsigned)frame * (2131u * 2131u);
@@ -138,7 +128,7 @@ static __device__ __forceinline__ bool se_mod_lookup(const SeMod* __restrict__ m
 //   IN_PLACE : out == in, only cells whose id changed are stored (blocks partition the grid, so the
 //              update is race-free in place -- SURVEY.md section 7)
 //   HAS_MODS : apply the modification override per cell
-// Thread (tx, ty) of the grid handles block column bx and BPT block rows.
+// Thread (tx, ty) of the grid handles block column bx of block row jb0 + by.
 // ---------------------------------------------------------------------------------------------
 template <bool IN_PLACE, bool HAS_MODS>
 static __device__ __forceinline__ void se_step_global_impl(const SeStepParams& p, const unsigned* __restrict__ fat_sm) {
@@ -718,10 +708,14 @@ struct SeLutStepParams {
 
 #define SE_K1C_THREADS 512
 #define SE_K1C_SPAN 8           // a work item = one block row x SPAN chunks of 32 blocks (amortises the row set-up)
-#define SE_K1C_BATCH 2          // chunks whose loads are issued together (the update is in place, so the compiler
-                                // cannot hoist loads over the previous chunk's stores by itself)
+#ifndef SE_K1C_BATCH
+#define SE_K1C_BATCH 4          // chunks whose loads are issued together (the update is in place, so the compiler
+#endif                          // cannot hoist loads over the previous chunk's stores by itself); 4: 425 us, 2: 461 us @16384^2
+#ifndef SE_K1C_MINCTAS
+#define SE_K1C_MINCTAS 2
+#endif
 
-extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, 2) se_step_lut_global(const SeLutStepParams p) {
+extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_step_lut_global(const SeLutStepParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned fat_sm[256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
