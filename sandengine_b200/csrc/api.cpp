@@ -57,6 +57,7 @@ struct Driver {
     decltype(&cuGetErrorString) GetErrorString = nullptr;
     decltype(&cuStreamWriteValue32) StreamWriteValue32 = nullptr;
     decltype(&cuStreamWaitValue32) StreamWaitValue32 = nullptr;
+    decltype(&cuOccupancyMaxActiveBlocksPerMultiprocessor) OccupancyMaxActiveBlocks = nullptr;
     bool ok = false;
     std::string why;
 };
@@ -78,7 +79,8 @@ Driver& driver() {
         d.ok = get("cuModuleLoadData", (void**)&d.ModuleLoadData) && get("cuModuleUnload", (void**)&d.ModuleUnload) &&
                get("cuModuleGetFunction", (void**)&d.ModuleGetFunction) && get("cuLaunchKernel", (void**)&d.LaunchKernel) &&
                get("cuFuncSetAttribute", (void**)&d.FuncSetAttribute) && get("cuGetErrorString", (void**)&d.GetErrorString) &&
-               get("cuStreamWriteValue32", (void**)&d.StreamWriteValue32) && get("cuStreamWaitValue32", (void**)&d.StreamWaitValue32);
+               get("cuStreamWriteValue32", (void**)&d.StreamWriteValue32) && get("cuStreamWaitValue32", (void**)&d.StreamWaitValue32) &&
+               get("cuOccupancyMaxActiveBlocksPerMultiprocessor", (void**)&d.OccupancyMaxActiveBlocks);
     });
     return d;
 }
@@ -111,10 +113,13 @@ struct SeStepParams {
     const SeMod* mods;
 };
 struct SeTileParams {
-    const unsigned* in;
-    unsigned* out;
+    unsigned* buf0;
+    unsigned* buf1;
     int W, Hl, gy0, Hg;
-    int frame0, nsub, HY, HX, PH;
+    int frame0, nblk, tsteps, nsub_last;
+    unsigned seq_base;
+    unsigned* done;
+    int HY, HX, PH;
     int tiles_x, tiles_y;
     int lut_words, pool_offset, tile_offset;
     const unsigned* lut;
@@ -194,6 +199,8 @@ struct se_sim {
     bool tiled = false;
     CUfunction f_tiles = nullptr, f_build_lut = nullptr, f_lut_global = nullptr;
     unsigned* d_lut = nullptr;
+    unsigned* d_tile_done = nullptr;   // per-tile sequence numbers (dataflow between the T-blocks of one launch)
+    unsigned tile_seq = 0;             // T-blocks completed so far
     int T = 0, HY = 0, HX = 0, PH = 0, tiles_x = 0, tiles_y = 0, lut_words = 0, pool_offset = 0, tile_offset = 0, tile_smem = 0, tile_grid = 0, tile_grid_max = 0, k1c_grid = 0;
     Neighbour nb[2];
     // Device-side exchange protocol: 4 flag words live right behind cells[0] (same allocation, so that one
@@ -455,6 +462,7 @@ int se_sim_destroy(se_sim* s) {
     if (s->ev_main) cudaEventDestroy(s->ev_main);
     for (auto& ev : s->census_done) if (ev) cudaEventDestroy(ev);
     if (s->d_lut) cudaFree(s->d_lut);
+    if (s->d_tile_done) cudaFree(s->d_tile_done);
     if (s->mod && driver().ok) driver().ModuleUnload(s->mod);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
@@ -593,7 +601,9 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
                 for (int PH = PH_max; PH >= 4 * T + 16; PH -= 2) {
                     const int ty = (s->Hl + (PH - 2 * HY) - 1) / (PH - 2 * HY);
                     const long tiles = (long)s->tiles_x * ty;
-                    const long rounds = (tiles + grid_max - 1) / grid_max;
+                    // launches usually carry several T-blocks whose tiles are dealt to the CTAs as one sequence
+                    // (dataflow inside the kernel), so the round count is taken over a typical 8-T-block launch
+                    const long rounds = (8 * tiles + grid_max - 1) / grid_max;
                     // useful rows per tile shrink with PH: account for the halo rows recomputed by every tile
                     // + 24: per-tile fixed work (table/phase set-up, barriers, exposed load/store) expressed in rows;
                     // fitted on B200 (16384 x 2116 rows: 3 rounds of PH 190 beat 4 rounds of PH 138)
@@ -614,8 +624,16 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
                 if (const char* kg = std::getenv("SE_K1C_GRID")) s->k1c_grid = std::max(1, std::atoi(kg));   // experiments only
                 SE_CU_S(driver().FuncSetAttribute(s->f_tiles, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->tile_smem));
                 SE_CU_S(driver().FuncSetAttribute(s->f_lut_global, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->tile_offset));
+                // the dataflow between T-blocks needs every CTA of the grid to be resident: size the grid from the
+                // occupancy the driver reports for this kernel / block size / shared-memory footprint
+                int occ = 0;
+                SE_CU_S(driver().OccupancyMaxActiveBlocks(&occ, s->f_tiles, rules->tile_threads, (size_t)s->tile_smem));
+                if (occ < 1) { fail(SE_ERR_CUDA, "se_step_tiles does not fit on an SM"); return bail(SE_ERR_CUDA); }
+                s->tile_grid_max = std::min(grid_max, occ * n_sm);
                 SE_CUDA_S(cudaMalloc(&s->cells[1], s->cells_bytes()));
                 SE_CUDA_S(cudaMemsetAsync(s->cells[1], 0, s->cells_bytes(), s->stream));
+                SE_CUDA_S(cudaMalloc(&s->d_tile_done, (size_t)s->tiles_x * s->tiles_y * sizeof(unsigned)));
+                SE_CUDA_S(cudaMemsetAsync(s->d_tile_done, 0, (size_t)s->tiles_x * s->tiles_y * sizeof(unsigned), s->stream));
                 s->tiled = true;
             }
         }
@@ -673,19 +691,27 @@ int se_sim_step(se_sim* s, uint32_t n_steps) {
                 k += 1;
                 continue;
             }
-            { int rc = guard_buffer_write(s, s->cur ^ 1); if (rc) return rc; }
+            // a run of plain steps: ONE launch of ceil(run / T) T-blocks (dataflow between them inside the kernel)
+            { int rc = guard_buffer_write(s, 0); if (rc) return rc; rc = guard_buffer_write(s, 1); if (rc) return rc; }
+            const uint32_t run = std::min<uint32_t>(n_steps - k, 64u * (uint32_t)s->T);     // bound the kernel duration
+            const int nblk = (int)((run + (uint32_t)s->T - 1) / (uint32_t)s->T);
             SeTileParams tp;
-            tp.in = s->cells[s->cur]; tp.out = s->cells[s->cur ^ 1];
+            tp.buf0 = s->cells[s->cur]; tp.buf1 = s->cells[s->cur ^ 1];
             tp.W = s->W; tp.Hl = s->Hl; tp.gy0 = s->gy0; tp.Hg = s->Hg;
-            tp.frame0 = s->frame + 1; tp.nsub = nsub; tp.HY = s->HY; tp.HX = s->HX; tp.PH = s->PH;
+            tp.frame0 = s->frame + 1; tp.nblk = nblk; tp.tsteps = s->T; tp.nsub_last = (int)(run - (uint32_t)(nblk - 1) * (uint32_t)s->T);
+            tp.seq_base = s->tile_seq; tp.done = s->d_tile_done;
+            tp.HY = s->HY; tp.HX = s->HX; tp.PH = s->PH;
             tp.tiles_x = s->tiles_x; tp.tiles_y = s->tiles_y; tp.lut_words = s->lut_words; tp.pool_offset = s->pool_offset; tp.tile_offset = s->tile_offset;
             tp.lut = s->d_lut;
             void* targs[] = {&tp};
-            int rc = launch(s, s->f_tiles, dim3(s->tile_grid), dim3(s->rules->tile_threads), targs, (unsigned)s->tile_smem);
+            const long long items = (long long)nblk * s->tiles_x * s->tiles_y;
+            const int grid = (int)std::min<long long>((long long)s->tile_grid_max, items);
+            int rc = launch(s, s->f_tiles, dim3(grid), dim3(s->rules->tile_threads), targs, (unsigned)s->tile_smem);
             if (rc) return rc;
-            s->frame += nsub;
-            s->cur ^= 1;
-            k += (uint32_t)nsub;
+            s->frame += (int)run;
+            s->tile_seq += (unsigned)nblk;
+            s->cur ^= (nblk & 1);
+            k += run;
             continue;
         }
         int rc = one_step(s, k == 0, n_mods);

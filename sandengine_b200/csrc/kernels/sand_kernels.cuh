@@ -473,11 +473,15 @@ extern "C" __global__ void __launch_bounds__(256) se_build_lut(unsigned short* _
 #endif
 
 struct SeTileParams {
-    const unsigned* in;     // local buffer (row 0 == global row gy0)
-    unsigned* out;          // the other ping-pong buffer
+    unsigned* buf0;         // local buffer (row 0 == global row gy0) read by the first T-block of the launch
+    unsigned* buf1;         // the other ping-pong buffer; T-block k reads buf[k & 1] and writes buf[(k + 1) & 1]
     int W, Hl, gy0, Hg;
     int frame0;             // frame number of the first sub-step of this launch
-    int nsub;               // sub-steps in this launch, 1..T
+    int nblk;               // T-blocks in this launch (>= 1)
+    int tsteps;             // sub-steps of every T-block but the last (<= the halo allows)
+    int nsub_last;          // sub-steps of the last T-block, 1..tsteps
+    unsigned seq_base;      // T-blocks completed by earlier launches (the per-tile flags count in this sequence)
+    unsigned* done;         // per tile: sequence number of its last completed T-block (dataflow between T-blocks)
     int HY;                 // halo depth in rows (even, >= nsub/2 + 1: the row offset changes every OTHER frame,
                             // operations.glsl:25-34, so validity shrinks by at most floor(n/2)+1 rows in n steps)
     int HX;                 // halo depth in columns (multiple of 4, >= nsub: the column offset alternates every frame)
@@ -624,8 +628,37 @@ extern "C" __global__ void __launch_bounds__(SE_TILE_THREADS, 2) se_step_tiles(c
     const int PW = SE_TILE_PW, PH = p.PH;
     const int TWo = PW - 2 * p.HX, THo = PH - 2 * p.HY;
     const int n_tiles = p.tiles_x * p.tiles_y;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    // Work items (k, t) = (T-block, tile), ordered by w = k * n_tiles + t and dealt round-robin to the persistent
+    // CTAs, each taking its items in increasing order.  A tile of T-block k needs the results of T-block k-1 in
+    // its 3x3 tile neighbourhood only, so instead of a grid-wide barrier (or a launch) between T-blocks every
+    // tile publishes a sequence number when its interior is stored and consumers wait on the nine flags they
+    // need.  CTAs that run out of work in T-block k move on to k+1: no launch gap, no table re-staging, and
+    // the partially filled last round of one T-block is filled with tiles of the next.  Deadlock-free because
+    // every dependency has a smaller w and all CTAs are co-resident (grid <= occupancy x SMs).
+    const long long total_items = (long long)p.nblk * n_tiles;
+    for (long long w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const int k = (int)(w / n_tiles), t = (int)(w - (long long)k * n_tiles);
+        const unsigned* in = (k & 1) ? p.buf1 : p.buf0;
+        unsigned* out = (k & 1) ? p.buf0 : p.buf1;
+        const int nsub = (k == p.nblk - 1) ? p.nsub_last : p.tsteps;
+        const int tframe0 = p.frame0 + k * p.tsteps;
         const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+        if (k > 0) {
+            if (tid < 9) {
+                const int ntx = tx + (tid % 3) - 1, nty = ty + (tid / 3) - 1;
+                if (ntx >= 0 && ntx < p.tiles_x && nty >= 0 && nty < p.tiles_y) {
+                    const unsigned* flag = p.done + (nty * p.tiles_x + ntx);
+                    const unsigned want = p.seq_base + (unsigned)k;
+                    unsigned v;
+                    while (true) {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                        if ((int)(v - want) >= 0) break;
+                        __nanosleep(100);
+                    }
+                }
+            }
+            __syncthreads();
+        }
         const int gx_org = tx * TWo - p.HX;              // global x of tile column 0 (multiple of 4)
         const int gy_org = p.gy0 + ty * THo - p.HY;      // global y of tile row 0 (even)
         const bool border = gx_org < 0 || gx_org + PW > p.W || gy_org < 0 || gy_org + PH > p.Hg;
@@ -634,21 +667,22 @@ extern "C" __global__ void __launch_bounds__(SE_TILE_THREADS, 2) se_step_tiles(c
         for (int r = warp; r < PH; r += nwarps) {
             const int gy = gy_org + r, lr = gy - p.gy0;
             const bool row_ok = gy >= 0 && gy < p.Hg && lr >= 0 && lr < p.Hl;
-            const uint4* src = reinterpret_cast<const uint4*>(p.in + (size_t)(row_ok ? lr : 0) * p.W);
+            const uint4* src = reinterpret_cast<const uint4*>(in + (size_t)(row_ok ? lr : 0) * p.W);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int q = lane + 32 * h;
                 const int gx = gx_org + 4 * q;
-                unsigned w = 0x02020202u;               // WALL outside the grid (operations.glsl:45-51)
-                if (row_ok && gx >= 0 && gx < p.W) w = se_pack_ids(__ldg(src + (gx >> 2)));
-                se_sts_u32(tile_sa + 4u * (unsigned)(r * (PW / 4) + q), w);
+                // __ldcg (L2 only): the data may have been written by another SM earlier in this very launch
+                unsigned wv = 0x02020202u;               // WALL outside the grid (operations.glsl:45-51)
+                if (row_ok && gx >= 0 && gx < p.W) wv = se_pack_ids(__ldcg(src + (gx >> 2)));
+                se_sts_u32(tile_sa + 4u * (unsigned)(r * (PW / 4) + q), wv);
             }
         }
         __syncthreads();
 
         // ---- nsub Margolus sub-steps in shared memory ----
-        for (int sub = 0; sub < p.nsub; ++sub) {
-            const int frame = p.frame0 + sub;
+        for (int sub = 0; sub < nsub; ++sub) {
+            const int frame = tframe0 + sub;
             int ox, oy;
             se_margolus_offset(frame, ox, oy);
             if (ox == 0) se_tile_substep<0>(tile_sa, tab, pool_off, fat_sm, PH, oy, frame, gx_org, gy_org, warp, nwarps, lane);
@@ -674,18 +708,22 @@ extern "C" __global__ void __launch_bounds__(SE_TILE_THREADS, 2) se_step_tiles(c
         for (int r = p.HY + warp; r < PH - p.HY; r += nwarps) {
             const int gy = gy_org + r, lr = gy - p.gy0;
             if (gy >= p.Hg || lr >= p.Hl) break;
-            uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)lr * p.W);
+            uint4* dst = reinterpret_cast<uint4*>(out + (size_t)lr * p.W);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int q = lane + 32 * h;
                 const int gx = gx_org + 4 * q;
                 if (4 * q >= p.HX && 4 * q < PW - p.HX && gx < p.W) {
-                    const unsigned w = se_lds_u32(tile_sa + 4u * (unsigned)(r * (PW / 4) + q));
-                    dst[gx >> 2] = make_uint4(w & 0xFFu, (w >> 8) & 0xFFu, (w >> 16) & 0xFFu, w >> 24);
+                    const unsigned wv = se_lds_u32(tile_sa + 4u * (unsigned)(r * (PW / 4) + q));
+                    dst[gx >> 2] = make_uint4(wv & 0xFFu, (wv >> 8) & 0xFFu, (wv >> 16) & 0xFFu, wv >> 24);
                 }
             }
         }
-        __syncthreads();
+        __syncthreads();                                  // every thread's stores are issued ...
+        if (tid == 0) {                                   // ... and made visible before the tile is published
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p.done + t), "r"(p.seq_base + (unsigned)k + 1u) : "memory");
+        }
     }
 }
 
