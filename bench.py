@@ -315,7 +315,8 @@ def run_ours(args):
         achieved = 8.0 * local_cells * K / t_dev / 1e9
         # physical DRAM bytes of one se_step_tiles launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full,
         # profiles/r1_k1b_ncu_full.txt): captured for exactly this configuration, null otherwise
-        traffic = 1.116995e9 + 1.023260e9 if (S == 16384 and world == 1 and launches * 8 == K) else None
+        # (captured on an 8-step T-block; a launch now carries K / launches steps = several T-blocks, same bytes per step)
+        traffic = (8.932404e9 + 8.540352e9) * (K / max(launches, 1)) / 64.0 if (S == 16384 and world == 1 and launches < K) else None
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": round(t_dev / K * 1e3, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -327,7 +328,8 @@ def run_ours(args):
                              "L2-RESIDENT workload: the cell buffer fits the 126 MB L2",
                        "cells_bytes": S * S * 4},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": traffic, "traffic_unit": "bytes per launch (8 fused steps; algorithmic bytes per launch = 8 B x 268435456 cells x 8 steps = 1.718e10)",
+                         "traffic": traffic, "traffic_unit": "bytes per launch, scaled from the ncu capture of a 64-step launch (dram read 8.93 GB + write 8.54 GB, profiles/r1_k1b_ncu_full.txt); "
+                                                             "algorithmic bytes per launch = 8 B x 268435456 cells x steps per launch",
                          "kernel": "se_step_tiles" if launches < K else "se_step_inplace", "peak_source": peak_src,
                          "algorithmic_bytes_per_cell_update": 8, "launches_timed": launches,
                          "steps_per_launch": round(K / max(launches, 1), 2), "avg_launch_us": round(per_launch_s * 1e6, 2),
