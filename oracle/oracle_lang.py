@@ -649,8 +649,8 @@ def emit_c_rules(res: ParsingResult) -> str:
     for m in res.materials:
         c, e = m.color, m.emission
         fl = lambda x: repr(float(np.float32(x))) + "f" if "." in repr(float(np.float32(x))) or "e" in repr(float(np.float32(x))) else repr(float(np.float32(x))) + ".0f"
-        o.append(f"  {{ {m.id}, {{{fl(c[0])}, {fl(c[1])}, {fl(c[2])}, {fl(c[3])}}}, {fl(m.density)}, "
-                 f"{{{fl(e[0])}, {fl(e[1])}, {fl(e[2])}, {fl(e[3])}}}, TYPE_{m.mattype} }},\n")
+        o.append(f"  {{ {m.id}, {{{{{fl(c[0])}, {fl(c[1])}, {fl(c[2])}, {fl(c[3])}}}}}, {fl(m.density)}, "
+                 f"{{{{{fl(e[0])}, {fl(e[1])}, {fl(e[2])}, {fl(e[3])}}}}}, TYPE_{m.mattype} }},\n")
     o.append("};\n")
     for m in res.materials:
         o.append(f"#define MAT_{m.name} (MATERIALS[{m.id}])\n")

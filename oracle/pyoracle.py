@@ -40,13 +40,22 @@ def hash43(px: int, py: int, pz: int):  # :115-120 (uvec3(ivec) keeps the bits o
     return [np.float32(u) / denom for u in lanes]
 
 
-@dataclass(frozen=True)
-class Material:  # :211-218 -- struct equality compares every member
+@dataclass(frozen=True, eq=False)
+class Material:  # :211-218 -- struct equality compares every member; ids are unique, so identity of the id
     id: int
-    color: tuple
+    color: object
     density: np.float32
-    emission: tuple
+    emission: object
     type: int
+
+    def __eq__(self, other):
+        return self.id == other.id
+
+    def __ne__(self, other):
+        return self.id != other.id
+
+    def __hash__(self):
+        return self.id
 
 
 class Cell:  # :221-224
@@ -59,6 +68,7 @@ class Cell:  # :221-224
 class _Vec4:
     def __init__(self, v):
         self.x, self.y, self.z, self.w = v
+        self.r, self.g, self.b, self.a = v
 
 
 class _Pos:
@@ -76,7 +86,8 @@ class PyOracle:
     def __init__(self, yaml_text: str):
         res = L.parse_string(yaml_text)
         self.types = {t.name: t.id for t in res.types}
-        self.mats = [Material(m.id, tuple(m.color), np.float32(m.density), tuple(m.emission), self.types.get(m.mattype, 0)) for m in res.materials]
+        self.mats = [Material(m.id, _Vec4([np.float32(x) for x in m.color]), np.float32(m.density), _Vec4([np.float32(x) for x in m.emission]),
+                              self.types.get(m.mattype, 0)) for m in res.materials]
         self.env = {f"MAT_{m.name}": self.mats[m.id] for m in res.materials}
         self.env.update({f"TYPE_{t.name}": t.id for t in res.types})
         for t in res.types:
@@ -118,7 +129,7 @@ class PyOracle:
             def scope():
                 e = dict(self.env)
                 e.update({n: q[i] for n, i in names.items()})
-                e["rand"], e["pos"] = rand, pos
+                e["rand"], e["pos"], e["frame"] = rand, pos, self._frame
                 return e
             if pre is not None and not eval(pre, {}, scope()):
                 continue
@@ -143,6 +154,7 @@ class PyOracle:
         """One dispatch (frame = value after the host increment), per-block form; returns the new grid."""
         H, W = cells.shape
         out = cells.copy()
+        self._frame = frame
         f = frame % 4
         ox, oy = {1: (1, 1), 2: (0, 1), 3: (1, 0), 0: (0, 0)}[f]   # :380-389
         for y0 in range(-oy, H, 2):

@@ -22,11 +22,18 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* GLSL vec4 with its component aliases, so that rule text such as `self.mat.emission.g` compiles as C */
+typedef union {
+    struct { float x, y, z, w; };
+    struct { float r, g, b, a; };
+    float v[4];
+} vec4;
+
 typedef struct {            /* falling_sand.glsl:211-218 */
     int id;
-    float color[4];
+    vec4 color;
     float density;
-    float emission[4];
+    vec4 emission;
     int type;
 } Material;
 
@@ -54,6 +61,10 @@ static inline Cell newCell(Material mat, ivec2 pos) {   /* falling_sand.glsl:226
 }
 
 static void swap_cells(Cell* a, Cell* b);
+
+/* `uniform int frame` of the shader (falling_sand.glsl:334): visible to the generated rule text; set by the
+ * step drivers below before the parallel loops (read-only inside them). */
+static int frame = 0;
 
 #include "rules_gen.h"   /* TYPE_*, isType_*, MATERIALS[], MAT_*, rule_*, apply{Mirrored,Left,Right}Rules */
 
@@ -123,7 +134,7 @@ static inline Cell getCell(const Ctx* c, int x, int y) {   /* :400-412, SCREEN_I
 }
 
 static inline int emission_rgb_zero(const Material* m) {
-    return m->emission[0] == 0.0f && m->emission[1] == 0.0f && m->emission[2] == 0.0f;
+    return m->emission.v[0] == 0.0f && m->emission.v[1] == 0.0f && m->emission.v[2] == 0.0f;
 }
 static inline int isLightObstacle(const Cell* cell) {   /* :423-425 */
     return emission_rgb_zero(&cell->mat) && !isType_EMPTY(*cell);
@@ -225,7 +236,7 @@ typedef struct {
 static void setCell(const Ctx* c, const Out* o, int x, int y, const Material* mat) {
     size_t idx = (size_t)y * c->W + x;
     if (o->output_color) {   /* :455-463, :525 */
-        float col[4] = {mat->color[0], mat->color[1], mat->color[2], mat->color[3]};
+        float col[4] = {mat->color.v[0], mat->color.v[1], mat->color.v[2], mat->color.v[3]};
         if (mat->id != MAT_EMPTY.id) {
             float rnd = noise((float)x, (float)y, 3, 2.0f, 0.25f) * 0.25f;
             col[0] = clamp01(col[0] - rnd); col[1] = clamp01(col[1] - rnd); col[2] = clamp01(col[2] - rnd);
@@ -240,7 +251,7 @@ static void setCell(const Ctx* c, const Out* o, int x, int y, const Material* ma
     static const int NY[8] = {1, -1, 1, -1, 1, -1, 0, 0};
     float light[4];
     if (!emission_rgb_zero(mat)) {                      /* :481-482 */
-        memcpy(light, mat->emission, sizeof light);
+        memcpy(light, mat->emission.v, sizeof light);
     } else if (y == 0) {                                /* :483-484 */
         light[0] = light[1] = light[2] = 1.0f; light[3] = 0.999999f;
     } else {                                            /* :485-523 */
@@ -310,12 +321,13 @@ static void shader_main(const Ctx* c, const Out* o, int x, int y) {
  * entries; like the host (simulation.rs:203-208) only the first 256 are used, the remaining UBO
  * slots have mod_size == 0.  `frame` is the value AFTER the host's increment (simulation.rs:201). */
 void so_step_cells(const uint32_t* in_cells, uint32_t* out_cells, const float* in_light, float* out_light,
-                   float* out_color, int W, int H, int frame, const SimModification* mods, int n_mods) {
+                   float* out_color, int W, int H, int frame_, const SimModification* mods, int n_mods) {
     SimModification ubo[MAX_MODIFICATIONS];
     memset(ubo, 0, sizeof ubo);
     if (n_mods > MAX_MODIFICATIONS) n_mods = MAX_MODIFICATIONS;
     if (n_mods > 0) memcpy(ubo, mods, (size_t)n_mods * sizeof(SimModification));
-    Ctx c = {in_cells, in_light, W, H, frame, ubo};
+    Ctx c = {in_cells, in_light, W, H, frame_, ubo};
+    frame = frame_;
     Out o = {out_cells, (in_light && out_light) ? out_light : NULL, out_color};
 #pragma omp parallel for schedule(static)
     for (int y = 0; y < H; y++)
@@ -327,7 +339,8 @@ void so_step_cells(const uint32_t* in_cells, uint32_t* out_cells, const float* i
  * so_step_cells because a cell's result depends only on its own block (falling_sand.glsl:687-690)
  * and blocks partition the grid; tests/test_oracle_kat.py checks the two drivers against each other.
  * This is the form timed as the CPU baseline (it does a quarter of the shader's redundant work). */
-void so_step_blocks_inplace(uint32_t* cells, int W, int H, int frame) {
+void so_step_blocks_inplace(uint32_t* cells, int W, int H, int frame_) {
+    frame = frame_;
     int off[2]; getMargolusOffset(frame, off);
     Ctx c = {cells, NULL, W, H, frame, NULL};
     int nby = (H + off[1] + 1) / 2, nbx = (W + off[0] + 1) / 2;
@@ -349,13 +362,13 @@ void so_step_blocks_inplace(uint32_t* cells, int W, int H, int frame) {
 
 /* n_steps of the host loop (simulation.rs:195-253) without modifications or lighting:
  * frame += 1, dispatch, (ping-pong is implicit in the in-place form). Returns the final frame. */
-int so_run_blocks(uint32_t* cells, int W, int H, int frame, int n_steps) {
+int so_run_blocks(uint32_t* cells, int W, int H, int frame0, int n_steps) {
     for (int s = 0; s < n_steps; s++) {
-        frame += 1;
-        if (frame == 1) { memset(cells, 0, (size_t)W * H * sizeof(uint32_t)); continue; }
-        so_step_blocks_inplace(cells, W, H, frame);
+        frame0 += 1;
+        if (frame0 == 1) { memset(cells, 0, (size_t)W * H * sizeof(uint32_t)); continue; }
+        so_step_blocks_inplace(cells, W, H, frame0);
     }
-    return frame;
+    return frame0;
 }
 
 /* Strip form of the per-block update, used ONLY by the CPU (gloo) emulation of the multi-GPU ghost-row
@@ -363,7 +376,8 @@ int so_run_blocks(uint32_t* cells, int W, int H, int frame, int n_steps) {
  * Rows outside the global grid read as WALL; a block that needs a row inside the grid but outside the
  * local buffer is skipped (its in-buffer row goes stale -- exactly what the ghost-row schedule accounts for).
  * Positions fed to the hash are GLOBAL (falling_sand.glsl:698). */
-void so_step_blocks_strip(uint32_t* cells, int W, int Hl, int gy0, int Hg, int frame) {
+void so_step_blocks_strip(uint32_t* cells, int W, int Hl, int gy0, int Hg, int frame_) {
+    frame = frame_;
     int off[2]; getMargolusOffset(frame, off);
     int jb0 = (gy0 + off[1]) / 2;
     int y_end = (gy0 + Hl < Hg) ? gy0 + Hl : Hg;

@@ -426,3 +426,16 @@ def test_snapshot_resume_is_bit_identical(se, default_rules, tmp_path):
     other = se.parse_string(Y.RICH_YAML)
     with pytest.raises(ValueError):
         snapshot.load(other, tmp_path / "s.npz")
+
+
+def test_expression_rule_set_on_gpu(se):
+    """Rule conditions with arithmetic, pos, frame, rand.z / rand.w, vector components (tests/yaml_cases.EXPR_YAML):
+    generic generated-code kernel (K1a) against the oracle."""
+    from oracle.build_oracle import load_oracle
+    rules = se.parse_string(Y.EXPR_YAML)
+    orc = load_oracle(Y.EXPR_YAML)
+    for (w, h, seed, steps, f0) in [(256, 192, 5, 120, 1), (67, 41, 6, 60, 1001)]:
+        g = synthetic_grid(w, h, seed, mix=Y.EXPR_MIX, ids=Y.EXPR_IDS)
+        ref, _, _ = orc.run(g, f0, steps, blocks=True)
+        got, _, _ = run_gpu(se, rules, g, steps, frame0=f0)
+        assert np.array_equal(got, ref) and not np.array_equal(got, g)

@@ -197,3 +197,48 @@ materials:
 RICH_IDS = {"EMPTY": 0, "m_rock": 3, "gravel": 4, "dust": 5, "m_water": 6, "oil": 7, "lava": 8, "steam": 9, "fire": 10, "moss": 11}
 RICH_MIX = (("EMPTY", 0.40), ("gravel", 0.10), ("dust", 0.08), ("m_water", 0.12), ("oil", 0.06), ("lava", 0.04), ("steam", 0.06),
             ("fire", 0.04), ("moss", 0.05), ("m_rock", 0.05))
+
+# Conditions that only "work by accident" in the reference (passed through verbatim as GLSL):
+# arithmetic, integer modulo on pos, the `frame` uniform, rand.z / rand.w, TYPE_ constants, .mat.id, vector
+# components of color / emission, nested parentheses, literal-on-the-left comparisons.
+EXPR_YAML = """
+rules:
+  arith_fall:
+    if: SELF.mat.density * 2 > DOWN.mat.density + 0.5 and (pos.x + 4) % 3 != 1
+    do: SWAP SELF DOWN
+    else:
+      if: 1.25 < SELF.mat.density and (DOWNRIGHT.mat.density - SELF.mat.density) < -0.25 and RIGHT.mat.id < 3
+      probability: 0.6
+      do: SWAP SELF DOWNRIGHT
+  frame_drift:
+    mirrored: false
+    if: frame % 2 == 0 and isType_EMPTY(RIGHT) and SELF.mat.type == TYPE_loose and (pos.y + 2) % 4 < 3
+    do: SWAP SELF RIGHT
+  glow_spread:
+    precondition: false
+    if: rand.z > 0.75 and isType_EMPTY(SELF) and DOWN.mat.emission.g > 0.5 and DOWN.mat.color.r <= 0.5
+    do: SET SELF spark
+  spark_fade:
+    if: rand.w <= 0.5 or (rand.x >= 0.9 and frame % 3 == 0)
+    do: SET SELF EMPTY
+  id_swap:
+    precondition: false
+    if: SELF.mat.id >= 4 and DOWN.mat.id == 0 and not (RIGHT.mat != pebble) and pos.x >= 0
+    probability: 0.3
+    do: SWAP SELF DOWN
+types:
+  loose:
+    base_rules: [arith_fall, frame_drift]
+  glowing:
+    base_rules: [glow_spread]
+  shortlived:
+    base_rules: [spark_fade]
+materials:
+  pebble: {type: loose, color: [0.5, 0.5, 0.5], density: 2.0, extra_rules: [id_swap]}
+  ash:    {type: loose, color: [0.3, 0.3, 0.3], density: 1.25}
+  ember:  {type: glowing, color: [0.4, 0.1, 0.1], density: 3.0, emission: [1.0, 0.6, 0.1, 0.9]}
+  lamp:   {type: glowing, color: [0.9, 0.9, 0.2], density: 3.0, emission: [0.2, 0.9, 0.2, 0.8]}
+  spark:  {type: shortlived, color: [1.0, 0.8, 0.2], density: 0.5, emission: [1.0, 0.8, 0.1, 0.7]}
+"""
+EXPR_IDS = {"EMPTY": 0, "pebble": 3, "ash": 4, "ember": 5, "lamp": 6, "spark": 7}
+EXPR_MIX = (("EMPTY", 0.5), ("pebble", 0.15), ("ash", 0.15), ("ember", 0.08), ("lamp", 0.06), ("spark", 0.06))
