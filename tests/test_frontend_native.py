@@ -165,3 +165,50 @@ def test_no_device_fails_loudly(default_rules):
     with pytest.raises(se.SandEngineError) as ei:
         se.Simulation(default_rules, (64, 64))
     assert ei.value.kind == "Cuda" and "no CPU fallback" in str(ei.value)
+
+
+def test_yaml_syntax_variants_parse_identically(native_lib):
+    """Block / flow / quoted / commented spellings of one document give the same parse (and the same GLSL text)."""
+    import sandengine_b200 as se
+    ref = se.parse_string(Y.BASE_OK, compile=False)
+    variants = [
+        # flow mappings everywhere, trailing commas, comments
+        """
+rules: {gravity: {if: DOWN.mat.density < SELF.mat.density, do: SWAP SELF DOWN, mirrored: false},   # falls
+        slide_diagonally: {if: DOWNRIGHT.mat.density < SELF.mat.density, do: SWAP SELF DOWNRIGHT, mirrored: true,}}
+types: {movable_solid: {base_rules: [gravity, slide_diagonally,]}}
+materials: {sand: {color: [1.0, 1.0, 0.0, 1.0], type: movable_solid, density: 1.5, selectable: true}}
+""",
+        # block sequences, quoted scalars and keys, a document marker, odd indentation widths
+        """---
+"rules":
+    gravity:
+        'if': "DOWN.mat.density < SELF.mat.density"
+        do: 'SWAP SELF DOWN'
+        mirrored: False
+    slide_diagonally:
+        if: DOWNRIGHT.mat.density < SELF.mat.density
+        do:
+        - SWAP SELF DOWNRIGHT
+        mirrored: TRUE
+types:
+    movable_solid:
+        base_rules:
+            - gravity
+            - "slide_diagonally"
+materials:
+    sand:
+        color:
+            - 1.0
+            - 1.0
+            - 0.0
+            - 1.0
+        type: movable_solid
+        density: 1.5e0
+        selectable: true
+""",
+    ]
+    for v in variants:
+        r = se.parse_string(v, compile=False)
+        assert r.glsl_materials == ref.glsl_materials and r.glsl_rules == ref.glsl_rules
+        assert L.emit_glsl_rules(L.parse_string(v)) == ref.glsl_rules       # PyYAML-based oracle parser agrees

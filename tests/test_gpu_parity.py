@@ -184,14 +184,14 @@ def test_lighting_frame1(se, default_rules, oracle):
 
 
 def test_4096_short_horizon_vs_oracle(se, default_rules, oracle):
-    """configs[1] size (4096^2): oracle comparison at steps 1..5 and 32."""
+    """configs[1] size (4096^2): oracle comparison at steps 1..5, 32 and 100."""
     g = synthetic_grid(4096, 4096, 2)
     sim = se.Simulation(default_rules, (4096, 4096))
     sim.upload_cells(g)
     sim.params.frame = 1
     ref = g.copy()
     frame = 1
-    for target in (1, 2, 3, 4, 5, 32):
+    for target in (1, 2, 3, 4, 5, 32, 100):
         k = target - (frame - 1)
         sim.step(k)
         frame = oracle.run_blocks(ref, frame, k)
@@ -439,3 +439,23 @@ def test_expression_rule_set_on_gpu(se):
         ref, _, _ = orc.run(g, f0, steps, blocks=True)
         got, _, _ = run_gpu(se, rules, g, steps, frame0=f0)
         assert np.array_equal(got, ref) and not np.array_equal(got, g)
+
+
+def test_16384_full_grid_short_horizon_vs_oracle(se, default_rules, oracle):
+    """BASELINE size (16384^2, configs[2]): the full grid against the oracle after 16 steps (two T-blocks of the
+    tiled kernel) -- SURVEY.md 8d item 3 -- plus census conservation."""
+    S = 16384
+    g = synthetic_grid(S, S, 3)
+    sim = se.Simulation(default_rules, (S, S))
+    sim.upload_cells(g)
+    sim.params.frame = 1
+    c0 = sim.census()
+    sim.step(16)
+    got = sim.download_cells()
+    c1 = sim.census()
+    sim.close()
+    frame = oracle.run_blocks(g, 1, 16)          # in place on g
+    assert frame == 17
+    assert np.array_equal(got, g)
+    for mat in (3, 4, 5, 6, 8, 10):
+        assert c1[mat] == c0[mat]
