@@ -379,7 +379,9 @@ def _update_rule_precondition(rule: SandRule, typename: str):  # types.rs:78-88
             rule.precondition = f"{rule.precondition} || isType_{typename}(self)"
 
 
-def _add_child_to_type(parent_name, childname, types):  # types.rs:186-200
+def _add_child_to_type(parent_name, childname, types, depth=0):  # types.rs:186-200
+    if depth > len(types) + 1:   # the reference overflows its stack on an inheritance cycle; a clean error here
+        raise _invalid("inherits", f"types/{childname}", "an acyclic chain of parent types")
     pp = ""
     for t in types:
         if t.name == parent_name:
@@ -387,17 +389,19 @@ def _add_child_to_type(parent_name, childname, types):  # types.rs:186-200
             pp = t.inherits
             break
     if pp:
-        _add_child_to_type(pp, childname, types)
+        _add_child_to_type(pp, childname, types, depth + 1)
 
 
-def _get_parents_rules(all_types, cur):  # types.rs:202-210
+def _get_parents_rules(all_types, cur, depth=0):  # types.rs:202-210
     if not cur.inherits:
         return []
+    if depth > len(all_types) + 1:
+        raise _invalid("inherits", f"types/{cur.name}", "an acyclic chain of parent types")
     parent = next((t for t in all_types if t.name == cur.inherits), None)
     if parent is None:
         # reference: `.unwrap()` on None panics (types.rs:206); surfaced as NotFound here.
         raise _notfound(cur.inherits, f"types/{cur.name}/inherits")
-    return list(parent.base_rules) + _get_parents_rules(all_types, parent)
+    return list(parent.base_rules) + _get_parents_rules(all_types, parent, depth + 1)
 
 
 def _parse_types(types, rules, rule_names, type_names):  # types.rs:51-182

@@ -216,8 +216,10 @@ void update_rule_precondition(SandRule& rule, const std::string& clause) {
     else rule.precondition += " || " + clause;
 }
 
-// types.rs:186-200
-void add_child_to_type(const std::string& parent_name, const std::string& child, std::vector<SandType>& types) {
+// types.rs:186-200.  The reference recurses without a guard and overflows the stack on an inheritance cycle
+// (`a: {inherits: a}`); here a cycle is an InvalidType error.
+void add_child_to_type(const std::string& parent_name, const std::string& child, std::vector<SandType>& types, size_t depth = 0) {
+    if (depth > types.size() + 1) throw invalid_type("inherits", "types/" + child, "an acyclic chain of parent types");
     std::string pp;
     for (auto& t : types) {
         if (t.name == parent_name) {
@@ -226,18 +228,19 @@ void add_child_to_type(const std::string& parent_name, const std::string& child,
             break;
         }
     }
-    if (!pp.empty()) add_child_to_type(pp, child, types);
+    if (!pp.empty()) add_child_to_type(pp, child, types, depth + 1);
 }
 
 // types.rs:202-210
-std::vector<std::string> get_parents_rules(const std::vector<SandType>& all, const SandType& cur) {
+std::vector<std::string> get_parents_rules(const std::vector<SandType>& all, const SandType& cur, size_t depth = 0) {
     if (cur.inherits.empty()) return {};
+    if (depth > all.size() + 1) throw invalid_type("inherits", "types/" + cur.name, "an acyclic chain of parent types");
     const SandType* parent = nullptr;
     for (auto& t : all)
         if (t.name == cur.inherits) { parent = &t; break; }
     if (!parent) throw not_found(cur.inherits, "types/" + cur.name + "/inherits");   // reference: unwrap() panic
     std::vector<std::string> rules = parent->base_rules;
-    auto more = get_parents_rules(all, *parent);
+    auto more = get_parents_rules(all, *parent, depth + 1);
     rules.insert(rules.end(), more.begin(), more.end());
     return rules;
 }

@@ -99,6 +99,10 @@ materials:
     ("extra_rules_not_seq", BASE_OK.replace("    selectable: true", "    extra_rules: gravity"), "InvalidType"),
     ("rules_not_mapping", "rules: [a, b]\ntypes: {}\nmaterials: {}\n", "InvalidType"),
     ("material_type_missing", BASE_OK.replace("    type: movable_solid\n", ""), "MissingField"),
+    # inheritance cycles overflow the reference's stack (types.rs:186-210 recurse unguarded); a clean error here
+    ("inherits_itself", BASE_OK.replace("    base_rules: [gravity, slide_diagonally]", "    inherits: movable_solid\n    base_rules: [gravity, slide_diagonally]"), "InvalidType"),
+    ("inheritance_cycle", BASE_OK.replace("  movable_solid:\n    base_rules: [gravity, slide_diagonally]",
+                                          "  aa:\n    inherits: bb\n  bb:\n    inherits: aa\n  movable_solid:\n    base_rules: [gravity, slide_diagonally]"), "InvalidType"),
     # LEFT handling defined by this build
     ("left_in_mirrored_rule", BASE_OK.replace("if: DOWNRIGHT.mat.density < SELF.mat.density\n    do: SWAP SELF DOWNRIGHT",
                                               "if: DOWNLEFT.mat.density < SELF.mat.density\n    do: SWAP SELF DOWNLEFT"), "NotRecognized"),
