@@ -459,3 +459,19 @@ def test_16384_full_grid_short_horizon_vs_oracle(se, default_rules, oracle):
     assert np.array_equal(got, g)
     for mat in (3, 4, 5, 6, 8, 10):
         assert c1[mat] == c0[mat]
+
+
+def test_gpu_matches_committed_state_hashes(se):
+    """The CUDA path against the committed fixtures tests/golden/oracle_state_sha256.json (no oracle run involved)."""
+    import importlib.util
+    import json
+    from pathlib import Path
+    here = Path(__file__).parent / "golden"
+    spec = importlib.util.spec_from_file_location("make_oracle_state_hashes", here / "make_oracle_state_hashes.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = json.loads((here / "oracle_state_sha256.json").read_text())
+    for name, text, g, steps, _ in mod.cases():
+        rules = se.parse_string(text)
+        got, _, _ = run_gpu(se, rules, g, steps)
+        assert hashlib.sha256(got.astype(np.uint32).tobytes()).hexdigest() == want[name]["final"], name

@@ -117,3 +117,23 @@ def test_unknown_ids_become_null(oracle):
     g[1, 1] = 200
     c, _, _ = oracle.run(g, 1, 1)
     assert c[1, 1] == 1
+
+
+def test_oracle_state_fixtures_do_not_drift():
+    """tests/golden/oracle_state_sha256.json (made by make_oracle_state_hashes.py): the oracle still produces them."""
+    import importlib.util
+    import json
+    from pathlib import Path
+    here = Path(__file__).parent / "golden"
+    spec = importlib.util.spec_from_file_location("make_oracle_state_hashes", here / "make_oracle_state_hashes.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = json.loads((here / "oracle_state_sha256.json").read_text())
+    got = mod.compute()
+    assert set(got) == set(want)
+    for k in want:
+        for field in ("init", "final", "histogram"):
+            if field in want[k]:
+                assert got[k][field] == want[k][field], (k, field)
+        if "light_sum" in want[k]:
+            np.testing.assert_allclose(got[k]["light_sum"], want[k]["light_sum"], rtol=1e-5)
