@@ -330,7 +330,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "traffic_unit": "bytes per launch, scaled from the ncu capture of a 64-step launch (dram read 8.93 GB + write 8.54 GB, profiles/r1_k1b_ncu_full.txt); "
                                                              "algorithmic bytes per launch = 8 B x 268435456 cells x steps per launch",
-                         "kernel": "se_step_tiles" if launches < K else "se_step_inplace", "peak_source": peak_src,
+                         "kernel": "se_step_tiles" if launches < K else ("se_step_lut_global" if K == 1 else "se_step_inplace"), "peak_source": peak_src,
                          "algorithmic_bytes_per_cell_update": 8, "launches_timed": launches,
                          "steps_per_launch": round(K / max(launches, 1), 2), "avg_launch_us": round(per_launch_s * 1e6, 2),
                          "note": "temporal blocking: physical DRAM bytes per launch are ~8/T per cell-update (see profiles/), "
@@ -344,7 +344,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
             try:
                 line["cpu_baseline"] = cpu_port_rate(min(S, 4096), args.cpu_seconds)
             except Exception as e:   # the baseline is a reported number, never a dependency of the GPU path
