@@ -53,6 +53,7 @@ struct Driver {
     decltype(&cuModuleUnload) ModuleUnload = nullptr;
     decltype(&cuModuleGetFunction) ModuleGetFunction = nullptr;
     decltype(&cuLaunchKernel) LaunchKernel = nullptr;
+    decltype(&cuLaunchCooperativeKernel) LaunchCooperativeKernel = nullptr;
     decltype(&cuFuncSetAttribute) FuncSetAttribute = nullptr;
     decltype(&cuGetErrorString) GetErrorString = nullptr;
     decltype(&cuStreamWriteValue32) StreamWriteValue32 = nullptr;
@@ -78,6 +79,7 @@ Driver& driver() {
         };
         d.ok = get("cuModuleLoadData", (void**)&d.ModuleLoadData) && get("cuModuleUnload", (void**)&d.ModuleUnload) &&
                get("cuModuleGetFunction", (void**)&d.ModuleGetFunction) && get("cuLaunchKernel", (void**)&d.LaunchKernel) &&
+               get("cuLaunchCooperativeKernel", (void**)&d.LaunchCooperativeKernel) &&
                get("cuFuncSetAttribute", (void**)&d.FuncSetAttribute) && get("cuGetErrorString", (void**)&d.GetErrorString) &&
                get("cuStreamWriteValue32", (void**)&d.StreamWriteValue32) && get("cuStreamWaitValue32", (void**)&d.StreamWaitValue32) &&
                get("cuOccupancyMaxActiveBlocksPerMultiprocessor", (void**)&d.OccupancyMaxActiveBlocks);
@@ -201,6 +203,10 @@ struct se_sim {
     unsigned* d_lut = nullptr;
     unsigned* d_tile_done = nullptr;   // per-tile sequence numbers (dataflow between the T-blocks of one launch)
     unsigned tile_seq = 0;             // T-blocks completed so far
+    // se_step_tiles spins on flags written by other CTAs of the same grid, so all of its CTAs must be resident
+    // together: it is launched cooperatively (the driver then places the whole grid at once, even when another
+    // stream's kernels share the device).  False only on a device / context that reports no support.
+    bool coop = false;
     int T = 0, HY = 0, HX = 0, PH = 0, tiles_x = 0, tiles_y = 0, lut_words = 0, pool_offset = 0, tile_offset = 0, tile_smem = 0, tile_grid = 0, tile_grid_max = 0, k1c_grid = 0;
     Neighbour nb[2];
     // Device-side exchange protocol: 4 flag words live right behind cells[0] (same allocation, so that one
@@ -301,8 +307,20 @@ int guard_buffer_write(se_sim* s, int buf) {
     return SE_OK;
 }
 
-int launch(se_sim* s, CUfunction f, dim3 grid, dim3 block, void** args, unsigned smem = 0) {
-    SE_CU(driver().LaunchKernel(f, grid.x, grid.y, grid.z, block.x, block.y, block.z, smem, (CUstream)s->stream, args, nullptr));
+int launch(se_sim* s, CUfunction f, dim3 grid, dim3 block, void** args, unsigned smem = 0, bool cooperative = false) {
+    if (cooperative) {
+        CUresult r = driver().LaunchCooperativeKernel(f, grid.x, grid.y, grid.z, block.x, block.y, block.z, smem, (CUstream)s->stream, args);
+        if (r == CUDA_ERROR_COOPERATIVE_LAUNCH_TOO_LARGE) {
+            // the context can hold fewer CTAs than the occupancy query promised (e.g. an MPS partition): the
+            // grid is still <= occupancy x SMs, so fall back to a plain launch of the same grid
+            s->coop = false;
+            cooperative = false;
+        } else {
+            SE_CU(r);
+        }
+    }
+    if (!cooperative)
+        SE_CU(driver().LaunchKernel(f, grid.x, grid.y, grid.z, block.x, block.y, block.z, smem, (CUstream)s->stream, args, nullptr));
     s->launches++;
     return SE_OK;
 }
@@ -446,7 +464,7 @@ int se_sim_destroy(se_sim* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (int w = 0; w < 2; ++w) {
-        if (s->nb[w].attached && s->nb[w].ipc)
+        if (s->nb[w].ipc)
             for (int b = 0; b < 2; ++b)
                 if (s->nb[w].cells[b]) cudaIpcCloseMemHandle(s->nb[w].cells[b]);
     }
@@ -478,6 +496,9 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
     uint32_t rb = prm->row_begin, re = prm->row_end ? prm->row_end : prm->height;
     if (rb >= re || re > prm->height) return fail(SE_ERR_INVALID_ARG, "bad row range");
     if ((rb & 1u) || ((re & 1u) && re != prm->height)) return fail(SE_ERR_INVALID_ARG, "strip boundaries must be even rows");
+    // per-step kernels index block rows with gridDim.y (<= 65535 CTAs of 4 block rows / 8 light rows)
+    if ((uint64_t)(re - rb) + 2ull * prm->halo_rows > 65535ull * 8ull)
+        return fail(SE_ERR_INVALID_ARG, "more than 524280 rows per device are not supported (shard the grid into strips)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -630,6 +651,9 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
                 SE_CU_S(driver().OccupancyMaxActiveBlocks(&occ, s->f_tiles, rules->tile_threads, (size_t)s->tile_smem));
                 if (occ < 1) { fail(SE_ERR_CUDA, "se_step_tiles does not fit on an SM"); return bail(SE_ERR_CUDA); }
                 s->tile_grid_max = std::min(grid_max, occ * n_sm);
+                int coop_attr = 0;
+                SE_CUDA_S(cudaDeviceGetAttribute(&coop_attr, cudaDevAttrCooperativeLaunch, s->device));
+                s->coop = coop_attr != 0 && !std::getenv("SE_NO_COOP_LAUNCH");   // env: experiments only
                 SE_CUDA_S(cudaMalloc(&s->cells[1], s->cells_bytes()));
                 SE_CUDA_S(cudaMemsetAsync(s->cells[1], 0, s->cells_bytes(), s->stream));
                 SE_CUDA_S(cudaMalloc(&s->d_tile_done, (size_t)s->tiles_x * s->tiles_y * sizeof(unsigned)));
@@ -706,7 +730,7 @@ int se_sim_step(se_sim* s, uint32_t n_steps) {
             void* targs[] = {&tp};
             const long long items = (long long)nblk * s->tiles_x * s->tiles_y;
             const int grid = (int)std::min<long long>((long long)s->tile_grid_max, items);
-            int rc = launch(s, s->f_tiles, dim3(grid), dim3(s->rules->tile_threads), targs, (unsigned)s->tile_smem);
+            int rc = launch(s, s->f_tiles, dim3(grid), dim3(s->rules->tile_threads), targs, (unsigned)s->tile_smem, s->coop);
             if (rc) return rc;
             s->frame += (int)run;
             s->tile_seq += (unsigned)nblk;
@@ -889,7 +913,14 @@ int se_sim_ipc_export(se_sim* s, void* handles, uint64_t* local_rows, uint64_t* 
 int se_sim_ipc_attach(se_sim* s, int which, const void* handles, uint64_t nb_local_rows, uint64_t nb_ghost_top, uint64_t nb_ghost_bottom) {
     if (!s || !handles || which < 0 || which > 1) return fail(SE_ERR_INVALID_ARG, "bad argument");
     SE_CUDA(cudaSetDevice(s->device));
+    const uint64_t owned = (uint64_t)(s->row_end - s->row_begin);
+    if ((which == 0 ? nb_ghost_bottom : nb_ghost_top) > owned || nb_ghost_top + nb_ghost_bottom >= nb_local_rows)
+        return fail(SE_ERR_INVALID_ARG, "neighbour's ghost rows exceed the rows this strip owns");
     Neighbour& nb = s->nb[which];
+    if (nb.ipc)
+        for (int b = 0; b < 2; ++b)
+            if (nb.cells[b]) { cudaIpcCloseMemHandle(nb.cells[b]); nb.cells[b] = nullptr; }
+    nb.attached = false;
     nb.local_rows = nb_local_rows;
     nb.ghost_top = nb_ghost_top;
     nb.ghost_bottom = nb_ghost_bottom;
@@ -919,7 +950,12 @@ int se_sim_attach_local(se_sim* s, int which, se_sim* other) {
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(SE_ERR_CUDA, cudaGetErrorString(e));
         (void)cudaGetLastError();
     }
+    if ((which == 0 ? other->ghost_bottom : other->ghost_top) > s->row_end - s->row_begin)
+        return fail(SE_ERR_INVALID_ARG, "neighbour's ghost rows exceed the rows this strip owns");
     Neighbour& nb = s->nb[which];
+    if (nb.ipc)
+        for (int b = 0; b < 2; ++b)
+            if (nb.cells[b]) { cudaIpcCloseMemHandle(nb.cells[b]); nb.cells[b] = nullptr; }
     nb.local_rows = (uint64_t)other->Hl;
     nb.ghost_top = (uint64_t)other->ghost_top;
     nb.ghost_bottom = (uint64_t)other->ghost_bottom;

@@ -167,6 +167,18 @@ def test_no_device_fails_loudly(default_rules):
     assert ei.value.kind == "Cuda" and "no CPU fallback" in str(ei.value)
 
 
+def test_create_rejects_bad_geometry_before_touching_a_device(default_rules):
+    """Argument validation of se_sim_create runs before any CUDA call (same errors with and without a GPU)."""
+    import sandengine_b200 as se
+    for size, kw in (((0, 64), {}), ((64, 0), {}), ((4, 600_000), {}),
+                     ((64, 64), dict(row_begin=3, row_end=33)),        # odd strip boundary
+                     ((64, 64), dict(row_begin=32, row_end=16)),       # empty strip
+                     ((64, 64), dict(row_begin=0, row_end=128))):      # beyond the grid
+        with pytest.raises(se.SandEngineError) as ei:
+            se.Simulation(default_rules, size, **kw)
+        assert ei.value.kind == "InvalidArg", (size, kw, str(ei.value))
+
+
 def test_yaml_syntax_variants_parse_identically(native_lib):
     """Block / flow / quoted / commented spellings of one document give the same parse (and the same GLSL text)."""
     import sandengine_b200 as se
