@@ -346,7 +346,7 @@ int one_step(se_sim* s, bool use_mods, int n_mods) {
         if (rc) return rc;
         SeLightParams lp{s->cells[s->cur], outb, s->light[s->lcur], s->light[s->lcur ^ 1], s->W, s->Hl, s->gy0, s->Hg};
         void* largs[] = {&lp};
-        rc = launch(s, s->f_light, dim3((s->W + 31) / 32, (s->Hl + 7) / 8), dim3(32, 8), largs);
+        rc = launch(s, s->f_light, dim3((s->W + 31) / 32, (s->Hl + 31) / 32), dim3(256), largs);
         if (rc) return rc;
         s->cur ^= 1;
         s->lcur ^= 1;
@@ -373,7 +373,7 @@ int one_step(se_sim* s, bool use_mods, int n_mods) {
     if (rc) return rc;
     SeLightParams lp{p.in, p.out, s->light[s->lcur], s->light[s->lcur ^ 1], s->W, s->Hl, s->gy0, s->Hg};
     void* largs[] = {&lp};
-    rc = launch(s, s->f_light, dim3((s->W + 31) / 32, (s->Hl + 7) / 8), dim3(32, 8), largs);
+    rc = launch(s, s->f_light, dim3((s->W + 31) / 32, (s->Hl + 31) / 32), dim3(256), largs);
     if (rc) return rc;
     s->cur ^= 1;
     s->lcur ^= 1;

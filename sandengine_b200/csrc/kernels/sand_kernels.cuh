@@ -223,12 +223,24 @@ SE_DEFINE_STEP_GLOBAL(se_step_inplace_mods, true, true)
 SE_DEFINE_STEP_GLOBAL(se_step_pingpong, false, false)
 SE_DEFINE_STEP_GLOBAL(se_step_pingpong_mods, false, true)
 
+#endif  // SE_HOST_EMU (K1a)
+
 // ---------------------------------------------------------------------------------------------
-// K3: lighting relaxation (operations.glsl:114-169), one thread per cell.
+// K3: lighting relaxation (operations.glsl:114-169).
 //   old_cells : material ids BEFORE this step (input_data)    new_cells : ids AFTER this step
 //   light_in / light_out : float4 per cell, ping-pong (simulation.rs:239)
 // The module is compiled with -fmad=false: every sum below is evaluated as written (no FMA), in the
 // shader's neighbour order DOWN, UP, DOWNLEFT, UPLEFT, DOWNRIGHT, UPRIGHT, RIGHT, LEFT (math.glsl:154-166).
+//
+// The per-neighbour term (rgb * keep * a, a) does not depend on which cell reads it, so a CTA computes it ONCE
+// per cell of its 32 x 32 tile (+ a one-cell ring) into shared memory -- one id load, one float4 load and one
+// table lookup per cell instead of eight.  Then each of the 256 threads walks 4 consecutive rows of one column
+// with a sliding 3 x 3 window of terms in registers (3 shared-memory loads per cell instead of 8) and combines
+// the 8 neighbours in the shader's order with the shader's arithmetic (the reader-dependent part is only
+// `falloff = (a == 0) ? max_falloff : a`).  CTAs whose tile + ring lies strictly inside the grid (and the local
+// buffer) take the INTERIOR path: all 8 neighbours exist, so there are no validity tests and the division by
+// `num` is the exact multiplication by 0.125; the CTAs on the rim keep the general form.
+// The two phases are plain per-thread functions so that tests/emu can run them on the host, CTA by CTA.
 // ---------------------------------------------------------------------------------------------
 struct SeLightParams {
     const unsigned* old_cells;
@@ -238,74 +250,133 @@ struct SeLightParams {
     int W, Hl, gy0, Hg;
 };
 
-// The per-neighbour term (rgb * keep * a, a) does not depend on which cell reads it, so each CTA computes it
-// ONCE per cell of its 32 x 8 tile (+ a one-cell ring) into shared memory -- one id load, one float4 load and
-// one table lookup per cell instead of eight -- and every cell then combines its 8 neighbours from shared
-// memory in the shader's order with the shader's arithmetic (the reader-dependent part is only
-// `falloff = (a == 0) ? max_falloff : a`).
-extern "C" __global__ void __launch_bounds__(256) se_light(const SeLightParams p) {
-    __shared__ unsigned fat_sm[256];
-    __shared__ float4 term[10][34];      // (vr, vg, vb, a) of cell (tile_x0 - 1 + j, tile_y0 - 1 + i)
-    __shared__ unsigned char ok[10][36]; // 1 = neighbour exists (inside the grid and the local buffer)
-    const int t = threadIdx.y * blockDim.x + threadIdx.x;
-    if (t < 256) fat_sm[t] = se_fat_table[t];
-    __syncthreads();
-    const int x0 = blockIdx.x * 32 - 1, yl0 = blockIdx.y * 8 - 1;
-    for (int e = t; e < 10 * 34; e += 256) {
-        const int i = e / 34, j = e - i * 34;
-        const int nx = x0 + j, nyl = yl0 + i, ny = p.gy0 + nyl;
-        unsigned char valid = 0;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (nx >= 0 && nx < p.W && ny >= 0 && ny < p.Hg && nyl >= 0 && nyl < p.Hl) {   // outOfBounds, :139-141
-            const size_t nidx = (size_t)nyl * p.W + nx;
-            const unsigned nf = fat_sm[min(p.old_cells[nidx], 255u)];
-            const float keep = (nf & SE_F_OBSTACLE) ? 0.0f : 1.0f;
-            const float4 li = p.light_in[nidx];
-            const float la = li.w * 1.0f;
-            v = make_float4((li.x * keep) * la, (li.y * keep) * la, (li.z * keep) * la, la);
-            valid = 1;
-        }
-        term[i][j] = v;
-        ok[i][j] = valid;
+#define SE_LT_W 32                       // tile width  (= lanes of a warp: one row segment of 512 B per warp access)
+#define SE_LT_H 32                       // tile height (8 warps x SE_LT_ROWS rows)
+#define SE_LT_ROWS 4                     // consecutive rows per thread
+#define SE_LT_STRIDE (SE_LT_W + 2)       // term row stride (float4)
+#define SE_LT_TERMS ((SE_LT_H + 2) * SE_LT_STRIDE)
+
+// true when the tile of CTA (bx, by) and its one-cell ring lie inside the grid and inside the local buffer
+static __device__ __forceinline__ bool se_light_tile_is_interior(const SeLightParams& p, int bx, int by) {
+    const int x_lo = bx * SE_LT_W - 1, x_hi = bx * SE_LT_W + SE_LT_W;         // ring columns
+    const int yl_lo = by * SE_LT_H - 1, yl_hi = by * SE_LT_H + SE_LT_H;       // ring rows (local)
+    return x_lo >= 0 && x_hi < p.W && yl_lo >= 0 && yl_hi < p.Hl && p.gy0 + yl_lo >= 0 && p.gy0 + yl_hi < p.Hg;
+}
+
+// term of ring/tile cell (i, j): i = local row - (tile row 0 - 1), j = column - (tile column 0 - 1)
+template <bool INTERIOR>
+static __device__ __forceinline__ void se_light_stage_one(const SeLightParams& p, const unsigned* fat, float4* term, int bx, int by, int i, int j) {
+    const int nx = bx * SE_LT_W - 1 + j, nyl = by * SE_LT_H - 1 + i, ny = p.gy0 + nyl;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (INTERIOR || (nx >= 0 && nx < p.W && ny >= 0 && ny < p.Hg && nyl >= 0 && nyl < p.Hl)) {   // outOfBounds, :139-141
+        const size_t nidx = (size_t)nyl * p.W + nx;
+        const unsigned id = p.old_cells[nidx];
+        const float4 li = p.light_in[nidx];
+        const unsigned nf = fat[id < 255u ? id : 255u];
+        const float keep = (nf & SE_F_OBSTACLE) ? 0.0f : 1.0f;     // vec4(vec3(float(!obstacle)), 1.0), :498
+        const float la = li.w;                                     // a * 1.0 == a
+        v = make_float4((li.x * keep) * la, (li.y * keep) * la, (li.z * keep) * la, la);
     }
-    __syncthreads();
-    const int x = blockIdx.x * 32 + threadIdx.x;
-    const int yl = blockIdx.y * 8 + threadIdx.y;
-    if (x >= p.W || yl >= p.Hl) return;
-    const int y = p.gy0 + yl;                     // global row
-    const size_t idx = (size_t)yl * p.W + x;
-    const unsigned me = min(p.new_cells[idx], 255u);
-    float4 light;
-    if (fat_sm[me] & SE_F_EMISSIVE) {             // :126-127
-        light = make_float4(se_emission_table[me * 4 + 0], se_emission_table[me * 4 + 1], se_emission_table[me * 4 + 2], se_emission_table[me * 4 + 3]);
-    } else if (y == 0) {                          // :128-129
-        light = make_float4(1.0f, 1.0f, 1.0f, 0.999999f);
-    } else {
-        // neighbour order DOWN, UP, DOWNLEFT, UPLEFT, DOWNRIGHT, UPRIGHT, RIGHT, LEFT (math.glsl:154-166)
-        const int NX[8] = {0, 0, -1, -1, 1, 1, 1, -1};
-        const int NY[8] = {1, -1, 1, -1, 1, -1, 0, 0};
-        float4 avg = make_float4(0.f, 0.f, 0.f, 0.f), mx = make_float4(0.f, 0.f, 0.f, 0.f);
-        float max_falloff = 0.0f;
-        int num = 0;
-        const int ci = threadIdx.y + 1, cj = threadIdx.x + 1;
+    term[i * SE_LT_STRIDE + j] = v;
+}
+
+// phase 1, thread `tid` of 256: tile columns row by row (one warp per row: aligned 512-byte segments), then the
+// two ring columns (68 cells) in one pass
+template <bool INTERIOR>
+static __device__ __forceinline__ void se_light_stage(const SeLightParams& p, const unsigned* fat, float4* term, int bx, int by, int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
-        for (int n = 0; n < 8; ++n) {
-            if (!ok[ci + NY[n]][cj + NX[n]]) continue;
-            const float4 v = term[ci + NY[n]][cj + NX[n]];
-            const float falloff = (v.w == 0.0f) ? max_falloff : v.w;
-            avg.x += v.x; avg.y += v.y; avg.z += v.z; avg.w += falloff;
-            max_falloff = fmaxf(falloff, max_falloff);
-            num += 1;
-            mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, falloff);
-        }
-        if (num > 0) {
-            const float dn = (float)num;
-            avg.x = __fdiv_rn(avg.x, dn); avg.y = __fdiv_rn(avg.y, dn); avg.z = __fdiv_rn(avg.z, dn); avg.w = __fdiv_rn(avg.w, dn);
-        }
-        // mix(avg.rgb, max.rgb, 0.5) = avg*(1-0.5) + max*0.5
-        light = make_float4(avg.x * 0.5f + mx.x * 0.5f, avg.y * 0.5f + mx.y * 0.5f, avg.z * 0.5f + mx.z * 0.5f, avg.w);
+    for (int it = 0; it < (SE_LT_H + 2 + 7) / 8; ++it) {
+        const int i = warp + 8 * it;
+        if (i < SE_LT_H + 2) se_light_stage_one<INTERIOR>(p, fat, term, bx, by, i, lane + 1);
     }
-    p.light_out[idx] = light;
+    if (tid < 2 * (SE_LT_H + 2)) se_light_stage_one<INTERIOR>(p, fat, term, bx, by, tid >> 1, (tid & 1) * (SE_LT_W + 1));
+}
+
+// one neighbour, in the shader's order (:500-513); `mx.w` is never read by the shader's result
+#define SE_LIGHT_ACC(v)                                                               \
+    {                                                                                 \
+        const float falloff_ = ((v).w == 0.0f) ? max_falloff : (v).w;                 \
+        avg.x += (v).x; avg.y += (v).y; avg.z += (v).z; avg.w += falloff_;            \
+        max_falloff = fmaxf(falloff_, max_falloff);                                   \
+        mx.x = fmaxf(mx.x, (v).x); mx.y = fmaxf(mx.y, (v).y); mx.z = fmaxf(mx.z, (v).z); \
+    }
+
+// phase 2, thread `tid` of 256: column tid & 31, rows 4 * (tid >> 5) .. + 3 of the tile
+template <bool INTERIOR>
+static __device__ __forceinline__ void se_light_compute(const SeLightParams& p, const unsigned* fat, const float4* term, int bx, int by, int tid) {
+    const int tx = tid & 31, row0 = (tid >> 5) * SE_LT_ROWS;
+    const int x = bx * SE_LT_W + tx;
+    if (!INTERIOR && x >= p.W) return;
+    const float4* tp = term + row0 * SE_LT_STRIDE + tx;            // term (row0 - 1, tx - 1) of the tile
+    float4 a0 = tp[0], a1 = tp[1], a2 = tp[2];                     // row above
+    float4 b0 = tp[SE_LT_STRIDE], b1 = tp[SE_LT_STRIDE + 1], b2 = tp[SE_LT_STRIDE + 2];   // own row
+#pragma unroll
+    for (int i = 0; i < SE_LT_ROWS; ++i) {
+        const int yl = by * SE_LT_H + row0 + i;
+        if (!INTERIOR && yl >= p.Hl) break;
+        const float4 c0 = tp[(i + 2) * SE_LT_STRIDE], c1 = tp[(i + 2) * SE_LT_STRIDE + 1], c2 = tp[(i + 2) * SE_LT_STRIDE + 2];   // row below
+        const int y = p.gy0 + yl;                                  // global row
+        const size_t idx = (size_t)yl * p.W + x;
+        const unsigned id = p.new_cells[idx];
+        const unsigned me = id < 255u ? id : 255u;
+        float4 light;
+        if (fat[me] & SE_F_EMISSIVE) {                             // :126-127
+            light = make_float4(se_emission_table[me * 4 + 0], se_emission_table[me * 4 + 1], se_emission_table[me * 4 + 2], se_emission_table[me * 4 + 3]);
+        } else if (!INTERIOR && y == 0) {                          // :128-129 (row 0 is never part of an interior tile)
+            light = make_float4(1.0f, 1.0f, 1.0f, 0.999999f);
+        } else {
+            float4 avg = make_float4(0.f, 0.f, 0.f, 0.f), mx = make_float4(0.f, 0.f, 0.f, 0.f);
+            float max_falloff = 0.0f;
+            if (INTERIOR) {
+                // DOWN, UP, DOWNLEFT, UPLEFT, DOWNRIGHT, UPRIGHT, RIGHT, LEFT (math.glsl:154-166)
+                SE_LIGHT_ACC(c1) SE_LIGHT_ACC(a1) SE_LIGHT_ACC(c0) SE_LIGHT_ACC(a0)
+                SE_LIGHT_ACC(c2) SE_LIGHT_ACC(a2) SE_LIGHT_ACC(b2) SE_LIGHT_ACC(b0)
+                // num == 8: x / 8.0f == x * 0.125f exactly (both are the correctly rounded x / 8)
+                avg.x *= 0.125f; avg.y *= 0.125f; avg.z *= 0.125f; avg.w *= 0.125f;
+            } else {
+                const bool up = yl - 1 >= 0 && y - 1 >= 0, down = yl + 1 < p.Hl && y + 1 < p.Hg;
+                const bool left = x - 1 >= 0, right = x + 1 < p.W;
+                int num = 0;
+                if (down) { SE_LIGHT_ACC(c1) ++num; }
+                if (up) { SE_LIGHT_ACC(a1) ++num; }
+                if (down && left) { SE_LIGHT_ACC(c0) ++num; }
+                if (up && left) { SE_LIGHT_ACC(a0) ++num; }
+                if (down && right) { SE_LIGHT_ACC(c2) ++num; }
+                if (up && right) { SE_LIGHT_ACC(a2) ++num; }
+                if (right) { SE_LIGHT_ACC(b2) ++num; }
+                if (left) { SE_LIGHT_ACC(b0) ++num; }
+                if (num > 0) {                                     // :516-518
+                    const float dn = (float)num;
+                    avg.x = __fdiv_rn(avg.x, dn); avg.y = __fdiv_rn(avg.y, dn); avg.z = __fdiv_rn(avg.z, dn); avg.w = __fdiv_rn(avg.w, dn);
+                }
+            }
+            // mix(avg.rgb, max.rgb, 0.5) = avg*(1-0.5) + max*0.5, :521
+            light = make_float4(avg.x * 0.5f + mx.x * 0.5f, avg.y * 0.5f + mx.y * 0.5f, avg.z * 0.5f + mx.z * 0.5f, avg.w);
+        }
+        p.light_out[idx] = light;
+        a0 = b0; a1 = b1; a2 = b2;
+        b0 = c0; b1 = c1; b2 = c2;
+    }
+}
+
+#ifndef SE_HOST_EMU
+extern "C" __global__ void __launch_bounds__(256, 4) se_light(const SeLightParams p) {
+    __shared__ unsigned fat_sm[256];
+    __shared__ float4 term[SE_LT_TERMS];
+    const int tid = threadIdx.x;
+    fat_sm[tid] = se_fat_table[tid];
+    __syncthreads();
+    const int bx = blockIdx.x, by = blockIdx.y;
+    if (se_light_tile_is_interior(p, bx, by)) {
+        se_light_stage<true>(p, fat_sm, term, bx, by, tid);
+        __syncthreads();
+        se_light_compute<true>(p, fat_sm, term, bx, by, tid);
+    } else {
+        se_light_stage<false>(p, fat_sm, term, bx, by, tid);
+        __syncthreads();
+        se_light_compute<false>(p, fat_sm, term, bx, by, tid);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -14,6 +14,8 @@
 #define __forceinline__ inline
 #define __restrict__
 struct uint4 { unsigned x, y, z, w; };
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 static inline float __uint2float_rn(unsigned u) { return (float)u; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
@@ -52,6 +54,27 @@ extern "C" void emu_step_inplace(uint32_t* cells, int W, int H, int frame) {
                 if (!(x < 0 || x >= W || y < 0 || y >= H)) cells[(size_t)y * W + x] = SE_ID(q[k]);
             }
         }
+}
+
+// K3 (lighting): the two per-thread phases of se_light, run CTA by CTA with a "__syncthreads" between them
+extern "C" void emu_light(const uint32_t* old_cells, const uint32_t* new_cells, const float* light_in, float* light_out,
+                          int W, int Hl, int gy0, int Hg, int* n_interior_ctas) {
+    SeLightParams p{old_cells, new_cells, reinterpret_cast<const float4*>(light_in), reinterpret_cast<float4*>(light_out), W, Hl, gy0, Hg};
+    std::vector<float4> term(SE_LT_TERMS);
+    int n_int = 0;
+    for (int by = 0; by < (Hl + SE_LT_H - 1) / SE_LT_H; ++by)
+        for (int bx = 0; bx < (W + SE_LT_W - 1) / SE_LT_W; ++bx) {
+            for (auto& t : term) t = make_float4(NAN, NAN, NAN, NAN);      // poison: every term read must have been staged
+            if (se_light_tile_is_interior(p, bx, by)) {
+                ++n_int;
+                for (int tid = 0; tid < 256; ++tid) se_light_stage<true>(p, se_fat_table, term.data(), bx, by, tid);
+                for (int tid = 0; tid < 256; ++tid) se_light_compute<true>(p, se_fat_table, term.data(), bx, by, tid);
+            } else {
+                for (int tid = 0; tid < 256; ++tid) se_light_stage<false>(p, se_fat_table, term.data(), bx, by, tid);
+                for (int tid = 0; tid < 256; ++tid) se_light_compute<false>(p, se_fat_table, term.data(), bx, by, tid);
+            }
+        }
+    if (n_interior_ctas) *n_interior_ctas = n_int;
 }
 
 extern "C" int emu_lut_eligible(void) { return SE_LUT_ELIGIBLE; }

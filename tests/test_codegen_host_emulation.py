@@ -93,3 +93,37 @@ def test_synthetic_64_material_rule_set(native_lib, tmp_path_factory):
     g = synthetic_grid(160, 128, 5, mix=mix, ids=ids)
     out = compare(lib, orc, g, 200)
     assert not np.array_equal(out, g)
+
+
+def test_lighting_kernel_phases_on_host(native_lib, tmp_path_factory, default_rules, oracle):
+    """se_light's two per-thread phases (term staging into the tile + ring, sliding-window combine; interior and
+    rim CTAs) run CTA by CTA on the host and must give the oracle's light field BIT FOR BIT: tile/ring indexing,
+    neighbour order, the x * 0.125 shortcut of the interior path and the general path on the rim."""
+    lib = build_emu(tmp_path_factory, "light", default_rules)
+    lib.emu_light.argtypes = [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]
+    rng = np.random.default_rng(11)
+    saw_interior = 0
+    for (w, h, seed, steps) in [(160, 128, 1, 6), (33, 17, 2, 4), (97, 99, 3, 4), (2, 2, 4, 3), (128, 33, 5, 3), (32, 32, 6, 3)]:
+        cells = synthetic_grid(w, h, seed)
+        light = rng.random((h, w, 4), dtype=np.float32)
+        light[rng.random((h, w)) < 0.2, 3] = 0.0                 # falloff == 0 takes the running maximum
+        light[rng.random((h, w)) < 0.1] = 0.0
+        frame = 1
+        for s in range(steps):
+            frame += 1
+            new_cells, want, _ = oracle.step_cells(cells, frame, light)
+            got = np.full_like(want, np.nan)
+            n_int = C.c_int(0)
+            lib.emu_light(cells.ctypes.data, new_cells.ctypes.data, light.ctypes.data, got.ctypes.data, w, h, 0, h, C.byref(n_int))
+            saw_interior += n_int.value
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"{w}x{h} step {s + 1}: light differs from the oracle"
+            if w == 160 and s == 0:
+                # a strip (local rows [32, 102) of the grid): every row except the first and last local one sees all of
+                # its neighbours, so it must equal the full-grid result
+                gy0, hl = 32, 70
+                part = np.full((hl, w, 4), np.nan, np.float32)
+                lib.emu_light(cells[gy0:gy0 + hl].ctypes.data, new_cells[gy0:gy0 + hl].ctypes.data,
+                              np.ascontiguousarray(light[gy0:gy0 + hl]).ctypes.data, part.ctypes.data, w, hl, gy0, h, None)
+                assert np.array_equal(part[1:-1].view(np.uint32), want[gy0 + 1:gy0 + hl - 1].view(np.uint32))
+            cells, light = new_cells, want
+    assert saw_interior > 0

@@ -173,6 +173,16 @@ def test_lighting_vs_oracle(se, default_rules, oracle):
     assert np.array_equal(got, ref)
     err = np.abs(gotL - refL).max()
     assert err <= LIGHT_ATOL, err
+    # large enough for se_light's interior CTAs (32 x 32 tiles whose ring is inside the grid) next to rim CTAs
+    w, h, steps = 200, 150, 12
+    g = synthetic_grid(w, h, 10)
+    L0 = rng.random((h, w, 4), dtype=np.float32)
+    L0[rng.random((h, w)) < 0.2, 3] = 0.0
+    ref, refL, _ = oracle.run(g, 1, steps, light=L0)
+    got, gotL, _ = run_gpu(se, default_rules, g, steps, lighting=True, light0=L0)
+    assert np.array_equal(got, ref)
+    err = np.abs(gotL - refL).max()
+    assert err <= LIGHT_ATOL, err
 
 
 def test_lighting_frame1(se, default_rules, oracle):
