@@ -496,6 +496,10 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
     uint32_t rb = prm->row_begin, re = prm->row_end ? prm->row_end : prm->height;
     if (rb >= re || re > prm->height) return fail(SE_ERR_INVALID_ARG, "bad row range");
     if ((rb & 1u) || ((re & 1u) && re != prm->height)) return fail(SE_ERR_INVALID_ARG, "strip boundaries must be even rows");
+    // Strips exchange ghost rows of the id buffer only; the light field of a strip would need its own ghost rows
+    // (one row per step, operations.glsl:114-160).  Not implemented: refuse instead of relaxing stale light.
+    if ((prm->flags & SE_FLAG_LIGHTING) && (rb > 0 || re < prm->height))
+        return fail(SE_ERR_UNSUPPORTED, "(Unsupported) lighting on a strip (row_begin/row_end) is not implemented: run lighting on one device");
     // per-step kernels index block rows with gridDim.y (<= 65535 CTAs of 4 block rows / 8 light rows)
     if ((uint64_t)(re - rb) + 2ull * prm->halo_rows > 65535ull * 8ull)
         return fail(SE_ERR_INVALID_ARG, "more than 524280 rows per device are not supported (shard the grid into strips)");

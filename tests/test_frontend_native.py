@@ -177,6 +177,9 @@ def test_create_rejects_bad_geometry_before_touching_a_device(default_rules):
         with pytest.raises(se.SandEngineError) as ei:
             se.Simulation(default_rules, size, **kw)
         assert ei.value.kind == "InvalidArg", (size, kw, str(ei.value))
+    with pytest.raises(se.SandEngineError) as ei:       # strips carry no light ghost rows: refused, not silently wrong
+        se.Simulation(default_rules, (64, 64), lighting=True, row_begin=0, row_end=32, halo_rows=4)
+    assert ei.value.kind == "Unsupported"
 
 
 def test_yaml_syntax_variants_parse_identically(native_lib):
