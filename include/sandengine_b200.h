@@ -62,7 +62,8 @@ typedef struct se_create_params {
     int32_t device;          /* CUDA device ordinal */
     /* Strip decomposition (multi-GPU): this sim owns global rows [row_begin, row_end) and keeps
      * `halo_rows` ghost rows towards each neighbour.  Single GPU: row_begin = 0, row_end = 0 (= height),
-     * halo_rows = 0.  row_begin/row_end must be even (Margolus blocks are 2 rows). */
+     * halo_rows = 0.  row_begin/row_end must be even (Margolus blocks are 2 rows).  Strips carry ghost rows of
+     * the id buffer only: SE_FLAG_LIGHTING on a strip returns SE_ERR_UNSUPPORTED. */
     uint32_t row_begin, row_end, halo_rows;
     uint32_t temporal_block; /* Margolus steps fused per launch by the tiled kernel; 0 = library default */
 } se_create_params;
