@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--temporal-block", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--running-census", action="store_true", help="EXPERIMENTAL: SE_FLAG_RUNNING_CENSUS (census maintained by the per-frame kernel)")
     ap.add_argument("--host-sync", action="store_true", help="order the ghost-row exchange with host barriers instead of device flags")
     ap.add_argument("--debug-no-exchange", action="store_true", help="DIAGNOSTIC ONLY: skip ghost exchanges (wrong results) to time ranks uncoupled")
     return ap.parse_args()
@@ -224,7 +225,7 @@ def run_ours(args):
     K, Wm = args.steps, max(args.warmup, 3)
     rules = se.parse_path(REPO / "data" / "materials.yaml")
     strip = StripSimulation(rules, (S, S), halo_rows=args.halo, device=local_rank, temporal_block=args.temporal_block,
-                            device_sync=not args.host_sync)
+                            device_sync=not args.host_sync, running_census=args.running_census)
     sim = strip.sim
     if args.debug_no_exchange:
         strip.exchange = lambda: None
@@ -347,6 +348,8 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if args.running_census:
+            line["config"]["experimental"] = "SE_FLAG_RUNNING_CENSUS"
         if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
             try:
                 line["cpu_baseline"] = cpu_port_rate(min(S, 4096), args.cpu_seconds)

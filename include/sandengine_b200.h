@@ -54,6 +54,11 @@ typedef struct se_modification {
 #define SE_MAX_MODIFICATIONS 256 /* simulation.rs:43 */
 
 #define SE_FLAG_LIGHTING 1u      /* evaluate the lighting relaxation every step (operations.glsl:114-169) */
+/* EXPERIMENTAL, off by default: keep the per-material census of the owned rows up to date inside the per-frame
+ * step kernel (population deltas of the blocks where a SET fired) so that se_sim_census[_async] after a
+ * se_sim_step(sim, 1) needs no pass over the grid.  Results are identical to the recount; only table-eligible
+ * rule sets with lighting off use it, elsewhere the flag is ignored. */
+#define SE_FLAG_RUNNING_CENSUS 2u
 
 typedef struct se_create_params {
     uint32_t width;          /* simSize.x */

@@ -20,6 +20,7 @@ SE_ERR_CUDA = -8
 SE_ERR_INVALID_ARG = -9
 
 SE_FLAG_LIGHTING = 1
+SE_FLAG_RUNNING_CENSUS = 2   # experimental, see the header
 SE_MODSHAPE_CIRCLE = 0
 SE_MODSHAPE_SQUARE = 1
 SE_MAX_MODIFICATIONS = 256

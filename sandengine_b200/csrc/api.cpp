@@ -139,6 +139,12 @@ struct SeLutStepParams {
     int lut_words, pool_offset;
     const unsigned* lut;
 };
+struct SeLutCensusParams {
+    unsigned long long* census;
+    const unsigned* popbits;
+    int pop_words, pop_offset;
+    int own_y0, own_y1;
+};
 struct SeLightParams {
     const unsigned* old_cells;
     const unsigned* new_cells;
@@ -208,6 +214,13 @@ struct se_sim {
     // stream's kernels share the device).  False only on a device / context that reports no support.
     bool coop = false;
     int T = 0, HY = 0, HX = 0, PH = 0, tiles_x = 0, tiles_y = 0, lut_words = 0, pool_offset = 0, tile_offset = 0, tile_smem = 0, tile_grid = 0, tile_grid_max = 0, k1c_grid = 0;
+    // running census (SE_FLAG_RUNNING_CENSUS, experimental): d_running is valid only between K1c-census steps
+    bool running = false, running_valid = false, running_copy_pending = false;
+    CUfunction f_lut_global_census = nullptr, f_build_popbits = nullptr;
+    unsigned* d_popbits = nullptr;
+    unsigned long long* d_running = nullptr;
+    int pop_words = 0, pop_offset = 0;
+    cudaEvent_t running_copy_done = nullptr;
     Neighbour nb[2];
     // Device-side exchange protocol: 4 flag words live right behind cells[0] (same allocation, so that one
     // IPC handle maps both): [0]/[1] = "done computing" epoch of the strip above/below, [2]/[3] = "ghost rows
@@ -481,6 +494,9 @@ int se_sim_destroy(se_sim* s) {
     for (auto& ev : s->census_done) if (ev) cudaEventDestroy(ev);
     if (s->d_lut) cudaFree(s->d_lut);
     if (s->d_tile_done) cudaFree(s->d_tile_done);
+    if (s->d_popbits) cudaFree(s->d_popbits);
+    if (s->d_running) cudaFree(s->d_running);
+    if (s->running_copy_done) cudaEventDestroy(s->running_copy_done);
     if (s->mod && driver().ok) driver().ModuleUnload(s->mod);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
@@ -663,6 +679,21 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
                 SE_CUDA_S(cudaMalloc(&s->d_tile_done, (size_t)s->tiles_x * s->tiles_y * sizeof(unsigned)));
                 SE_CUDA_S(cudaMemsetAsync(s->d_tile_done, 0, (size_t)s->tiles_x * s->tiles_y * sizeof(unsigned), s->stream));
                 s->tiled = true;
+                if (prm->flags & SE_FLAG_RUNNING_CENSUS) {
+                    SE_CU_S(driver().ModuleGetFunction(&s->f_lut_global_census, s->mod, "se_step_lut_global_census"));
+                    SE_CU_S(driver().ModuleGetFunction(&s->f_build_popbits, s->mod, "se_build_popbits"));
+                    s->pop_words = (N4 + 31) / 32;
+                    s->pop_offset = s->tile_offset;                       // behind the staged table (16-aligned)
+                    SE_CUDA_S(cudaMalloc(&s->d_popbits, (size_t)s->pop_words * sizeof(unsigned)));
+                    SE_CUDA_S(cudaMemsetAsync(s->d_popbits, 0, (size_t)s->pop_words * sizeof(unsigned), s->stream));
+                    SE_CUDA_S(cudaMalloc(&s->d_running, 256 * sizeof(unsigned long long)));
+                    SE_CUDA_S(cudaEventCreateWithFlags(&s->running_copy_done, cudaEventDisableTiming));
+                    void* pargs[] = {&s->d_popbits};
+                    SE_TRY(launch(s, s->f_build_popbits, dim3((N4 + 255) / 256), dim3(256), pargs));
+                    SE_CU_S(driver().FuncSetAttribute(s->f_lut_global_census, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                                      s->pop_offset + ((s->pop_words * 4 + 15) & ~15)));
+                    s->running = true;
+                }
             }
         }
     }
@@ -713,13 +744,21 @@ int se_sim_step(se_sim* s, uint32_t n_steps) {
                 lp.W = s->W; lp.Hl = s->Hl; lp.gy0 = s->gy0; lp.Hg = s->Hg; lp.frame = s->frame + 1;
                 lp.lut_words = s->lut_words; lp.pool_offset = s->pool_offset; lp.lut = s->d_lut;
                 void* largs[] = {&lp};
-                int rc = launch(s, s->f_lut_global, dim3(s->k1c_grid), dim3(512), largs, (unsigned)s->tile_offset);   // SE_K1C_THREADS
+                int rc;
+                if (s->running && s->running_valid) {
+                    SeLutCensusParams cx{s->d_running, s->d_popbits, s->pop_words, s->pop_offset, s->row_begin, s->row_end};
+                    void* cargs[] = {&lp, &cx};
+                    rc = launch(s, s->f_lut_global_census, dim3(s->k1c_grid), dim3(512), cargs, (unsigned)(s->pop_offset + ((s->pop_words * 4 + 15) & ~15)));
+                } else {
+                    rc = launch(s, s->f_lut_global, dim3(s->k1c_grid), dim3(512), largs, (unsigned)s->tile_offset);   // SE_K1C_THREADS
+                }
                 if (rc) return rc;
                 s->frame += 1;
                 k += 1;
                 continue;
             }
             // a run of plain steps: ONE launch of ceil(run / T) T-blocks (dataflow between them inside the kernel)
+            s->running_valid = false;
             { int rc = guard_buffer_write(s, 0); if (rc) return rc; rc = guard_buffer_write(s, 1); if (rc) return rc; }
             const uint32_t run = std::min<uint32_t>(n_steps - k, 64u * (uint32_t)s->T);     // bound the kernel duration
             const int nblk = (int)((run + (uint32_t)s->T - 1) / (uint32_t)s->T);
@@ -742,6 +781,7 @@ int se_sim_step(se_sim* s, uint32_t n_steps) {
             k += run;
             continue;
         }
+        s->running_valid = false;
         int rc = one_step(s, k == 0, n_mods);
         if (rc) return rc;
         ++k;
@@ -773,6 +813,7 @@ int se_sim_upload_cells(se_sim* s, const uint32_t* host) {
     if (!s || !host) return fail(SE_ERR_INVALID_ARG, "null argument");
     SE_CUDA(cudaSetDevice(s->device));
     { int rc = guard_buffer_write(s, s->cur); if (rc) return rc; }
+    s->running_valid = false;
     SE_CUDA(cudaMemcpyAsync(s->cells[s->cur] + s->owned_offset(), host, s->owned_cells() * sizeof(unsigned), cudaMemcpyHostToDevice, s->stream));
     SE_CUDA(cudaStreamSynchronize(s->stream));
     return SE_OK;
@@ -834,9 +875,27 @@ int se_sim_device_cells(se_sim* s, void** dptr, size_t* pitch) {
     return SE_OK;
 }
 
+// running census: (re)count into d_running on the main stream when a step other than K1c-census ran since
+static int ensure_running_census(se_sim* s) {
+    if (s->running_valid) return SE_OK;
+    SE_CUDA(cudaMemsetAsync(s->d_running, 0, 256 * sizeof(unsigned long long), s->stream));
+    se_static::launch_census(s->cells[s->cur] + s->owned_offset(), s->owned_cells(), s->d_running, s->stream);
+    s->launches++;
+    SE_CUDA(cudaGetLastError());
+    s->running_valid = true;
+    return SE_OK;
+}
+
 int se_sim_census(se_sim* s, uint64_t* counts256) {
     if (!s || !counts256) return fail(SE_ERR_INVALID_ARG, "null argument");
     SE_CUDA(cudaSetDevice(s->device));
+    if (s->running) {
+        int rc = ensure_running_census(s);
+        if (rc) return rc;
+        SE_CUDA(cudaMemcpyAsync(counts256, s->d_running, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+        SE_CUDA(cudaStreamSynchronize(s->stream));
+        return SE_OK;
+    }
     SE_CUDA(cudaMemsetAsync(s->d_census, 0, 256 * sizeof(unsigned long long), s->stream));
     se_static::launch_census(s->cells[s->cur] + s->owned_offset(), s->owned_cells(), s->d_census, s->stream);
     s->launches++;
@@ -849,6 +908,15 @@ int se_sim_census(se_sim* s, uint64_t* counts256) {
 int se_sim_census_async(se_sim* s, uint64_t* host_counts256) {
     if (!s || !host_counts256) return fail(SE_ERR_INVALID_ARG, "null argument");
     SE_CUDA(cudaSetDevice(s->device));
+    if (s->running) {
+        // the running census lives on the main stream: a 2 KB copy in stream order, no pass over the grid
+        int rc = ensure_running_census(s);
+        if (rc) return rc;
+        SE_CUDA(cudaMemcpyAsync(host_counts256, s->d_running, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+        SE_CUDA(cudaEventRecord(s->running_copy_done, s->stream));
+        s->running_copy_pending = true;
+        return SE_OK;
+    }
     const int buf = s->cur;
     if (s->census_pending[buf]) {
         // the previous census of this buffer is still being tracked by the same event: finish it first
@@ -872,6 +940,10 @@ int se_sim_census_wait(se_sim* s) {
     if (!s) return fail(SE_ERR_INVALID_ARG, "null sim");
     SE_CUDA(cudaSetDevice(s->device));
     SE_CUDA(cudaStreamSynchronize(s->aux_stream));
+    if (s->running_copy_pending) {
+        SE_CUDA(cudaEventSynchronize(s->running_copy_done));
+        s->running_copy_pending = false;
+    }
     return SE_OK;
 }
 

@@ -633,6 +633,83 @@ static __device__ __forceinline__ unsigned se_block_lut(unsigned v, unsigned see
     return mirror ? __byte_perm(rr, 0u, 0x2301) : rr;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Running census (EXPERIMENTAL, SE_FLAG_RUNNING_CENSUS; off by default): the per-material population of the
+// owned rows is kept up to date by the per-frame kernel K1c instead of being recounted by a pass over the grid.
+// Guarded swaps only permute the cells of a block, so the population changes only where a SET fired (or where a
+// block straddles the first/last owned row of a strip, or holds an id the table does not know).  `popbits` is
+// a bit per block state: 1 = some outcome of the state (any rand.y class, either mirror view) is not a
+// permutation of its four ids.  It is only a filter: blocks that pass it are compared cell by cell.
+// ---------------------------------------------------------------------------------------------
+static __device__ __forceinline__ unsigned se_sorted4(unsigned a, unsigned b, unsigned c, unsigned d) {
+    unsigned t;
+    if (a > b) { t = a; a = b; b = t; }
+    if (c > d) { t = c; c = d; d = t; }
+    if (a > c) { t = a; a = c; c = t; }
+    if (b > d) { t = b; b = d; d = t; }
+    if (b > c) { t = b; b = c; c = t; }
+    return a | (b << 8) | (c << 16) | (d << 24);
+}
+
+// same evaluation as se_build_lut_entry: every rand.y class of the unmirrored view
+static __device__ __forceinline__ bool se_popchange_entry(int idx) {
+    const int N = SE_N_MATERIALS;
+    const unsigned ia = idx / (N * N * N), ib = (idx / (N * N)) % N, ic = (idx / N) % N, id = idx % N;
+    if ((se_fat_table[ia] | se_fat_table[ib] | se_fat_table[ic] | se_fat_table[id]) & SE_F_NOSWAP) return true;   // generic path
+    if (idx == 0) return false;
+    const unsigned before = se_sorted4(ia, ib, ic, id);
+#pragma unroll
+    for (int cls = 0; cls < SE_LUT_NCLS; ++cls) {
+        unsigned s = se_fat_table[ia], r = se_fat_table[ib], d = se_fat_table[ic], dr = se_fat_table[id];
+        SeRand rnd;
+        rnd.u[0] = 0xFFFFFFFFu;
+        rnd.u[1] = cls == 0 ? 0u : se_lut_thresholds[cls - 1] + 1u;
+        rnd.u[2] = 0u; rnd.u[3] = 0u;
+        se_block_with_rand(s, r, d, dr, rnd, 0, 0, 0);
+        if ((s | r | d | dr) & SE_F_NOSWAP) return true;
+        if (se_sorted4(SE_ID(s), SE_ID(r), SE_ID(d), SE_ID(dr)) != before) return true;
+    }
+    return false;
+}
+
+// sets the bit of state idx and of its mirror image (the lookup uses the unmirrored block whatever rand.x says)
+static __device__ __forceinline__ void se_build_popbits_entry(int idx, unsigned* __restrict__ popbits) {
+    if (!se_popchange_entry(idx)) return;
+    const int N = SE_N_MATERIALS;
+    const int ia = idx / (N * N * N), ib = (idx / (N * N)) % N, ic = (idx / N) % N, id = idx % N;
+    const int mirrored = ((ib * N + ia) * N + id) * N + ic;
+    atomicOr(popbits + (idx >> 5), 1u << (idx & 31));
+    atomicOr(popbits + (mirrored >> 5), 1u << (mirrored & 31));
+}
+
+#ifdef SE_HOST_EMU
+typedef const unsigned* se_pop_t;
+static inline unsigned se_popbit(se_pop_t pop, unsigned idx) { return (pop[idx >> 5] >> (idx & 31)) & 1u; }
+#else
+typedef unsigned se_pop_t;   // shared-space address
+static __device__ __forceinline__ unsigned se_popbit(se_pop_t pop, unsigned idx) {
+    unsigned w;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(pop + 4u * (idx >> 5)));
+    return (w >> (idx & 31)) & 1u;
+}
+#endif
+
+// One block of K1c: v = clamped ids (what the table saw), raw* = the words read from memory, nv = new ids,
+// cm = bit k set when cell k (a, b, c, d) is inside the grid AND in an owned row.  Adds the population deltas of
+// the counted cells to hist[256] (CTA-local, flushed once per launch).
+static __device__ __forceinline__ void se_census_block(int* hist, se_pop_t pop, unsigned v, unsigned ra, unsigned rb, unsigned rc, unsigned rd,
+                                                       unsigned nv, unsigned cm) {
+    const unsigned na = nv & 0xFFu, nb = (nv >> 8) & 0xFFu, nc = (nv >> 16) & 0xFFu, nd = nv >> 24;
+    if (cm == 0u || (na == ra && nb == rb && nc == rc && nd == rd)) return;
+    // all four cells counted and every outcome of this state is a permutation: nothing to do.  (A raw id the
+    // table does not know reads as NULL, NULL states have their bit set, so v is what decides.)
+    if (cm == 0xFu && !se_popbit(pop, se_idx4(v))) return;
+    if ((cm & 1u) && na != ra) { atomicAdd(hist + (ra < 255u ? ra : 255u), -1); atomicAdd(hist + na, 1); }
+    if ((cm & 2u) && nb != rb) { atomicAdd(hist + (rb < 255u ? rb : 255u), -1); atomicAdd(hist + nb, 1); }
+    if ((cm & 4u) && nc != rc) { atomicAdd(hist + (rc < 255u ? rc : 255u), -1); atomicAdd(hist + nc, 1); }
+    if ((cm & 8u) && nd != rd) { atomicAdd(hist + (rd < 255u ? rd : 255u), -1); atomicAdd(hist + nd, 1); }
+}
+
 #ifndef SE_HOST_EMU
 // one Margolus sub-step over the whole tile; OX (column phase) is a template parameter so that the
 // aligned 16-bit and the byte access variants are separate straight-line loops
@@ -824,12 +901,27 @@ struct SeLutStepParams {
 #define SE_K1C_MINCTAS 2
 #endif
 
-extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_step_lut_global(const SeLutStepParams p) {
+// running census (EXPERIMENTAL): extra arguments of se_step_lut_global_census
+struct SeLutCensusParams {
+    unsigned long long* census;   // 256 bins: population of the owned rows, updated in place
+    const unsigned* popbits;      // ceil(N^4 / 32) words
+    int pop_words;
+    int pop_offset;               // byte offset of the staged popbits in dynamic shared memory (16-aligned, behind the table)
+    int own_y0, own_y1;           // owned global rows [own_y0, own_y1)
+};
+
+template <bool CENSUS>
+static __device__ __forceinline__ void se_k1c_body(const SeLutStepParams& p, const SeLutCensusParams& cx, int* hist_sm) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned fat_sm[256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     unsigned smem_sa;
     asm volatile("mov.u32 %0, %1;" : "=r"(smem_sa) : "r"((unsigned)__cvta_generic_to_shared(smem)));
+    if (CENSUS) {
+        for (int i = tid; i < cx.pop_words; i += blockDim.x)
+            asm volatile("st.shared.u32 [%0], %1;" :: "r"(smem_sa + (unsigned)cx.pop_offset + 4u * i), "r"(__ldg(cx.popbits + i)) : "memory");
+        for (int i = tid; i < 256; i += blockDim.x) hist_sm[i] = 0;
+    }
     {
         const uint4* lut4 = reinterpret_cast<const uint4*>(p.lut);
         const int n4 = (p.lut_words + 3) >> 2;
@@ -863,6 +955,8 @@ extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_
         unsigned* base0 = p.cells + (size_t)(st0 == 0 ? y0 - p.gy0 : 0) * (size_t)p.W;
         unsigned* base1 = p.cells + (size_t)(st1 == 0 ? y1 - p.gy0 : 0) * (size_t)p.W;
         const unsigned rowseed = (unsigned)y0 * 2131u + fterm;
+        // census: which of the two rows are counted (inside the grid and owned by this strip)
+        const unsigned cm_rows = !CENSUS ? 0u : ((st0 == 0 && y0 >= cx.own_y0 && y0 < cx.own_y1) ? 3u : 0u) | ((st1 == 0 && y1 >= cx.own_y0 && y1 < cx.own_y1) ? 12u : 0u);
         const int c_begin = (int)sp * SE_K1C_SPAN, c_end = min((int)chunks_x, c_begin + SE_K1C_SPAN);
         for (int cb = c_begin; cb < c_end; cb += SE_K1C_BATCH) {
             unsigned a[SE_K1C_BATCH], b[SE_K1C_BATCH], c[SE_K1C_BATCH], d[SE_K1C_BATCH];
@@ -895,6 +989,10 @@ extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_
                     const unsigned seed = (unsigned)x0 * 461u + rowseed;
                     const unsigned nv = se_block_lut(v, seed, x0, y0, p.frame, tab, pool_off, fat_sm);
                     const unsigned na = nv & 0xFFu, nb = (nv >> 8) & 0xFFu, nc = (nv >> 16) & 0xFFu, nd = nv >> 24;
+                    if (CENSUS) {
+                        const unsigned cm_cols = (x0 >= 0 ? 5u : 0u) | ((x0 + 1) < p.W ? 10u : 0u);
+                        se_census_block(hist_sm, smem_sa + (unsigned)cx.pop_offset, v, a[u], b[u], c[u], d[u], nv, cm_rows & cm_cols);
+                    }
                     if (vec_ok) {
                         if (st0 == 0 && (na != a[u] || nb != b[u])) *reinterpret_cast<uint2*>(base0 + x0) = make_uint2(na, nb);
                         if (st1 == 0 && (nc != c[u] || nd != d[u])) *reinterpret_cast<uint2*>(base1 + x0) = make_uint2(nc, nd);
@@ -909,6 +1007,27 @@ extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_
             }
         }
     }
+    if (CENSUS) {
+        __syncthreads();
+        for (int i = tid; i < 256; i += blockDim.x) {
+            const int dlt = hist_sm[i];
+            if (dlt != 0) atomicAdd(cx.census + i, (unsigned long long)(long long)dlt);   // two's complement: negative deltas wrap correctly
+        }
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_step_lut_global(const SeLutStepParams p) {
+    se_k1c_body<false>(p, SeLutCensusParams{}, nullptr);
+}
+
+extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_step_lut_global_census(const SeLutStepParams p, const SeLutCensusParams cx) {
+    __shared__ int hist_sm[256];
+    se_k1c_body<true>(p, cx, hist_sm);
+}
+
+extern "C" __global__ void __launch_bounds__(256) se_build_popbits(unsigned* __restrict__ popbits) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < SE_N4) se_build_popbits_entry(idx, popbits);
 }
 #endif  // SE_HOST_EMU
 #endif  // SE_LUT_ELIGIBLE

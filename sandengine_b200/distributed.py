@@ -64,7 +64,8 @@ class StripPlan:
 class StripSimulation:
     """One rank's strip of a sharded `Simulation` (lighting off)."""
 
-    def __init__(self, rules, size, halo_rows: int = 32, device=None, temporal_block: int = 0, device_sync: bool = True):
+    def __init__(self, rules, size, halo_rows: int = 32, device=None, temporal_block: int = 0, device_sync: bool = True,
+                 running_census: bool = False):
         import torch
         import torch.distributed as dist
 
@@ -78,7 +79,7 @@ class StripSimulation:
         self.row_begin, self.row_end = self.plan.rows(self.rank)
         dev = torch.cuda.current_device() if device is None else device
         self.sim = Simulation(rules, size, lighting=False, device=dev, row_begin=self.row_begin, row_end=self.row_end,
-                              halo_rows=self.plan.halo_rows, temporal_block=temporal_block)
+                              halo_rows=self.plan.halo_rows, temporal_block=temporal_block, running_census=running_census)
         if self.world > 1:
             mine = self.sim.ipc_export()
             everyone = [None] * self.world

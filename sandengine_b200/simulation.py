@@ -54,7 +54,8 @@ class Simulation:
     """`Simulation` of the reference, backed by CUDA kernels on packed-u32 device cell buffers."""
 
     def __init__(self, rules: ParsingResult, size: Tuple[int, int], lighting: bool = False, device: int = 0,
-                 row_begin: int = 0, row_end: int = 0, halo_rows: int = 0, temporal_block: int = 0):
+                 row_begin: int = 0, row_end: int = 0, halo_rows: int = 0, temporal_block: int = 0,
+                 running_census: bool = False):
         if not rules.compiled:
             raise ValueError("rules must be compiled (parse_string(..., compile=True))")
         self.rules = rules
@@ -64,7 +65,8 @@ class Simulation:
         self.row_end = int(row_end) if row_end else self.size[1]
         self.params = Params()
         self.modifications: List[np.ndarray] = []
-        prm = _capi.se_create_params(self.size[0], self.size[1], _capi.SE_FLAG_LIGHTING if lighting else 0, device,
+        flags = (_capi.SE_FLAG_LIGHTING if lighting else 0) | (_capi.SE_FLAG_RUNNING_CENSUS if running_census else 0)   # 2nd: experimental
+        prm = _capi.se_create_params(self.size[0], self.size[1], flags, device,
                                      self.row_begin, self.row_end, int(halo_rows), int(temporal_block))
         h = C.c_void_p()
         _capi.check(_capi.lib().se_sim_create(rules._h, C.byref(prm), C.byref(h)))

@@ -1,0 +1,20 @@
+# Round-2 opener: validate and time the experimental, default-off paths in ONE gpurun call.
+#   gpurun --timeout 600 -- 'bash scripts/gpu_experiments.sh'
+mkdir -p gpurun_out
+# 1. running census (SE_FLAG_RUNNING_CENSUS): correctness, then the e2e leg with and without it
+SE_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -k running_census 2>&1 | tail -3
+timeout 200 python bench.py --steps 400 --warmup 16 --no-cpu-baseline > gpurun_out/exp_e2e_base.json 2> gpurun_out/exp_e2e_base.err
+timeout 200 python bench.py --steps 400 --warmup 16 --no-cpu-baseline --running-census > gpurun_out/exp_e2e_running.json 2> gpurun_out/exp_e2e_running.err
+python - <<'PY'
+import json
+for n in ("base", "running"):
+    try:
+        d = json.load(open(f"gpurun_out/exp_e2e_{n}.json"))
+        print(n, "value", d["value"], "e2e", d["e2e"]["value"])
+    except Exception as e:
+        print(n, "failed:", e)
+PY
+# 2. lighting path after the se_light rewrite: launch list + one full capture of the new kernel
+timeout 100 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/light_launches_r2.csv python scripts/light_probe.py 8192 12 > /dev/null 2>&1
+timeout 120 ncu --set full --clock-control none --import-source on -k regex:se_light -s 16 -c 1 -o gpurun_out/prof_r2_light python scripts/light_probe.py 8192 12 > /dev/null 2>&1
+python scripts/light_probe.py 8192 48

@@ -31,6 +31,8 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
     return r;
 }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p += v; return o; }
+static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }
+static inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p |= v; return o; }
 using std::abs;
 
 #include "sand_kernels.cuh"
@@ -119,7 +121,53 @@ extern "C" void emu_step_lut_inplace(uint32_t* cells, int W, int H, int frame) {
             }
         }
 }
+
+// ---- running census (experimental): popbits filter + per-block deltas, decisions exactly as in se_k1c_body<true> ----
+static std::vector<unsigned> g_pop;
+extern "C" int emu_build_popbits(void) {
+    g_pop.assign((SE_N4 + 31) / 32, 0u);
+    for (int idx = 0; idx < SE_N4; ++idx) se_build_popbits_entry(idx, g_pop.data());
+    int n = 0;
+    for (int idx = 0; idx < SE_N4; ++idx) n += (int)se_popbit(g_pop.data(), (unsigned)idx);
+    return n;
+}
+
+// one in-place table step of a full grid (gy0 = 0) that also maintains census256 for the owned rows [own_y0, own_y1);
+// n_filtered counts the changed, fully counted blocks that the popbits filter let skip the per-cell comparison
+extern "C" void emu_step_lut_census(uint32_t* cells, int W, int H, int frame, int own_y0, int own_y1, long long* census256, long long* n_filtered) {
+    int ox, oy;
+    se_margolus_offset(frame, ox, oy);
+    int hist[256] = {0};
+    for (int y0 = -oy; y0 < H; y0 += 2)
+        for (int x0 = -ox; x0 < W; x0 += 2) {
+            const int y1 = y0 + 1;
+            const int st0 = (y0 < 0) ? 1 : 0, st1 = (y1 >= H) ? 1 : 0;
+            const bool cx0 = x0 >= 0, cx1 = (x0 + 1) < W;
+            unsigned raw[4] = {2u, 2u, 2u, 2u};
+            if (st0 == 0 && cx0) raw[0] = cells[(size_t)y0 * W + x0];
+            if (st0 == 0 && cx1) raw[1] = cells[(size_t)y0 * W + x0 + 1];
+            if (st1 == 0 && cx0) raw[2] = cells[(size_t)y1 * W + x0];
+            if (st1 == 0 && cx1) raw[3] = cells[(size_t)y1 * W + x0 + 1];
+            unsigned v = 0;
+            for (int k = 0; k < 4; ++k) v |= (raw[k] < SE_N_MATERIALS ? raw[k] : 1u) << (8 * k);
+            const unsigned seed = (unsigned)x0 * 461u + (unsigned)y0 * 2131u + (unsigned)frame * (2131u * 2131u);
+            const unsigned nv = se_block_lut(v, seed, x0, y0, frame, g_table.data(), g_pool_off, se_fat_table);
+            const unsigned cm_rows = ((st0 == 0 && y0 >= own_y0 && y0 < own_y1) ? 3u : 0u) | ((st1 == 0 && y1 >= own_y0 && y1 < own_y1) ? 12u : 0u);
+            const unsigned cm_cols = (cx0 ? 5u : 0u) | (cx1 ? 10u : 0u);
+            const unsigned cm = cm_rows & cm_cols;
+            if (n_filtered && cm == 0xFu && nv != v && !se_popbit(g_pop.data(), se_idx4(v))) ++*n_filtered;
+            se_census_block(hist, g_pop.data(), v, raw[0], raw[1], raw[2], raw[3], nv, cm);
+            const unsigned nn[4] = {nv & 0xFFu, (nv >> 8) & 0xFFu, (nv >> 16) & 0xFFu, nv >> 24};
+            if (st0 == 0 && cx0 && nn[0] != raw[0]) cells[(size_t)y0 * W + x0] = nn[0];
+            if (st0 == 0 && cx1 && nn[1] != raw[1]) cells[(size_t)y0 * W + x0 + 1] = nn[1];
+            if (st1 == 0 && cx0 && nn[2] != raw[2]) cells[(size_t)y1 * W + x0] = nn[2];
+            if (st1 == 0 && cx1 && nn[3] != raw[3]) cells[(size_t)y1 * W + x0 + 1] = nn[3];
+        }
+    for (int i = 0; i < 256; ++i) census256[i] += hist[i];
+}
 #else
+extern "C" int emu_build_popbits(void) { return -2; }
+extern "C" void emu_step_lut_census(uint32_t*, int, int, int, int, int, long long*, long long*) {}
 extern "C" int emu_build_lut(void) { return -2; }
 extern "C" void emu_step_lut_inplace(uint32_t*, int, int, int) {}
 #endif

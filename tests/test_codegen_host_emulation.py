@@ -127,3 +127,38 @@ def test_lighting_kernel_phases_on_host(native_lib, tmp_path_factory, default_ru
                 assert np.array_equal(part[1:-1].view(np.uint32), want[gy0 + 1:gy0 + hl - 1].view(np.uint32))
             cells, light = new_cells, want
     assert saw_interior > 0
+
+
+def test_running_census_deltas_on_host(native_lib, tmp_path_factory, default_rules, oracle):
+    """EXPERIMENTAL running census (SE_FLAG_RUNNING_CENSUS): the popbits filter and the per-block deltas that K1c's
+    census variant applies, run on the host: after every step the maintained census equals a recount of the owned
+    rows -- full grids, ragged sizes, WALL / NULL / unknown ids, and strips (owned rows inside a larger buffer)."""
+    lib = build_emu(tmp_path_factory, "census", default_rules)
+    lib.emu_step_lut_census.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    assert lib.emu_build_lut() > 0
+    n_pop = lib.emu_build_popbits()
+    n4 = len(default_rules.materials) ** 4
+    assert 0 < n_pop < n4          # a real filter: some states change the population (SET rules, NULL/WALL), most do not
+
+    def recount(cells, y0, y1):
+        return np.bincount(np.minimum(cells[y0:y1], 255).ravel(), minlength=256).astype(np.int64)
+
+    filtered = C.c_longlong(0)
+    cases = [(96, 64, 1, 200, 0, 64), (33, 17, 2, 80, 0, 17), (2, 2, 3, 12, 0, 2), (64, 96, 5, 150, 32, 64), (40, 50, 6, 100, 10, 11)]
+    for (w, h, seed, steps, own0, own1) in cases:
+        g = synthetic_grid(w, h, seed)
+        if seed == 5:
+            rng = np.random.default_rng(3)
+            g[rng.integers(0, h, 40), rng.integers(0, w, 40)] = 2          # WALL inside the grid
+            g[rng.integers(0, h, 15), rng.integers(0, w, 15)] = 1          # NULL
+            g[40, 5] = 77; g[33, 9] = 4000000000; g[31, 2] = 300           # unknown ids (normalised to NULL when written)
+        ref = g.copy()
+        census = recount(g, own0, own1)
+        frame = 1
+        for s in range(steps):
+            frame += 1
+            oracle.step_blocks_inplace(ref, frame)
+            lib.emu_step_lut_census(g.ctypes.data, w, h, frame, own0, own1, census.ctypes.data, C.byref(filtered))
+            assert np.array_equal(g, ref), f"{w}x{h} step {s + 1}: cells"
+            assert np.array_equal(census, recount(g, own0, own1)), f"{w}x{h} rows {own0}..{own1} step {s + 1}: census"
+    assert filtered.value > 1000       # the filter did skip changed blocks (pure swaps)

@@ -1,6 +1,7 @@
 """Parity of the CUDA path (through the C ABI) against the oracle -- the gate for every kernel.
 Bit-exact for cell state; light within 1e-6 absolute (f32, same expression order, no FMA)."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -485,3 +486,33 @@ def test_gpu_matches_committed_state_hashes(se):
         rules = se.parse_string(text)
         got, _, _ = run_gpu(se, rules, g, steps)
         assert hashlib.sha256(got.astype(np.uint32).tobytes()).hexdigest() == want[name]["final"], name
+
+
+@pytest.mark.skipif(os.environ.get("SE_TEST_EXPERIMENTAL") != "1",
+                    reason="EXPERIMENTAL SE_FLAG_RUNNING_CENSUS: off by default, not yet validated on a GPU (SE_TEST_EXPERIMENTAL=1 runs it)")
+def test_running_census_experimental(se, default_rules, oracle):
+    """SE_FLAG_RUNNING_CENSUS: cells stay bit-exact and every census (sync and async, after K1c steps, after runs that
+    fall back to a recount, with WALL / NULL / unknown ids, odd widths) equals a host recount."""
+    import torch
+    for (w, h, seed) in [(516, 130, 41), (1024, 768, 42), (260, 258, 43)]:
+        g = synthetic_grid(w, h, seed)
+        rng = np.random.default_rng(seed)
+        g[rng.integers(0, h, 100), rng.integers(0, w, 100)] = 2
+        g[rng.integers(0, h, 30), rng.integers(0, w, 30)] = 1
+        g[3, 3] = 77; g[5, 9] = 4000000000
+        sim = se.Simulation(default_rules, (w, h), running_census=True)
+        sim.upload_cells(g); sim.params.frame = 1
+        ref = g.copy(); frame = 1
+        ring = torch.zeros((4, 256), dtype=torch.int64).pin_memory()
+        for k in range(40):
+            n = 1 if k % 7 else 9                       # mostly the per-frame kernel, sometimes a tiled run (invalidates)
+            sim.step(n)
+            frame = oracle.run_blocks(ref, frame, n)
+            want = np.bincount(np.minimum(ref, 255).ravel(), minlength=256)
+            if k % 2:
+                assert np.array_equal(sim.census(), want), (w, h, k)
+            else:
+                sim.census_async(ring[k % 4].data_ptr()); sim.census_wait()
+                assert np.array_equal(ring[k % 4].numpy(), want), (w, h, k)
+        assert np.array_equal(sim.download_cells(), ref)
+        sim.close()
