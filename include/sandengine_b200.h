@@ -59,6 +59,11 @@ typedef struct se_modification {
  * se_sim_step(sim, 1) needs no pass over the grid.  Results are identical to the recount; only table-eligible
  * rule sets with lighting off use it, elsewhere the flag is ignored. */
 #define SE_FLAG_RUNNING_CENSUS 2u
+/* EXPERIMENTAL opt-in: allow SE_FLAG_LIGHTING on a strip.  The light field then gets ghost rows too: attach the
+ * neighbours' light buffers (se_sim_ipc_export_light / _attach_light, or se_sim_attach_local) and exchange every
+ * `halo_rows` steps (the light stencil uses up one ghost row per step).  Without this flag lighting on a strip is
+ * refused with SE_ERR_UNSUPPORTED. */
+#define SE_FLAG_LIT_STRIP_EXPERIMENTAL 4u
 
 typedef struct se_create_params {
     uint32_t width;          /* simSize.x */
@@ -68,7 +73,8 @@ typedef struct se_create_params {
     /* Strip decomposition (multi-GPU): this sim owns global rows [row_begin, row_end) and keeps
      * `halo_rows` ghost rows towards each neighbour.  Single GPU: row_begin = 0, row_end = 0 (= height),
      * halo_rows = 0.  row_begin/row_end must be even (Margolus blocks are 2 rows).  Strips carry ghost rows of
-     * the id buffer only: SE_FLAG_LIGHTING on a strip returns SE_ERR_UNSUPPORTED. */
+     * the id buffer only: SE_FLAG_LIGHTING on a strip returns SE_ERR_UNSUPPORTED (but see
+     * SE_FLAG_LIT_STRIP_EXPERIMENTAL). */
     uint32_t row_begin, row_end, halo_rows;
     uint32_t temporal_block; /* Margolus steps fused per launch by the tiled kernel; 0 = library default */
 } se_create_params;
@@ -138,6 +144,9 @@ int se_sim_ipc_export(se_sim* s, void* handles_2x64, uint64_t* local_rows, uint6
  * exported handles. */
 int se_sim_ipc_attach(se_sim* s, int which, const void* handles_2x64, uint64_t nb_local_rows,
                       uint64_t nb_ghost_top, uint64_t nb_ghost_bottom);
+/* Same pair for the two light buffers of a lit strip (SE_FLAG_LIT_STRIP_EXPERIMENTAL); call after se_sim_ipc_attach. */
+int se_sim_ipc_export_light(se_sim* s, void* handles_2x64);
+int se_sim_ipc_attach_light(se_sim* s, int which, const void* handles_2x64);
 /* Attach a neighbour that lives in THIS process (one process driving several strips / devices, the
  * reference's single-process model); peer access is enabled when the devices differ. */
 int se_sim_attach_local(se_sim* s, int which, se_sim* neighbour);

@@ -21,6 +21,7 @@ SE_ERR_INVALID_ARG = -9
 
 SE_FLAG_LIGHTING = 1
 SE_FLAG_RUNNING_CENSUS = 2   # experimental, see the header
+SE_FLAG_LIT_STRIP_EXPERIMENTAL = 4
 SE_MODSHAPE_CIRCLE = 0
 SE_MODSHAPE_SQUARE = 1
 SE_MAX_MODIFICATIONS = 256
@@ -31,7 +32,7 @@ EXPORTS = [
     "se_sim_create", "se_sim_destroy", "se_sim_step", "se_sim_push_modifications", "se_sim_set_frame", "se_sim_get_frame",
     "se_sim_upload_cells", "se_sim_download_cells", "se_sim_upload_light", "se_sim_download_light", "se_sim_download_color", "se_sim_device_cells",
     "se_sim_census", "se_sim_census_async", "se_sim_census_wait", "se_sim_set_stream", "se_sim_synchronize", "se_sim_launch_count",
-    "se_sim_ipc_export", "se_sim_ipc_attach", "se_sim_attach_local", "se_sim_halo_push", "se_sim_halo_exchange_async", "se_last_error", "se_version",
+    "se_sim_ipc_export", "se_sim_ipc_attach", "se_sim_ipc_export_light", "se_sim_ipc_attach_light", "se_sim_attach_local", "se_sim_halo_push", "se_sim_halo_exchange_async", "se_last_error", "se_version",
 ]
 
 
@@ -90,6 +91,8 @@ def lib() -> C.CDLL:
     L.se_sim_launch_count.argtypes = [vp, P(C.c_uint64)]
     L.se_sim_ipc_export.argtypes = [vp, vp, P(C.c_uint64), P(C.c_uint64), P(C.c_uint64)]
     L.se_sim_ipc_attach.argtypes = [vp, C.c_int, vp, C.c_uint64, C.c_uint64, C.c_uint64]
+    L.se_sim_ipc_export_light.argtypes = [vp, vp]
+    L.se_sim_ipc_attach_light.argtypes = [vp, C.c_int, vp]
     L.se_sim_attach_local.argtypes = [vp, C.c_int, vp]
     L.se_sim_halo_push.argtypes = [vp]
     L.se_sim_halo_exchange_async.argtypes = [vp]

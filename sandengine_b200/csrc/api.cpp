@@ -168,6 +168,8 @@ struct Neighbour {
     bool attached = false;
     bool ipc = false;
     unsigned* cells[2] = {nullptr, nullptr};
+    float4* light[2] = {nullptr, nullptr};   // lit strips only
+    bool light_ipc = false;
     unsigned* flags = nullptr;   // the neighbour's flag words (inside its cells[0] allocation)
     uint64_t local_rows = 0, ghost_top = 0, ghost_bottom = 0;
 };
@@ -480,6 +482,9 @@ int se_sim_destroy(se_sim* s) {
         if (s->nb[w].ipc)
             for (int b = 0; b < 2; ++b)
                 if (s->nb[w].cells[b]) cudaIpcCloseMemHandle(s->nb[w].cells[b]);
+        if (s->nb[w].light_ipc)
+            for (int b = 0; b < 2; ++b)
+                if (s->nb[w].light[b]) cudaIpcCloseMemHandle(s->nb[w].light[b]);
     }
     for (int b = 0; b < 2; ++b) {
         if (s->cells[b]) cudaFree(s->cells[b]);
@@ -514,7 +519,7 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
     if ((rb & 1u) || ((re & 1u) && re != prm->height)) return fail(SE_ERR_INVALID_ARG, "strip boundaries must be even rows");
     // Strips exchange ghost rows of the id buffer only; the light field of a strip would need its own ghost rows
     // (one row per step, operations.glsl:114-160).  Not implemented: refuse instead of relaxing stale light.
-    if ((prm->flags & SE_FLAG_LIGHTING) && (rb > 0 || re < prm->height))
+    if ((prm->flags & SE_FLAG_LIGHTING) && (rb > 0 || re < prm->height) && !(prm->flags & SE_FLAG_LIT_STRIP_EXPERIMENTAL))
         return fail(SE_ERR_UNSUPPORTED, "(Unsupported) lighting on a strip (row_begin/row_end) is not implemented: run lighting on one device");
     // per-step kernels index block rows with gridDim.y (<= 65535 CTAs of 4 block rows / 8 light rows)
     if ((uint64_t)(re - rb) + 2ull * prm->halo_rows > 65535ull * 8ull)
@@ -1038,6 +1043,10 @@ int se_sim_attach_local(se_sim* s, int which, se_sim* other) {
     nb.ipc = false;
     nb.cells[0] = other->cells[0];
     nb.cells[1] = other->cells[1];
+    if (s->lighting != other->lighting) return fail(SE_ERR_INVALID_ARG, "neighbour differs in SE_FLAG_LIGHTING");
+    nb.light[0] = other->light[0];
+    nb.light[1] = other->light[1];
+    nb.light_ipc = false;
     nb.flags = other->flags;
     nb.attached = true;
     return SE_OK;
@@ -1060,6 +1069,51 @@ int se_sim_halo_push(se_sim* s) {
         const unsigned* src = s->cells[s->cur] + s->owned_offset() + (size_t)(s->row_end - s->row_begin - (int)nb.ghost_top) * s->W;
         unsigned* dst = nb.cells[s->cur];
         SE_CUDA(cudaMemcpyAsync(dst, src, rowb * nb.ghost_top, cudaMemcpyDeviceToDevice, s->stream));
+    }
+    if (s->lighting) {
+        // lit strips: the same rows of the current light buffer (the neighbours step in lock-step, so lcur agrees)
+        const size_t lrowb = (size_t)s->W * sizeof(float4);
+        for (int w = 0; w < 2; ++w) {
+            const Neighbour& nb = s->nb[w];
+            const uint64_t g = (w == 0) ? nb.ghost_bottom : nb.ghost_top;
+            if (!nb.attached || g == 0) continue;
+            if (!nb.light[s->lcur]) return fail(SE_ERR_INVALID_ARG, "lit strip: the neighbour's light buffers are not attached (se_sim_ipc_attach_light)");
+            const float4* src = s->light[s->lcur] + s->owned_offset() + (w == 0 ? 0 : (size_t)(s->row_end - s->row_begin - (int)g) * s->W);
+            float4* dst = nb.light[s->lcur] + (w == 0 ? (size_t)(nb.local_rows - g) * s->W : 0);
+            SE_CUDA(cudaMemcpyAsync(dst, src, lrowb * g, cudaMemcpyDeviceToDevice, s->stream));
+        }
+    }
+    return SE_OK;
+}
+
+int se_sim_ipc_export_light(se_sim* s, void* handles) {
+    if (!s || !handles) return fail(SE_ERR_INVALID_ARG, "null argument");
+    if (!s->lighting) return fail(SE_ERR_INVALID_ARG, "sim was created without SE_FLAG_LIGHTING");
+    SE_CUDA(cudaSetDevice(s->device));
+    std::memset(handles, 0, 128);
+    for (int b = 0; b < 2; ++b) {
+        cudaIpcMemHandle_t h;
+        SE_CUDA(cudaIpcGetMemHandle(&h, s->light[b]));
+        std::memcpy((char*)handles + 64 * b, &h, 64);
+    }
+    return SE_OK;
+}
+
+int se_sim_ipc_attach_light(se_sim* s, int which, const void* handles) {
+    if (!s || !handles || which < 0 || which > 1) return fail(SE_ERR_INVALID_ARG, "bad argument");
+    if (!s->lighting) return fail(SE_ERR_INVALID_ARG, "sim was created without SE_FLAG_LIGHTING");
+    SE_CUDA(cudaSetDevice(s->device));
+    Neighbour& nb = s->nb[which];
+    if (nb.light_ipc)
+        for (int b = 0; b < 2; ++b)
+            if (nb.light[b]) { cudaIpcCloseMemHandle(nb.light[b]); nb.light[b] = nullptr; }
+    nb.light_ipc = true;
+    for (int b = 0; b < 2; ++b) {
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, (const char*)handles + 64 * b, 64);
+        void* p = nullptr;
+        SE_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        nb.light[b] = (float4*)p;
     }
     return SE_OK;
 }

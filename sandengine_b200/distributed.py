@@ -23,6 +23,7 @@ class StripPlan:
     height: int
     world: int
     halo_rows: int
+    lighting: bool = False
 
     def __post_init__(self):
         if self.halo_rows % 2:
@@ -49,7 +50,10 @@ class StripPlan:
 
     @property
     def steps_per_exchange(self) -> int:
-        """n with floor(n/2) + 1 <= halo_rows, rounded down to a multiple of 8 (whole fused launches) when possible."""
+        """n with floor(n/2) + 1 <= halo_rows, rounded down to a multiple of 8 (whole fused launches) when possible.
+        With lighting the 8-neighbour light stencil (operations.glsl:114-160) eats one ghost row per step: n = halo_rows."""
+        if self.lighting:
+            return self.halo_rows
         n = 2 * (self.halo_rows - 1)
         return n // 8 * 8 if n >= 8 else n
 
@@ -62,10 +66,11 @@ class StripPlan:
 
 
 class StripSimulation:
-    """One rank's strip of a sharded `Simulation` (lighting off)."""
+    """One rank's strip of a sharded `Simulation`.  lighting=True is EXPERIMENTAL (SE_FLAG_LIT_STRIP_EXPERIMENTAL):
+    the light field gets ghost rows too and the exchange happens every `halo_rows` steps."""
 
     def __init__(self, rules, size, halo_rows: int = 32, device=None, temporal_block: int = 0, device_sync: bool = True,
-                 running_census: bool = False):
+                 running_census: bool = False, lighting: bool = False):
         import torch
         import torch.distributed as dist
 
@@ -75,10 +80,10 @@ class StripSimulation:
         self.device_sync = device_sync
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
-        self.plan = StripPlan(int(size[0]), int(size[1]), self.world, int(halo_rows) if self.world > 1 else 0)
+        self.plan = StripPlan(int(size[0]), int(size[1]), self.world, int(halo_rows) if self.world > 1 else 0, lighting=bool(lighting))
         self.row_begin, self.row_end = self.plan.rows(self.rank)
         dev = torch.cuda.current_device() if device is None else device
-        self.sim = Simulation(rules, size, lighting=False, device=dev, row_begin=self.row_begin, row_end=self.row_end,
+        self.sim = Simulation(rules, size, lighting=bool(lighting), lit_strip=bool(lighting) and self.world > 1, device=dev, row_begin=self.row_begin, row_end=self.row_end,
                               halo_rows=self.plan.halo_rows, temporal_block=temporal_block, running_census=running_census)
         if self.world > 1:
             mine = self.sim.ipc_export()
@@ -90,6 +95,13 @@ class StripSimulation:
             if self.rank < self.world - 1:
                 h, lr, gt, gb = everyone[self.rank + 1]
                 self.sim.ipc_attach(1, h, lr, gt, gb)
+            if lighting:
+                lights = [None] * self.world
+                dist.all_gather_object(lights, self.sim.ipc_export_light())
+                if self.rank > 0:
+                    self.sim.ipc_attach_light(0, lights[self.rank - 1])
+                if self.rank < self.world - 1:
+                    self.sim.ipc_attach_light(1, lights[self.rank + 1])
             dist.barrier()
 
     @property
@@ -102,6 +114,13 @@ class StripSimulation:
 
     def download_cells(self, out=None):
         return self.sim.download_cells(out)
+
+    def upload_light(self, owned_rows) -> None:
+        self.sim.upload_light(owned_rows)
+        self.exchange()
+
+    def download_light(self):
+        return self.sim.download_light()
 
     def exchange(self) -> None:
         """Everyone has finished computing -> push boundary rows into the neighbours' ghosts -> everyone has landed.

@@ -55,7 +55,7 @@ class Simulation:
 
     def __init__(self, rules: ParsingResult, size: Tuple[int, int], lighting: bool = False, device: int = 0,
                  row_begin: int = 0, row_end: int = 0, halo_rows: int = 0, temporal_block: int = 0,
-                 running_census: bool = False):
+                 running_census: bool = False, lit_strip: bool = False):
         if not rules.compiled:
             raise ValueError("rules must be compiled (parse_string(..., compile=True))")
         self.rules = rules
@@ -65,7 +65,8 @@ class Simulation:
         self.row_end = int(row_end) if row_end else self.size[1]
         self.params = Params()
         self.modifications: List[np.ndarray] = []
-        flags = (_capi.SE_FLAG_LIGHTING if lighting else 0) | (_capi.SE_FLAG_RUNNING_CENSUS if running_census else 0)   # 2nd: experimental
+        flags = ((_capi.SE_FLAG_LIGHTING if lighting else 0) | (_capi.SE_FLAG_RUNNING_CENSUS if running_census else 0)
+                 | (_capi.SE_FLAG_LIT_STRIP_EXPERIMENTAL if lit_strip else 0))   # the last two: experimental, see the header
         prm = _capi.se_create_params(self.size[0], self.size[1], flags, device,
                                      self.row_begin, self.row_end, int(halo_rows), int(temporal_block))
         h = C.c_void_p()
@@ -195,6 +196,15 @@ class Simulation:
     def ipc_attach(self, which: int, handles: bytes, local_rows: int, ghost_top: int, ghost_bottom: int):
         buf = (C.c_ubyte * 128).from_buffer_copy(handles.ljust(128, b"\0"))
         _capi.check(_capi.lib().se_sim_ipc_attach(self._h, which, buf, local_rows, ghost_top, ghost_bottom))
+
+    def ipc_export_light(self) -> bytes:
+        buf = (C.c_ubyte * 128)()
+        _capi.check(_capi.lib().se_sim_ipc_export_light(self._h, buf))
+        return bytes(buf)
+
+    def ipc_attach_light(self, which: int, handles: bytes):
+        buf = (C.c_ubyte * 128).from_buffer_copy(handles.ljust(128, b"\0"))
+        _capi.check(_capi.lib().se_sim_ipc_attach_light(self._h, which, buf))
 
     def attach_local(self, which: int, neighbour: "Simulation"):
         """Neighbour strip owned by this process (0 = above, 1 = below)."""

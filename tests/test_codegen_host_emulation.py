@@ -162,3 +162,59 @@ def test_running_census_deltas_on_host(native_lib, tmp_path_factory, default_rul
             assert np.array_equal(g, ref), f"{w}x{h} step {s + 1}: cells"
             assert np.array_equal(census, recount(g, own0, own1)), f"{w}x{h} rows {own0}..{own1} step {s + 1}: census"
     assert filtered.value > 1000       # the filter did skip changed blocks (pure swaps)
+
+
+def test_lit_strip_schedule_on_host(native_lib, tmp_path_factory, default_rules, oracle):
+    """Strips WITH lighting: the light stencil invalidates one ghost row per step, so G ghost rows of ids
+    and light are good for G steps (StripPlan(lighting=True)).  Emulated rank by rank with the kernels' strip semantics
+    (oracle strip step for the ids, se_light's host phases for the light); the rows that the schedule declares invalid
+    are POISONED after every step, so agreement with the full-grid oracle proves that owned rows never read them."""
+    from sandengine_b200.distributed import StripPlan
+    lib = build_emu(tmp_path_factory, "litstrip", default_rules)
+    lib.emu_light.argtypes = [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]
+    rng = np.random.default_rng(5)
+    for (w, h, world, G, steps) in [(96, 120, 3, 4, 19), (70, 64, 2, 2, 9), (64, 200, 4, 6, 14)]:
+        plan = StripPlan(w, h, world, G, lighting=True)
+        assert plan.steps_per_exchange == G
+        cells = synthetic_grid(w, h, 7)
+        light = rng.random((h, w, 4), dtype=np.float32)
+        light[rng.random((h, w)) < 0.2, 3] = 0.0
+        # ranks: local buffers with ghosts
+        loc = []
+        for r in range(world):
+            b, e = plan.rows(r); gt, gb = plan.ghosts(r)
+            loc.append(dict(gy0=b - gt, b=b, e=e, gt=gt, gb=gb, cells=cells[b - gt:e + gb].copy(), light=light[b - gt:e + gb].copy()))
+        ref_c, ref_l, frame = cells, light, 1
+        done = 0
+        for chunk in plan.chunks(steps):
+            for n in range(1, chunk + 1):
+                frame += 1
+                ref_c, ref_l, _ = oracle.step_cells(ref_c, frame, ref_l)
+                for L in loc:
+                    old = L["cells"].copy()
+                    oracle.step_blocks_strip(L["cells"], L["gy0"], h, frame)
+                    out = np.empty_like(L["light"])
+                    hl = L["cells"].shape[0]
+                    lib.emu_light(old.ctypes.data, L["cells"].ctypes.data, L["light"].ctypes.data, out.ctypes.data, w, hl, L["gy0"], h, None)
+                    L["light"] = out
+                    # rows the schedule gives up after n steps since the last exchange: n from each inner edge
+                    if L["gt"]:
+                        L["cells"][:n] = 3; L["light"][:n] = np.float32(1e9)
+                    if L["gb"]:
+                        L["cells"][hl - n:] = 3; L["light"][hl - n:] = np.float32(1e9)
+            # exchange: owners push their boundary rows (ids + light) into the neighbours' ghosts
+            for r, L in enumerate(loc):
+                if r > 0:
+                    up = loc[r - 1]
+                    L["cells"][:L["gt"]] = up["cells"][up["gt"] + (up["e"] - up["b"]) - L["gt"]:up["gt"] + (up["e"] - up["b"])]
+                    L["light"][:L["gt"]] = up["light"][up["gt"] + (up["e"] - up["b"]) - L["gt"]:up["gt"] + (up["e"] - up["b"])]
+                if r < world - 1:
+                    dn = loc[r + 1]
+                    hl = L["cells"].shape[0]
+                    L["cells"][hl - L["gb"]:] = dn["cells"][dn["gt"]:dn["gt"] + L["gb"]]
+                    L["light"][hl - L["gb"]:] = dn["light"][dn["gt"]:dn["gt"] + L["gb"]]
+            done += chunk
+            for L in loc:
+                own = slice(L["gt"], L["gt"] + L["e"] - L["b"])
+                assert np.array_equal(L["cells"][own], ref_c[L["b"]:L["e"]]), f"{w}x{h}/{world} ids after {done} steps"
+                assert np.array_equal(L["light"][own].view(np.uint32), ref_l[L["b"]:L["e"]].view(np.uint32)), f"{w}x{h}/{world} light after {done} steps"

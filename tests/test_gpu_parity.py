@@ -516,3 +516,42 @@ def test_running_census_experimental(se, default_rules, oracle):
                 assert np.array_equal(ring[k % 4].numpy(), want), (w, h, k)
         assert np.array_equal(sim.download_cells(), ref)
         sim.close()
+
+
+@pytest.mark.skipif(os.environ.get("SE_TEST_EXPERIMENTAL") != "1",
+                    reason="EXPERIMENTAL lit strips (SE_FLAG_LIT_STRIP_EXPERIMENTAL): not yet validated on a GPU (SE_TEST_EXPERIMENTAL=1 runs it)")
+@pytest.mark.parametrize("n_strips,halo,w,h", [(2, 4, 96, 64), (3, 6, 200, 150), (4, 2, 64, 64)])
+def test_lit_strips_experimental(se, default_rules, oracle, n_strips, halo, w, h):
+    """Strips with lighting in one process (se_sim_attach_local): ids bit-exact, light bit-exact against the oracle's
+    full-grid run; ghost rows of ids AND light are exchanged every `halo` steps (StripPlan(lighting=True))."""
+    from sandengine_b200.distributed import StripPlan
+    rng = np.random.default_rng(23)
+    g = synthetic_grid(w, h, 21)
+    L0 = rng.random((h, w, 4), dtype=np.float32)
+    L0[rng.random((h, w)) < 0.2, 3] = 0.0
+    steps = 3 * halo + 1
+    ref, refL, _ = oracle.run(g, 1, steps, light=L0)
+    plan = StripPlan(w, h, n_strips, halo, lighting=True)
+    sims = []
+    for r in range(n_strips):
+        b, e = plan.rows(r)
+        s = se.Simulation(default_rules, (w, h), lighting=True, lit_strip=True, row_begin=b, row_end=e, halo_rows=halo)
+        s.upload_cells(g[b:e]); s.upload_light(np.ascontiguousarray(L0[b:e])); s.params.frame = 1
+        sims.append(s)
+    for r, s in enumerate(sims):
+        if r > 0: s.attach_local(0, sims[r - 1])
+        if r < n_strips - 1: s.attach_local(1, sims[r + 1])
+
+    def exchange():
+        for s in sims: s.synchronize()
+        for s in sims: s.halo_push()
+        for s in sims: s.synchronize()
+    exchange()
+    for k in plan.chunks(steps):
+        for s in sims: s.step(k)
+        exchange()
+    got = np.concatenate([s.download_cells() for s in sims], axis=0)
+    gotL = np.concatenate([s.download_light() for s in sims], axis=0)
+    for s in sims: s.close()
+    assert np.array_equal(got, ref)
+    assert np.abs(gotL - refL).max() <= LIGHT_ATOL
