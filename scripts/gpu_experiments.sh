@@ -14,6 +14,7 @@ for n in ("base", "running"):
     except Exception as e:
         print(n, "failed:", e)
 PY
+SE_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_c_abi_example.py -q -m gpu 2>&1 | tail -3
 # 2. lighting path after the se_light rewrite: launch list + one full capture of the new kernel
 timeout 100 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/light_launches_r2.csv python scripts/light_probe.py 8192 12 > /dev/null 2>&1
 timeout 120 ncu --set full --clock-control none --import-source on -k regex:se_light -s 16 -c 1 -o gpurun_out/prof_r2_light python scripts/light_probe.py 8192 12 > /dev/null 2>&1
