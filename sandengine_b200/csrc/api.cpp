@@ -162,6 +162,7 @@ struct se_rules {
     std::string nvrtc_log;
     bool compiled = false;
     int tile_threads = 1024;   // CTA size of the tile kernel (compile-time launch bound; tunable: env SE_TILE_THREADS)
+    int light_rows = 4;        // rows per thread of se_light => tile height 8 * light_rows (tunable: env SE_LT_ROWS)
 };
 
 struct Neighbour {
@@ -273,6 +274,14 @@ int compile_front(const char* yaml, size_t len, se_rules** out, bool with_nvrtc)
         }
         const std::string def_threads = "-DSE_TILE_THREADS=" + std::to_string(r->tile_threads);
         std::vector<std::string> extra;                       // experiments only: SE_NVRTC_DEFS="-DX=1 -DY=2"
+        if (const char* lr = std::getenv("SE_LT_ROWS")) {     // experiments only: se_light tile height
+            const int v = std::atoi(lr);
+            if (v == 2 || v == 4 || v == 8) { r->light_rows = v; extra.push_back("-DSE_LT_ROWS=" + std::to_string(v)); }
+        }
+        if (const char* mc = std::getenv("SE_LT_MINCTAS")) {
+            const int v = std::atoi(mc);
+            if (v >= 1 && v <= 8) extra.push_back("-DSE_LT_MINCTAS=" + std::to_string(v));
+        }
         if (const char* defs = std::getenv("SE_NVRTC_DEFS")) {
             std::string d(defs), tok;
             for (size_t i = 0; i <= d.size(); ++i) {
@@ -361,7 +370,7 @@ int one_step(se_sim* s, bool use_mods, int n_mods) {
         if (rc) return rc;
         SeLightParams lp{s->cells[s->cur], outb, s->light[s->lcur], s->light[s->lcur ^ 1], s->W, s->Hl, s->gy0, s->Hg};
         void* largs[] = {&lp};
-        rc = launch(s, s->f_light, dim3((s->W + 31) / 32, (s->Hl + 31) / 32), dim3(256), largs);
+        rc = launch(s, s->f_light, dim3((s->W + 31) / 32, (s->Hl + 8 * s->rules->light_rows - 1) / (8 * s->rules->light_rows)), dim3(256), largs);
         if (rc) return rc;
         s->cur ^= 1;
         s->lcur ^= 1;
@@ -388,7 +397,7 @@ int one_step(se_sim* s, bool use_mods, int n_mods) {
     if (rc) return rc;
     SeLightParams lp{p.in, p.out, s->light[s->lcur], s->light[s->lcur ^ 1], s->W, s->Hl, s->gy0, s->Hg};
     void* largs[] = {&lp};
-    rc = launch(s, s->f_light, dim3((s->W + 31) / 32, (s->Hl + 31) / 32), dim3(256), largs);
+    rc = launch(s, s->f_light, dim3((s->W + 31) / 32, (s->Hl + 8 * s->rules->light_rows - 1) / (8 * s->rules->light_rows)), dim3(256), largs);
     if (rc) return rc;
     s->cur ^= 1;
     s->lcur ^= 1;

@@ -251,8 +251,13 @@ struct SeLightParams {
 };
 
 #define SE_LT_W 32                       // tile width  (= lanes of a warp: one row segment of 512 B per warp access)
-#define SE_LT_H 32                       // tile height (8 warps x SE_LT_ROWS rows)
-#define SE_LT_ROWS 4                     // consecutive rows per thread
+#ifndef SE_LT_ROWS
+#define SE_LT_ROWS 4                     // consecutive rows per thread (tunable at rule-compile time: env SE_LT_ROWS = 2 | 4 | 8)
+#endif
+#ifndef SE_LT_MINCTAS
+#define SE_LT_MINCTAS 4                  // resident CTAs per SM the register allocation aims at (env SE_LT_MINCTAS)
+#endif
+#define SE_LT_H (8 * SE_LT_ROWS)         // tile height (8 warps x SE_LT_ROWS rows)
 #define SE_LT_STRIDE (SE_LT_W + 2)       // term row stride (float4)
 #define SE_LT_TERMS ((SE_LT_H + 2) * SE_LT_STRIDE)
 
@@ -361,7 +366,7 @@ static __device__ __forceinline__ void se_light_compute(const SeLightParams& p, 
 }
 
 #ifndef SE_HOST_EMU
-extern "C" __global__ void __launch_bounds__(256, 4) se_light(const SeLightParams p) {
+extern "C" __global__ void __launch_bounds__(256, SE_LT_MINCTAS) se_light(const SeLightParams p) {
     __shared__ unsigned fat_sm[256];
     __shared__ float4 term[SE_LT_TERMS];
     const int tid = threadIdx.x;

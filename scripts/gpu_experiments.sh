@@ -19,3 +19,5 @@ SE_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_c_abi_example.py 
 timeout 100 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/light_launches_r2.csv python scripts/light_probe.py 8192 12 > /dev/null 2>&1
 timeout 120 ncu --set full --clock-control none --import-source on -k regex:se_light -s 16 -c 1 -o gpurun_out/prof_r2_light python scripts/light_probe.py 8192 12 > /dev/null 2>&1
 python scripts/light_probe.py 8192 48
+# 3. se_light tile-height / occupancy variants (rule-compile-time env; all three tile heights are host-checked)
+for v in "SE_LT_ROWS=2" "SE_LT_ROWS=8" "SE_LT_MINCTAS=3" "SE_LT_MINCTAS=5"; do echo "$v"; env $v python scripts/light_probe.py 8192 48; done

@@ -14,11 +14,11 @@ from conftest import DEFAULT_YAML, REPO
 from sandengine_b200.grids import DEFAULT_IDS, DEFAULT_MIX, synthetic_grid
 
 
-def build_emu(tmp_path_factory, tag, rules):
+def build_emu(tmp_path_factory, tag, rules, defs=()):
     d = tmp_path_factory.mktemp(f"emu_{tag}")
     (d / "rules_gen.cuh").write_text(rules.cuda_header)
     so = d / "emu.so"
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-I", str(d),
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", *defs, "-I", str(d),
                            "-I", str(REPO / "sandengine_b200" / "csrc" / "kernels"),
                            str(REPO / "tests" / "emu" / "host_emu.cpp"), "-o", str(so)])
     lib = C.CDLL(str(so))
@@ -95,11 +95,12 @@ def test_synthetic_64_material_rule_set(native_lib, tmp_path_factory):
     assert not np.array_equal(out, g)
 
 
-def test_lighting_kernel_phases_on_host(native_lib, tmp_path_factory, default_rules, oracle):
+@pytest.mark.parametrize("rows", [4, 2, 8])      # 4 = the shipped tile height (32 rows); 2 / 8: the SE_LT_ROWS experiments
+def test_lighting_kernel_phases_on_host(native_lib, tmp_path_factory, default_rules, oracle, rows):
     """se_light's two per-thread phases (term staging into the tile + ring, sliding-window combine; interior and
     rim CTAs) run CTA by CTA on the host and must give the oracle's light field BIT FOR BIT: tile/ring indexing,
     neighbour order, the x * 0.125 shortcut of the interior path and the general path on the rim."""
-    lib = build_emu(tmp_path_factory, "light", default_rules)
+    lib = build_emu(tmp_path_factory, f"light{rows}", default_rules, defs=(f"-DSE_LT_ROWS={rows}",))
     lib.emu_light.argtypes = [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]
     rng = np.random.default_rng(11)
     saw_interior = 0
