@@ -104,7 +104,7 @@ def test_lighting_kernel_phases_on_host(native_lib, tmp_path_factory, default_ru
     lib.emu_light.argtypes = [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]
     rng = np.random.default_rng(11)
     saw_interior = 0
-    for (w, h, seed, steps) in [(160, 128, 1, 6), (33, 17, 2, 4), (97, 99, 3, 4), (2, 2, 4, 3), (128, 33, 5, 3), (32, 32, 6, 3)]:
+    for (w, h, seed, steps) in [(160, 128, 1, 6), (33, 17, 2, 4), (97, 99, 3, 4), (2, 2, 4, 3), (128, 33, 5, 3), (32, 32, 6, 3), (100, 200, 7, 3)]:
         cells = synthetic_grid(w, h, seed)
         light = rng.random((h, w, 4), dtype=np.float32)
         light[rng.random((h, w)) < 0.2, 3] = 0.0                 # falloff == 0 takes the running maximum
