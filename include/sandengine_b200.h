@@ -64,6 +64,9 @@ typedef struct se_modification {
  * `halo_rows` steps (the light stencil uses up one ghost row per step).  Without this flag lighting on a strip is
  * refused with SE_ERR_UNSUPPORTED. */
 #define SE_FLAG_LIT_STRIP_EXPERIMENTAL 4u
+/* EXPERIMENTAL, off by default: with SE_FLAG_LIGHTING and a table-eligible rule set, run the Margolus step, the
+ * modification override and the lighting relaxation as ONE kernel (se_light_fused) instead of two.  Same results. */
+#define SE_FLAG_FUSED_LIGHT_EXPERIMENTAL 8u
 
 typedef struct se_create_params {
     uint32_t width;          /* simSize.x */

@@ -22,6 +22,7 @@ SE_ERR_INVALID_ARG = -9
 SE_FLAG_LIGHTING = 1
 SE_FLAG_RUNNING_CENSUS = 2   # experimental, see the header
 SE_FLAG_LIT_STRIP_EXPERIMENTAL = 4
+SE_FLAG_FUSED_LIGHT_EXPERIMENTAL = 8
 SE_MODSHAPE_CIRCLE = 0
 SE_MODSHAPE_SQUARE = 1
 SE_MAX_MODIFICATIONS = 256

@@ -152,6 +152,16 @@ struct SeLightParams {
     float4* light_out;
     int W, Hl, gy0, Hg;
 };
+struct SeFusedParams {
+    SeLightParams lp;
+    int frame;
+    int n_mods;
+    const SeMod* mods;
+    int lut_words, pool_offset;
+    int tile_offset;
+    const unsigned* lut;
+    int tiles_x, tiles_y;
+};
 
 }  // namespace
 
@@ -217,6 +227,10 @@ struct se_sim {
     // stream's kernels share the device).  False only on a device / context that reports no support.
     bool coop = false;
     int T = 0, HY = 0, HX = 0, PH = 0, tiles_x = 0, tiles_y = 0, lut_words = 0, pool_offset = 0, tile_offset = 0, tile_smem = 0, tile_grid = 0, tile_grid_max = 0, k1c_grid = 0;
+    // fused step + modifications + lighting (SE_FLAG_FUSED_LIGHT_EXPERIMENTAL)
+    bool fused_light = false;
+    CUfunction f_light_fused = nullptr;
+    int lf_smem = 0, lf_grid = 0, lf_tiles_x = 0, lf_tiles_y = 0;
     // running census (SE_FLAG_RUNNING_CENSUS, experimental): d_running is valid only between K1c-census steps
     bool running = false, running_valid = false, running_copy_pending = false;
     CUfunction f_lut_global_census = nullptr, f_build_popbits = nullptr;
@@ -390,6 +404,19 @@ int one_step(se_sim* s, bool use_mods, int n_mods) {
         p.in = s->cells[s->cur];
         p.out = s->cells[s->cur];
         return launch(s, p.n_mods ? s->f_inplace_mods : s->f_inplace, grid, block, args);
+    }
+    if (s->fused_light) {
+        SeFusedParams fp;
+        fp.lp = SeLightParams{s->cells[s->cur], s->cells[s->cur ^ 1], s->light[s->lcur], s->light[s->lcur ^ 1], s->W, s->Hl, s->gy0, s->Hg};
+        fp.frame = frame; fp.n_mods = p.n_mods; fp.mods = s->d_mods;
+        fp.lut_words = s->lut_words; fp.pool_offset = s->pool_offset; fp.tile_offset = s->tile_offset; fp.lut = s->d_lut;
+        fp.tiles_x = s->lf_tiles_x; fp.tiles_y = s->lf_tiles_y;
+        void* fargs[] = {&fp};
+        int rcf = launch(s, s->f_light_fused, dim3(s->lf_grid), dim3(256), fargs, (unsigned)s->lf_smem);
+        if (rcf) return rcf;
+        s->cur ^= 1;
+        s->lcur ^= 1;
+        return SE_OK;
     }
     p.in = s->cells[s->cur];
     p.out = s->cells[s->cur ^ 1];
@@ -707,6 +734,52 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
                     SE_CU_S(driver().FuncSetAttribute(s->f_lut_global_census, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
                                                       s->pop_offset + ((s->pop_words * 4 + 15) & ~15)));
                     s->running = true;
+                }
+            }
+        }
+    }
+    // ---- K3f (experimental): table step + override + lighting in one kernel --------------------------------
+    if ((prm->flags & SE_FLAG_FUSED_LIGHT_EXPERIMENTAL) && s->lighting && rules->cr.lut_eligible) {
+        // the table is built exactly as for K1b above (kept separate so that the default path is untouched)
+        const int N = rules->cr.tables.n_materials;
+        const int N4 = N * N * N * N;
+        const int POOL_MAX = 4095;
+        const size_t pool_off = ((size_t)N4 * 2 + 7) / 8 * 8;
+        const size_t lut_cap = pool_off + (size_t)POOL_MAX * 8 + 16;
+        unsigned* d_counter = nullptr;
+        CUfunction f_build = nullptr;
+        SE_CU_S(driver().ModuleGetFunction(&f_build, s->mod, "se_build_lut"));
+        SE_CU_S(driver().ModuleGetFunction(&s->f_light_fused, s->mod, "se_light_fused"));
+        SE_CUDA_S(cudaMalloc(&s->d_lut, lut_cap));
+        SE_CUDA_S(cudaMalloc(&d_counter, sizeof(unsigned)));
+        SE_CUDA_S(cudaMemsetAsync(s->d_lut, 0, lut_cap, s->stream));
+        SE_CUDA_S(cudaMemsetAsync(d_counter, 0, sizeof(unsigned), s->stream));
+        unsigned short* base = reinterpret_cast<unsigned short*>(s->d_lut);
+        void* pool = reinterpret_cast<char*>(s->d_lut) + pool_off;
+        void* bargs[] = {&base, &pool, &d_counter};
+        SE_TRY(launch(s, f_build, dim3((N4 + 255) / 256), dim3(256), bargs));
+        unsigned n_pool = 0;
+        SE_CUDA_S(cudaMemcpyAsync(&n_pool, d_counter, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
+        SE_CUDA_S(cudaStreamSynchronize(s->stream));
+        cudaFree(d_counter);
+        if ((int)n_pool <= POOL_MAX) {
+            const size_t lut_bytes = pool_off + (size_t)n_pool * 8;
+            const int tile_h = 8 * rules->light_rows;
+            s->pool_offset = (int)pool_off;
+            s->lut_words = (int)((lut_bytes + 3) / 4);
+            s->tile_offset = (int)((lut_bytes + 15) / 16 * 16);
+            s->lf_smem = s->tile_offset + (tile_h + 2) * 34 * 16 + (tile_h + 2) * 36;     // table + term[] + ids[] (SE_LT_TERMS, SE_LF_IDS_BYTES)
+            s->lf_tiles_x = (s->W + 31) / 32;
+            s->lf_tiles_y = (s->Hl + tile_h - 1) / tile_h;
+            int n_sm = 0, occ = 0, smem_optin = 0;
+            SE_CUDA_S(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device));
+            SE_CUDA_S(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
+            if (s->lf_smem <= smem_optin) {
+                SE_CU_S(driver().FuncSetAttribute(s->f_light_fused, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->lf_smem));
+                SE_CU_S(driver().OccupancyMaxActiveBlocks(&occ, s->f_light_fused, 256, (size_t)s->lf_smem));
+                if (occ >= 1) {
+                    s->lf_grid = (int)std::min<long long>((long long)occ * n_sm, (long long)s->lf_tiles_x * s->lf_tiles_y);
+                    s->fused_light = true;
                 }
             }
         }

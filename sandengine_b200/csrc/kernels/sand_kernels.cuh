@@ -308,8 +308,15 @@ static __device__ __forceinline__ void se_light_stage(const SeLightParams& p, co
     }
 
 // phase 2, thread `tid` of 256: column tid & 31, rows 4 * (tid >> 5) .. + 3 of the tile
-template <bool INTERIOR>
-static __device__ __forceinline__ void se_light_compute(const SeLightParams& p, const unsigned* fat, const float4* term, int bx, int by, int tid) {
+// `new_id(idx, x, y, tile_row)` supplies the cell's material id AFTER this step: se_light reads it from new_cells,
+// the fused kernel takes it from its shared-memory tile (and stores it).
+struct SeNewIdFromGlobal {
+    const unsigned* new_cells;
+    __device__ __forceinline__ unsigned operator()(size_t idx, int, int, int, int) const { return new_cells[idx]; }
+};
+
+template <bool INTERIOR, class NewId>
+static __device__ __forceinline__ void se_light_compute(const SeLightParams& p, const unsigned* fat, const float4* term, int bx, int by, int tid, const NewId& new_id) {
     const int tx = tid & 31, row0 = (tid >> 5) * SE_LT_ROWS;
     const int x = bx * SE_LT_W + tx;
     if (!INTERIOR && x >= p.W) return;
@@ -323,7 +330,7 @@ static __device__ __forceinline__ void se_light_compute(const SeLightParams& p, 
         const float4 c0 = tp[(i + 2) * SE_LT_STRIDE], c1 = tp[(i + 2) * SE_LT_STRIDE + 1], c2 = tp[(i + 2) * SE_LT_STRIDE + 2];   // row below
         const int y = p.gy0 + yl;                                  // global row
         const size_t idx = (size_t)yl * p.W + x;
-        const unsigned id = p.new_cells[idx];
+        const unsigned id = new_id(idx, x, y, row0 + i, tx);
         const unsigned me = id < 255u ? id : 255u;
         float4 light;
         if (fat[me] & SE_F_EMISSIVE) {                             // :126-127
@@ -376,11 +383,11 @@ extern "C" __global__ void __launch_bounds__(256, SE_LT_MINCTAS) se_light(const 
     if (se_light_tile_is_interior(p, bx, by)) {
         se_light_stage<true>(p, fat_sm, term, bx, by, tid);
         __syncthreads();
-        se_light_compute<true>(p, fat_sm, term, bx, by, tid);
+        se_light_compute<true>(p, fat_sm, term, bx, by, tid, SeNewIdFromGlobal{p.new_cells});
     } else {
         se_light_stage<false>(p, fat_sm, term, bx, by, tid);
         __syncthreads();
-        se_light_compute<false>(p, fat_sm, term, bx, by, tid);
+        se_light_compute<false>(p, fat_sm, term, bx, by, tid, SeNewIdFromGlobal{p.new_cells});
     }
 }
 
@@ -715,6 +722,114 @@ static __device__ __forceinline__ void se_census_block(int* hist, se_pop_t pop, 
     if ((cm & 8u) && nd != rd) { atomicAdd(hist + (rd < 255u ? rd : 255u), -1); atomicAdd(hist + nd, 1); }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K3f (EXPERIMENTAL, SE_FLAG_FUSED_LIGHT_EXPERIMENTAL; off by default): Margolus step + modification override +
+// lighting relaxation in ONE pass over the grid for table-eligible rule sets.  se_light already stages the old ids
+// of its 32 x SE_LT_H tile and a one-cell ring; every 2x2 block that covers a tile cell lies inside tile + ring
+// (the block offset is 0 or 1), so the CTA can run the transition table on those ids in shared memory, apply the
+// modification override per cell, and feed the new ids straight into the light combine: the separate step kernel
+// (K1a ping-pong) and one read of the id buffer disappear (48 -> 40 physical bytes per cell).
+// Blocks cut by a tile edge are evaluated by both CTAs (deterministic: RAND depends on position and frame only).
+// Three per-thread phases, run CTA by CTA on the host by tests/emu:
+//   stage  : old id (clamped; WALL outside the grid; MISSING inside the grid but outside the local buffer) and
+//            the light term of every tile + ring cell
+//   blocks : transition table on the blocks covering the tile, in place in the shared id array
+//   compute: override, store the new id, combine the eight neighbour terms (se_light_compute)
+// ---------------------------------------------------------------------------------------------
+#define SE_LF_IDS_STRIDE (SE_LT_W + 4)
+#define SE_LF_IDS_BYTES ((SE_LT_H + 2) * SE_LF_IDS_STRIDE)
+#define SE_LF_MISSING 0xFFu
+
+struct SeFusedParams {
+    SeLightParams lp;        // old_cells: ids before the step; new_cells: ids after the step (WRITTEN by this kernel)
+    int frame;
+    int n_mods;              // already cut at the first mod_size == 0
+    const SeMod* mods;
+    int lut_words, pool_offset;
+    int tile_offset;         // byte offset of term[] in dynamic shared memory (behind the staged table, 16-aligned)
+    const unsigned* lut;
+    int tiles_x, tiles_y;
+};
+
+// can record m touch a cell of the rectangle?  (both shapes lie inside the square |dx|,|dy| <= size; negative sizes never match)
+static __device__ __forceinline__ bool se_mod_touches(const SeMod& m, int x_lo, int x_hi, int y_lo, int y_hi) {
+    return m.size >= 0 && m.px + m.size >= x_lo && m.px - m.size <= x_hi && m.py + m.size >= y_lo && m.py - m.size <= y_hi;
+}
+
+template <bool INTERIOR>
+static __device__ __forceinline__ void se_fused_stage_one(const SeLightParams& p, const unsigned* fat, float4* term, unsigned char* ids,
+                                                          int bx, int by, int i, int j) {
+    const int nx = bx * SE_LT_W - 1 + j, nyl = by * SE_LT_H - 1 + i, ny = p.gy0 + nyl;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    unsigned idb;
+    const bool in_grid = INTERIOR || (nx >= 0 && nx < p.W && ny >= 0 && ny < p.Hg);
+    if (INTERIOR || (in_grid && nyl >= 0 && nyl < p.Hl)) {
+        const size_t nidx = (size_t)nyl * p.W + nx;
+        const unsigned id = p.old_cells[nidx];
+        const float4 li = p.light_in[nidx];
+        const unsigned nf = fat[id < 255u ? id : 255u];
+        const float keep = (nf & SE_F_OBSTACLE) ? 0.0f : 1.0f;
+        const float la = li.w;
+        v = make_float4((li.x * keep) * la, (li.y * keep) * la, (li.z * keep) * la, la);
+        idb = id < SE_N_MATERIALS ? id : 1u;                       // unknown ids read as NULL (gen/materials.glsl:79-86)
+    } else {
+        idb = in_grid ? SE_LF_MISSING : 2u;                        // WALL outside the grid (operations.glsl:45-51)
+    }
+    term[i * SE_LT_STRIDE + j] = v;
+    ids[i * SE_LF_IDS_STRIDE + j] = (unsigned char)idb;
+}
+
+template <bool INTERIOR>
+static __device__ __forceinline__ void se_fused_stage(const SeLightParams& p, const unsigned* fat, float4* term, unsigned char* ids, int bx, int by, int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int it = 0; it < (SE_LT_H + 2 + 7) / 8; ++it) {
+        const int i = warp + 8 * it;
+        if (i < SE_LT_H + 2) se_fused_stage_one<INTERIOR>(p, fat, term, ids, bx, by, i, lane + 1);
+    }
+    if (tid < 2 * (SE_LT_H + 2)) se_fused_stage_one<INTERIOR>(p, fat, term, ids, bx, by, tid >> 1, (tid & 1) * (SE_LT_W + 1));
+}
+
+// the blocks that cover the tile: (SE_LT_W/2 + ox) x (SE_LT_H/2 + oy) of them, in place in ids[]
+static __device__ __forceinline__ void se_fused_blocks(const SeLightParams& p, int frame, se_tab_t tab, unsigned pool_off, const unsigned* fat,
+                                                       unsigned char* ids, int bx, int by, int tid) {
+    int ox, oy;
+    se_margolus_offset(frame, ox, oy);
+    const int nbx = SE_LT_W / 2 + ox, nby = SE_LT_H / 2 + oy;
+    const unsigned fterm = (unsigned)frame * (2131u * 2131u);
+    for (int b = tid; b < nbx * nby; b += 256) {
+        const int bj = b / nbx, bi = b - bj * nbx;
+        const int cx = 2 * bi + 1 - ox, cy = 2 * bj + 1 - oy;      // ring coordinates of the block's top-left cell
+        const int x0 = bx * SE_LT_W - 1 + cx, y0 = p.gy0 + by * SE_LT_H - 1 + cy;
+        unsigned char* q = ids + cy * SE_LF_IDS_STRIDE + cx;
+        const unsigned a = q[0], bb = q[1], c = q[SE_LF_IDS_STRIDE], d = q[SE_LF_IDS_STRIDE + 1];
+        if ((a | bb | c | d) & 0x80u) continue;                    // a row of the block is not in the local buffer: skipped (see K1a)
+        const unsigned v = a | (bb << 8) | (c << 16) | (d << 24);
+        const unsigned seed = (unsigned)x0 * 461u + (unsigned)y0 * 2131u + fterm;
+        const unsigned nv = se_block_lut(v, seed, x0, y0, frame, tab, pool_off, fat);
+        q[0] = (unsigned char)(nv & 0xFFu); q[1] = (unsigned char)((nv >> 8) & 0xFFu);
+        q[SE_LF_IDS_STRIDE] = (unsigned char)((nv >> 16) & 0xFFu); q[SE_LF_IDS_STRIDE + 1] = (unsigned char)(nv >> 24);
+    }
+}
+
+// new id of a tile cell: the table's result, overridden by the (culled) modification list, stored to the id buffer
+template <bool HAS_MODS>
+struct SeNewIdFused {
+    const unsigned char* ids;
+    unsigned* new_cells;
+    const SeMod* mods;
+    int n_mods;
+    __device__ __forceinline__ unsigned operator()(size_t idx, int x, int y, int tile_row, int tile_col) const {
+        unsigned id = ids[(tile_row + 1) * SE_LF_IDS_STRIDE + tile_col + 1];
+        if (HAS_MODS) {
+            unsigned m;
+            if (se_mod_lookup(mods, n_mods, x, y, m)) id = m;
+        }
+        new_cells[idx] = id;
+        return id;
+    }
+};
+
 #ifndef SE_HOST_EMU
 // one Margolus sub-step over the whole tile; OX (column phase) is a template parameter so that the
 // aligned 16-bit and the byte access variants are separate straight-line loops
@@ -1028,6 +1143,64 @@ extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_
 extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_step_lut_global_census(const SeLutStepParams p, const SeLutCensusParams cx) {
     __shared__ int hist_sm[256];
     se_k1c_body<true>(p, cx, hist_sm);
+}
+
+#ifndef SE_LF_MINCTAS
+#define SE_LF_MINCTAS 3
+#endif
+extern "C" __global__ void __launch_bounds__(256, SE_LF_MINCTAS) se_light_fused(const SeFusedParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ unsigned fat_sm[256];
+    __shared__ SeMod mods_sm[256];
+    __shared__ int warp_counts[8];
+    const int tid = threadIdx.x;
+    unsigned smem_sa;
+    asm volatile("mov.u32 %0, %1;" : "=r"(smem_sa) : "r"((unsigned)__cvta_generic_to_shared(smem)));
+    {
+        const uint4* lut4 = reinterpret_cast<const uint4*>(p.lut);
+        const int n4 = (p.lut_words + 3) >> 2;
+        for (int i = tid; i < n4; i += blockDim.x) {
+            const uint4 v = __ldg(lut4 + i);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(smem_sa + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        }
+    }
+    fat_sm[tid] = se_fat_table[tid];
+    __syncthreads();
+    const se_tab_t tab = smem_sa;
+    float4* term = reinterpret_cast<float4*>(smem + p.tile_offset);
+    unsigned char* ids = reinterpret_cast<unsigned char*>(term + SE_LT_TERMS);
+    const int n_tiles = p.tiles_x * p.tiles_y;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {        // persistent: the table is staged once per CTA
+        const int by = t / p.tiles_x, bx = t - by * p.tiles_x;
+        int n_cull = 0;
+        if (p.n_mods > 0) {
+            // cull the modification list against this tile, keeping the order (last match wins, falling_sand.glsl:764-773)
+            const int x_lo = bx * SE_LT_W, y_lo = p.lp.gy0 + by * SE_LT_H;
+            bool keep = false;
+            SeMod m;
+            if (tid < p.n_mods) { m = p.mods[tid]; keep = se_mod_touches(m, x_lo, x_lo + SE_LT_W - 1, y_lo, y_lo + SE_LT_H - 1); }
+            const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
+            const int warp = tid >> 5, lane = tid & 31;
+            if (lane == 0) warp_counts[warp] = __popc(ballot);
+            __syncthreads();
+            int base = 0;
+            for (int w = 0; w < 8; ++w) { if (w < warp) base += warp_counts[w]; n_cull += warp_counts[w]; }
+            if (keep) mods_sm[base + __popc(ballot & ((1u << lane) - 1u))] = m;
+        }
+        if (se_light_tile_is_interior(p.lp, bx, by)) se_fused_stage<true>(p.lp, fat_sm, term, ids, bx, by, tid);
+        else se_fused_stage<false>(p.lp, fat_sm, term, ids, bx, by, tid);
+        __syncthreads();
+        se_fused_blocks(p.lp, p.frame, tab, (unsigned)p.pool_offset, fat_sm, ids, bx, by, tid);
+        __syncthreads();
+        if (se_light_tile_is_interior(p.lp, bx, by)) {
+            if (n_cull) se_light_compute<true>(p.lp, fat_sm, term, bx, by, tid, SeNewIdFused<true>{ids, const_cast<unsigned*>(p.lp.new_cells), mods_sm, n_cull});
+            else se_light_compute<true>(p.lp, fat_sm, term, bx, by, tid, SeNewIdFused<false>{ids, const_cast<unsigned*>(p.lp.new_cells), mods_sm, 0});
+        } else {
+            if (n_cull) se_light_compute<false>(p.lp, fat_sm, term, bx, by, tid, SeNewIdFused<true>{ids, const_cast<unsigned*>(p.lp.new_cells), mods_sm, n_cull});
+            else se_light_compute<false>(p.lp, fat_sm, term, bx, by, tid, SeNewIdFused<false>{ids, const_cast<unsigned*>(p.lp.new_cells), mods_sm, 0});
+        }
+        __syncthreads();                                           // the next tile overwrites term[] / ids[] / mods_sm[]
+    }
 }
 
 extern "C" __global__ void __launch_bounds__(256) se_build_popbits(unsigned* __restrict__ popbits) {

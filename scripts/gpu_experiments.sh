@@ -2,7 +2,7 @@
 #   gpurun --timeout 600 -- 'bash scripts/gpu_experiments.sh'
 mkdir -p gpurun_out
 # 1. running census (SE_FLAG_RUNNING_CENSUS): correctness, then the e2e leg with and without it
-SE_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "running_census or lit_strips" 2>&1 | tail -5
+SE_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "running_census or lit_strips or fused_light" 2>&1 | tail -5
 timeout 200 python bench.py --steps 400 --warmup 16 --no-cpu-baseline > gpurun_out/exp_e2e_base.json 2> gpurun_out/exp_e2e_base.err
 timeout 200 python bench.py --steps 400 --warmup 16 --no-cpu-baseline --running-census > gpurun_out/exp_e2e_running.json 2> gpurun_out/exp_e2e_running.err
 python - <<'PY'
@@ -21,3 +21,7 @@ timeout 120 ncu --set full --clock-control none --import-source on -k regex:se_l
 python scripts/light_probe.py 8192 48
 # 3. se_light tile-height / occupancy variants (rule-compile-time env; all three tile heights are host-checked)
 for v in "SE_LT_ROWS=2" "SE_LT_ROWS=8" "SE_LT_MINCTAS=3" "SE_LT_MINCTAS=5"; do echo "$v"; env $v python scripts/light_probe.py 8192 48; done
+# 4. fused step + lighting kernel (K3f) against the two-kernel path
+SE_FUSED=1 python scripts/light_probe.py 8192 48
+SE_FUSED=1 python scripts/light_probe.py 4096 100
+SE_FUSED=1 timeout 120 ncu --set full --clock-control none --import-source on -k regex:se_light_fused -s 16 -c 1 -o gpurun_out/prof_r2_light_fused python scripts/light_probe.py 8192 12 > /dev/null 2>&1

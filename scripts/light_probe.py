@@ -1,8 +1,9 @@
 """Per-frame path with lighting + modifications (BASELINE configs[3] shape), short: for ncu launch lists / captures.
-  python scripts/light_probe.py [S] [frames]
+  python scripts/light_probe.py [S] [frames]          (env SE_FUSED=1: the experimental one-kernel path K3f)
 Prints CUDA-event time per frame; under ncu the kernels of interest are se_step_pingpong_mods and se_light.
 """
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -20,7 +21,8 @@ S = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 24
 rules = se.parse_path(REPO / "data" / "materials.yaml")
 sel = [m.id for m in rules.selectable_materials]
-sim = se.Simulation(rules, (S, S), lighting=True)
+FUSED = os.environ.get("SE_FUSED") == "1"
+sim = se.Simulation(rules, (S, S), lighting=True, fused_light=FUSED)
 st = torch.cuda.Stream(); torch.cuda.set_stream(st); sim.set_stream(st.cuda_stream)
 sim.upload_cells(synthetic_grid(S, S, 4)); sim.upload_light(np.zeros((S, S, 4), np.float32)); sim.params.frame = 1
 mods = [frame_mods(k, S, S, sel) for k in range(K + 8)]
@@ -32,5 +34,5 @@ for k in range(8, K + 8):
     sim.push_modifications(mods[k]); sim.run()
 e1.record(st); torch.cuda.synchronize()
 t = e0.elapsed_time(e1) / 1e3
-print(json.dumps({"S": S, "frames": K, "ms_per_frame": round(t / K * 1e3, 4), "gcell_per_s": round(S * S * K / t / 1e9, 1),
+print(json.dumps({"S": S, "frames": K, "fused": FUSED, "ms_per_frame": round(t / K * 1e3, 4), "gcell_per_s": round(S * S * K / t / 1e9, 1),
                   "frac_40B": round(40.0 * S * S * K / t / 1e9 / 6549.8, 4)}))

@@ -70,10 +70,10 @@ extern "C" void emu_light(const uint32_t* old_cells, const uint32_t* new_cells, 
             if (se_light_tile_is_interior(p, bx, by)) {
                 ++n_int;
                 for (int tid = 0; tid < 256; ++tid) se_light_stage<true>(p, se_fat_table, term.data(), bx, by, tid);
-                for (int tid = 0; tid < 256; ++tid) se_light_compute<true>(p, se_fat_table, term.data(), bx, by, tid);
+                for (int tid = 0; tid < 256; ++tid) se_light_compute<true>(p, se_fat_table, term.data(), bx, by, tid, SeNewIdFromGlobal{p.new_cells});
             } else {
                 for (int tid = 0; tid < 256; ++tid) se_light_stage<false>(p, se_fat_table, term.data(), bx, by, tid);
-                for (int tid = 0; tid < 256; ++tid) se_light_compute<false>(p, se_fat_table, term.data(), bx, by, tid);
+                for (int tid = 0; tid < 256; ++tid) se_light_compute<false>(p, se_fat_table, term.data(), bx, by, tid, SeNewIdFromGlobal{p.new_cells});
             }
         }
     if (n_interior_ctas) *n_interior_ctas = n_int;
@@ -122,6 +122,39 @@ extern "C" void emu_step_lut_inplace(uint32_t* cells, int W, int H, int frame) {
         }
 }
 
+// ---- K3f (experimental fused step + modifications + lighting): the three per-thread phases, CTA by CTA ----
+extern "C" void emu_light_fused(const uint32_t* old_cells, uint32_t* new_cells, const float* light_in, float* light_out,
+                                int W, int Hl, int gy0, int Hg, int frame, const SeMod* mods, int n_mods) {
+    SeLightParams p{old_cells, new_cells, reinterpret_cast<const float4*>(light_in), reinterpret_cast<float4*>(light_out), W, Hl, gy0, Hg};
+    std::vector<float4> term(SE_LT_TERMS);
+    std::vector<unsigned char> ids(SE_LF_IDS_BYTES);
+    std::vector<SeMod> culled(256);
+    for (int by = 0; by < (Hl + SE_LT_H - 1) / SE_LT_H; ++by)
+        for (int bx = 0; bx < (W + SE_LT_W - 1) / SE_LT_W; ++bx) {
+            for (auto& t : term) t = make_float4(NAN, NAN, NAN, NAN);
+            for (auto& b : ids) b = 0xEE;                                       // poison: must be staged before use
+            int n_cull = 0;
+            const int x_lo = bx * SE_LT_W, y_lo = gy0 + by * SE_LT_H;
+            for (int i = 0; i < n_mods; ++i)
+                if (se_mod_touches(mods[i], x_lo, x_lo + SE_LT_W - 1, y_lo, y_lo + SE_LT_H - 1)) culled[n_cull++] = mods[i];
+            const bool interior = se_light_tile_is_interior(p, bx, by);
+            for (int tid = 0; tid < 256; ++tid) {
+                if (interior) se_fused_stage<true>(p, se_fat_table, term.data(), ids.data(), bx, by, tid);
+                else se_fused_stage<false>(p, se_fat_table, term.data(), ids.data(), bx, by, tid);
+            }
+            for (int tid = 0; tid < 256; ++tid) se_fused_blocks(p, frame, g_table.data(), g_pool_off, se_fat_table, ids.data(), bx, by, tid);
+            for (int tid = 0; tid < 256; ++tid) {
+                if (interior) {
+                    if (n_cull) se_light_compute<true>(p, se_fat_table, term.data(), bx, by, tid, SeNewIdFused<true>{ids.data(), new_cells, culled.data(), n_cull});
+                    else se_light_compute<true>(p, se_fat_table, term.data(), bx, by, tid, SeNewIdFused<false>{ids.data(), new_cells, culled.data(), 0});
+                } else {
+                    if (n_cull) se_light_compute<false>(p, se_fat_table, term.data(), bx, by, tid, SeNewIdFused<true>{ids.data(), new_cells, culled.data(), n_cull});
+                    else se_light_compute<false>(p, se_fat_table, term.data(), bx, by, tid, SeNewIdFused<false>{ids.data(), new_cells, culled.data(), 0});
+                }
+            }
+        }
+}
+
 // ---- running census (experimental): popbits filter + per-block deltas, decisions exactly as in se_k1c_body<true> ----
 static std::vector<unsigned> g_pop;
 extern "C" int emu_build_popbits(void) {
@@ -166,6 +199,7 @@ extern "C" void emu_step_lut_census(uint32_t* cells, int W, int H, int frame, in
     for (int i = 0; i < 256; ++i) census256[i] += hist[i];
 }
 #else
+extern "C" void emu_light_fused(const uint32_t*, uint32_t*, const float*, float*, int, int, int, int, int, const void*, int) {}
 extern "C" int emu_build_popbits(void) { return -2; }
 extern "C" void emu_step_lut_census(uint32_t*, int, int, int, int, int, long long*, long long*) {}
 extern "C" int emu_build_lut(void) { return -2; }

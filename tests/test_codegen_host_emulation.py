@@ -219,3 +219,71 @@ def test_lit_strip_schedule_on_host(native_lib, tmp_path_factory, default_rules,
                 own = slice(L["gt"], L["gt"] + L["e"] - L["b"])
                 assert np.array_equal(L["cells"][own], ref_c[L["b"]:L["e"]]), f"{w}x{h}/{world} ids after {done} steps"
                 assert np.array_equal(L["light"][own].view(np.uint32), ref_l[L["b"]:L["e"]].view(np.uint32)), f"{w}x{h}/{world} light after {done} steps"
+
+
+def _stage_mods(se, mods, n_materials):
+    """What se_sim_step stages for the kernels: the first min(len, 256) records up to the first mod_size == 0, unknown
+    material ids replaced by NULL (api.cpp)."""
+    out = np.zeros(len(mods), se.MOD_DTYPE)
+    n = 0
+    for m in mods[:256]:
+        if m["mod_size"] == 0:
+            break
+        out[n] = m
+        if not (0 <= m["mod_matID"] < n_materials):
+            out[n]["mod_matID"] = 1
+        n += 1
+    return out[:n]
+
+
+@pytest.mark.parametrize("rows", [4, 8])
+def test_fused_step_light_kernel_phases_on_host(native_lib, tmp_path_factory, default_rules, oracle, rows):
+    """EXPERIMENTAL K3f (se_light_fused): table step + modification override + lighting in one pass, its three per-thread
+    phases run CTA by CTA on the host: ids AND light bit-identical to the oracle's per-cell form -- all Margolus phases,
+    ragged sizes, WALL / NULL / unknown ids, modifications (incl. unknown material, size 0 mid-list), strips."""
+    import sandengine_b200 as se
+    lib = build_emu(tmp_path_factory, f"fused{rows}", default_rules, defs=(f"-DSE_LT_ROWS={rows}",))
+    lib.emu_light_fused.argtypes = [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p, C.c_int]
+    assert lib.emu_build_lut() > 0
+    n_mat = len(default_rules.materials)
+    rng = np.random.default_rng(17)
+    for (w, h, seed, steps, with_mods) in [(160, 128, 1, 9, True), (33, 17, 2, 6, True), (97, 99, 3, 5, False), (2, 2, 4, 4, False),
+                                           (100, 200, 7, 5, True), (64, 64, 8, 8, True)]:
+        cells = synthetic_grid(w, h, seed)
+        if seed == 8:
+            cells[rng.integers(0, h, 40), rng.integers(0, w, 40)] = 2
+            cells[rng.integers(0, h, 15), rng.integers(0, w, 15)] = 1
+            cells[3, 3] = 77; cells[9, 5] = 4000000000
+        light = rng.random((h, w, 4), dtype=np.float32)
+        light[rng.random((h, w)) < 0.2, 3] = 0.0
+        frame = 1
+        for s in range(steps):
+            frame += 1
+            mods = np.zeros(0, se.MOD_DTYPE)
+            if with_mods and s % 2 == 0:
+                mods = np.zeros(6, se.MOD_DTYPE)
+                for i in range(6):
+                    mods[i]["position"] = (int(rng.integers(-5, w + 5)), int(rng.integers(-5, h + 5)))
+                    mods[i]["mod_shape"] = int(rng.integers(0, 2)); mods[i]["mod_size"] = int(rng.integers(1, 12))
+                    mods[i]["mod_matID"] = int(rng.integers(0, n_mat))
+                mods[2]["mod_matID"] = 99                       # unknown id: NULL cancels an earlier hit
+                if s % 4 == 0:
+                    mods[4]["mod_size"] = 0                     # the shader stops at the first size-0 record
+            want_c, want_l, _ = oracle.step_cells(cells, frame, light, mods)
+            staged = _stage_mods(se, mods, n_mat)
+            got_c = np.full_like(cells, 12345)
+            got_l = np.full_like(light, np.nan)
+            lib.emu_light_fused(cells.ctypes.data, got_c.ctypes.data, light.ctypes.data, got_l.ctypes.data, w, h, 0, h, frame,
+                                staged.ctypes.data if len(staged) else None, len(staged))
+            assert np.array_equal(got_c, want_c), f"{w}x{h} step {s + 1}: ids"
+            assert np.array_equal(got_l.view(np.uint32), want_l.view(np.uint32)), f"{w}x{h} step {s + 1}: light"
+            if w == 160 and s == 1:
+                # a strip: local rows [32, 102); ids two rows in and light one row in from the buffer edges equal the full grid
+                gy0, hl = 32, 70
+                pc = np.full((hl, w), 12345, np.uint32); pl = np.full((hl, w, 4), np.nan, np.float32)
+                lib.emu_light_fused(np.ascontiguousarray(cells[gy0:gy0 + hl]).ctypes.data, pc.ctypes.data,
+                                    np.ascontiguousarray(light[gy0:gy0 + hl]).ctypes.data, pl.ctypes.data, w, hl, gy0, h, frame,
+                                    staged.ctypes.data if len(staged) else None, len(staged))
+                assert np.array_equal(pc[2:-2], want_c[gy0 + 2:gy0 + hl - 2])
+                assert np.array_equal(pl[2:-2].view(np.uint32), want_l[gy0 + 2:gy0 + hl - 2].view(np.uint32))
+            cells, light = want_c, want_l

@@ -555,3 +555,27 @@ def test_lit_strips_experimental(se, default_rules, oracle, n_strips, halo, w, h
     for s in sims: s.close()
     assert np.array_equal(got, ref)
     assert np.abs(gotL - refL).max() <= LIGHT_ATOL
+
+
+@pytest.mark.skipif(os.environ.get("SE_TEST_EXPERIMENTAL") != "1",
+                    reason="EXPERIMENTAL fused step + lighting kernel (SE_FLAG_FUSED_LIGHT_EXPERIMENTAL): not yet validated on a GPU")
+def test_fused_light_experimental(se, default_rules, oracle):
+    """se_light_fused: ids bit-exact and light within tolerance against the oracle, with modifications, frame 1 included."""
+    rng = np.random.default_rng(29)
+    for (w, h, steps, frame0) in [(200, 150, 24, 1), (80, 64, 30, 1), (33, 17, 10, 0), (516, 130, 12, 1)]:
+        g = synthetic_grid(w, h, 31)
+        g[rng.integers(0, h, 20), rng.integers(0, w, 20)] = 2
+        g[rng.integers(0, h, 10), rng.integers(0, w, 10)] = 1
+        L0 = rng.random((h, w, 4), dtype=np.float32)
+        L0[rng.random((h, w)) < 0.2, 3] = 0.0
+        mods = [make_mods(se, s, 11, w, h, rng) if s % 2 else np.zeros(0, se.MOD_DTYPE) for s in range(steps)]
+        ref, refL, _ = oracle.run(g, frame0, steps, light=L0, mods_per_step=mods)
+        sim = se.Simulation(default_rules, (w, h), lighting=True, fused_light=True)
+        sim.upload_cells(g); sim.upload_light(L0); sim.params.frame = frame0
+        for s in range(steps):
+            if len(mods[s]): sim.push_modifications(mods[s])
+            sim.run()
+        got, gotL = sim.download_cells(), sim.download_light()
+        sim.close()
+        assert np.array_equal(got, ref), (w, h)
+        assert np.abs(gotL - refL).max() <= LIGHT_ATOL, (w, h)
