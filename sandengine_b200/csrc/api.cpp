@@ -348,13 +348,12 @@ int guard_buffer_write(se_sim* s, int buf) {
 int launch(se_sim* s, CUfunction f, dim3 grid, dim3 block, void** args, unsigned smem = 0, bool cooperative = false) {
     if (cooperative) {
         CUresult r = driver().LaunchCooperativeKernel(f, grid.x, grid.y, grid.z, block.x, block.y, block.z, smem, (CUstream)s->stream, args);
-        if (r == CUDA_ERROR_COOPERATIVE_LAUNCH_TOO_LARGE) {
-            // the context can hold fewer CTAs than the occupancy query promised (e.g. an MPS partition): the
-            // grid is still <= occupancy x SMs, so fall back to a plain launch of the same grid
+        if (r != CUDA_SUCCESS) {
+            // e.g. CUDA_ERROR_COOPERATIVE_LAUNCH_TOO_LARGE when the context can hold fewer CTAs than the occupancy
+            // query promised (an MPS partition), or a driver without support: the grid is still <= occupancy x SMs,
+            // so the same grid is launched normally from now on; a real launch error then surfaces from that call.
             s->coop = false;
             cooperative = false;
-        } else {
-            SE_CU(r);
         }
     }
     if (!cooperative)
