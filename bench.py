@@ -152,7 +152,23 @@ def cpu_port_rate(size_sample: int, budget_s: float, seed: int = SEED):
         if dt >= budget_s or steps >= 4000:
             break
     rate = size_sample * size_sample * steps / dt / 1e9
-    return {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port",
+    # the same code on ONE thread (SURVEY.md 8d asks for it): 1024^2, ~2 s
+    one = None
+    try:
+        import ctypes
+        gomp = ctypes.CDLL("libgomp.so.1")
+        gomp.omp_set_num_threads(1)
+        g1 = synthetic_grid(1024, 1024, seed)
+        f1 = orc.run_blocks(g1, 1, 2)
+        n1, t1 = 0, time.perf_counter()
+        while time.perf_counter() - t1 < 2.0:
+            f1 = orc.run_blocks(g1, f1, 4)
+            n1 += 4
+        one = round(1024 * 1024 * n1 / (time.perf_counter() - t1) / 1e9, 4)
+        gomp.omp_set_num_threads(cores)
+    except Exception:
+        pass
+    return {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port", "value_1_thread": one,
             "sample": f"{size_sample}x{size_sample} crop-sized grid of the same generator (seed {seed}), {steps} steps in {dt:.1f} s, "
                       f"C restatement of the reference shader (per-block form), gcc -O2 -fopenmp, {cores} threads; "
                       "llvmpipe GL 4.3 is not available in this image"}
