@@ -13,7 +13,9 @@
 int main(int argc, char** argv) {
     std::vector<std::string> seeds;
     for (int i = 2; i < argc; ++i) { std::ifstream f(argv[i]); std::stringstream ss; ss << f.rdbuf(); seeds.push_back(ss.str()); }
-    int n_iter = std::atoi(argv[1]); std::mt19937 rng(12345);
+    int n_iter = std::atoi(argv[1]);
+    const char* seed_env = std::getenv("FUZZ_SEED");          // default: the fixed seed the test suite uses
+    std::mt19937 rng(seed_env ? (unsigned)std::strtoul(seed_env, nullptr, 10) : 12345u);
     const char alphabet[] = " \n:-[]{},#'\"!|&<>=.()_abcdefSELFDOWNRIGHTLEFTmat0123456789\t%*+/";
     long ok = 0, perr = 0, other = 0;
     for (int it = 0; it < n_iter; ++it) {
@@ -34,6 +36,9 @@ int main(int argc, char** argv) {
             se::emit_glsl_materials(r); se::emit_glsl_rules(r);
             se::CompiledRules c = se::compile_rules(r);
             ++ok;
+            if (const char* dump = std::getenv("FUZZ_DUMP_DIR")) {     // keep accepted mutants (e.g. to push them through NVRTC)
+                std::ofstream(std::string(dump) + "/ok_" + std::to_string(it) + ".yaml") << s;
+            }
         } catch (const se::ParseError&) { ++perr; }
         catch (const std::exception& e) { ++other; if (other < 10) std::printf("other exception: %s\n", e.what()); }
     }
