@@ -22,8 +22,9 @@ def _rng(seed: int):
     return nxt
 
 
-def synthetic_rule_set(n_materials: int = 64, n_rules: int = 28, seed: int = 5):
-    """Returns (yaml_text, ids, mix): ids maps material names to ids, mix is a DEFAULT_MIX-style tuple for grids."""
+def synthetic_rule_set(n_materials: int = 64, n_rules: int = 28, seed: int = 5, kinds=("mirrored", "mirrored", "right", "left")):
+    """Returns (yaml_text, ids, mix): ids maps material names to ids, mix is a DEFAULT_MIX-style tuple for grids.
+    `kinds` is the cycle of rule kinds; ("mirrored",) with n_materials <= 12 gives a transition-table-eligible set."""
     rnd = _rng(seed)
     n_user_mats = n_materials - 3
     n_types = 14
@@ -52,7 +53,7 @@ def synthetic_rule_set(n_materials: int = 64, n_rules: int = 28, seed: int = 5):
     rules = []
     for k in range(n_rules):
         name = f"r{k:02d}"
-        kind = ["mirrored", "mirrored", "right", "left"][k % 4]
+        kind = kinds[k % len(kinds)]
         side, dside = ("LEFT", "DOWNLEFT") if kind == "left" else ("RIGHT", "DOWNRIGHT")
         tA, tB = types[rnd(n_types)]["name"], types[rnd(n_types)]["name"]
         mA, mB = mats[rnd(n_user_mats)]["name"], mats[rnd(n_user_mats)]["name"]

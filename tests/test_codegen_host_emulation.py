@@ -287,3 +287,23 @@ def test_fused_step_light_kernel_phases_on_host(native_lib, tmp_path_factory, de
                 assert np.array_equal(pc[2:-2], want_c[gy0 + 2:gy0 + hl - 2])
                 assert np.array_equal(pl[2:-2].view(np.uint32), want_l[gy0 + 2:gy0 + hl - 2].view(np.uint32))
             cells, light = want_c, want_l
+
+
+@pytest.mark.parametrize("seed,n_mat,n_rules,kinds", [(201, 7, 23, ("mirrored",)), (216, 12, 22, ("mirrored",)), (110, 20, 28, None)])
+def test_random_rule_sets_differential(native_lib, tmp_path_factory, seed, n_mat, n_rules, kinds):
+    """Random rule sets (scripts/diff_campaign.py runs many more): oracle == generated code on the host == transition
+    table (when the set is eligible: mirrored-only, <= 12 materials)."""
+    import sandengine_b200 as se
+    from oracle.build_oracle import load_oracle
+    from sandengine_b200.synth_rules import synthetic_rule_set
+    text, ids, mix = synthetic_rule_set(n_mat, n_rules, seed=seed, **({"kinds": kinds} if kinds else {}))
+    rules = se.parse_string(text)
+    assert ("#define SE_LUT_ELIGIBLE 1" in rules.cuda_header) == (kinds is not None)
+    orc = load_oracle(text)
+    lib = build_emu(tmp_path_factory, f"rand{seed}", rules)
+    g = synthetic_grid(48, 40, seed, mix=mix, ids=ids)
+    ref = compare(lib, orc, g, 60)
+    assert (ref != g).sum() > 500
+    if kinds is not None:
+        assert lib.emu_lut_eligible() == 1 and lib.emu_build_lut() >= 0
+        compare(lib, orc, g, 60, lut=True)

@@ -579,3 +579,27 @@ def test_fused_light_experimental(se, default_rules, oracle):
         sim.close()
         assert np.array_equal(got, ref), (w, h)
         assert np.abs(gotL - refL).max() <= LIGHT_ATOL, (w, h)
+
+
+@pytest.mark.skipif(os.environ.get("SE_TEST_EXPERIMENTAL") != "1",
+                    reason="added without a GPU at hand: run once with SE_TEST_EXPERIMENTAL=1 (scripts/gpu_experiments.sh), then un-gate")
+@pytest.mark.parametrize("seed,n_mat,n_rules", [(201, 7, 23), (216, 12, 22)])
+def test_table_kernels_on_random_eligible_rule_sets(se, seed, n_mat, n_rules):
+    """K1b / K1c with table-eligible rule sets OTHER than the default one (different material count, table size,
+    rand.y thresholds): random mirrored-only sets from synth_rules against the oracle."""
+    from oracle.build_oracle import load_oracle
+    from sandengine_b200.synth_rules import synthetic_rule_set
+    text, ids, mix = synthetic_rule_set(n_mat, n_rules, seed=seed, kinds=("mirrored",))
+    rules = se.parse_string(text)
+    assert "#define SE_LUT_ELIGIBLE 1" in rules.cuda_header
+    orc = load_oracle(text)
+    for (w, h, steps) in [(512, 300, 67), (260, 130, 33)]:
+        g = synthetic_grid(w, h, seed, mix=mix, ids=ids)
+        ref, _, _ = orc.run(g, 1, steps, blocks=True)
+        got, _, _ = run_gpu(se, rules, g, steps)                      # K1b
+        assert np.array_equal(got, ref), ("K1b", w, h)
+        sim = se.Simulation(rules, (w, h))
+        sim.upload_cells(g); sim.params.frame = 1
+        for _ in range(steps): sim.step(1)                            # K1c
+        assert np.array_equal(sim.download_cells(), ref), ("K1c", w, h)
+        sim.close()
