@@ -629,9 +629,10 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
     if (rules->cr.lut_eligible && !s->lighting && (s->W % 4) == 0 && prm->temporal_block != 1) {
         const int N = rules->cr.tables.n_materials, NCLS = (int)rules->cr.lut_thresholds.size() + 1;
         const int N4 = N * N * N * N;
+        const int NE = N4 * rules->cr.lut_tables;                 // table entries (two tables for Left/Right rule sets, experimental)
         const int POOL_MAX = 4095;
         (void)NCLS;
-        const size_t pool_off = ((size_t)N4 * 2 + 7) / 8 * 8;     // pool entries are 8 bytes {thr, A, B}
+        const size_t pool_off = ((size_t)NE * 2 + 7) / 8 * 8;     // pool entries are 8 bytes {thr, A, B}
         const size_t lut_cap = pool_off + (size_t)POOL_MAX * 8 + 16;
         unsigned* d_counter = nullptr;
         SE_CU_S(driver().ModuleGetFunction(&s->f_tiles, s->mod, "se_step_tiles"));
@@ -644,7 +645,7 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
         unsigned short* base = reinterpret_cast<unsigned short*>(s->d_lut);
         void* pool = reinterpret_cast<char*>(s->d_lut) + pool_off;
         void* bargs[] = {&base, &pool, &d_counter};
-        SE_TRY(launch(s, s->f_build_lut, dim3((N4 + 255) / 256), dim3(256), bargs));
+        SE_TRY(launch(s, s->f_build_lut, dim3((NE + 255) / 256), dim3(256), bargs));
         unsigned n_pool = 0;
         SE_CUDA_S(cudaMemcpyAsync(&n_pool, d_counter, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
         SE_CUDA_S(cudaStreamSynchronize(s->stream));
@@ -719,7 +720,7 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
                 SE_CUDA_S(cudaMalloc(&s->d_tile_done, (size_t)s->tiles_x * s->tiles_y * sizeof(unsigned)));
                 SE_CUDA_S(cudaMemsetAsync(s->d_tile_done, 0, (size_t)s->tiles_x * s->tiles_y * sizeof(unsigned), s->stream));
                 s->tiled = true;
-                if (prm->flags & SE_FLAG_RUNNING_CENSUS) {
+                if ((prm->flags & SE_FLAG_RUNNING_CENSUS) && rules->cr.lut_tables == 1) {
                     SE_CU_S(driver().ModuleGetFunction(&s->f_lut_global_census, s->mod, "se_step_lut_global_census"));
                     SE_CU_S(driver().ModuleGetFunction(&s->f_build_popbits, s->mod, "se_build_popbits"));
                     s->pop_words = (N4 + 31) / 32;
@@ -741,7 +742,7 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
     if ((prm->flags & SE_FLAG_FUSED_LIGHT_EXPERIMENTAL) && s->lighting && rules->cr.lut_eligible) {
         // the table is built exactly as for K1b above (kept separate so that the default path is untouched)
         const int N = rules->cr.tables.n_materials;
-        const int N4 = N * N * N * N;
+        const int N4 = N * N * N * N * rules->cr.lut_tables;
         const int POOL_MAX = 4095;
         const size_t pool_off = ((size_t)N4 * 2 + 7) / 8 * 8;
         const size_t lut_cap = pool_off + (size_t)POOL_MAX * 8 + 16;

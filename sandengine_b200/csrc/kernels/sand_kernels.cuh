@@ -494,6 +494,10 @@ extern "C" __global__ void __launch_bounds__(256) se_fill_cells(unsigned* cells,
 // =============================================================================================
 #if SE_LUT_ELIGIBLE
 #define SE_N4 (SE_N_MATERIALS * SE_N_MATERIALS * SE_N_MATERIALS * SE_N_MATERIALS)
+// SE_LUT_TWO_TABLES (rule sets with Left/Right rules, EXPERIMENTAL): entries [0, N^4) hold the unmirrored view, entries
+// [N^4, 2 N^4) the final result of the MIRRORED evaluation (swap, mirrored + left rules, swap back) of the same state,
+// so the lookup needs no byte swaps; without Left/Right rules one table serves both views through the mirror symmetry.
+#define SE_LUT_ENTRIES (SE_N4 * (SE_LUT_TWO_TABLES ? 2 : 1))
 #define SE_TILE_PW 256          // tile width in cells (= bytes); 64 words per row
 #define SE_LUT_POOL_MAX 4095
 #define SE_LUT_SLOW 0xFFFFu
@@ -507,6 +511,11 @@ struct SePoolEntry { unsigned thr; unsigned short a, b; };   // 8 bytes
 static __device__ __forceinline__ void se_build_lut_entry(int idx, unsigned short* __restrict__ base, SePoolEntry* __restrict__ pool,
                                                           unsigned* __restrict__ counter) {
     const int N = SE_N_MATERIALS;
+#if SE_LUT_TWO_TABLES
+    const int entry = idx;
+    const bool mirror_table = entry >= SE_N4;
+    idx = entry - (mirror_table ? SE_N4 : 0);
+#endif
     const unsigned ia = idx / (N * N * N), ib = (idx / (N * N)) % N, ic = (idx / N) % N, id = idx % N;
     unsigned short res[SE_LUT_NCLS];
     // class c <=> rand.y hash lane u1 in (U_{c-1}, U_c]  (U_{-1} = -1, U_{NCLS-1} = 2^32-1)
@@ -516,7 +525,11 @@ static __device__ __forceinline__ void se_build_lut_entry(int idx, unsigned shor
         unsigned s = se_fat_table[ia], r = se_fat_table[ib], d = se_fat_table[ic], dr = se_fat_table[id];
         if (idx != 0) {
             SeRand rnd;
+#if SE_LUT_TWO_TABLES
+            rnd.u[0] = mirror_table ? 0u : 0xFFFFFFFFu;                   // rand.x < 0.5: the mirrored evaluation, start to finish
+#else
             rnd.u[0] = 0xFFFFFFFFu;                                       // rand.x >= 0.5: unmirrored view
+#endif
             rnd.u[1] = cls == 0 ? 0u : se_lut_thresholds[cls - 1] + 1u;  // representative of the class
             rnd.u[2] = 0u; rnd.u[3] = 0u;
             se_block_with_rand(s, r, d, dr, rnd, 0, 0, 0);
@@ -524,6 +537,9 @@ static __device__ __forceinline__ void se_build_lut_entry(int idx, unsigned shor
         if ((s | r | d | dr) & SE_F_NOSWAP) noswap = true;
         res[cls] = (unsigned short)(SE_ID(s) | (SE_ID(r) << 4) | (SE_ID(d) << 8) | (SE_ID(dr) << 12));
     }
+#if SE_LUT_TWO_TABLES
+    idx = entry;                                                          // the slot written below
+#endif
     if (noswap) { base[idx] = SE_LUT_SLOW; return; }
     int n_breaks = 0;
 #pragma unroll
@@ -551,7 +567,7 @@ static __device__ __forceinline__ void se_build_lut_entry(int idx, unsigned shor
 extern "C" __global__ void __launch_bounds__(256) se_build_lut(unsigned short* __restrict__ base, SePoolEntry* __restrict__ pool,
                                                                unsigned* __restrict__ counter) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < SE_N4) se_build_lut_entry(idx, base, pool, counter);
+    if (idx < SE_LUT_ENTRIES) se_build_lut_entry(idx, base, pool, counter);
 }
 #endif
 
@@ -620,8 +636,12 @@ static __device__ __forceinline__ unsigned se_block_lut(unsigned v, unsigned see
                                                         se_tab_t tab, unsigned pool_off, const unsigned* __restrict__ fat_sm) {
     const unsigned u0 = se_hashi(seed * 213u);
     const bool mirror = u0 <= SE_MIRROR_UMAX;
+#if SE_LUT_TWO_TABLES
+    unsigned e = se_tab_u16(tab, (se_idx4(v) + (mirror ? (unsigned)SE_N4 : 0u)) * 2u);
+#else
     const unsigned vv = mirror ? __byte_perm(v, 0u, 0x2301) : v;
     unsigned e = se_tab_u16(tab, se_idx4(vv) * 2u);
+#endif
     if (e >= 0xF000u) {
         if (e != SE_LUT_SLOW) {
             const unsigned u1 = se_hashi(seed * 2131u);
@@ -641,8 +661,12 @@ static __device__ __forceinline__ unsigned se_block_lut(unsigned v, unsigned see
             return SE_ID(s) | (SE_ID(r) << 8) | (SE_ID(d) << 16) | (SE_ID(dr) << 24);
         }
     }
+#if SE_LUT_TWO_TABLES
+    return se_nibbles_to_bytes(e);
+#else
     const unsigned rr = se_nibbles_to_bytes(e);
     return mirror ? __byte_perm(rr, 0u, 0x2301) : rr;
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <sstream>
@@ -629,12 +630,19 @@ CompiledRules compile_rules(const ParsingResult& parsed) {
     std::sort(y_thr.begin(), y_thr.end());
     y_thr.erase(std::unique(y_thr.begin(), y_thr.end()), y_thr.end());
     // table budget: 2 mirror variants x N^4 states x 2 B must leave room for a tile in shared memory
-    out.lut_eligible = lut_ok && tb.n_materials <= 12 && y_thr.size() <= 15 && !out.have_left && !out.have_right;
+    // Left/Right rules break the mirror symmetry the single table relies on; with SE_LUT_LR=1 (EXPERIMENTAL, read when
+    // the rules are compiled) such sets get one table per view instead of falling back to the generated code.
+    const bool lr = out.have_left || out.have_right;
+    const char* lr_env = std::getenv("SE_LUT_LR");
+    const bool allow_lr = lr_env && std::string(lr_env) == "1";
+    out.lut_eligible = lut_ok && tb.n_materials <= 12 && y_thr.size() <= 15 && (!lr || allow_lr);
+    out.lut_tables = (out.lut_eligible && lr) ? 2 : 1;
     out.lut_thresholds = y_thr;
 
     std::ostringstream h;
     h << "// GENERATED by sandengine_b200 (CUDA C back end of the rule language). Do not edit.\n";
     h << "#define SE_LUT_ELIGIBLE " << (out.lut_eligible ? 1 : 0) << "\n";
+    h << "#define SE_LUT_TWO_TABLES " << (out.lut_tables == 2 ? 1 : 0) << "\n";
     h << "#define SE_LUT_NCLS " << (y_thr.size() + 1) << "\n";
     h << "// class c of a block = number of thresholds its rand.y hash lane exceeds (u1 > U_i)\n";
     h << "#define SE_LUT_CLASS(u1) (0u";

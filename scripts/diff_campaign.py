@@ -1,6 +1,6 @@
 """Tooling: differential campaign over RANDOM rule sets (sandengine_b200.synth_rules): the oracle's C restatement vs the
 generated CUDA rule code compiled for the host (tests/emu), plus the transition table when the set is eligible; every
-set also goes through NVRTC.   python scripts/diff_campaign.py <seed_lo> <seed_hi> [mirrored]
+set also goes through NVRTC.   python scripts/diff_campaign.py <seed_lo> <seed_hi> [mirrored|small]
 Round 1: 36 mixed sets (LEFT / RIGHT rules, 6-29 materials) and 36 mirrored-only, table-eligible sets (5-12 materials),
 80 steps each on a 48 x 40 grid: no mismatch."""
 import sys, ctypes as C, subprocess, tempfile, time
@@ -25,10 +25,11 @@ def build_emu(rules, d):
 
 lo, hi = int(sys.argv[1]), int(sys.argv[2])
 MIRRORED_ONLY = len(sys.argv) > 3 and sys.argv[3] == 'mirrored'
+SMALL = MIRRORED_ONLY or (len(sys.argv) > 3 and sys.argv[3] == 'small')     # 'small' + env SE_LUT_LR=1: two-table sets
 bad = 0
 for seed in range(lo, hi):
     rng = np.random.default_rng(seed)
-    n_mat = int(rng.integers(5, 13) if MIRRORED_ONLY else rng.integers(6, 30)); n_rules = int(rng.integers(4, 24) if MIRRORED_ONLY else rng.integers(4, 30))
+    n_mat = int(rng.integers(5, 13) if SMALL else rng.integers(6, 30)); n_rules = int(rng.integers(4, 24) if SMALL else rng.integers(4, 30))
     try:
         text, ids, mix = synthetic_rule_set(n_mat, n_rules, seed=seed, **({"kinds": ("mirrored",)} if MIRRORED_ONLY else {}))
     except Exception as e:

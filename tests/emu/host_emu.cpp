@@ -88,12 +88,12 @@ static unsigned g_pool_off = 0, g_pool_entries = 0;
 
 // returns the number of pool entries, or -1 on pool overflow
 extern "C" int emu_build_lut(void) {
-    g_pool_off = ((unsigned)SE_N4 * 2u + 7u) / 8u * 8u;
+    g_pool_off = ((unsigned)SE_LUT_ENTRIES * 2u + 7u) / 8u * 8u;
     g_table.assign(g_pool_off + (size_t)SE_LUT_POOL_MAX * 8, 0);
     g_pool_entries = 0;
     unsigned short* base = reinterpret_cast<unsigned short*>(g_table.data());
     SePoolEntry* pool = reinterpret_cast<SePoolEntry*>(g_table.data() + g_pool_off);
-    for (int idx = 0; idx < SE_N4; ++idx) se_build_lut_entry(idx, base, pool, &g_pool_entries);
+    for (int idx = 0; idx < SE_LUT_ENTRIES; ++idx) se_build_lut_entry(idx, base, pool, &g_pool_entries);
     return g_pool_entries > SE_LUT_POOL_MAX ? -1 : (int)g_pool_entries;
 }
 

@@ -307,3 +307,35 @@ def test_random_rule_sets_differential(native_lib, tmp_path_factory, seed, n_mat
     if kinds is not None:
         assert lib.emu_lut_eligible() == 1 and lib.emu_build_lut() >= 0
         compare(lib, orc, g, 60, lut=True)
+
+
+def test_two_table_lut_for_left_right_rule_sets(native_lib, tmp_path_factory, monkeypatch):
+    """EXPERIMENTAL (env SE_LUT_LR=1 when the rules are compiled): rule sets with Left/Right rules get one transition
+    table per view instead of falling back to the generated code.  Table build + lookup on the host vs the oracle for
+    random mixed rule sets (<= 12 materials) and for the Left/Right test YAMLs that use no pos / rand.x."""
+    import sandengine_b200 as se
+    from oracle.build_oracle import load_oracle
+    from sandengine_b200.synth_rules import synthetic_rule_set
+    cases = []
+    for seed, n_mat, n_rules in [(401, 9, 20), (402, 12, 24), (403, 6, 9)]:
+        text, ids, mix = synthetic_rule_set(n_mat, n_rules, seed=seed)      # mirrored + right + left rules
+        cases.append((f"synth{seed}", text, dict(mix=mix, ids=ids)))
+    cases.append(("base_ok", Y.BASE_OK, {}))
+    off = se.parse_string(cases[0][1])
+    assert "#define SE_LUT_ELIGIBLE 0" in off.cuda_header                     # default: not eligible
+    monkeypatch.setenv("SE_LUT_LR", "1")
+    n_two = 0
+    for name, text, gk in cases:
+        rules = se.parse_string(text)
+        if "#define SE_LUT_TWO_TABLES 1" not in rules.cuda_header:
+            continue                                                           # uses pos / other rand lanes: stays on the generated code
+        n_two += 1
+        orc = load_oracle(text)
+        lib = build_emu(tmp_path_factory, f"lr_{name}", rules)
+        assert lib.emu_lut_eligible() == 1 and lib.emu_build_lut() >= 0
+        for (w, h, seed, steps) in [(48, 40, 5, 80), (33, 17, 6, 40)]:
+            g = synthetic_grid(w, h, seed, **gk) if gk else (synthetic_grid(w, h, seed) % len(rules.materials)).astype(np.uint32)
+            ref = compare(lib, orc, g, steps, lut=True)
+            compare(lib, orc, g, steps)
+            assert (ref != g).sum() > 50, name
+    assert n_two >= 3

@@ -603,3 +603,27 @@ def test_table_kernels_on_random_eligible_rule_sets(se, seed, n_mat, n_rules):
         for _ in range(steps): sim.step(1)                            # K1c
         assert np.array_equal(sim.download_cells(), ref), ("K1c", w, h)
         sim.close()
+
+
+@pytest.mark.skipif(os.environ.get("SE_TEST_EXPERIMENTAL") != "1",
+                    reason="EXPERIMENTAL two-table transition tables for Left/Right rule sets (env SE_LUT_LR=1): not yet validated on a GPU")
+def test_two_table_lut_experimental(se, monkeypatch):
+    """K1b / K1c for rule sets with Left/Right rules through one table per view (SE_LUT_LR=1 at rule-compile time)."""
+    from oracle.build_oracle import load_oracle
+    from sandengine_b200.synth_rules import synthetic_rule_set
+    monkeypatch.setenv("SE_LUT_LR", "1")
+    for seed, n_mat, n_rules in [(401, 9, 20), (505, 11, 21)]:
+        text, ids, mix = synthetic_rule_set(n_mat, n_rules, seed=seed)
+        rules = se.parse_string(text)
+        assert "#define SE_LUT_TWO_TABLES 1" in rules.cuda_header
+        orc = load_oracle(text)
+        for (w, h, steps) in [(512, 300, 67), (260, 130, 33)]:
+            g = synthetic_grid(w, h, seed, mix=mix, ids=ids)
+            ref, _, _ = orc.run(g, 1, steps, blocks=True)
+            got, _, _ = run_gpu(se, rules, g, steps)
+            assert np.array_equal(got, ref), ("K1b", seed, w, h)
+            sim = se.Simulation(rules, (w, h))
+            sim.upload_cells(g); sim.params.frame = 1
+            for _ in range(steps): sim.step(1)
+            assert np.array_equal(sim.download_cells(), ref), ("K1c", seed, w, h)
+            sim.close()
