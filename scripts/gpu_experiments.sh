@@ -2,7 +2,7 @@
 #   gpurun --timeout 600 -- 'bash scripts/gpu_experiments.sh'
 mkdir -p gpurun_out
 # 1. running census (SE_FLAG_RUNNING_CENSUS): correctness, then the e2e leg with and without it
-SE_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "running_census or lit_strips or fused_light or random_eligible or two_table" 2>&1 | tail -5
+SE_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "running_census or lit_strips or fused_light or random_eligible or two_table or strips_with_modifications" 2>&1 | tail -5
 timeout 200 python bench.py --steps 400 --warmup 16 --no-cpu-baseline > gpurun_out/exp_e2e_base.json 2> gpurun_out/exp_e2e_base.err
 timeout 200 python bench.py --steps 400 --warmup 16 --no-cpu-baseline --running-census > gpurun_out/exp_e2e_running.json 2> gpurun_out/exp_e2e_running.err
 python - <<'PY'

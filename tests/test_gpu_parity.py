@@ -627,3 +627,41 @@ def test_two_table_lut_experimental(se, monkeypatch):
             for _ in range(steps): sim.step(1)
             assert np.array_equal(sim.download_cells(), ref), ("K1c", seed, w, h)
             sim.close()
+
+
+@pytest.mark.skipif(os.environ.get("SE_TEST_EXPERIMENTAL") != "1",
+                    reason="added without a GPU at hand: run once with SE_TEST_EXPERIMENTAL=1 (scripts/gpu_experiments.sh), then un-gate")
+@pytest.mark.parametrize("n_strips,halo", [(2, 4), (3, 8)])
+def test_strips_with_modifications(se, default_rules, oracle, n_strips, halo):
+    """modifications are broadcast to every strip (global coordinates, clipped by the kernels); the
+    sharded result stays bit-identical to the oracle's full-grid run."""
+    from sandengine_b200.distributed import StripPlan
+    rng = np.random.default_rng(77)
+    w, h, steps = 96, 100, 40
+    g = synthetic_grid(w, h, 17)
+    mods = [make_mods(se, s, 11, w, h, rng) if s % 3 == 0 else np.zeros(0, se.MOD_DTYPE) for s in range(steps)]
+    ref, _, _ = oracle.run(g, 1, steps, mods_per_step=mods)
+    plan = StripPlan(w, h, n_strips, halo)
+    sims = []
+    for r in range(n_strips):
+        b, e = plan.rows(r)
+        s = se.Simulation(default_rules, (w, h), row_begin=b, row_end=e, halo_rows=halo)
+        s.upload_cells(g[b:e]); s.params.frame = 1
+        sims.append(s)
+    for r, s in enumerate(sims):
+        if r > 0: s.attach_local(0, sims[r - 1])
+        if r < n_strips - 1: s.attach_local(1, sims[r + 1])
+
+    def exchange():
+        for s in sims: s.synchronize()
+        for s in sims: s.halo_push()
+        for s in sims: s.synchronize()
+    exchange()
+    for k in range(steps):                       # one frame at a time: exchange after every step keeps it simple
+        for s in sims:
+            if len(mods[k]): s.push_modifications(mods[k])
+            s.step(1)
+        exchange()
+    got = np.concatenate([s.download_cells() for s in sims], axis=0)
+    for s in sims: s.close()
+    assert np.array_equal(got, ref)
