@@ -239,6 +239,8 @@ def run_ours(args):
         sampler.start()
     S = args.size
     K, Wm = args.steps, max(args.warmup, 3)
+    if args.running_census:
+        os.environ["SE_EXPERIMENTAL_KERNELS"] = "1"       # the experimental kernels are compiled only on request
     rules = se.parse_path(REPO / "data" / "materials.yaml")
     strip = StripSimulation(rules, (S, S), halo_rows=args.halo, device=local_rank, temporal_block=args.temporal_block,
                             device_sync=not args.host_sync, running_census=args.running_census)

@@ -57,7 +57,9 @@ typedef struct se_modification {
 /* EXPERIMENTAL, off by default: keep the per-material census of the owned rows up to date inside the per-frame
  * step kernel (population deltas of the blocks where a SET fired) so that se_sim_census[_async] after a
  * se_sim_step(sim, 1) needs no pass over the grid.  Results are identical to the recount; only table-eligible
- * rule sets with lighting off use it, elsewhere the flag is ignored. */
+ * rule sets with lighting off use it, elsewhere the flag is ignored.  Its kernels (and those of
+ * SE_FLAG_FUSED_LIGHT_EXPERIMENTAL) are compiled only when the rules are compiled with env SE_EXPERIMENTAL_KERNELS=1;
+ * otherwise se_sim_create refuses the flag with SE_ERR_INVALID_ARG. */
 #define SE_FLAG_RUNNING_CENSUS 2u
 /* EXPERIMENTAL opt-in: allow SE_FLAG_LIGHTING on a strip.  The light field then gets ghost rows too: attach the
  * neighbours' light buffers (se_sim_ipc_export_light / _attach_light, or se_sim_attach_local) and exchange every

@@ -172,6 +172,7 @@ struct se_rules {
     std::string nvrtc_log;
     bool compiled = false;
     int tile_threads = 1024;   // CTA size of the tile kernel (compile-time launch bound; tunable: env SE_TILE_THREADS)
+    bool experimental_kernels = false;   // compiled with env SE_EXPERIMENTAL_KERNELS=1
     int light_rows = 4;        // rows per thread of se_light => tile height 8 * light_rows (tunable: env SE_LT_ROWS)
 };
 
@@ -288,6 +289,9 @@ int compile_front(const char* yaml, size_t len, se_rules** out, bool with_nvrtc)
         }
         const std::string def_threads = "-DSE_TILE_THREADS=" + std::to_string(r->tile_threads);
         std::vector<std::string> extra;                       // experiments only: SE_NVRTC_DEFS="-DX=1 -DY=2"
+        if (const char* ek = std::getenv("SE_EXPERIMENTAL_KERNELS")) {   // the kernels behind the experimental SE_FLAG_*s
+            if (std::string(ek) == "1") { extra.push_back("-DSE_EXPERIMENTAL_KERNELS=1"); r->experimental_kernels = true; }
+        }
         if (const char* lr = std::getenv("SE_LT_ROWS")) {     // experiments only: se_light tile height
             const int v = std::atoi(lr);
             if (v == 2 || v == 4 || v == 8) { r->light_rows = v; extra.push_back("-DSE_LT_ROWS=" + std::to_string(v)); }
@@ -559,6 +563,8 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
     // per-step kernels index block rows with gridDim.y (<= 65535 CTAs of 4 block rows / 8 light rows)
     if ((uint64_t)(re - rb) + 2ull * prm->halo_rows > 65535ull * 8ull)
         return fail(SE_ERR_INVALID_ARG, "more than 524280 rows per device are not supported (shard the grid into strips)");
+    if ((prm->flags & (SE_FLAG_RUNNING_CENSUS | SE_FLAG_FUSED_LIGHT_EXPERIMENTAL)) && !rules->experimental_kernels)
+        return fail(SE_ERR_INVALID_ARG, "experimental flag: compile the rules with env SE_EXPERIMENTAL_KERNELS=1 (the kernels are not built by default)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {

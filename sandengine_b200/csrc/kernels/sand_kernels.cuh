@@ -44,6 +44,10 @@ struct SeRand { unsigned u[4]; };
 
 #include "rules_gen.cuh"
 
+#ifndef SE_EXPERIMENTAL_KERNELS
+#define SE_EXPERIMENTAL_KERNELS 0   // se_step_lut_global_census / se_build_popbits / se_light_fused (see the SE_FLAG_*_EXPERIMENTAL flags)
+#endif
+
 typedef unsigned long long se_u64;
 
 struct SeMod { int px, py, shape, size, mat, pad0, pad1, pad2; };   // 32 B == simulation.rs:45-56
@@ -1164,6 +1168,7 @@ extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_
     se_k1c_body<false>(p, SeLutCensusParams{}, nullptr);
 }
 
+#if SE_EXPERIMENTAL_KERNELS      // compiled only on request (env SE_EXPERIMENTAL_KERNELS=1 when the rules are compiled)
 extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_step_lut_global_census(const SeLutStepParams p, const SeLutCensusParams cx) {
     __shared__ int hist_sm[256];
     se_k1c_body<true>(p, cx, hist_sm);
@@ -1231,5 +1236,6 @@ extern "C" __global__ void __launch_bounds__(256) se_build_popbits(unsigned* __r
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < SE_N4) se_build_popbits_entry(idx, popbits);
 }
+#endif  // SE_EXPERIMENTAL_KERNELS
 #endif  // SE_HOST_EMU
 #endif  // SE_LUT_ELIGIBLE

@@ -19,9 +19,11 @@ from run_configs import frame_mods  # noqa: E402
 
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 24
+FUSED = os.environ.get("SE_FUSED") == "1"
+if FUSED:
+    os.environ["SE_EXPERIMENTAL_KERNELS"] = "1"      # read when the rules are compiled
 rules = se.parse_path(REPO / "data" / "materials.yaml")
 sel = [m.id for m in rules.selectable_materials]
-FUSED = os.environ.get("SE_FUSED") == "1"
 sim = se.Simulation(rules, (S, S), lighting=True, fused_light=FUSED)
 st = torch.cuda.Stream(); torch.cuda.set_stream(st); sim.set_stream(st.cuda_stream)
 sim.upload_cells(synthetic_grid(S, S, 4)); sim.upload_light(np.zeros((S, S, 4), np.float32)); sim.params.frame = 1

@@ -490,10 +490,12 @@ def test_gpu_matches_committed_state_hashes(se):
 
 @pytest.mark.skipif(os.environ.get("SE_TEST_EXPERIMENTAL") != "1",
                     reason="EXPERIMENTAL SE_FLAG_RUNNING_CENSUS: off by default, not yet validated on a GPU (SE_TEST_EXPERIMENTAL=1 runs it)")
-def test_running_census_experimental(se, default_rules, oracle):
+def test_running_census_experimental(se, oracle, monkeypatch):
     """SE_FLAG_RUNNING_CENSUS: cells stay bit-exact and every census (sync and async, after K1c steps, after runs that
     fall back to a recount, with WALL / NULL / unknown ids, odd widths) equals a host recount."""
     import torch
+    monkeypatch.setenv("SE_EXPERIMENTAL_KERNELS", "1")          # the experimental kernels are not compiled by default
+    default_rules = se.parse_path(DEFAULT_YAML)
     for (w, h, seed) in [(516, 130, 41), (1024, 768, 42), (260, 258, 43)]:
         g = synthetic_grid(w, h, seed)
         rng = np.random.default_rng(seed)
@@ -559,8 +561,10 @@ def test_lit_strips_experimental(se, default_rules, oracle, n_strips, halo, w, h
 
 @pytest.mark.skipif(os.environ.get("SE_TEST_EXPERIMENTAL") != "1",
                     reason="EXPERIMENTAL fused step + lighting kernel (SE_FLAG_FUSED_LIGHT_EXPERIMENTAL): not yet validated on a GPU")
-def test_fused_light_experimental(se, default_rules, oracle):
+def test_fused_light_experimental(se, oracle, monkeypatch):
     """se_light_fused: ids bit-exact and light within tolerance against the oracle, with modifications, frame 1 included."""
+    monkeypatch.setenv("SE_EXPERIMENTAL_KERNELS", "1")          # the experimental kernels are not compiled by default
+    default_rules = se.parse_path(DEFAULT_YAML)
     rng = np.random.default_rng(29)
     for (w, h, steps, frame0) in [(200, 150, 24, 1), (80, 64, 30, 1), (33, 17, 10, 0), (516, 130, 12, 1)]:
         g = synthetic_grid(w, h, 31)
