@@ -58,6 +58,17 @@ extern "C" void emu_step_inplace(uint32_t* cells, int W, int H, int frame) {
         }
 }
 
+// D2: the per-cell modification override exactly as the *_mods kernels decide it (se_mod_lookup on the records that
+// se_sim_step staged).  out[y * W + x] = overriding material id, or 0xFFFFFFFF when the cell is left to simulate().
+extern "C" void emu_mod_override(const void* mods, int n_mods, int W, int H, uint32_t* out) {
+    const SeMod* m = (const SeMod*)mods;
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            unsigned mat = 0;
+            out[(size_t)y * W + x] = se_mod_lookup(m, n_mods, x, y, mat) ? mat : 0xFFFFFFFFu;
+        }
+}
+
 // K3 (lighting): the two per-thread phases of se_light, run CTA by CTA with a "__syncthreads" between them
 extern "C" void emu_light(const uint32_t* old_cells, const uint32_t* new_cells, const float* light_in, float* light_out,
                           int W, int Hl, int gy0, int Hg, int* n_interior_ctas) {
