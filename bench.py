@@ -133,7 +133,7 @@ class ClockSampler:
                 "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
-def cpu_port_rate(size_sample: int, budget_s: float, seed: int = SEED):
+def cpu_port_rate(size_sample: int, budget_s: float, seed: int = SEED, one_thread: bool = True):
     """Oracle (C restatement of the shader, OpenMP over all host cores) on a bounded sample of the workload."""
     import numpy as np
 
@@ -155,6 +155,8 @@ def cpu_port_rate(size_sample: int, budget_s: float, seed: int = SEED):
     # the same code on ONE thread (SURVEY.md 8d asks for it): 1024^2, ~2 s
     one = None
     try:
+        if not one_thread:
+            raise RuntimeError("skipped")
         import ctypes
         gomp = ctypes.CDLL("libgomp.so.1")
         gomp.omp_set_num_threads(1)
@@ -174,42 +176,117 @@ def cpu_port_rate(size_sample: int, budget_s: float, seed: int = SEED):
                       "llvmpipe GL 4.3 is not available in this image"}
 
 
+def load_ref_shader():
+    """The reference's own compute shader compiled for the CPU (oracle/build_ref.py -> oracle/_ref/).  Built here when
+    /root/reference is present (build container), otherwise the prebuilt .so that travelled with the snapshot; None
+    when neither exists (the callers then fall back to the oracle port and say so)."""
+    try:
+        from oracle import build_ref
+        return build_ref.load_ref()
+    except Exception:
+        return None
+
+
+REF_WHAT = ("the reference's own compute shader (shaders/compute/falling_sand.glsl, text unmodified) compiled for the CPU through a "
+            "GLSL-types shim (oracle/build_ref.py; g++ -O2 -march=x86-64-v3 -fopenmp, one invocation per cell like the GL "
+            "dispatch; it always computes light and colour too -- the shader has no switch for them); Mesa llvmpipe GL 4.3 is "
+            "not available in this image")
+
+
+def cpu_reference_rate(size_sample: int, budget_s: float, seed: int = SEED):
+    """oracle/_ref on a bounded sample of the workload, all host cores; None when oracle/_ref does not exist."""
+    from sandengine_b200.grids import synthetic_grid
+
+    ref = load_ref_shader()
+    if ref is None:
+        return None
+    cores = len(os.sched_getaffinity(0))
+    g = synthetic_grid(size_sample, size_sample, seed)
+    ref.create(size_sample, size_sample)
+    ref.upload_ids(g)
+    ref.frame = 1
+    ref.step(1)                                            # page-in, thread pool
+    steps, t0 = 0, time.perf_counter()
+    while True:
+        ref.step(1)
+        steps += 1
+        dt = time.perf_counter() - t0
+        if dt >= budget_s or steps >= 4000:
+            break
+    rate = size_sample * size_sample * steps / dt / 1e9
+    return {"value": round(rate, 6), "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"{size_sample}x{size_sample} grid of the same generator (seed {seed}), {steps} steps in {dt:.1f} s, {cores} threads; " + REF_WHAT}
+
+
 def run_reference(args):
-    """Reference arm: the reference's own algorithm on the host cores (oracle port; no GL in this image)."""
+    """Reference arm: the reference's own implementation of the path on the host cores -- its compute shader compiled
+    for the CPU (oracle/_ref) when that exists, else the oracle port (no GL in this image either way)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     # each "step" of this arm is one Margolus step over a bounded sample of the workload; K + W of them.  The sample
-    # is the largest of 4096^2 / 2048^2 / 1024^2 whose projected run (probed with 2 steps) stays under ~2 minutes.
+    # is the largest power-of-two square whose projected run (probed with 2 steps) stays under ~2 minutes.
     from oracle.build_oracle import load_oracle
     from sandengine_b200.grids import synthetic_grid
 
-    orc = load_oracle()
     cores = len(os.sched_getaffinity(0))
     K, Wm = max(1, args.steps), max(0, args.warmup)
-    for sample in (4096, 2048, 1024):
+    ref = load_ref_shader()
+    port_note = None
+    if ref is not None:
+        kind = "reference"
+        ladder = (2048, 1024, 512, 256, 128, 64)           # 256^2 is BASELINE configs[0], the reference's own CPU-sized case
+
+        def start(g):
+            ref.create(g.shape[1], g.shape[0]); ref.upload_ids(g); ref.frame = 1
+
+        def steps(n):
+            ref.step(n)
+    else:
+        kind = "port"
+        ladder = (4096, 2048, 1024)
+        orc = load_oracle()
+        state = {}
+
+        def start(g):
+            state["g"], state["f"] = g.copy(), 1
+
+        def steps(n):
+            state["f"] = orc.run_blocks(state["g"], state["f"], n)
+    for sample in ladder:
         sample = min(sample, args.size)
         g = synthetic_grid(sample, sample, SEED)
-        orc.run_blocks(g.copy(), 1, 1)                    # page-in, thread pool
+        start(g); steps(1)                                 # page-in, thread pool
         t0 = time.perf_counter()
-        orc.run_blocks(g.copy(), 1, 2)
-        if (time.perf_counter() - t0) / 2 * (K + Wm) <= 120.0 or sample == min(1024, args.size):
+        steps(2)
+        if (time.perf_counter() - t0) / 2 * (K + Wm) <= 120.0 or sample == min(ladder[-1], args.size):
             break
-    frame = orc.run_blocks(g, 1, Wm) if Wm else 1
+    start(g)
+    if Wm:
+        steps(Wm)
     t0 = time.perf_counter()
-    frame = orc.run_blocks(g, frame, K)
+    steps(K)
     dt = time.perf_counter() - t0
     rate = sample * sample * K / dt / 1e9
+    what = REF_WHAT if kind == "reference" else ("C restatement of the reference shader (oracle/sand_oracle.c, per-block form), gcc -O2 -fopenmp; "
+                                                 "oracle/_ref (the reference's shader compiled for the CPU) was not found; the reference's GLSL needs GL 4.3 "
+                                                 "(llvmpipe) which this image does not have")
+    cpu = {"value": round(rate, 6), "unit": UNIT, "cores": cores, "kind": kind, "sample": f"{sample}x{sample}, {K} steps, {cores} threads; " + what}
+    if kind == "reference":                                # for context: the hand-optimised port of the same algorithm (ids only), ~3 s
+        try:
+            port = cpu_port_rate(min(args.size, 2048), 3.0, one_thread=False)
+            cpu["port"] = {"value": port["value"], "unit": UNIT, "cores": port["cores"], "sample": port["sample"]}
+        except Exception as e:  # noqa: BLE001
+            cpu["port"] = {"error": repr(e)}
     line = {
-        "impl": "reference", "metric": METRIC, "value": round(rate, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": Wm,
+        "impl": "reference", "metric": METRIC, "value": round(rate, 6), "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": Wm,
         "ms_per_step": round(dt / K * 1e3, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
         "config": {"workload": f"bounded sample of the {args.size}^2 workload: {sample}x{sample} grid, same generator (seed {SEED}), "
-                               "default rule set, lighting off, no modifications", "rules": "data/materials.yaml"},
-        "cpu_baseline": {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample}x{sample}, {K} steps; C restatement of the reference shader (oracle/), gcc -O2 -fopenmp, {cores} threads; "
-                                   "the reference's GLSL needs GL 4.3 (llvmpipe) which this image does not have"},
-        "e2e": {"value": round(rate, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                               "default rule set, no modifications" + (", lighting off" if kind == "port" else " (the shader relaxes light and shades colour every step)"),
+                   "rules": "data/materials.yaml"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": round(rate, 6), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
@@ -370,7 +447,15 @@ def run_ours(args):
             line["config"]["experimental"] = "SE_FLAG_RUNNING_CENSUS"
         if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
             try:
-                line["cpu_baseline"] = cpu_port_rate(min(S, 4096), args.cpu_seconds)
+                # the reference's own shader compiled for the CPU when oracle/_ref exists ("reference"), with the
+                # hand-optimised port of the same algorithm beside it; the port alone otherwise
+                refcpu = cpu_reference_rate(min(S, 1024), args.cpu_seconds)
+                port = cpu_port_rate(min(S, 4096), args.cpu_seconds if refcpu is None else min(args.cpu_seconds, 6.0))
+                if refcpu is not None:
+                    refcpu["port"] = port
+                    line["cpu_baseline"] = refcpu
+                else:
+                    line["cpu_baseline"] = port
             except Exception as e:   # the baseline is a reported number, never a dependency of the GPU path
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": len(os.sched_getaffinity(0)), "kind": "port", "sample": f"failed: {e}"}
         print(json.dumps(line), flush=True)

@@ -1,7 +1,7 @@
 """ORACLE build + ctypes binding (test infrastructure, not product code).
 
 `load_oracle(yaml_text)` generates rules_gen.h for the rule set with oracle_lang.emit_c_rules(),
-compiles oracle/sand_oracle.c against it (gcc -O2 -ffp-contract=off -fopenmp) into
+compiles oracle/sand_oracle.c against it (gcc -O2 -march=x86-64-v3 -ffp-contract=off -fopenmp) into
 oracle/_build/<sha16>/liboracle.so and returns an `Oracle` wrapper.  Nothing here is imported by the
 product package; the product path never falls back to it.
 """
@@ -37,7 +37,10 @@ def _compile(yaml_text: str) -> Path:
     res = oracle_lang.parse_string(yaml_text)
     gen = oracle_lang.emit_c_rules(res)
     src = (HERE / "sand_oracle.c").read_bytes()
-    key = hashlib.sha256(gen.encode() + b"\0" + src).hexdigest()[:16]
+    # x86-64-v3 (AVX2), not -march=native: the .so is built in the build container and travels to the GPU box, whose
+    # host CPU may lack this one's extensions (AVX-512 / AMX here)
+    flags = ["-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fopenmp"]
+    key = hashlib.sha256(gen.encode() + b"\0" + src + b"\0" + " ".join(flags).encode()).hexdigest()[:16]
     out_dir = BUILD / key
     so = out_dir / "liboracle.so"
     if so.exists():
@@ -45,7 +48,7 @@ def _compile(yaml_text: str) -> Path:
     out_dir.mkdir(parents=True, exist_ok=True)
     (out_dir / "rules_gen.h").write_text(gen)
     tmp = out_dir / f"liboracle.{os.getpid()}.tmp.so"
-    cmd = ["gcc", "-O2", "-march=native", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-shared", "-fPIC",
+    cmd = ["gcc", *flags, "-shared", "-fPIC",
            "-std=gnu11", "-Wall", "-Wno-unused-function", "-Wno-unused-variable", "-I", str(out_dir),
            str(HERE / "sand_oracle.c"), "-o", str(tmp), "-lm"]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -8,8 +8,8 @@ module does exactly that:
 
     read  /root/reference/shaders/compute/falling_sand.glsl (+ its #includes, where they lie; never copied into the repo)
     ->    translate()  — the rewrites listed below, nothing semantic
-    ->    oracle/_ref/<key>/ref_shader.cpp  = shim + translated shader + harness (oracle/ref_harness.inc)
-    ->    g++ -std=c++20 -O2 -ffp-contract=off -fopenmp  ->  oracle/_ref/<key>/libref_shader.so
+    ->    oracle/_ref/<key>/ref_shader.cpp  = shim + translated shader + harness (oracle/ref_harness.inc); deleted after the compile
+    ->    g++ -std=c++20 -O2 -march=x86-64-v3 -ffp-contract=off -fopenmp  ->  oracle/_ref/<key>/libref_shader.so
 
 The harness replays `Simulation::run` (simulation.rs:195-253) around the shader's `main()`: frame += 1, first
 min(len, 256) modifications into the uniform block, one invocation per cell (the over-dispatched invocations of the
@@ -126,7 +126,7 @@ def build(materials_glsl: str | None = None, rules_glsl: str | None = None, forc
     glsl = shader_source(materials_glsl, rules_glsl)
     shim = (HERE / "glsl_shim.hpp").read_text()
     harness = (HERE / "ref_harness.inc").read_text()
-    stamp = hashlib.sha256((glsl + "\0" + shim + "\0" + harness + "\0" + translate.__code__.co_code.hex()).encode()).hexdigest()
+    stamp = hashlib.sha256((glsl + "\0" + shim + "\0" + harness + "\0" + translate.__code__.co_code.hex() + "\0x86-64-v3").encode()).hexdigest()
     stamp_file = out_dir / "stamp.json"
     if so.exists() and not force and stamp_file.exists() and json.loads(stamp_file.read_text()).get("stamp") == stamp:
         return so
@@ -137,9 +137,11 @@ def build(materials_glsl: str | None = None, rules_glsl: str | None = None, forc
                    + translate(glsl) +
                    "\n// ---- harness (oracle/ref_harness.inc) ----\n" + harness + "\n}  // namespace glsl\n")
     tmp = out_dir / f"libref_shader.{os.getpid()}.tmp.so"
-    cmd = ["g++", "-std=c++20", "-O2", "-march=native", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-w",
+    cmd = ["g++", "-std=c++20", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-w",
            "-shared", "-fPIC", "-I", str(HERE), str(cpp), "-o", str(tmp)]
     r = subprocess.run(cmd, capture_output=True, text=True)
+    if os.environ.get("SE_REF_KEEP_CPP") != "1":
+        cpp.unlink()          # the translated text is derived from reference source: only the binary stays in oracle/_ref/
     if r.returncode != 0:
         raise RuntimeError("reference shader did not compile as C++:\n" + r.stderr[-6000:])
     os.replace(tmp, so)
