@@ -8,14 +8,17 @@
  * "rules_gen.h", the same split the reference has between hand-written GLSL and gen/{materials,rules}.glsl.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
- * this.  Build: oracle/build_oracle.py (gcc -O2 -ffp-contract=off -fopenmp).  -ffp-contract=off is
+ * this.  Build: oracle/build_oracle.py (gcc -O2 -march=x86-64-v3 -ffp-contract=off -fopenmp).  -ffp-contract=off is
  * REQUIRED: the lighting sums must be evaluated as written (no FMA), SURVEY.md section 7 "hard parts".
  *
- * Parity status: the reference ships no state-level tests or fixtures and its
- * GLSL cannot be executed in this image, so cell-state parity is pinned only by (a) the survey's
- * cross-check vectors (hash KATs, state SHA-256 KATs, lighting probes: tests/test_oracle_kat.py) and
- * (b) agreement of this file with the independently written pure-Python restatement oracle/pyoracle.py.
- * LEFT-rule semantics are a definition (oracle_lang.py docstring), i.e. "parity unpinned" for that row.
+ * Parity status: PINNED by the reference's own shader.  The reference ships no state-level tests or fixtures
+ *  and its GLSL cannot run as GLSL in this image, but oracle/build_ref.py compiles the shader
+ * text itself for the CPU (oracle/_ref/, GLSL-types shim + syntactic translation); this file agrees with it bit for bit
+ * on cell ids and with error 0 on light for every case of tests/ref_cases.py (tests/test_ref_shader.py), and with the
+ * committed outputs of that shader (tests/golden/ref_shader_goldens.json) where /root/reference is absent.  Also kept:
+ * the survey's cross-check vectors (tests/test_oracle_kat.py) and the independently written pure-Python restatement
+ * oracle/pyoracle.py.  The one exception: LEFT-rule semantics are a definition (oracle_lang.py docstring) -- the
+ * reference cannot compile such rules -- i.e. "parity unpinned" for that row only.
  */
 #include <math.h>
 #include <stdint.h>
