@@ -3,7 +3,7 @@
 seeded inputs of tests/ref_cases.py.  Unlike oracle_state_sha256.json these are reference outputs: they pin the C
 oracle (tests/test_ref_shader.py, no /root/reference needed) and the CUDA path (tests/test_gpu_ref_goldens.py).
 
-Run in the build container (needs /root/reference):   python tests/golden/make_ref_shader_goldens.py
+Run in the build container (needs /root/reference):   python tests/golden/make_ref_shader_goldens.py [case names...]
 """
 import hashlib
 import json
@@ -25,7 +25,14 @@ PROBES = ((0, 0), (1, 3), (5, 5), (8, 8), (-1, -1))   # (y, x), negative = from 
 def main():
     assert build_ref.reference_available(), "needs /root/reference"
     meta, arrays = {}, {}
+    only = set(sys.argv[1:])            # optional: regenerate just these cases and merge them into the existing fixtures
+    if only:
+        assert only <= set(R.CASE_BY_NAME), only - set(R.CASE_BY_NAME)
+        meta = json.loads(R.GOLDEN_JSON.read_text())["cases"]
+        arrays = dict(np.load(R.GOLDEN_NPZ))
     for case in R.CASES:
+        if only and case.name not in only:
+            continue
         t = time.time()
         out = R.run_case(case, R.RefEngine, want_color=case.store_color)
         last = out["ids"][case.steps]
@@ -45,6 +52,7 @@ def main():
             arrays[case.name + "/color"] = out["color"]
         meta[case.name] = m
         print(f"{case.name}: {time.time() - t:.1f} s", flush=True)
+    meta = {c.name: meta[c.name] for c in R.CASES}          # keep the order of ref_cases.CASES
     doc = {"_what": "outputs of the reference's own compute shader compiled for the CPU (oracle/build_ref.py); inputs: tests/ref_cases.py",
            "_shader_sha256": hashlib.sha256(build_ref.shader_source().encode()).hexdigest(),
            "cases": meta}

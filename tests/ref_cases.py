@@ -38,7 +38,7 @@ class Case:
     checkpoints: Tuple[int, ...] = ()      # ids hashed after these step counts (the last step always)
     lighting: bool = False
     light0: str = "zero"                   # "zero" | "hash"
-    mods: str = "none"                     # "none" | "stamps" | "edge"
+    mods: str = "none"                     # "none" | "stamps" | "edge" | "config3"
     grid: str = "synthetic"                # "synthetic" | "unknown_ids"
     store_light: str = "none"              # "full" | "sub8" | "none" (what goes into the .npz)
     store_color: bool = False
@@ -52,6 +52,8 @@ CASES = [
     # BASELINE configs[0]: 256 x 256, default rule set, 1000 steps, seed 1 -- ids every 100 steps, lighting on
     Case("default_256x256_seed1_lit_1000", W=256, H=256, seed=1, steps=1000, checkpoints=tuple(range(100, 1001, 100)),
          lighting=True, store_light="sub8", slow=True),
+    # BASELINE configs[1] at full size (4096 x 4096, seed 2): the short horizon SURVEY.md 8d names, steps 1-5 and 100
+    Case("default_4096x4096_seed2_100", W=4096, H=4096, seed=2, steps=100, checkpoints=(1, 2, 3, 4, 5), slow=True),
     Case("default_130x66_seed11_257", W=130, H=66, seed=11, steps=257, checkpoints=(1, 2, 3, 4, 5, 100)),
     Case("default_33x17_seed4_90", W=33, H=17, seed=4, steps=90),
     Case("default_1x9_seed3_40", W=1, H=9, seed=3, steps=40),
@@ -61,6 +63,9 @@ CASES = [
     Case("default_96x72_seed4_mods_edge_60", W=96, H=72, seed=4, steps=60, mods="edge", checkpoints=(4, 6, 8)),
     Case("default_80x64_seed9_lit_hashlight_stamps_50", W=80, H=64, seed=9, steps=50, lighting=True, light0="hash", mods="stamps",
          store_light="full"),
+    # BASELINE configs[3] semantics at a size the CPU shader finishes in seconds: stamps + explosion every frame, lighting on
+    Case("default_512x512_seed4_config3_lit_24", W=512, H=512, seed=4, steps=24, lighting=True, mods="config3", checkpoints=(1, 8, 16),
+         store_light="sub8"),
     Case("default_32x32_seed2_frame0_lit_3", W=32, H=32, seed=2, steps=3, frame0=0, lighting=True, light0="hash", mods="stamps",
          checkpoints=(1, 2), store_light="full"),
     Case("default_40x30_seed8_unknown_ids_50", W=40, H=30, seed=8, steps=50, grid="unknown_ids", checkpoints=(1, 2)),
@@ -133,6 +138,26 @@ def mods_for(case: Case, n_materials: int):
             m[i]["mod_size"] = 1 + _h(case.seed, s, i, 5) % 11
             m[i]["mod_matID"] = _h(case.seed, s, i, 6) % n_materials        # includes 0 = explosion (EMPTY), 1 = NULL, 2 = WALL
         out.append(m)
+    if case.mods == "config3":
+        # BASELINE configs[3] (scripts/run_configs.py::frame_mods): per frame 4 brush stamps (CIRCLE / SQUARE, size 3..32,
+        # a selectable material) + 1 explosion (CIRCLE of EMPTY, size 16..64)
+        selectable = list(range(3, n_materials))
+        out = []
+        for s in range(case.steps):
+            k = s + 1
+            m = np.zeros(5, MOD_DTYPE)
+            hv = hashi(np.arange(k * 16, k * 16 + 16, dtype=np.uint32))
+            for i in range(4):
+                m[i]["position"] = (int(hv[3 * i] % W), int(hv[3 * i + 1] % H))
+                m[i]["mod_shape"] = int(hv[3 * i + 2] & 1)
+                m[i]["mod_size"] = 3 + int((hv[3 * i + 2] >> 1) % 30)
+                m[i]["mod_matID"] = selectable[int((hv[3 * i + 2] >> 8) % len(selectable))]
+            m[4]["position"] = (int(hv[12] % W), int(hv[13] % H))
+            m[4]["mod_shape"] = 0
+            m[4]["mod_size"] = 16 + int(hv[14] % 49)
+            m[4]["mod_matID"] = 0
+            out.append(m)
+        return out
     if case.mods == "edge":
         m = np.zeros(4, MOD_DTYPE)      # a mod_size == 0 record in the middle ends the scan (falling_sand.glsl:139-141)
         m[0] = ((20, 20), 0, 6, 3, (0, 0, 0)); m[1] = ((30, 30), 1, 0, 4, (0, 0, 0)); m[2] = ((40, 40), 1, 5, 4, (0, 0, 0))
