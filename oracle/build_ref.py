@@ -90,7 +90,7 @@ def translate(glsl: str) -> str:
     s = re.sub(r"\bin\s+(\w+)\s+(\w+)", r"\1 \2", s)
     s = re.sub(r"\b([A-Za-z_]\w*)\[(\d+)\]\s+(?=[A-Za-z_])", r"glsl_array<\1, \2> ", s)           # R5: T[N] name
     s = re.sub(r"\b([A-Za-z_]\w*)\s+([A-Za-z_]\w*)\[(\d+)\]\s*(=|;)", r"glsl_array<\1, \3> \2 \4", s)   # T name[N]
-    s = re.sub(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][-+]?\d+)?)(?![\w.])", r"\1f", s)            # R6
+    s = re.sub(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][-+]?\d+)?|\d+[eE][-+]?\d+)(?![\w.])", r"\1f", s)   # R6
     s = re.sub(r"\bstruct\s+(\w+)\s*\{", r"struct \1 { bool operator==(const \1&) const = default;", s)  # R7
     s = re.sub(r"\bvoid\s+main\s*\(\s*\)", "void shader_main()", s)                               # R8
     s = re.sub(r"(\bcase\s+\w+\s*:\s*)(float|int|uint|bool)\s+(\w+)\s*=", r"\1\2 \3; \3 =", s)          # R9

@@ -600,18 +600,35 @@ def emit_glsl_materials(res: ParsingResult) -> str:
     return s
 
 
-def emit_glsl_rules(res: ParsingResult) -> str:
+def emit_glsl_rules(res: ParsingResult, patched_left: bool = False) -> str:
+    """gen/rules.glsl.  patched_left=False reproduces the reference byte for byte (incl. its broken Left rules, which do
+    not compile as GLSL).  patched_left=True is the MINIMAL PATCH of the reference's emitter that realises the LEFT
+    definition of the module docstring inside the reference's unmodified shader template:
+      * a Left rule (effective_type) gets the parameters (self, left, down, downleft) instead of (self, right, down,
+        downright)                                                             [rules.rs:77-80]
+      * applyLeftRules -- which simulate() calls with the UN-mirrored cells when shouldMirror (falling_sand.glsl:99-103)
+        -- re-enters the mirrored view with the same guarded swaps as :86-90, calls the rules, and leaves it again
+        (a guarded un-swap followed by the same guarded swap is the identity, so this equals "before the un-mirror")
+                                                                               [sandengine-lang/src/lib.rs:88-98]"""
     funcs, mir, left, right = "", "", "", ""
     for r in res.rules:
         if not r.used:
             continue
-        funcs += f"{r.get_glsl_code()}\n\n"
-        if r.ruletype == "Mirrored":
+        kind = r.effective_type if patched_left else r.ruletype
+        code = r.get_glsl_code()
+        if patched_left and kind == "Left":
+            code = code.replace("(inout Cell self, inout Cell right, inout Cell down, inout Cell downright,",
+                                "(inout Cell self, inout Cell left, inout Cell down, inout Cell downleft,", 1)
+        funcs += f"{code}\n\n"
+        if kind == "Mirrored":
             mir += f"rule_{r.name}(self, right, down, downright, rand, pos);\n"
-        elif r.ruletype == "Left":
-            left += f"rule_{r.name}(self, left, down, downright, rand, pos);\n"
+        elif kind == "Left":
+            left += (f"rule_{r.name}(self, right, down, downright, rand, pos);\n" if patched_left
+                     else f"rule_{r.name}(self, left, down, downright, rand, pos);\n")
         else:
             right += f"rule_{r.name}(self, right, down, downright, rand, pos);\n"
+    if patched_left and left:
+        left = "swap(self, right);\nswap(down, downright);\n" + left + "swap(self, right);\nswap(down, downright);\n"
     hdr = ("(\n    inout Cell self,\n    inout Cell right,\n    inout Cell down,\n    inout Cell downright,\n"
            "    vec4 rand,\n    ivec2 pos) {\n    ")
     return (f"\n// =============== RULES ===============\n{funcs}\n\n\n// =============== CALLERS ===============\n"

@@ -29,7 +29,7 @@ MOD_DTYPE = np.dtype([("position", "<i4", (2,)), ("mod_shape", "<i4"), ("mod_siz
 @dataclass
 class Case:
     name: str
-    rules: str = "default"                 # "default" | "expr" | "synthR:<n_materials>:<n_rules>:<seed>"
+    rules: str = "default"                 # "default" | "expr" | "rich" | "synthR:<n_materials>:<n_rules>:<seed>" | "synthLR:..."
     W: int = 64
     H: int = 48
     seed: int = 1
@@ -73,6 +73,9 @@ CASES = [
     Case("expr_96x64_seed5_120", rules="expr", W=96, H=64, seed=5, steps=120),
     Case("synthR12_96x64_seed7_100", rules="synthR:12:20:7", W=96, H=64, seed=7, steps=100),
     Case("synthR64_96x64_seed5_60", rules="synthR:64:28:5", W=96, H=64, seed=5, steps=60, slow=True),
+    # LEFT rules: outputs of the reference's shader template with gen/rules.glsl from the PATCHED emitter (see RefEngine)
+    Case("rich_patchedleft_128x96_seed5_200", rules="rich", W=128, H=96, seed=5, steps=200, checkpoints=(1, 2, 3, 4)),
+    Case("synthLR64_patchedleft_96x64_seed5_60", rules="synthLR:64:28:5", W=96, H=64, seed=5, steps=60, slow=True),
 ]
 CASE_BY_NAME = {c.name: c for c in CASES}
 
@@ -85,7 +88,11 @@ def rules_for(case: Case):
         return (REPO / "data" / "materials.yaml").read_text(), None, None
     if case.rules == "expr":
         return Y.EXPR_YAML, Y.EXPR_IDS, Y.EXPR_MIX
+    if case.rules == "rich":             # Left + Right rules, precedence, pos, rand.x: runs in the shader only with the patched emitter
+        return Y.RICH_YAML, Y.RICH_IDS, Y.RICH_MIX
     kind, nm, nr, seed = case.rules.split(":")
+    if kind == "synthLR":                # mirrored + RIGHT + LEFT rules (BASELINE configs[4] rule set): patched emitter
+        return synthetic_rule_set(int(nm), int(nr), seed=int(seed))
     assert kind == "synthR"
     return synthetic_rule_set(int(nm), int(nr), seed=int(seed), kinds=("mirrored", "right", "mirrored", "right"))
 
@@ -185,8 +192,11 @@ class RefEngine:
         if is_default:
             self.ref = load_ref()                      # the reference's own gen/materials.glsl + gen/rules.glsl
         else:
-            res = oracle_lang.parse_string(yaml_text)  # the emitter is pinned byte-exact on the reference's gen/*.glsl
-            self.ref = load_ref(oracle_lang.emit_glsl_materials(res), oracle_lang.emit_glsl_rules(res))
+            # the emitter is pinned byte-exact on the reference's gen/*.glsl.  patched_left: identical text for rule sets
+            # without LEFT rules; for LEFT rules the minimal emitter patch of oracle_lang.emit_glsl_rules (the reference
+            # itself cannot compile them)
+            res = oracle_lang.parse_string(yaml_text)
+            self.ref = load_ref(oracle_lang.emit_glsl_materials(res), oracle_lang.emit_glsl_rules(res, patched_left=True))
 
     def start(self, W, H, lighting, grid, light0, frame0):
         self.ref.create(W, H)

@@ -81,7 +81,7 @@ void main() { switch (k) { case A: float d = sqrt(2.0); break; case B: break; } 
     assert "struct Thing { bool operator==(const Thing&) const = default;" in t
     assert "glsl_array<ivec2, 2> pair(vec2 p, uint& x, float& y)" in t
     assert "glsl_array<ivec2, 2> arr =" in t and "glsl_array<ivec2, 4> n =" in t
-    assert "1.5f * .5f + 2.f + 1e3 + 7" in t          # only literals with a decimal point are floats in the shader
+    assert "1.5f * .5f + 2.f + 1e3f + 7" in t         # float literals get the suffix, integer literals stay
     assert "void shader_main()" in t and "case A: float d; d = sqrt(2.0f);" in t
 
 
@@ -156,6 +156,37 @@ def test_left_rules_do_not_compile_in_the_reference():
     res = oracle_lang.parse_string(Y.RICH_YAML)
     with pytest.raises(RuntimeError, match="was not declared in this scope"):
         build_ref.build(oracle_lang.emit_glsl_materials(res), oracle_lang.emit_glsl_rules(res))
+
+
+@needs_reference
+def test_left_rules_through_the_patched_emitter(default_yaml_text):
+    """LEFT rules cannot be pinned by the reference as it is.  oracle_lang.emit_glsl_rules(patched_left=
+    True) is the minimal patch of its emitter (Left rules take `left` / `downleft`; applyLeftRules enters the mirrored view)
+    and leaves the shader template untouched: with it the reference's shader equals the oracle on rule sets with LEFT
+    rules, the LEFT rules demonstrably fire, and rule sets without LEFT rules get byte-identical text."""
+    import yaml_cases as Y
+    from oracle import oracle_lang
+    from oracle.build_oracle import load_oracle
+    res = oracle_lang.parse_string(default_yaml_text)
+    assert oracle_lang.emit_glsl_rules(res, patched_left=True) == oracle_lang.emit_glsl_rules(res)
+    res = oracle_lang.parse_string(Y.RICH_YAML)
+    assert any(r.effective_type == "Left" for r in res.rules if r.used)
+    mats, rules = oracle_lang.emit_glsl_materials(res), oracle_lang.emit_glsl_rules(res, patched_left=True)
+    g = synthetic_grid(100, 80, 15, mix=Y.RICH_MIX, ids=Y.RICH_IDS)
+    want, _, _ = load_oracle(Y.RICH_YAML).run(g, 1, 150, blocks=True)
+
+    def run(rules_text):
+        ref = build_ref.load_ref(mats, rules_text)
+        ref.create(100, 80); ref.upload_ids(g); ref.frame = 1
+        ref.step(150)
+        return ref.download_ids()
+
+    assert np.array_equal(run(rules), want)
+    # the same text with an empty applyLeftRules: a different simulation, i.e. the LEFT rules did something above
+    head, tail = rules.split("void applyLeftRules", 1)
+    body_end = tail.index("}\n\nvoid applyRightRules")
+    no_left = head + "void applyLeftRules" + tail[:tail.index("{") + 1] + "\n" + tail[body_end:]
+    assert not np.array_equal(run(no_left), want)
 
 
 @needs_reference
