@@ -177,12 +177,14 @@ def cpu_port_rate(size_sample: int, budget_s: float, seed: int = SEED, one_threa
 
 
 def load_ref_shader():
-    """The reference's own compute shader compiled for the CPU (oracle/build_ref.py -> oracle/_ref/).  Built here when
-    /root/reference is present (build container), otherwise the prebuilt .so that travelled with the snapshot; None
-    when neither exists (the callers then fall back to the oracle port and say so)."""
+    """The reference's own compute shader compiled for the CPU (oracle/build_ref.py -> oracle/_ref/).  Only the
+    PREBUILT library is loaded (`__graft_entry__.build()` makes it in the build container and it travels with the
+    snapshot): bench.py never reads the reference's sources.  None when it does not exist -- the callers then fall back
+    to the oracle port and say so."""
     try:
         from oracle import build_ref
-        return build_ref.load_ref()
+        so = build_ref.prebuilt_default()
+        return build_ref.RefShader(so) if so is not None else None
     except Exception:
         return None
 
