@@ -35,7 +35,8 @@ typedef enum se_status {
     SE_ERR_UNSUPPORTED = -6,     /* valid in the reference's grammar but outside this build's limits */
     SE_ERR_COMPILE = -7,         /* NVRTC failure (the reference panics on a GLSL compile error, simulation.rs:133-137) */
     SE_ERR_CUDA = -8,
-    SE_ERR_INVALID_ARG = -9
+    SE_ERR_INVALID_ARG = -9,
+    SE_ERR_INTERNAL = -10        /* host allocation failure or an unexpected C++ exception: caught at the boundary, never thrown across it */
 } se_status;
 
 typedef struct se_rules se_rules;   /* parsed rule set + generated CUDA C + sm_100a cubin */

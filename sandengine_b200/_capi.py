@@ -18,6 +18,7 @@ SE_ERR_UNSUPPORTED = -6
 SE_ERR_COMPILE = -7
 SE_ERR_CUDA = -8
 SE_ERR_INVALID_ARG = -9
+SE_ERR_INTERNAL = -10
 
 SE_FLAG_LIGHTING = 1
 SE_FLAG_RUNNING_CENSUS = 2   # experimental, see the header
@@ -109,7 +110,7 @@ class SandEngineError(RuntimeError):
     """Raised for every non-zero se_status.  `.status` is the code, `.kind` the ParsingErr class name."""
     KINDS = {SE_ERR_YAML: "Yaml", SE_ERR_MISSING_FIELD: "MissingField", SE_ERR_INVALID_TYPE: "InvalidType",
              SE_ERR_NOT_FOUND: "NotFound", SE_ERR_NOT_RECOGNIZED: "NotRecognized", SE_ERR_UNSUPPORTED: "Unsupported",
-             SE_ERR_COMPILE: "Compile", SE_ERR_CUDA: "Cuda", SE_ERR_INVALID_ARG: "InvalidArg"}
+             SE_ERR_COMPILE: "Compile", SE_ERR_CUDA: "Cuda", SE_ERR_INVALID_ARG: "InvalidArg", SE_ERR_INTERNAL: "Internal"}
 
     def __init__(self, status: int, msg: str):
         super().__init__(msg)

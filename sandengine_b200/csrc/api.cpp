@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -30,6 +31,21 @@ int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
+
+// No C++ exception may cross the C ABI (std::bad_alloc from the host-side containers, anything unexpected from the
+// front end): every extern "C" entry point is a function-try-block that ends in SE_ABI_CATCH.
+int fail_nothrow(int code, const char* where, const char* what) noexcept {
+    try {
+        g_err = std::string(where) + ": " + what;
+    } catch (...) {
+        g_err.clear();
+    }
+    return code;
+}
+#define SE_ABI_CATCH(NAME)                                                                                  \
+    catch (const std::bad_alloc&) { return fail_nothrow(SE_ERR_INTERNAL, NAME, "out of host memory"); }     \
+    catch (const std::exception& e_) { return fail_nothrow(SE_ERR_INTERNAL, NAME, e_.what()); }             \
+    catch (...) { return fail_nothrow(SE_ERR_INTERNAL, NAME, "unknown C++ exception"); }
 
 int map_kind(se::ErrKind k) {
     switch (k) {
@@ -441,15 +457,19 @@ extern "C" {
 const char* se_last_error(void) { return g_err.c_str(); }
 const char* se_version(void) { return "sandengine_b200 0.1 (sm_100a)"; }
 
-int se_rules_compile_yaml(const char* yaml, size_t len, se_rules** out) { return compile_front(yaml, len, out, true); }
-int se_rules_parse_only(const char* yaml, size_t len, se_rules** out) { return compile_front(yaml, len, out, false); }
+int se_rules_compile_yaml(const char* yaml, size_t len, se_rules** out) try {
+    return compile_front(yaml, len, out, true);
+} SE_ABI_CATCH("se_rules_compile_yaml")
+int se_rules_parse_only(const char* yaml, size_t len, se_rules** out) try {
+    return compile_front(yaml, len, out, false);
+} SE_ABI_CATCH("se_rules_parse_only")
 
-int se_rules_destroy(se_rules* r) {
+int se_rules_destroy(se_rules* r) try {
     delete r;
     return SE_OK;
-}
+} SE_ABI_CATCH("se_rules_destroy")
 
-int se_rules_text(const se_rules* r, int which, const char** text, size_t* len) {
+int se_rules_text(const se_rules* r, int which, const char** text, size_t* len) try {
     if (!r || !text || !len) return fail(SE_ERR_INVALID_ARG, "null argument");
     const std::string* s = nullptr;
     switch (which) {
@@ -462,26 +482,26 @@ int se_rules_text(const se_rules* r, int which, const char** text, size_t* len) 
     *text = s->c_str();
     *len = s->size();
     return SE_OK;
-}
+} SE_ABI_CATCH("se_rules_text")
 
-int se_rules_cubin(const se_rules* r, const void** data, size_t* len) {
+int se_rules_cubin(const se_rules* r, const void** data, size_t* len) try {
     if (!r || !data || !len) return fail(SE_ERR_INVALID_ARG, "null argument");
     if (!r->compiled) return fail(SE_ERR_INVALID_ARG, "rules were parsed without NVRTC compilation");
     *data = r->cubin.data();
     *len = r->cubin.size();
     return SE_OK;
-}
+} SE_ABI_CATCH("se_rules_cubin")
 
-int se_rules_counts(const se_rules* r, int32_t* n_rules, int32_t* n_types, int32_t* n_materials) {
+int se_rules_counts(const se_rules* r, int32_t* n_rules, int32_t* n_types, int32_t* n_materials) try {
     if (!r) return fail(SE_ERR_INVALID_ARG, "null argument");
     if (n_rules) *n_rules = (int32_t)r->cr.parsed.rules.size();
     if (n_types) *n_types = (int32_t)r->cr.parsed.types.size();
     if (n_materials) *n_materials = (int32_t)r->cr.parsed.materials.size();
     return SE_OK;
-}
+} SE_ABI_CATCH("se_rules_counts")
 
 int se_rules_material(const se_rules* r, int32_t id, const char** name, const char** type_name, float* density, float* color4,
-                      float* emission4, int32_t* selectable) {
+                      float* emission4, int32_t* selectable) try {
     if (!r) return fail(SE_ERR_INVALID_ARG, "null argument");
     if (id < 0 || id >= (int32_t)r->cr.parsed.materials.size()) return fail(SE_ERR_INVALID_ARG, "material id out of range");
     const se::SandMaterial& m = r->cr.parsed.materials[id];
@@ -492,16 +512,16 @@ int se_rules_material(const se_rules* r, int32_t id, const char** name, const ch
     if (emission4) std::memcpy(emission4, m.emission, sizeof m.emission);
     if (selectable) *selectable = m.selectable ? 1 : 0;
     return SE_OK;
-}
+} SE_ABI_CATCH("se_rules_material")
 
-int se_rules_material_id(const se_rules* r, const char* name, int32_t* id) {
+int se_rules_material_id(const se_rules* r, const char* name, int32_t* id) try {
     if (!r || !name || !id) return fail(SE_ERR_INVALID_ARG, "null argument");
     for (auto& m : r->cr.parsed.materials)
         if (m.name == name) { *id = m.id; return SE_OK; }
     return fail(SE_ERR_NOT_FOUND, std::string("(NotFound) material '") + name + "'");
-}
+} SE_ABI_CATCH("se_rules_material_id")
 
-int se_rules_rule(const se_rules* r, int32_t index, const char** name, int32_t* used, int32_t* kind, const char** precondition) {
+int se_rules_rule(const se_rules* r, int32_t index, const char** name, int32_t* used, int32_t* kind, const char** precondition) try {
     if (!r) return fail(SE_ERR_INVALID_ARG, "null argument");
     if (index < 0 || index >= (int32_t)r->cr.parsed.rules.size()) return fail(SE_ERR_INVALID_ARG, "rule index out of range");
     const se::SandRule& ru = r->cr.parsed.rules[index];
@@ -510,10 +530,10 @@ int se_rules_rule(const se_rules* r, int32_t index, const char** name, int32_t* 
     if (kind) *kind = ru.effective_type() == se::SandRuleType::Mirrored ? 0 : ru.effective_type() == se::SandRuleType::Left ? 1 : 2;
     if (precondition) *precondition = ru.has_precondition ? ru.precondition.c_str() : nullptr;
     return SE_OK;
-}
+} SE_ABI_CATCH("se_rules_rule")
 
 // ---------------------------------------------------------------------------------------------
-int se_sim_destroy(se_sim* s) {
+int se_sim_destroy(se_sim* s) try {
     if (!s) return SE_OK;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
@@ -545,9 +565,9 @@ int se_sim_destroy(se_sim* s) {
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_destroy")
 
-int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** out) {
+int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** out) try {
     if (!rules || !prm || !out) return fail(SE_ERR_INVALID_ARG, "null argument");
     *out = nullptr;
     if (!rules->compiled) return fail(SE_ERR_INVALID_ARG, "rules were not compiled (use se_rules_compile_yaml)");
@@ -793,9 +813,9 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
     SE_CUDA_S(cudaStreamSynchronize(s->stream));
     *out = s;
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_create")
 
-int se_sim_step(se_sim* s, uint32_t n_steps) {
+int se_sim_step(se_sim* s, uint32_t n_steps) try {
     if (!s) return fail(SE_ERR_INVALID_ARG, "null sim");
     if (n_steps == 0) return SE_OK;
     SE_CUDA(cudaSetDevice(s->device));
@@ -881,28 +901,28 @@ int se_sim_step(se_sim* s, uint32_t n_steps) {
     }
     s->pending.clear();   // simulation.rs:252
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_step")
 
-int se_sim_push_modifications(se_sim* s, const se_modification* mods, uint32_t n) {
+int se_sim_push_modifications(se_sim* s, const se_modification* mods, uint32_t n) try {
     if (!s || (!mods && n)) return fail(SE_ERR_INVALID_ARG, "null argument");
     s->pending.insert(s->pending.end(), mods, mods + n);
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_push_modifications")
 
-int se_sim_set_frame(se_sim* s, int32_t frame) {
+int se_sim_set_frame(se_sim* s, int32_t frame) try {
     if (!s) return fail(SE_ERR_INVALID_ARG, "null sim");
     if (frame < 0) return fail(SE_ERR_INVALID_ARG, "frame must be >= 0");
     s->frame = frame;
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_set_frame")
 
-int se_sim_get_frame(const se_sim* s, int32_t* frame) {
+int se_sim_get_frame(const se_sim* s, int32_t* frame) try {
     if (!s || !frame) return fail(SE_ERR_INVALID_ARG, "null argument");
     *frame = s->frame;
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_get_frame")
 
-int se_sim_upload_cells(se_sim* s, const uint32_t* host) {
+int se_sim_upload_cells(se_sim* s, const uint32_t* host) try {
     if (!s || !host) return fail(SE_ERR_INVALID_ARG, "null argument");
     SE_CUDA(cudaSetDevice(s->device));
     { int rc = guard_buffer_write(s, s->cur); if (rc) return rc; }
@@ -910,35 +930,35 @@ int se_sim_upload_cells(se_sim* s, const uint32_t* host) {
     SE_CUDA(cudaMemcpyAsync(s->cells[s->cur] + s->owned_offset(), host, s->owned_cells() * sizeof(unsigned), cudaMemcpyHostToDevice, s->stream));
     SE_CUDA(cudaStreamSynchronize(s->stream));
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_upload_cells")
 
-int se_sim_download_cells(se_sim* s, uint32_t* host) {
+int se_sim_download_cells(se_sim* s, uint32_t* host) try {
     if (!s || !host) return fail(SE_ERR_INVALID_ARG, "null argument");
     SE_CUDA(cudaSetDevice(s->device));
     SE_CUDA(cudaMemcpyAsync(host, s->cells[s->cur] + s->owned_offset(), s->owned_cells() * sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
     SE_CUDA(cudaStreamSynchronize(s->stream));
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_download_cells")
 
-int se_sim_upload_light(se_sim* s, const float* host) {
+int se_sim_upload_light(se_sim* s, const float* host) try {
     if (!s || !host) return fail(SE_ERR_INVALID_ARG, "null argument");
     if (!s->lighting) return fail(SE_ERR_INVALID_ARG, "sim was created without SE_FLAG_LIGHTING");
     SE_CUDA(cudaSetDevice(s->device));
     SE_CUDA(cudaMemcpyAsync(s->light[s->lcur] + s->owned_offset(), host, s->owned_cells() * sizeof(float4), cudaMemcpyHostToDevice, s->stream));
     SE_CUDA(cudaStreamSynchronize(s->stream));
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_upload_light")
 
-int se_sim_download_light(se_sim* s, float* host) {
+int se_sim_download_light(se_sim* s, float* host) try {
     if (!s || !host) return fail(SE_ERR_INVALID_ARG, "null argument");
     if (!s->lighting) return fail(SE_ERR_INVALID_ARG, "sim was created without SE_FLAG_LIGHTING");
     SE_CUDA(cudaSetDevice(s->device));
     SE_CUDA(cudaMemcpyAsync(host, s->light[s->lcur] + s->owned_offset(), s->owned_cells() * sizeof(float4), cudaMemcpyDeviceToHost, s->stream));
     SE_CUDA(cudaStreamSynchronize(s->stream));
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_download_light")
 
-int se_sim_download_color(se_sim* s, float* host_f32, uint32_t* host_rgba8) {
+int se_sim_download_color(se_sim* s, float* host_f32, uint32_t* host_rgba8) try {
     if (!s || (!host_f32 && !host_rgba8)) return fail(SE_ERR_INVALID_ARG, "null argument");
     SE_CUDA(cudaSetDevice(s->device));
     const int rows = s->row_end - s->row_begin;
@@ -959,14 +979,14 @@ int se_sim_download_color(se_sim* s, float* host_f32, uint32_t* host_rgba8) {
     if (rc) return rc;
     if (e != cudaSuccess) return fail(SE_ERR_CUDA, cudaGetErrorString(e));
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_download_color")
 
-int se_sim_device_cells(se_sim* s, void** dptr, size_t* pitch) {
+int se_sim_device_cells(se_sim* s, void** dptr, size_t* pitch) try {
     if (!s || !dptr) return fail(SE_ERR_INVALID_ARG, "null argument");
     *dptr = s->cells[s->cur] + s->owned_offset();
     if (pitch) *pitch = (size_t)s->W * sizeof(unsigned);
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_device_cells")
 
 // running census: (re)count into d_running on the main stream when a step other than K1c-census ran since
 static int ensure_running_census(se_sim* s) {
@@ -979,7 +999,7 @@ static int ensure_running_census(se_sim* s) {
     return SE_OK;
 }
 
-int se_sim_census(se_sim* s, uint64_t* counts256) {
+int se_sim_census(se_sim* s, uint64_t* counts256) try {
     if (!s || !counts256) return fail(SE_ERR_INVALID_ARG, "null argument");
     SE_CUDA(cudaSetDevice(s->device));
     if (s->running) {
@@ -996,9 +1016,9 @@ int se_sim_census(se_sim* s, uint64_t* counts256) {
     SE_CUDA(cudaMemcpyAsync(counts256, s->d_census, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
     SE_CUDA(cudaStreamSynchronize(s->stream));
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_census")
 
-int se_sim_census_async(se_sim* s, uint64_t* host_counts256) {
+int se_sim_census_async(se_sim* s, uint64_t* host_counts256) try {
     if (!s || !host_counts256) return fail(SE_ERR_INVALID_ARG, "null argument");
     SE_CUDA(cudaSetDevice(s->device));
     if (s->running) {
@@ -1027,9 +1047,9 @@ int se_sim_census_async(se_sim* s, uint64_t* host_counts256) {
     SE_CUDA(cudaEventRecord(s->census_done[buf], s->aux_stream));
     s->census_pending[buf] = true;
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_census_async")
 
-int se_sim_census_wait(se_sim* s) {
+int se_sim_census_wait(se_sim* s) try {
     if (!s) return fail(SE_ERR_INVALID_ARG, "null sim");
     SE_CUDA(cudaSetDevice(s->device));
     SE_CUDA(cudaStreamSynchronize(s->aux_stream));
@@ -1038,31 +1058,31 @@ int se_sim_census_wait(se_sim* s) {
         s->running_copy_pending = false;
     }
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_census_wait")
 
-int se_sim_set_stream(se_sim* s, void* stream) {
+int se_sim_set_stream(se_sim* s, void* stream) try {
     if (!s) return fail(SE_ERR_INVALID_ARG, "null sim");
     SE_CUDA(cudaSetDevice(s->device));
     SE_CUDA(cudaStreamSynchronize(s->stream));
     s->stream = stream ? (cudaStream_t)stream : s->own_stream;
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_set_stream")
 
-int se_sim_synchronize(se_sim* s) {
+int se_sim_synchronize(se_sim* s) try {
     if (!s) return fail(SE_ERR_INVALID_ARG, "null sim");
     SE_CUDA(cudaSetDevice(s->device));
     SE_CUDA(cudaStreamSynchronize(s->stream));
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_synchronize")
 
-int se_sim_launch_count(const se_sim* s, uint64_t* n) {
+int se_sim_launch_count(const se_sim* s, uint64_t* n) try {
     if (!s || !n) return fail(SE_ERR_INVALID_ARG, "null argument");
     *n = s->launches;
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_launch_count")
 
 // ---- strips ----------------------------------------------------------------------------------
-int se_sim_ipc_export(se_sim* s, void* handles, uint64_t* local_rows, uint64_t* ghost_top, uint64_t* ghost_bottom) {
+int se_sim_ipc_export(se_sim* s, void* handles, uint64_t* local_rows, uint64_t* ghost_top, uint64_t* ghost_bottom) try {
     if (!s || !handles) return fail(SE_ERR_INVALID_ARG, "null argument");
     SE_CUDA(cudaSetDevice(s->device));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -1077,9 +1097,9 @@ int se_sim_ipc_export(se_sim* s, void* handles, uint64_t* local_rows, uint64_t* 
     if (ghost_top) *ghost_top = (uint64_t)s->ghost_top;
     if (ghost_bottom) *ghost_bottom = (uint64_t)s->ghost_bottom;
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_ipc_export")
 
-int se_sim_ipc_attach(se_sim* s, int which, const void* handles, uint64_t nb_local_rows, uint64_t nb_ghost_top, uint64_t nb_ghost_bottom) {
+int se_sim_ipc_attach(se_sim* s, int which, const void* handles, uint64_t nb_local_rows, uint64_t nb_ghost_top, uint64_t nb_ghost_bottom) try {
     if (!s || !handles || which < 0 || which > 1) return fail(SE_ERR_INVALID_ARG, "bad argument");
     SE_CUDA(cudaSetDevice(s->device));
     const uint64_t owned = (uint64_t)(s->row_end - s->row_begin);
@@ -1105,9 +1125,9 @@ int se_sim_ipc_attach(se_sim* s, int which, const void* handles, uint64_t nb_loc
     nb.flags = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(nb.cells[0]) + se_sim::flags_offset((size_t)s->W, (size_t)nb_local_rows));
     nb.attached = true;
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_ipc_attach")
 
-int se_sim_attach_local(se_sim* s, int which, se_sim* other) {
+int se_sim_attach_local(se_sim* s, int which, se_sim* other) try {
     if (!s || !other || which < 0 || which > 1) return fail(SE_ERR_INVALID_ARG, "bad argument");
     if (s->W != other->W || s->Hg != other->Hg) return fail(SE_ERR_INVALID_ARG, "neighbour belongs to a different grid");
     SE_CUDA(cudaSetDevice(s->device));
@@ -1138,9 +1158,9 @@ int se_sim_attach_local(se_sim* s, int which, se_sim* other) {
     nb.flags = other->flags;
     nb.attached = true;
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_attach_local")
 
-int se_sim_halo_push(se_sim* s) {
+int se_sim_halo_push(se_sim* s) try {
     if (!s) return fail(SE_ERR_INVALID_ARG, "null sim");
     SE_CUDA(cudaSetDevice(s->device));
     const size_t rowb = (size_t)s->W * sizeof(unsigned);
@@ -1172,9 +1192,9 @@ int se_sim_halo_push(se_sim* s) {
         }
     }
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_halo_push")
 
-int se_sim_ipc_export_light(se_sim* s, void* handles) {
+int se_sim_ipc_export_light(se_sim* s, void* handles) try {
     if (!s || !handles) return fail(SE_ERR_INVALID_ARG, "null argument");
     if (!s->lighting) return fail(SE_ERR_INVALID_ARG, "sim was created without SE_FLAG_LIGHTING");
     SE_CUDA(cudaSetDevice(s->device));
@@ -1185,9 +1205,9 @@ int se_sim_ipc_export_light(se_sim* s, void* handles) {
         std::memcpy((char*)handles + 64 * b, &h, 64);
     }
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_ipc_export_light")
 
-int se_sim_ipc_attach_light(se_sim* s, int which, const void* handles) {
+int se_sim_ipc_attach_light(se_sim* s, int which, const void* handles) try {
     if (!s || !handles || which < 0 || which > 1) return fail(SE_ERR_INVALID_ARG, "bad argument");
     if (!s->lighting) return fail(SE_ERR_INVALID_ARG, "sim was created without SE_FLAG_LIGHTING");
     SE_CUDA(cudaSetDevice(s->device));
@@ -1204,9 +1224,9 @@ int se_sim_ipc_attach_light(se_sim* s, int which, const void* handles) {
         nb.light[b] = (float4*)p;
     }
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_ipc_attach_light")
 
-int se_sim_halo_exchange_async(se_sim* s) {
+int se_sim_halo_exchange_async(se_sim* s) try {
     if (!s) return fail(SE_ERR_INVALID_ARG, "null sim");
     SE_CUDA(cudaSetDevice(s->device));
     if (!driver().ok) return fail(SE_ERR_CUDA, driver().why);
@@ -1228,6 +1248,6 @@ int se_sim_halo_exchange_async(se_sim* s) {
     for (int w = 0; w < 2; ++w)
         if (s->nb[w].attached) SE_CU(driver().StreamWaitValue32(st, (CUdeviceptr)(s->flags + (w == 0 ? 2 : 3)), e, CU_STREAM_WAIT_VALUE_GEQ));
     return SE_OK;
-}
+} SE_ABI_CATCH("se_sim_halo_exchange_async")
 
 }  // extern "C"
