@@ -150,6 +150,11 @@ class Simulation:
             _capi.check(_capi.lib().se_sim_download_color(self._h, out.ctypes.data, None))
         return out
 
+    def save_color_png(self, path) -> None:
+        """Headless frame dump: the reference's `output_color` as an 8-bit RGBA PNG (render.py)."""
+        from .render import write_png
+        write_png(path, self.download_color(rgba8=True))
+
     def upload_cells_ptr(self, host_ptr: int) -> None:
         _capi.check(_capi.lib().se_sim_upload_cells(self._h, C.c_void_p(host_ptr)))
 
