@@ -12,7 +12,7 @@ import pytest
 
 import ref_cases as R
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.first_gpu_run]
 
 LIGHT_ATOL = 1e-6
 
