@@ -143,7 +143,10 @@ def cpu_port_rate(size_sample: int, budget_s: float, seed: int = SEED, one_threa
     orc = load_oracle()
     g = synthetic_grid(size_sample, size_sample, seed)
     cores = len(os.sched_getaffinity(0))
-    frame = orc.run_blocks(g, 1, 2)   # warm-up (page-in, thread pool)
+    frame = orc.run_blocks(g, 1, 2)   # warm-up (page-in, thread pool) ...
+    tw = time.perf_counter()
+    while time.perf_counter() - tw < 1.0:   # ... and ~1 s of untimed work: host clocks / worker threads ramp up (seen: 0.07 -> 0.12 Gcell/s)
+        frame = orc.run_blocks(g, frame, 2)
     steps, t0 = 0, time.perf_counter()
     while True:
         frame = orc.run_blocks(g, frame, 4)
@@ -207,7 +210,10 @@ def cpu_reference_rate(size_sample: int, budget_s: float, seed: int = SEED):
     ref.create(size_sample, size_sample)
     ref.upload_ids(g)
     ref.frame = 1
-    ref.step(1)                                            # page-in, thread pool
+    ref.step(1)                                            # page-in, thread pool ...
+    tw = time.perf_counter()
+    while time.perf_counter() - tw < 1.0:                  # ... and ~1 s of untimed work (host clocks / worker threads ramp up)
+        ref.step(1)
     steps, t0 = 0, time.perf_counter()
     while True:
         ref.step(1)
@@ -216,7 +222,25 @@ def cpu_reference_rate(size_sample: int, budget_s: float, seed: int = SEED):
         if dt >= budget_s or steps >= 4000:
             break
     rate = size_sample * size_sample * steps / dt / 1e9
-    return {"value": round(rate, 6), "unit": UNIT, "cores": cores, "kind": "reference",
+    # the same library on ONE thread: 256^2 (BASELINE configs[0]), ~2 s
+    one = None
+    try:
+        small = min(256, size_sample)
+        ref.set_threads(1)
+        ref.create(small, small)
+        ref.upload_ids(synthetic_grid(small, small, seed))
+        ref.frame = 1
+        ref.step(1)
+        n1, t1 = 0, time.perf_counter()
+        while time.perf_counter() - t1 < 2.0:
+            ref.step(1)
+            n1 += 1
+        one = round(small * small * n1 / (time.perf_counter() - t1) / 1e9, 6)
+    except Exception:
+        pass
+    finally:
+        ref.set_threads(cores)
+    return {"value": round(rate, 6), "unit": UNIT, "cores": cores, "kind": "reference", "value_1_thread": one,
             "sample": f"{size_sample}x{size_sample} grid of the same generator (seed {seed}), {steps} steps in {dt:.1f} s, {cores} threads; " + REF_WHAT}
 
 
