@@ -1,6 +1,9 @@
 # Round-2 opener: validate and time the experimental, default-off paths in ONE gpurun call.
 #   gpurun --timeout 600 -- 'bash scripts/gpu_experiments.sh'
 mkdir -p gpurun_out
+# 0. GPU tests written after round 1's GPU budget was spent (marker first_gpu_run: CUDA path vs reference-shader goldens,
+#    long horizons at full size, the C++ mirror).  Once green: drop the marker from those files.
+timeout 600 python -m pytest tests -q -m "gpu and first_gpu_run" 2>&1 | tail -5
 # 1. running census (SE_FLAG_RUNNING_CENSUS): correctness, then the e2e leg with and without it
 SE_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "running_census or lit_strips or fused_light or random_eligible or two_table or strips_with_modifications" 2>&1 | tail -5
 timeout 200 python bench.py --steps 400 --warmup 16 --no-cpu-baseline > gpurun_out/exp_e2e_base.json 2> gpurun_out/exp_e2e_base.err
