@@ -28,3 +28,10 @@ for v in "SE_LT_ROWS=2" "SE_LT_ROWS=8" "SE_LT_MINCTAS=3" "SE_LT_MINCTAS=5"; do e
 SE_FUSED=1 python scripts/light_probe.py 8192 48
 SE_FUSED=1 python scripts/light_probe.py 4096 100
 SE_FUSED=1 timeout 120 ncu --set full --clock-control none --import-source on -k regex:se_light_fused -s 16 -c 1 -o gpurun_out/prof_r2_light_fused python scripts/light_probe.py 8192 12 > /dev/null 2>&1
+# 5. K1c occupancy (no code change: rule-compile-time defines + grid override).  Default: 54 registers, 2 CTAs of 512
+#    threads per SM (50 %).  Checked with ptxas on the build host: MINCTAS=3 (<= 42 registers) and MINCTAS=4 with BATCH=2
+#    (<= 32 registers) compile WITHOUT spills; MINCTAS=4 with BATCH=4 spills.  Staged table 43.6 KB per CTA fits 4 per SM.
+python scripts/k1c_probe.py
+SE_NVRTC_DEFS="-DSE_K1C_MINCTAS=3" SE_K1C_GRID=444 python scripts/k1c_probe.py
+SE_NVRTC_DEFS="-DSE_K1C_MINCTAS=4 -DSE_K1C_BATCH=2" SE_K1C_GRID=592 python scripts/k1c_probe.py
+SE_NVRTC_DEFS="-DSE_K1C_MINCTAS=3 -DSE_K1C_BATCH=2" SE_K1C_GRID=444 python scripts/k1c_probe.py
