@@ -23,7 +23,10 @@ timeout 100 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --c
 timeout 120 ncu --set full --clock-control none --import-source on -k regex:se_light -s 16 -c 1 -o gpurun_out/prof_r2_light python scripts/light_probe.py 8192 12 > /dev/null 2>&1
 python scripts/light_probe.py 8192 48
 # 3. se_light tile-height / occupancy variants (rule-compile-time env; all three tile heights are host-checked)
-for v in "SE_LT_ROWS=2" "SE_LT_ROWS=8" "SE_LT_MINCTAS=3" "SE_LT_MINCTAS=5"; do echo "$v"; env $v python scripts/light_probe.py 8192 48; done
+#    ptxas on the build host: default 64 registers / 0 spills (also what MINCTAS=3 gives: identical code, dropped here);
+#    ROWS=2: 56 registers, 10.8 KB smem; ROWS=8: 64 registers, 36.9 KB smem; MINCTAS=5: 48 registers with 24 B of spills
+#    (worth one timing); MINCTAS >= 6 spills 200-450 B (not worth GPU time).
+for v in "SE_LT_ROWS=2" "SE_LT_ROWS=8" "SE_LT_MINCTAS=5"; do echo "$v"; env $v python scripts/light_probe.py 8192 48; done
 # 4. fused step + lighting kernel (K3f) against the two-kernel path
 SE_FUSED=1 python scripts/light_probe.py 8192 48
 SE_FUSED=1 python scripts/light_probe.py 4096 100
