@@ -38,3 +38,5 @@ python scripts/k1c_probe.py
 SE_NVRTC_DEFS="-DSE_K1C_MINCTAS=3" SE_K1C_GRID=444 python scripts/k1c_probe.py
 SE_NVRTC_DEFS="-DSE_K1C_MINCTAS=4 -DSE_K1C_BATCH=2" SE_K1C_GRID=592 python scripts/k1c_probe.py
 SE_NVRTC_DEFS="-DSE_K1C_MINCTAS=3 -DSE_K1C_BATCH=2" SE_K1C_GRID=444 python scripts/k1c_probe.py
+# 6. BASELINE configs[0] on the GPU (timing + comparison with the reference shader output)
+python scripts/run_configs.py 1 > gpurun_out/config1.json

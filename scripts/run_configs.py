@@ -1,4 +1,5 @@
 """Secondary BASELINE.json configs (not bench lines): timing + parity spot checks, one JSON line each on stderr/stdout.
+  python scripts/run_configs.py 1        # 256^2, 1000 steps (BASELINE configs[0]): timing + comparison with the reference shader's output
   python scripts/run_configs.py 2        # 4096^2, lighting off, 10k steps (L2-resident)
   python scripts/run_configs.py 4        # 4096^2, brush stamps + explosion every frame, lighting on
   torchrun ... scripts/run_configs.py 5  # synthetic 64-material rule set, 65536^2 over the ranks (K1a path)
@@ -32,6 +33,41 @@ def frame_mods(k, w, h, n_mats_selectable):
     m[4]["mod_size"] = 16 + int(hv[14] % 49)
     m[4]["mod_matID"] = 0
     return m
+
+
+def config1():
+    """configs[0]: 256 x 256, default rule set, 1000 steps, seed 1 -- the reference's own CPU-sized case.  Lighting on (the
+    reference's shader always relaxes light); final ids are compared with the output of the reference's shader compiled
+    for the CPU (tests/golden/ref_shader_goldens.json), light with its sub-sampled copy; timing per frame and batched."""
+    import hashlib
+    S, K = 256, 1000
+    gold = json.loads((REPO / "tests" / "golden" / "ref_shader_goldens.json").read_text())["cases"]["default_256x256_seed1_lit_1000"]
+    gold_light = np.load(REPO / "tests" / "golden" / "ref_shader_arrays.npz")["default_256x256_seed1_lit_1000/light_sub8"]
+    rules = se.parse_path(REPO / "data" / "materials.yaml")
+    out = {"config": 1, "workload": "256x256, default rules, 1000 steps, seed 1 (BASELINE configs[0])"}
+    for lighting in (True, False):
+        sim = se.Simulation(rules, (S, S), lighting=lighting)
+        st = torch.cuda.Stream(); torch.cuda.set_stream(st); sim.set_stream(st.cuda_stream)
+        g = synthetic_grid(S, S, 1)
+        for batched in (False, True):
+            sim.upload_cells(g); sim.params.frame = 1
+            if lighting: sim.upload_light(np.zeros((S, S, 4), np.float32))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); e0.record(st)
+            if batched: sim.step(K)
+            else:
+                for _ in range(K): sim.run()
+            e1.record(st); torch.cuda.synchronize()
+            t = e0.elapsed_time(e1) / 1e3
+            ids = sim.download_cells()
+            ok = hashlib.sha256(np.ascontiguousarray(ids, np.uint32).tobytes()).hexdigest() == gold["ids_sha256"]["1000"]
+            key = ("lit" if lighting else "unlit") + ("_batched" if batched else "_per_frame")
+            out[key] = {"gcell_per_s": round(S * S * K / t / 1e9, 3), "us_per_step": round(t / K * 1e6, 2), "ids_equal_reference_shader": bool(ok)}
+            if lighting:
+                out[key]["light_max_abs_err_vs_reference_shader"] = float(np.abs(sim.download_light()[::8, ::8] - gold_light).max())
+        sim.close()
+    out["note"] = "launch-latency bound at this size (65 536 cells): us_per_step is the figure of merit, not Gcell/s"
+    print(json.dumps(out), flush=True)
 
 
 def config2():
@@ -123,4 +159,4 @@ def config5():
 
 
 if __name__ == "__main__":
-    {"2": config2, "4": config4, "5": config5}[sys.argv[1]]()
+    {"1": config1, "2": config2, "4": config4, "5": config5}[sys.argv[1]]()
