@@ -283,3 +283,31 @@ def test_modification_override_vs_reference_shader(native_lib, tmp_path_factory,
         got = np.where(over == 0xFFFFFFFF, wall, over)
         assert np.array_equal(got, want)
         assert (want != 2).any() or len(staged) == 0 or all(m["mod_matID"] in (1, 2) for m in staged)
+
+
+@needs_reference
+def test_lighting_kernel_phases_vs_reference_shader(native_lib, tmp_path_factory, default_rules):
+    """se_light's two per-thread phases (staging of the neighbour terms, sliding-window combine; interior and rim CTAs),
+    compiled for the host, against the light the reference's shader writes -- bit for bit, no oracle in between.
+    The new ids come from the shader's own step (modifications included), the old ids and the light go in as they are."""
+    lib = _build_emu(tmp_path_factory, default_rules)
+    lib.emu_light.argtypes = [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]
+    ref = build_ref.load_ref()
+    for name in ("default_80x64_seed9_lit_hashlight_stamps_50", "default_512x512_seed4_config3_lit_24"):
+        case = R.CASE_BY_NAME[name]
+        w, h = case.W, case.H
+        g, L0, mods = R.grid_for(case), R.light0_for(case), R.mods_for(case, 11)
+        if L0 is None or not L0.any():
+            L0 = R.light0_for(R.Case("x", W=w, H=h, seed=case.seed, lighting=True, light0="hash"))
+        ref.create(w, h); ref.upload_ids(g); ref.upload_light(L0); ref.frame = 1
+        old, light = g.copy(), L0.copy()
+        n_int = C.c_int(0)
+        for s in range(min(case.steps, 12)):
+            ref.push_modifications(mods[s])
+            ref.step(1)
+            new, want = ref.download_ids(), ref.download_light()
+            got = np.full((h, w, 4), np.nan, np.float32)
+            lib.emu_light(old.ctypes.data, new.ctypes.data, light.ctypes.data, got.ctypes.data, w, h, 0, h, C.byref(n_int))
+            assert np.array_equal(got, want), (name, s, float(np.nanmax(np.abs(got - want))))
+            old, light = new, want
+        assert n_int.value > 0 or w < 96          # the large case exercises the interior fast path (x 0.125 instead of / n)
