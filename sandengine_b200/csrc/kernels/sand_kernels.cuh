@@ -394,6 +394,7 @@ extern "C" __global__ void __launch_bounds__(256, SE_LT_MINCTAS) se_light(const 
         se_light_compute<false>(p, fat_sm, term, bx, by, tid, SeNewIdFromGlobal{p.new_cells});
     }
 }
+#endif  // SE_HOST_EMU (se_light kernel)
 
 // ---------------------------------------------------------------------------------------------
 // K5: colour shading (operations.glsl:100-108, math.glsl:82-111) -- the render product of `setCell`:
@@ -403,7 +404,6 @@ extern "C" __global__ void __launch_bounds__(256, SE_LT_MINCTAS) se_light(const 
 // Uses sinf (not __sinf); the hash `fract(sin(p) * 43758.5453)` amplifies last-bit differences of sin, so
 // parity with the CPU restatement is a tolerance statement (tests/test_gpu_parity.py::test_colour_shading).
 // ---------------------------------------------------------------------------------------------
-#ifndef SE_HOST_EMU
 static __device__ __forceinline__ float se_fract(float x) { return x - floorf(x); }
 static __device__ __forceinline__ float2 se_old_hash2(float px, float py) {   // math.glsl:40-44
     const float a = px * 127.1f + py * 311.7f;
@@ -430,6 +430,24 @@ static __device__ float se_simplex(float px, float py) {                      //
     return 0.25f + 0.5f * (n0 * 70.0f + n1 * 70.0f + n2 * 70.0f);
 }
 
+// colour of one cell (the kernel below and tests/emu run exactly this)
+static __device__ __forceinline__ float4 se_shade_cell(unsigned id, int x, int y) {
+    float4 col = make_float4(se_color_table[id * 4 + 0], se_color_table[id * 4 + 1], se_color_table[id * 4 + 2], se_color_table[id * 4 + 3]);
+    if (id != 0u) {                                                            // cell.mat != MAT_EMPTY
+        float fx = (float)x, fy = (float)y, f = 0.0f;
+        for (int o = 1; o < 4; ++o) {                                          // noise(pos, 3, 2.0, 0.25), math.glsl:98-107
+            f += 1.0f / (float)o * se_simplex(fx * 0.25f, fy * 0.25f);
+            fx *= 2.0f; fy *= 2.0f;
+        }
+        const float rnd = f * 0.25f;
+        col.x = fminf(fmaxf(col.x - rnd, 0.0f), 1.0f);
+        col.y = fminf(fmaxf(col.y - rnd, 0.0f), 1.0f);
+        col.z = fminf(fmaxf(col.z - rnd, 0.0f), 1.0f);
+    }
+    return col;
+}
+
+#ifndef SE_HOST_EMU
 struct SeShadeParams {
     const unsigned* cells;   // first OWNED row
     float4* rgba_f32;        // or nullptr
@@ -443,18 +461,7 @@ extern "C" __global__ void __launch_bounds__(256) se_shade(const SeShadeParams p
     if (x >= p.W || yl >= p.rows) return;
     const size_t idx = (size_t)yl * p.W + x;
     const unsigned id = min(p.cells[idx], 255u);
-    float4 col = make_float4(se_color_table[id * 4 + 0], se_color_table[id * 4 + 1], se_color_table[id * 4 + 2], se_color_table[id * 4 + 3]);
-    if (id != 0u) {                                                            // cell.mat != MAT_EMPTY
-        float fx = (float)x, fy = (float)(p.y0 + yl), f = 0.0f;
-        for (int o = 1; o < 4; ++o) {                                          // noise(pos, 3, 2.0, 0.25), math.glsl:98-107
-            f += 1.0f / (float)o * se_simplex(fx * 0.25f, fy * 0.25f);
-            fx *= 2.0f; fy *= 2.0f;
-        }
-        const float rnd = f * 0.25f;
-        col.x = fminf(fmaxf(col.x - rnd, 0.0f), 1.0f);
-        col.y = fminf(fmaxf(col.y - rnd, 0.0f), 1.0f);
-        col.z = fminf(fmaxf(col.z - rnd, 0.0f), 1.0f);
-    }
+    const float4 col = se_shade_cell(id, x, p.y0 + yl);
     if (p.rgba_f32) p.rgba_f32[idx] = col;
     if (p.rgba8) {
         const unsigned r = (unsigned)__float2int_rn(fminf(fmaxf(col.x, 0.f), 1.f) * 255.0f), g = (unsigned)__float2int_rn(fminf(fmaxf(col.y, 0.f), 1.f) * 255.0f);
@@ -462,8 +469,9 @@ extern "C" __global__ void __launch_bounds__(256) se_shade(const SeShadeParams p
         p.rgba8[idx] = r | (g << 8) | (b << 16) | (a << 24);
     }
 }
-#endif  // SE_HOST_EMU
+#endif  // SE_HOST_EMU (se_shade kernel)
 
+#ifndef SE_HOST_EMU
 // frame == 1: every cell becomes EMPTY (falling_sand.glsl:743-746); lighting (if on) then runs with
 // new_cells == all-EMPTY through se_light.
 extern "C" __global__ void __launch_bounds__(256) se_fill_cells(unsigned* cells, size_t n, unsigned value) {

@@ -15,7 +15,9 @@
 #define __restrict__
 struct uint4 { unsigned x, y, z, w; };
 struct float4 { float x, y, z, w; };
+struct float2 { float x, y; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float __uint2float_rn(unsigned u) { return (float)u; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
@@ -66,6 +68,17 @@ extern "C" void emu_mod_override(const void* mods, int n_mods, int W, int H, uin
         for (int x = 0; x < W; ++x) {
             unsigned mat = 0;
             out[(size_t)y * W + x] = se_mod_lookup(m, n_mods, x, y, mat) ? mat : 0xFFFFFFFFu;
+        }
+}
+
+// K5 (colour shading): se_shade_cell over the grid (glibc sinf here, CUDA sinf on the device)
+extern "C" void emu_shade(const uint32_t* cells, int W, int H, float* rgba) {
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const uint32_t raw = cells[(size_t)y * W + x];
+            const float4 c = se_shade_cell(raw < 255u ? raw : 255u, x, y);
+            float* o = rgba + 4 * ((size_t)y * W + x);
+            o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = c.w;
         }
 }
 

@@ -311,3 +311,23 @@ def test_lighting_kernel_phases_vs_reference_shader(native_lib, tmp_path_factory
             assert np.array_equal(got, want), (name, s, float(np.nanmax(np.abs(got - want))))
             old, light = new, want
         assert n_int.value > 0 or w < 96          # the large case exercises the interior fast path (x 0.125 instead of / n)
+
+
+@needs_reference
+def test_colour_function_vs_reference_shader(native_lib, tmp_path_factory, default_rules):
+    """se_shade_cell (what kernel se_shade evaluates per cell), compiled for the host, against the `output_color` the
+    reference's shader writes: bit for bit here, where both sides call the same sinf.  On the device the same code runs
+    with CUDA's sinf, whose last-bit differences the noise hash amplifies -- hence the tolerance in the GPU test; this
+    test is what shows the expression structure (simplex noise, 3 octaves, clamp) is the reference's."""
+    lib = _build_emu(tmp_path_factory, default_rules)
+    lib.emu_shade.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    ref = build_ref.load_ref()
+    for (w, h, seed) in [(64, 48, 23), (131, 77, 5)]:
+        g = synthetic_grid(w, h, seed)
+        ref.create(w, h); ref.upload_ids(g); ref.frame = 1
+        ref.step(3)
+        ids, want = ref.download_ids(), ref.download_color()
+        got = np.empty((h, w, 4), np.float32)
+        lib.emu_shade(np.ascontiguousarray(ids).ctypes.data, w, h, got.ctypes.data)
+        assert np.array_equal(got, want), float(np.abs(got - want).max())
+        assert (ids != 0).mean() > 0.3 and np.abs(want[ids != 0][:, :3] - want[ids != 0][:, :3].round(2)).max() > 0   # noise was applied
