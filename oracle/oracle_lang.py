@@ -109,6 +109,25 @@ _Loader.add_constructor("tag:yaml.org,2002:int", _construct_int)
 _Loader.add_constructor("tag:yaml.org,2002:float", _construct_float)
 
 
+def _construct_mapping_no_duplicates(loader, node):
+    """serde_yaml 0.9 refuses a mapping with a repeated key ("duplicate entry with key ...") when it builds the `Value`
+    that parser.rs:95-98 deserialises into; PyYAML would silently keep the last one.  Found by scripts/diff_frontends.py."""
+    loader.flatten_mapping(node)
+    seen = set()
+    for key_node, _ in node.value:
+        key = loader.construct_object(key_node, deep=True)
+        try:
+            if key in seen:
+                raise yaml.constructor.ConstructorError(None, None, f"duplicate entry with key {key!r}", key_node.start_mark)
+            seen.add(key)
+        except TypeError:      # unhashable key (a sequence or mapping as key): left to PyYAML
+            pass
+    return loader.construct_mapping(node, deep=True)
+
+
+_Loader.add_constructor("tag:yaml.org,2002:map", _construct_mapping_no_duplicates)
+
+
 def _as_str(v):
     return v if isinstance(v, str) else None
 

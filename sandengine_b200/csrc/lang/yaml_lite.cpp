@@ -331,8 +331,23 @@ struct BlockParser {
                 else if (pos < lines.size() && lines[pos].indent == indent && is_seq_item(lines[pos])) val = parse_seq(indent);
                 // else: null
             } else {
+                // A plain (unquoted, non-flow) scalar continues on following lines that are indented deeper than its
+                // key; YAML folds each line break into one space (libyaml / serde_yaml do, e.g. a long `if:` condition
+                // wrapped over two lines).  A continuation line that itself looks like `key: value` is an error there too.
+                const char c0 = rest[0];
+                const bool plain = !(c0 == '"' || c0 == '\'' || c0 == '[' || c0 == '{' || c0 == '&' || c0 == '*' || c0 == '!' || c0 == '|' ||
+                                     c0 == '>' || c0 == '%' || c0 == '@' || c0 == '`');
+                int last_no = l.no;
+                while (pos < lines.size() && lines[pos].indent > indent) {
+                    const Line& c = lines[pos];
+                    if (!plain) fail(c.no, "unexpected indented line after a complete 'key: value'");
+                    if (c.no != last_no + 1) fail(c.no, "blank or comment line inside a multi-line plain scalar is not supported");
+                    if (find_key_sep(c.text) != std::string::npos) fail(c.no, "mapping values are not allowed in this context");
+                    rest += " " + c.text;
+                    last_no = c.no;
+                    ++pos;
+                }
                 val = parse_inline(rest, l.no);
-                if (pos < lines.size() && lines[pos].indent > indent) fail(lines[pos].no, "unexpected indented line after a complete 'key: value'");
             }
             for (auto& kv : m.map)
                 if (kv.first.kind == key.kind && kv.first.s == key.s) fail(l.no, "duplicate entry with key '" + key.s + "'");

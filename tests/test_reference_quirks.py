@@ -118,3 +118,44 @@ def test_non_mirrored_rules_are_all_classified_right_by_the_reference(se):
     nat = se.parse_string(text, compile=False)
     assert nat.glsl_rules == oracle_lang.emit_glsl_rules(orc)
     assert "swap(self, left);" in nat.glsl_rules and "inout Cell left" not in nat.glsl_rules      # the uncompilable text of the reference
+
+
+def test_duplicate_mapping_keys_are_a_yaml_error(se):
+    """serde_yaml 0.9 (unsafe-libyaml 0.2.11) refuses a repeated key while building the Value that parser.rs:95-98
+    deserialises into ("duplicate entry with key ..."); PyYAML would keep the last one.  Found by scripts/diff_frontends.py."""
+    both_fail(se, Y.BASE_OK.replace("    do: SWAP SELF DOWN\n", "    do: SWAP SELF DOWN\n    do: SWAP SELF RIGHT\n", 1), "Yaml")
+    both_fail(se, Y.BASE_OK + "types:\n  other:\n    base_rules: [gravity]\n", "Yaml")
+
+
+def test_wrapped_plain_scalars_are_folded(se):
+    """A long condition wrapped over several deeper-indented lines is ONE plain scalar in YAML (line breaks fold into
+    spaces); both front ends must read it like libyaml does.  Found by scripts/diff_frontends.py."""
+    wrapped = Y.BASE_OK.replace("if: DOWN.mat.density < SELF.mat.density",
+                                "if: DOWN.mat.density < SELF.mat.density\n        and isType_EMPTY(DOWN)\n        or SELF.mat == sand", 1)
+    flat = Y.BASE_OK.replace("if: DOWN.mat.density < SELF.mat.density",
+                             "if: DOWN.mat.density < SELF.mat.density and isType_EMPTY(DOWN) or SELF.mat == sand", 1)
+    nat_w, _ = both(se, wrapped)
+    nat_f, _ = both(se, flat)
+    assert nat_w.glsl_rules == nat_f.glsl_rules and "&& isType_EMPTY(down) || self.mat == MAT_sand" in nat_w.glsl_rules
+    # a folded value is re-typed as a whole: `mirrored: false` + a continuation line is a string, not a bool
+    both_fail(se, Y.BASE_OK.replace("    mirrored: false\n", "    mirrored: false\n      - SWAP SELF DOWN\n", 1), "InvalidType")
+    # a continuation line that looks like `key: value` is not a continuation (libyaml: "mapping values are not allowed")
+    both_fail(se, Y.BASE_OK.replace("    mirrored: false\n", "    mirrored: false\n      extra: 1\n", 1), "Yaml")
+
+
+def test_front_ends_agree_on_random_mutants(se):
+    """Fixed-seed slice of scripts/diff_frontends.py: same ParsingErr class or byte-identical generated text."""
+    import importlib.util
+    import random
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("diff_frontends", Path(__file__).resolve().parent.parent / "scripts" / "diff_frontends.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = random.Random(20261017)
+    outcomes = set()
+    for _ in range(400):
+        text = mod.mutate(rng.choice(mod.SOURCES), rng)
+        nat, orc = mod.run(text)
+        assert nat == orc, (nat[0], orc[0], text)
+        outcomes.add(nat[0])
+    assert {"ok", "Yaml", "MissingField", "InvalidType", "NotFound"} <= outcomes
