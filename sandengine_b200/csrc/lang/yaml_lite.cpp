@@ -299,6 +299,26 @@ struct BlockParser {
 
     bool is_seq_item(const Line& l) const { return l.text == "-" || (l.text.size() >= 2 && l.text[0] == '-' && l.text[1] == ' '); }
 
+    // Multi-line plain scalar: `text` (first line, already consumed) continues on the following lines as long as they
+    // are indented deeper than `parent_indent`; YAML folds each line break into one space (libyaml / serde_yaml do, e.g.
+    // a long `if:` condition wrapped over two lines).  Quoted / flow / tagged values do not continue here, and a
+    // continuation line that itself looks like `key: value` is an error in libyaml too.
+    void fold_plain(std::string& text, int parent_indent, int first_no) {
+        const char c0 = text.empty() ? ' ' : text[0];
+        const bool plain = !(c0 == '"' || c0 == '\'' || c0 == '[' || c0 == '{' || c0 == '&' || c0 == '*' || c0 == '!' || c0 == '|' ||
+                             c0 == '>' || c0 == '%' || c0 == '@' || c0 == '`');
+        int last_no = first_no;
+        while (pos < lines.size() && lines[pos].indent > parent_indent) {
+            const Line& c = lines[pos];
+            if (!plain) fail(c.no, "unexpected indented line after a complete value");
+            if (c.no != last_no + 1) fail(c.no, "blank or comment line inside a multi-line plain scalar is not supported");
+            if (find_key_sep(c.text) != std::string::npos) fail(c.no, "mapping values are not allowed in this context");
+            text += " " + c.text;
+            last_no = c.no;
+            ++pos;
+        }
+    }
+
     YamlValue parse_block(int indent) {
         const Line& l = lines[pos];
         if (is_seq_item(l)) return parse_seq(indent);
@@ -331,22 +351,7 @@ struct BlockParser {
                 else if (pos < lines.size() && lines[pos].indent == indent && is_seq_item(lines[pos])) val = parse_seq(indent);
                 // else: null
             } else {
-                // A plain (unquoted, non-flow) scalar continues on following lines that are indented deeper than its
-                // key; YAML folds each line break into one space (libyaml / serde_yaml do, e.g. a long `if:` condition
-                // wrapped over two lines).  A continuation line that itself looks like `key: value` is an error there too.
-                const char c0 = rest[0];
-                const bool plain = !(c0 == '"' || c0 == '\'' || c0 == '[' || c0 == '{' || c0 == '&' || c0 == '*' || c0 == '!' || c0 == '|' ||
-                                     c0 == '>' || c0 == '%' || c0 == '@' || c0 == '`');
-                int last_no = l.no;
-                while (pos < lines.size() && lines[pos].indent > indent) {
-                    const Line& c = lines[pos];
-                    if (!plain) fail(c.no, "unexpected indented line after a complete 'key: value'");
-                    if (c.no != last_no + 1) fail(c.no, "blank or comment line inside a multi-line plain scalar is not supported");
-                    if (find_key_sep(c.text) != std::string::npos) fail(c.no, "mapping values are not allowed in this context");
-                    rest += " " + c.text;
-                    last_no = c.no;
-                    ++pos;
-                }
+                fold_plain(rest, indent, l.no);
                 val = parse_inline(rest, l.no);
             }
             for (auto& kv : m.map)
@@ -379,9 +384,10 @@ struct BlockParser {
                 l.text = item;
                 s.seq.push_back(parse_block(l.indent));
             } else {
-                s.seq.push_back(parse_inline(item, l.no));
-                ++pos;
-                if (pos < lines.size() && lines[pos].indent > indent) fail(lines[pos].no, "multi-line plain scalars are not supported");
+                const int item_no = l.no;
+                ++pos;                          // (l is not used below: fold_plain may walk past it)
+                fold_plain(item, indent, item_no);
+                s.seq.push_back(parse_inline(item, item_no));
             }
         }
         return s;

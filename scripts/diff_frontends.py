@@ -24,7 +24,7 @@ TOKENS = ["SELF", "DOWN", "RIGHT", "LEFT", "DOWNRIGHT", "DOWNLEFT", "SWAP", "SET
 def mutate(text, rng):
     lines = text.split("\n")
     for _ in range(rng.randint(1, 3)):
-        k = rng.randrange(8)
+        k = rng.randrange(14)
         i = rng.randrange(len(lines))
         if k == 0 and len(lines) > 3:
             del lines[i]
@@ -47,8 +47,42 @@ def mutate(text, rng):
             m = re.match(r"^(\s*)([\w-]+)(:.*)$", lines[i])
             if m:
                 lines[i] = m.group(1) + rng.choice(TOKENS + [m.group(2) + "x"]) + m.group(3)
-        else:                                          # toggle a bool
+        elif k == 7:                                   # toggle a bool
             lines[i] = lines[i].replace("true", "false") if "true" in lines[i] else lines[i].replace("false", "true")
+        elif k == 8:                                   # quote the value (single / double)
+            m = re.match(r"^(\s*[\w-]+:\s*)(\S.*)$", lines[i])
+            if m and not m.group(2).startswith(("[", "{", "'", '"')):
+                q = rng.choice("'\"")
+                if q not in m.group(2) and "\\" not in m.group(2):
+                    lines[i] = m.group(1) + q + m.group(2) + q
+        elif k == 9:                                   # a YAML 1.2 core-schema special scalar as value
+            m = re.match(r"^(\s*[\w-]+:\s*)(\S.*)$", lines[i])
+            if m:
+                lines[i] = m.group(1) + rng.choice(["~", "null", "Null", "yes", "no", "on", "off", "y", "n", "True", "FALSE", "0x10", "0o17", "010",
+                                                    "1e3", "1E-2", ".5", "5.", "+3", "-0.0", ".inf", "-.INF", ".nan", "1_000", "0b11", "''", '""'])
+        elif k == 10:                                  # flow list -> block list
+            m = re.match(r"^(\s*)([\w-]+):\s*\[(.*)\]\s*$", lines[i])
+            if m and "[" not in m.group(3):
+                items = [x.strip() for x in m.group(3).split(",") if x.strip()]
+                lines[i:i + 1] = [f"{m.group(1)}{m.group(2)}:"] + [f"{m.group(1)}  - {x}" for x in items]
+        elif k == 11:                                  # trailing comment / blank line / comment line
+            c = rng.randrange(3)
+            if c == 0 and lines[i].strip():
+                lines[i] = lines[i] + "   # note: x"
+            elif c == 1:
+                lines.insert(i, "")
+            else:
+                lines.insert(i, " " * rng.choice([0, 2, 4, 7]) + "# comment: [not, a, list]")
+        elif k == 12:                                  # shift the indentation of one line
+            lines[i] = (" " * rng.choice([1, 2])) + lines[i] if rng.random() < 0.5 else lines[i][min(2, len(lines[i]) - len(lines[i].lstrip())):]
+        else:                                          # shift a whole block (a line and everything deeper below it) by two columns
+            ind = len(lines[i]) - len(lines[i].lstrip())
+            j = i + 1
+            while j < len(lines) and (not lines[j].strip() or len(lines[j]) - len(lines[j].lstrip()) > ind):
+                j += 1
+            for t in range(i + 1, j):
+                if lines[t].strip():
+                    lines[t] = "  " + lines[t]
     return "\n".join(lines)
 
 

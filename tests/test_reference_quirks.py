@@ -139,6 +139,17 @@ def test_wrapped_plain_scalars_are_folded(se):
     assert nat_w.glsl_rules == nat_f.glsl_rules and "&& isType_EMPTY(down) || self.mat == MAT_sand" in nat_w.glsl_rules
     # a folded value is re-typed as a whole: `mirrored: false` + a continuation line is a string, not a bool
     both_fail(se, Y.BASE_OK.replace("    mirrored: false\n", "    mirrored: false\n      - SWAP SELF DOWN\n", 1), "InvalidType")
+    # ... also inside a sequence item: `- SET SELF sand` + a deeper `- SWAP SELF DOWN` is ONE item "SET SELF sand - SWAP SELF DOWN"
+    seq = Y.BASE_OK.replace("    do: SWAP SELF DOWN\n", "    do:\n    - SET SELF sand\n      - SWAP SELF DOWN\n", 1)
+    try:
+        nat = ("ok", se.parse_string(seq, compile=False).glsl_rules)
+    except se.SandEngineError as e:
+        nat = (e.kind,)
+    try:
+        orc = ("ok", oracle_lang.emit_glsl_rules(oracle_lang.parse_string(seq)))
+    except oracle_lang.ParsingErr as e:
+        orc = (e.kind,)
+    assert nat == orc
     # a continuation line that looks like `key: value` is not a continuation (libyaml: "mapping values are not allowed")
     both_fail(se, Y.BASE_OK.replace("    mirrored: false\n", "    mirrored: false\n      extra: 1\n", 1), "Yaml")
 
