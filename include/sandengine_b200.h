@@ -110,7 +110,8 @@ int se_sim_destroy(se_sim* s);
  * pending modifications are consumed by the FIRST step only and then cleared (:246-252). */
 int se_sim_step(se_sim* s, uint32_t n_steps);
 /* sim.modifications.push(..) (sandengine-core/src/lib.rs:59-67).  Appends; only the first 256 pending
- * entries are used by the next step (simulation.rs:205), like the reference. */
+ * entries are used by the next step (simulation.rs:205), like the reference.  mod_size values above 2^30 are applied as
+ * 2^30 (same cells as the shader's test for any position within +-2^29 of the grid: all of them). */
 int se_sim_push_modifications(se_sim* s, const se_modification* mods, uint32_t n);
 int se_sim_set_frame(se_sim* s, int32_t frame);     /* params.frame, simulation.rs:78 */
 int se_sim_get_frame(const se_sim* s, int32_t* frame);

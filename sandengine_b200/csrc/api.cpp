@@ -834,7 +834,11 @@ int se_sim_step(se_sim* s, uint32_t n_steps) try {
             const se_modification& m = s->pending[i];
             if (m.mod_size == 0) open = false;
             SeMod d;
-            d.px = m.position[0]; d.py = m.position[1]; d.shape = m.mod_shape; d.size = m.mod_size;
+            d.px = m.position[0]; d.py = m.position[1]; d.shape = m.mod_shape;
+            // Sizes above 2^30 are staged as 2^30: for every position within +-2^29 of the grid the record still covers
+            // exactly the cells the shader's test covers (all of them), and the per-CTA culling (px +- size, 32-bit) cannot
+            // overflow.  mod_size = INT_MAX ("fill everything") fills the grid in the reference, too.
+            d.size = std::min(m.mod_size, 1 << 30);
             // getMaterialFromID: unknown id => MAT_NULL (id 1), gen/materials.glsl:79-86
             d.mat = (m.mod_matID >= 0 && m.mod_matID < s->rules->cr.tables.n_materials) ? m.mod_matID : 1;
             d.pad0 = d.pad1 = d.pad2 = 0;

@@ -38,7 +38,7 @@ class Case:
     checkpoints: Tuple[int, ...] = ()      # ids hashed after these step counts (the last step always)
     lighting: bool = False
     light0: str = "zero"                   # "zero" | "hash"
-    mods: str = "none"                     # "none" | "stamps" | "edge" | "config3"
+    mods: str = "none"                     # "none" | "stamps" | "edge" | "config3" | "huge"
     grid: str = "synthetic"                # "synthetic" | "unknown_ids"
     store_light: str = "none"              # "full" | "sub8" | "none" (what goes into the .npz)
     store_color: bool = False
@@ -76,6 +76,8 @@ CASES = [
     # LEFT rules: outputs of the reference's shader template with gen/rules.glsl from the PATCHED emitter (see RefEngine)
     Case("rich_patchedleft_128x96_seed5_200", rules="rich", W=128, H=96, seed=5, steps=200, checkpoints=(1, 2, 3, 4)),
     Case("synthLR64_patchedleft_96x64_seed5_60", rules="synthLR:64:28:5", W=96, H=64, seed=5, steps=60, slow=True),
+    # mod_size up to INT_MAX (kept last: the CUDA path stages such sizes as 2^30, see api.cpp::se_sim_step)
+    Case("default_48x40_seed3_mods_huge_10", W=48, H=40, seed=3, steps=10, mods="huge", checkpoints=tuple(range(1, 10))),
 ]
 CASE_BY_NAME = {c.name: c for c in CASES}
 
@@ -164,6 +166,16 @@ def mods_for(case: Case, n_materials: int):
             m[4]["mod_size"] = 16 + int(hv[14] % 49)
             m[4]["mod_matID"] = 0
             out.append(m)
+        return out
+    if case.mods == "huge":
+        # mod_size up to INT_MAX ("fill everything"): the shader's tests are true for every cell of the grid
+        I = 2 ** 31 - 1
+        out = [np.zeros(0, MOD_DTYPE) for _ in range(case.steps)]
+        for s, (px, py, shape, size, mat) in enumerate([(10, 10, 0, I, 3), (20, 5, 1, I, 5), (W // 2, H // 2, 0, 2 ** 30, 0),
+                                                        (7, 9, 1, 2 ** 30 + 12345, 10), (30, 20, 0, 6, 4)]):
+            m = np.zeros(1, MOD_DTYPE)
+            m[0] = ((px, py), shape, size, mat, (0, 0, 0))
+            out[2 * s] = m                     # every other frame, so the material also gets to move in between
         return out
     if case.mods == "edge":
         m = np.zeros(4, MOD_DTYPE)      # a mod_size == 0 record in the middle ends the scan (falling_sand.glsl:139-141)

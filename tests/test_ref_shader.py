@@ -262,6 +262,8 @@ def test_modification_override_vs_reference_shader(native_lib, tmp_path_factory,
         [rec(i % w, (i * 7) % h, i % 2, 1 + i % 3, 3 + i % 8) for i in range(300)],
         [rec(36, 28, 0, r, 3 + r % 8) for r in range(30, 0, -1)],                 # concentric circles, every radius 1..30
         [rec(5, 5, 0, 4, 1), rec(8, 8, 1, 2, -1)],                               # NULL and a negative id never apply
+        [rec(10, 10, 0, 2 ** 31 - 1, 3)], [rec(20, 5, 1, 2 ** 31 - 1, 5)],       # mod_size INT_MAX fills the grid (staged as 2^30)
+        [rec(10, 10, 0, 2 ** 30 + 7, 6), rec(40, 30, 1, 3, 4)],
     ]
     for mods in lists:
         arr = np.array(mods, R.MOD_DTYPE)
@@ -269,13 +271,14 @@ def test_modification_override_vs_reference_shader(native_lib, tmp_path_factory,
         ref.push_modifications(arr)
         ref.step(1)
         want = ref.download_ids()
-        staged = []                       # api.cpp::se_sim_step: first min(len, 256), cut at mod_size == 0, unknown id -> NULL
+        staged = []                       # api.cpp::se_sim_step: first min(len, 256), cut at mod_size == 0, unknown id -> NULL, size <= 2^30
         for m in arr[:256]:
             if m["mod_size"] == 0:
                 break
             m = m.copy()
             if not (0 <= m["mod_matID"] < 11):
                 m["mod_matID"] = 1
+            m["mod_size"] = min(int(m["mod_size"]), 1 << 30)
             staged.append(m)
         staged = np.array(staged, R.MOD_DTYPE) if staged else np.zeros(0, R.MOD_DTYPE)
         over = np.empty((h, w), np.uint32)
