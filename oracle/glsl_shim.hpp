@@ -6,8 +6,8 @@
 // Nothing of the reference is copied here: this file only supplies what a GLSL compiler has built in —
 //   * vecN / ivecN / uvecN with component views (.x .r .xy .rgb ...), constructors that flatten their arguments,
 //     component-wise operators with GLSL's implicit int -> uint -> float promotions, == / != yielding bool;
-//   * the built-in functions the shader calls (floor fract sin cos tan abs sqrt pow step min max clamp mix dot
-//     distance), all evaluated in f32 (float literals get an `f` suffix in the translation, -ffp-contract=off);
+//   * the built-in functions the shader calls (floor ceil fract sign mod sin cos tan abs sqrt pow step min max clamp
+//     mix dot distance), all evaluated in f32 (float literals get an `f` suffix in the translation, -ffp-contract=off);
 //   * sampler2D / image2D over plain RGBA32F host arrays, texelFetch / imageStore, gl_GlobalInvocationID.
 // Everything is in namespace glsl; the translated shader is placed in the same namespace so its unqualified
 // calls (sin, pow, abs, ...) resolve here and never to <cmath>'s double overloads.
@@ -226,6 +226,18 @@ template <operand A> auto abs(const A& a) {
         return a < 0 ? -a : a;
     }
 }
+template <operand A> auto ceil(const A& a) { return map1f(a, [](float x) { return std::ceil(x); }); }
+template <operand A> auto sign(const A& a) {
+    if constexpr (vecish<A>) {
+        vec<elem_t<A>, comps<A>()> out;
+        for (int i = 0; i < comps<A>(); ++i) { const auto x = comp(a, i); out.d[i] = x > 0 ? 1 : (x < 0 ? -1 : 0); }
+        return out;
+    } else {
+        return static_cast<A>(a > 0 ? 1 : (a < 0 ? -1 : 0));
+    }
+}
+// mod(x, y) = x - y * floor(x / y)   (GLSL 4.30 spec, 8.3)
+template <operand A, operand B> auto mod(const A& a, const B& b) { return map2f(a, b, [](float x, float y) { return x - y * std::floor(x / y); }); }
 template <operand A, operand B> auto pow(const A& a, const B& b) { return map2f(a, b, [](float x, float y) { return std::pow(x, y); }); }
 template <operand A, operand B> auto step(const A& edge, const B& x) { return map2f(edge, x, [](float e, float v) { return v < e ? 0.0f : 1.0f; }); }
 template <operand A, operand B> auto max(const A& a, const B& b) {

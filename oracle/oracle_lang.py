@@ -669,7 +669,13 @@ _SWAPCALL_RE = re.compile(r"swap\((\w+), (\w+)\);")
 _FLOATLIT_RE = re.compile(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][-+]?\d+)?|\d+[eE][-+]?\d+)(?![\w.])")
 
 
+# GLSL built-ins a condition may call (the reference hands conditions to the GLSL compiler verbatim): renamed to the
+# type-generic se_* helpers of sand_oracle.c; `float(x)` / `int(x)` constructor syntax is not C.
+_BUILTIN_RE = re.compile(r"\b(abs|min|max|clamp|mod|floor|ceil|fract|sign|step|sqrt|float|int)\(")
+
+
 def _to_c(text: str) -> str:
+    text = _BUILTIN_RE.sub(lambda m: f"se_{m.group(1)}(", text)
     text = _MATCMP_RE.sub(lambda m: f"({m.group(1)}.mat.id {m.group(2)} {m.group(3)}.id)", text)
     text = _SWAPCALL_RE.sub(lambda m: f"swap_cells(&{m.group(1)}, &{m.group(2)});", text)
     text = _FLOATLIT_RE.sub(lambda m: m.group(1) + "f", text)

@@ -69,6 +69,29 @@ static void swap_cells(Cell* a, Cell* b);
  * step drivers below before the parallel loops (read-only inside them). */
 static int frame = 0;
 
+/* Scalar GLSL built-ins for rule conditions (GLSL 4.30 section 8.3 definitions; oracle_lang._to_c renames the calls).
+ * Type-generic like GLSL's overloads: an int argument list stays int, anything with a float is float. */
+static inline float se_minf(float a, float b) { return b < a ? b : a; }
+static inline int se_mini(int a, int b) { return b < a ? b : a; }
+static inline float se_maxf(float a, float b) { return a < b ? b : a; }
+static inline int se_maxi(int a, int b) { return a < b ? b : a; }
+static inline float se_signf(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
+static inline int se_signi(int x) { return x > 0 ? 1 : (x < 0 ? -1 : 0); }
+static inline int se_absi(int x) { return x < 0 ? -x : x; }
+static inline float se_mod(float x, float y) { return x - y * floorf(x / y); }
+static inline float se_fract(float x) { return x - floorf(x); }
+static inline float se_step(float edge, float x) { return x < edge ? 0.0f : 1.0f; }
+#define se_abs(x) _Generic((x), float: fabsf, double: fabsf, default: se_absi)(x)
+#define se_sign(x) _Generic((x), float: se_signf, double: se_signf, default: se_signi)(x)
+#define se_min(a, b) _Generic((a) + (b), float: se_minf, double: se_minf, default: se_mini)((a), (b))
+#define se_max(a, b) _Generic((a) + (b), float: se_maxf, double: se_maxf, default: se_maxi)((a), (b))
+#define se_clamp(x, lo, hi) se_min(se_max((x), (lo)), (hi))
+#define se_floor(x) floorf(x)
+#define se_ceil(x) ceilf(x)
+#define se_sqrt(x) sqrtf(x)
+#define se_float(x) ((float)(x))
+#define se_int(x) ((int)(x))
+
 #include "rules_gen.h"   /* TYPE_*, isType_*, MATERIALS[], MAT_*, rule_*, apply{Mirrored,Left,Right}Rules */
 
 /* falling_sand.glsl:371-378 -- guarded swap: no-op when either side is WALL or NULL typed. */

@@ -95,7 +95,7 @@ struct Lexer {
             kind = Number;
             return;
         }
-        static const char* two[] = {"||", "&&", "==", "!=", "<=", ">="};
+        static const char* two[] = {"||", "&&", "==", "!=", "<=", ">=", "<<", ">>"};
         for (auto* t : two)
             if (s.compare(p, 2, t) == 0) { tok = t; p += 2; kind = Op; return; }
         tok = std::string(1, c);
@@ -264,15 +264,50 @@ struct Parser {
         return mk_float(std::string(fn) + "(" + as_float_code(a) + ", " + as_float_code(b) + ")");
     }
 
-    // ---- grammar ----
+    // ---- grammar (precedence of GLSL 4.30, lowest first): ?:  ||  &&  |  ^  &  == !=  < > <= >=  << >>  + -  * / %  unary ----
+    // The reference passes conditions to the GLSL compiler verbatim, so anything a scalar GLSL expression may contain
+    // can appear in a rule file; what has no bit-exact meaning (transcendentals, vectors) is refused with a clean error.
+    Val parse_ternary() {
+        Val c = parse_or();
+        if (!lx.is_op("?")) return c;
+        lx.next();
+        Val a = parse_ternary();
+        if (!lx.is_op(":")) bad("missing ':' of the conditional operator");
+        lx.next();
+        Val b = parse_ternary();
+        const std::string cc = to_bool(c).code;
+        if (a.type == VT::Bool && b.type == VT::Bool) return mk_bool("(" + cc + " ? " + a.code + " : " + b.code + ")");
+        if (a.type == VT::Int && b.type == VT::Int) return mk_int("(" + cc + " ? " + a.code + " : " + b.code + ")");
+        if (is_num(a) && is_num(b)) return mk_float("(" + cc + " ? " + as_float_code(a) + " : " + as_float_code(b) + ")");
+        bad("the two branches of '?:' must both be booleans or both be numbers");
+    }
     Val parse_or() {
         Val a = parse_and();
         while (lx.is_op("||")) { lx.next(); Val b = parse_and(); a = mk_bool("(" + to_bool(a).code + " || " + to_bool(b).code + ")"); }
         return a;
     }
     Val parse_and() {
+        Val a = parse_bitor();
+        while (lx.is_op("&&")) { lx.next(); Val b = parse_bitor(); a = mk_bool("(" + to_bool(a).code + " && " + to_bool(b).code + ")"); }
+        return a;
+    }
+    Val int_op(const Val& a, const std::string& op, const Val& b) {
+        if (a.type != VT::Int || b.type != VT::Int) bad("'" + op + "' needs integer operands");
+        return mk_int("(" + a.code + " " + op + " " + b.code + ")");
+    }
+    Val parse_bitor() {
+        Val a = parse_bitxor();
+        while (lx.is_op("|")) { lx.next(); Val b = parse_bitxor(); a = int_op(a, "|", b); }
+        return a;
+    }
+    Val parse_bitxor() {
+        Val a = parse_bitand();
+        while (lx.is_op("^")) { lx.next(); Val b = parse_bitand(); a = int_op(a, "^", b); }
+        return a;
+    }
+    Val parse_bitand() {
         Val a = parse_eq();
-        while (lx.is_op("&&")) { lx.next(); Val b = parse_eq(); a = mk_bool("(" + to_bool(a).code + " && " + to_bool(b).code + ")"); }
+        while (lx.is_op("&")) { lx.next(); Val b = parse_eq(); a = int_op(a, "&", b); }
         return a;
     }
     Val parse_eq() {
@@ -281,8 +316,13 @@ struct Parser {
         return a;
     }
     Val parse_rel() {
+        Val a = parse_shift();
+        while (lx.is_op("<") || lx.is_op(">") || lx.is_op("<=") || lx.is_op(">=")) { std::string op = lx.tok; lx.next(); Val b = parse_shift(); a = compare(a, op, b); }
+        return a;
+    }
+    Val parse_shift() {
         Val a = parse_add();
-        while (lx.is_op("<") || lx.is_op(">") || lx.is_op("<=") || lx.is_op(">=")) { std::string op = lx.tok; lx.next(); Val b = parse_add(); a = compare(a, op, b); }
+        while (lx.is_op("<<") || lx.is_op(">>")) { std::string op = lx.tok; lx.next(); Val b = parse_add(); a = int_op(a, op, b); }
         return a;
     }
     Val parse_add() {
@@ -307,6 +347,12 @@ struct Parser {
             bad("unary '-' on a non-number");
         }
         if (lx.is_op("+")) { lx.next(); return parse_unary(); }
+        if (lx.is_op("~")) {
+            lx.next();
+            Val a = parse_unary();
+            if (a.type != VT::Int) bad("'~' needs an integer operand");
+            return mk_int("(~" + a.code + ")");
+        }
         return parse_postfix();
     }
     Val parse_postfix() {
@@ -369,10 +415,71 @@ struct Parser {
         }
         bad("'." + m + "' applied to a value without members");
     }
+    static bool is_num(const Val& v) { return v.type == VT::Int || v.type == VT::Float; }
+
+    // Scalar GLSL built-ins with an exact meaning (GLSL 4.30 section 8.3 definitions, evaluated in f32 without
+    // contraction, or on ints).  min(x,y) = y < x ? y : x;  max(x,y) = x < y ? y : x;  clamp = min(max(x,lo),hi);
+    // mod(x,y) = x - y*floor(x/y);  fract(x) = x - floor(x);  step(e,x) = x < e ? 0 : 1;  int() truncates.
+    static bool is_builtin(const std::string& id) {
+        static const char* names[] = {"abs", "min", "max", "clamp", "mod", "floor", "ceil", "fract", "sign", "step", "sqrt", "float", "int"};
+        for (auto* n : names)
+            if (id == n) return true;
+        return false;
+    }
+    Val call_builtin(const std::string& id, const std::vector<Val>& a) {
+        auto need = [&](size_t n) { if (a.size() != n) bad(id + "() takes " + std::to_string(n) + " argument(s)"); };
+        auto nums = [&]() { for (auto& v : a) if (!is_num(v)) bad(id + "() needs numeric arguments"); };
+        auto all_int = [&]() { for (auto& v : a) if (v.type != VT::Int) return false; return true; };
+        auto pick = [&](const Val& x, const Val& y, bool take_y_if_less_than_x) {   // min: y < x ? y : x   max: x < y ? y : x
+            const bool ints = x.type == VT::Int && y.type == VT::Int;
+            const std::string X = ints ? x.code : as_float_code(x), Y = ints ? y.code : as_float_code(y);
+            const std::string c = take_y_if_less_than_x ? "(" + Y + " < " + X + " ? " + Y + " : " + X + ")" : "(" + X + " < " + Y + " ? " + Y + " : " + X + ")";
+            return ints ? mk_int(c) : mk_float(c);
+        };
+        if (id == "float") {
+            need(1);
+            if (a[0].type == VT::Bool) return mk_float("(" + a[0].code + " ? 1.0f : 0.0f)");
+            nums();
+            return mk_float(as_float_code(a[0]));
+        }
+        if (id == "int") {
+            need(1);
+            if (a[0].type == VT::Bool) return mk_int("(" + a[0].code + " ? 1 : 0)");
+            nums();
+            return a[0].type == VT::Int ? mk_int(a[0].code) : mk_int("((int)(" + as_float_code(a[0]) + "))");
+        }
+        nums();
+        if (id == "abs") {
+            need(1);
+            if (all_int()) return mk_int("(" + a[0].code + " < 0 ? (-" + a[0].code + ") : " + a[0].code + ")");
+            return mk_float("fabsf(" + as_float_code(a[0]) + ")");
+        }
+        if (id == "min") { need(2); return pick(a[0], a[1], true); }
+        if (id == "max") { need(2); return pick(a[0], a[1], false); }
+        if (id == "clamp") { need(3); return pick(pick(a[0], a[1], false), a[2], true); }
+        if (id == "sign") {
+            need(1);
+            if (all_int()) return mk_int("(" + a[0].code + " > 0 ? 1 : (" + a[0].code + " < 0 ? -1 : 0))");
+            const std::string X = as_float_code(a[0]);
+            return mk_float("(" + X + " > 0.0f ? 1.0f : (" + X + " < 0.0f ? -1.0f : 0.0f))");
+        }
+        if (id == "floor") { need(1); return mk_float("floorf(" + as_float_code(a[0]) + ")"); }
+        if (id == "ceil") { need(1); return mk_float("ceilf(" + as_float_code(a[0]) + ")"); }
+        if (id == "sqrt") { need(1); return mk_float("__fsqrt_rn(" + as_float_code(a[0]) + ")"); }
+        if (id == "fract") { need(1); const std::string X = as_float_code(a[0]); return mk_float("__fsub_rn(" + X + ", floorf(" + X + "))"); }
+        if (id == "step") { need(2); return mk_float("(" + as_float_code(a[1]) + " < " + as_float_code(a[0]) + " ? 0.0f : 1.0f)"); }
+        if (id == "mod") {
+            need(2);
+            const std::string X = as_float_code(a[0]), Y = as_float_code(a[1]);
+            return mk_float("__fsub_rn(" + X + ", __fmul_rn(" + Y + ", floorf(__fdiv_rn(" + X + ", " + Y + "))))");
+        }
+        bad("unknown function '" + id + "'");
+    }
+
     Val parse_primary() {
         if (lx.is_op("(")) {
             lx.next();
-            Val v = parse_or();
+            Val v = parse_ternary();
             if (!lx.is_op(")")) bad("missing ')'");
             lx.next();
             if (v.type == VT::Bool || v.type == VT::Int || v.type == VT::Float) {
@@ -405,6 +512,20 @@ struct Parser {
             std::string id = lx.tok;
             lx.next();
             if (id == "true" || id == "false") return mk_bool(id);
+            if (is_builtin(id) && lx.is_op("(")) {
+                lx.next();
+                std::vector<Val> args;
+                if (!lx.is_op(")")) {
+                    for (;;) {
+                        args.push_back(parse_ternary());
+                        if (lx.is_op(",")) { lx.next(); continue; }
+                        break;
+                    }
+                }
+                if (!lx.is_op(")")) bad("missing ')' after the arguments of " + id + "()");
+                lx.next();
+                return call_builtin(id, args);
+            }
             if (id == "rand") { Val v; v.type = VT::RandVec; return v; }
             if (id == "pos") { Val v; v.type = VT::PosVec; return v; }
             if (id == "frame") { *cx.lut_ok = false; return mk_int("frame"); }
@@ -425,7 +546,7 @@ struct Parser {
                 if (t < 0) throw not_found(id.substr(7), cx.where + " -> isType_");
                 if (!lx.is_op("(")) bad("isType_* needs a cell argument");
                 lx.next();
-                Val arg = parse_or();
+                Val arg = parse_ternary();
                 if (arg.type != VT::Cell) bad("isType_* needs a cell argument");
                 if (!lx.is_op(")")) bad("missing ')'");
                 lx.next();
@@ -441,7 +562,7 @@ struct Parser {
     }
 
     Val parse_all() {
-        Val v = parse_or();
+        Val v = parse_ternary();
         if (lx.kind != Lexer::End) bad("unexpected trailing '" + lx.tok + "'");
         return v;
     }

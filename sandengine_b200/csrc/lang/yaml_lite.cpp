@@ -351,6 +351,12 @@ struct BlockParser {
                 else if (pos < lines.size() && lines[pos].indent == indent && is_seq_item(lines[pos])) val = parse_seq(indent);
                 // else: null
             } else {
+                {   // a plain scalar cannot contain ": " (libyaml: "mapping values are not allowed in this context"),
+                    // e.g. an unquoted `a ? b : c` condition
+                    const char c0 = rest[0];
+                    if (c0 != '"' && c0 != '\'' && c0 != '[' && c0 != '{' && find_key_sep(rest) != std::string::npos)
+                        fail(l.no, "mapping values are not allowed in this context (quote the value)");
+                }
                 fold_plain(rest, indent, l.no);
                 val = parse_inline(rest, l.no);
             }

@@ -1,7 +1,11 @@
 """Tooling (CPU): differential fuzz of the two independent restatements of the reference's parser -- the C++ front end
 behind the ABI and oracle/oracle_lang.py -- over line-level mutants of the rule files.  For every mutant both must
 either fail with the same ParsingErr class or succeed with byte-identical gen/materials.glsl + gen/rules.glsl text.
-   python scripts/diff_frontends.py <seed> <n_mutants>
+   python scripts/diff_frontends.py <seed> <n_mutants> [indicators]
+`indicators` adds a mutation that drops YAML indicator characters ({ } [ ] : ? # & * ! | > % @ `) into the middle of values.
+That mode is exploratory, not a gate: ~1 % of its mutants get a different ERROR CLASS from the two YAML readers (stray
+brackets inside a plain scalar, empty flow entries `[a, , b]`, a bare `!` tag, `]#x`) -- malformed documents all, no valid
+rule file among them; see DESIGN.md section 7.
 Mutations keep the YAML shape simple (the C++ reader is a YAML-1.2-core subset): delete / duplicate / swap lines, replace a
 scalar by another token of the same file, rename an identifier, tweak a number, toggle a bool."""
 import random
@@ -15,7 +19,8 @@ import sandengine_b200 as se  # noqa: E402
 import yaml_cases as Y  # noqa: E402
 from oracle import oracle_lang  # noqa: E402
 
-SOURCES = [(REPO / "data" / "materials.yaml").read_text(), Y.BASE_OK, Y.RICH_YAML, Y.EXPR_YAML]
+INDICATORS = "indicators" in sys.argv[3:]
+SOURCES = [(REPO / "data" / "materials.yaml").read_text(), Y.BASE_OK, Y.RICH_YAML, Y.EXPR_YAML, Y.FUNC_YAML]
 TOKENS = ["SELF", "DOWN", "RIGHT", "LEFT", "DOWNRIGHT", "DOWNLEFT", "SWAP", "SET", "EMPTY", "empty", "and", "or", "not ", "true", "false",
           "0.5", "1", "1.0", "255", "-1", "mirrored", "probability", "precondition", "if", "do", "else", "inherits", "base_rules",
           "extra_rules", "type", "color", "density", "emission", "selectable"]
@@ -24,7 +29,9 @@ TOKENS = ["SELF", "DOWN", "RIGHT", "LEFT", "DOWNRIGHT", "DOWNLEFT", "SWAP", "SET
 def mutate(text, rng):
     lines = text.split("\n")
     for _ in range(rng.randint(1, 3)):
-        k = rng.randrange(14)
+        k = rng.randrange(15)
+        if k == 13 and not INDICATORS:
+            k = 14
         i = rng.randrange(len(lines))
         if k == 0 and len(lines) > 3:
             del lines[i]
@@ -75,6 +82,12 @@ def mutate(text, rng):
                 lines.insert(i, " " * rng.choice([0, 2, 4, 7]) + "# comment: [not, a, list]")
         elif k == 12:                                  # shift the indentation of one line
             lines[i] = (" " * rng.choice([1, 2])) + lines[i] if rng.random() < 0.5 else lines[i][min(2, len(lines[i]) - len(lines[i].lstrip())):]
+        elif k == 13:                                  # YAML indicator characters inside a value
+            m = re.match(r"^(\s*[\w-]+:\s*)(\S.*)$", lines[i])
+            if m:
+                v = m.group(2)
+                cut = rng.randrange(len(v) + 1)
+                lines[i] = m.group(1) + v[:cut] + rng.choice([" : ", ": ", " :", " ? 1 : 2", " #x", "#x", " - ", ", ", " [", "] ", " {", "} ", " & ", " * ", " ! ", " | ", " > ", "%", "@", "`"]) + v[cut:]
         else:                                          # shift a whole block (a line and everything deeper below it) by two columns
             ind = len(lines[i]) - len(lines[i].lstrip())
             j = i + 1

@@ -29,7 +29,7 @@ MOD_DTYPE = np.dtype([("position", "<i4", (2,)), ("mod_shape", "<i4"), ("mod_siz
 @dataclass
 class Case:
     name: str
-    rules: str = "default"                 # "default" | "expr" | "rich" | "synthR:<n_materials>:<n_rules>:<seed>" | "synthLR:..."
+    rules: str = "default"                 # "default" | "expr" | "func" | "rich" | "synthR:<n_materials>:<n_rules>:<seed>" | "synthLR:..."
     W: int = 64
     H: int = 48
     seed: int = 1
@@ -76,6 +76,7 @@ CASES = [
     # LEFT rules: outputs of the reference's shader template with gen/rules.glsl from the PATCHED emitter (see RefEngine)
     Case("rich_patchedleft_128x96_seed5_200", rules="rich", W=128, H=96, seed=5, steps=200, checkpoints=(1, 2, 3, 4)),
     Case("synthLR64_patchedleft_96x64_seed5_60", rules="synthLR:64:28:5", W=96, H=64, seed=5, steps=60, slow=True),
+    Case("func_64x40_seed5_120", rules="func", W=64, H=40, seed=5, steps=120, checkpoints=(1, 2, 3, 4, 40)),
     # mod_size up to INT_MAX (kept last: the CUDA path stages such sizes as 2^30, see api.cpp::se_sim_step)
     Case("default_48x40_seed3_mods_huge_10", W=48, H=40, seed=3, steps=10, mods="huge", checkpoints=tuple(range(1, 10))),
 ]
@@ -90,6 +91,8 @@ def rules_for(case: Case):
         return (REPO / "data" / "materials.yaml").read_text(), None, None
     if case.rules == "expr":
         return Y.EXPR_YAML, Y.EXPR_IDS, Y.EXPR_MIX
+    if case.rules == "func":             # scalar GLSL built-ins, bit operators, ?: in conditions
+        return Y.FUNC_YAML, Y.FUNC_IDS, Y.FUNC_MIX
     if case.rules == "rich":             # Left + Right rules, precedence, pos, rand.x: runs in the shader only with the patched emitter
         return Y.RICH_YAML, Y.RICH_IDS, Y.RICH_MIX
     kind, nm, nr, seed = case.rules.split(":")

@@ -28,7 +28,41 @@ def test_expression_grammar_three_way(native_lib, tmp_path_factory):
     compare(lib, c_orc, synthetic_grid(17, 9, 6, mix=Y.EXPR_MIX, ids=Y.EXPR_IDS), 40, frame=997)
 
 
+def test_glsl_builtins_bit_operators_and_conditional_three_way(native_lib, tmp_path_factory):
+    """The reference hands conditions to the GLSL compiler verbatim, so scalar built-ins (abs min max clamp mod floor ceil
+    fract sign step sqrt float() int()), integer & | ^ ~ << >> and ?: are legal in a rule file.  Generated CUDA code (host)
+    == C oracle step by step; with the reference present also == its own shader compiled for the CPU."""
+    import sandengine_b200 as se
+    from oracle import build_ref, oracle_lang
+    rules = se.parse_string(Y.FUNC_YAML)                  # incl. NVRTC for sm_100a
+    hdr = rules.cuda_header
+    for needle in ("floorf(", "ceilf(", "__fsqrt_rn(", " >> 1)", " & 1)", "(~px)", " ? "):
+        assert needle in hdr, needle
+    lib = build_emu(tmp_path_factory, "func", rules)
+    c_orc = load_oracle(Y.FUNC_YAML)
+    g = synthetic_grid(64, 40, 5, mix=Y.FUNC_MIX, ids=Y.FUNC_IDS)
+    out = compare(lib, c_orc, g, 120)
+    assert int((out != g).sum()) > 500 and len(np.unique(out)) >= 5
+    compare(lib, c_orc, synthetic_grid(33, 17, 6, mix=Y.FUNC_MIX, ids=Y.FUNC_IDS), 40, frame=2001)
+    if build_ref.reference_available():
+        res = oracle_lang.parse_string(Y.FUNC_YAML)
+        assert rules.glsl_rules == oracle_lang.emit_glsl_rules(res)
+        ref = build_ref.load_ref(oracle_lang.emit_glsl_materials(res), oracle_lang.emit_glsl_rules(res))
+        ref.create(64, 40); ref.upload_ids(g); ref.frame = 1
+        ref.step(120)
+        assert np.array_equal(ref.download_ids(), out)
+
+
 @pytest.mark.parametrize("cond,kind", [
+    ("sin(rand.x) > 0.5", "NotFound"),          # transcendentals have no bit-exact meaning: refused, not approximated
+    ("abs(1, 2) > 0", "NotRecognized"),
+    ("min(SELF, 1) > 0", "NotRecognized"),
+    ("1 & 2.0", "NotRecognized"),
+    ("pos.x << 1.5 > 0", "NotRecognized"),
+    ('"(pos.x > 1 ? 1 : true) == 1"', "NotRecognized"),       # (a ?: needs YAML quotes: ': ' cannot occur in a plain scalar)
+    ("(pos.x > 1 ? 1 : true) == 1", "Yaml"),
+    ("pos.x > 1 ? true", "NotRecognized"),
+    ("SELF.mat.emission.rgb != vec3(0.0)", "NotRecognized"),
     ("SELF.mat.density +", "NotRecognized"),
     ("SELF.density < 1.0", "NotRecognized"),
     ("isType_movable_solid(SELF", "NotRecognized"),

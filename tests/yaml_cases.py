@@ -246,3 +246,46 @@ materials:
 """
 EXPR_IDS = {"EMPTY": 0, "pebble": 3, "ash": 4, "ember": 5, "lamp": 6, "spark": 7}
 EXPR_MIX = (("EMPTY", 0.5), ("pebble", 0.15), ("ash", 0.15), ("ember", 0.08), ("lamp", 0.06), ("spark", 0.06))
+
+# Scalar GLSL built-ins, integer bit operators and the conditional operator in conditions (the reference passes
+# conditions to the GLSL compiler verbatim, so all of this is legal there).  Same materials as EXPR_YAML.
+FUNC_YAML = """
+rules:
+  band_fall:
+    if: abs(pos.x - 20) < 12 and DOWN.mat.density < SELF.mat.density
+    do: SWAP SELF DOWN
+    else:
+      if: mod(float(pos.x + 1), 4.0) < 2.0 and min(RIGHT.mat.density, DOWNRIGHT.mat.density) < SELF.mat.density and max(pos.y, 3) > 3
+      probability: 0.7
+      do: SWAP SELF DOWNRIGHT
+  parity_drift:
+    mirrored: false
+    if: ((pos.x + 1) & 1) == (frame & 1) and isType_EMPTY(RIGHT) and ((pos.y + 1) >> 1) % 3 != 0 and (frame ^ 5) > 1
+    do: SWAP SELF RIGHT
+  heat:
+    precondition: false
+    if: isType_EMPTY(SELF) and floor(DOWN.mat.density * 2.0) == 6.0 and clamp(rand.z, 0.25, 0.75) > 0.5 and fract(DOWN.mat.emission.r * 3.0) < 0.5
+    do: SET SELF spark
+  fade:
+    if: "(rand.w <= 0.4 ? frame % 2 == 0 : step(0.8, rand.x) > 0.5) or sign(float(pos.x) - 30.5) * sqrt(float(frame % 16)) > 3.0"   # ': ' needs quotes in YAML
+    do: SET SELF EMPTY
+  sink_int:
+    precondition: false
+    if: int(SELF.mat.density * 2.0) >= 4 and DOWN.mat.id == 0 and ceil(SELF.mat.density) == 2.0 and (~pos.x | 1) != 0 and sign(pos.y - 5) >= 0
+    probability: 0.5
+    do: SWAP SELF DOWN
+types:
+  loose:
+    base_rules: [band_fall, parity_drift]
+  glowing:
+    base_rules: [heat]
+  shortlived:
+    base_rules: [fade]
+materials:
+  pebble: {type: loose, color: [0.5, 0.5, 0.5], density: 2.0, extra_rules: [sink_int]}
+  ash:    {type: loose, color: [0.3, 0.3, 0.3], density: 1.25}
+  ember:  {type: glowing, color: [0.4, 0.1, 0.1], density: 3.0, emission: [1.0, 0.6, 0.1, 0.9]}
+  lamp:   {type: glowing, color: [0.9, 0.9, 0.2], density: 3.0, emission: [0.2, 0.9, 0.2, 0.8]}
+  spark:  {type: shortlived, color: [1.0, 0.8, 0.2], density: 0.5, emission: [1.0, 0.8, 0.1, 0.7]}
+"""
+FUNC_IDS, FUNC_MIX = EXPR_IDS, EXPR_MIX
