@@ -6,7 +6,8 @@ through four evaluators and compared after every step:
    the transition table, when the rule set is table-eligible
    the C oracle (oracle/sand_oracle.c + generated rules_gen.h)
    the reference's own shader compiled for the CPU (oracle/build_ref.py) with gen/*.glsl emitted for the rule set
-python scripts/diff_expressions.py <seed_lo> <seed_hi>
+python scripts/diff_expressions.py <seed_lo> <seed_hi> [eligible]      (eligible: mirrored-only rules without pos / frame / free rand,
+                                                                     so that the transition table is built and compared too)
 """
 import ctypes as C
 import random
@@ -42,8 +43,8 @@ COMP = "rgba"
 
 
 class Gen:
-    def __init__(self, rng, cells):
-        self.r, self.cells = rng, cells
+    def __init__(self, rng, cells, eligible=False):
+        self.r, self.cells, self.eligible = rng, cells, eligible      # eligible: only what a transition table can capture
 
     def cell(self):
         return self.r.choice(self.cells)
@@ -52,6 +53,7 @@ class Gen:
         r = self.r
         if d <= 0 or r.random() < 0.3:
             k = r.randrange(6)
+            if self.eligible and k == 3: k = 1
             if k == 0: return f"{self.cell()}.mat.density"
             if k == 1: return f"{self.cell()}.mat.color.{r.choice(COMP)}"
             if k == 2: return f"{self.cell()}.mat.emission.{r.choice(COMP)}"
@@ -79,13 +81,14 @@ class Gen:
 
     def Fsmall(self, d):          # factors that cannot blow up (products of 9999s overflow nothing, but keep magnitudes modest)
         r = self.r
-        return r.choice([f"rand.{r.choice('xyzw')}", r.choice(FLITS[:12]), f"{self.cell()}.mat.color.{r.choice(COMP)}",
+        return r.choice([r.choice(FLITS[:12]) if self.eligible else f"rand.{r.choice('xyzw')}", r.choice(FLITS[:12]), f"{self.cell()}.mat.color.{r.choice(COMP)}",
                          f"{self.cell()}.mat.emission.{r.choice(COMP)}", f"min({self.cell()}.mat.density, 4.0)"])
 
     def I(self, d):
         r = self.r
         if d <= 0 or r.random() < 0.35:
             k = r.randrange(7)
+            if self.eligible and k in (2, 3, 4): k = r.choice([0, 1, 5])
             if k == 0: return f"{self.cell()}.mat.id"
             if k == 1: return f"{self.cell()}.mat.type"
             if k == 2: return "pos.x"
@@ -117,7 +120,7 @@ class Gen:
             k = r.randrange(8)
             if k == 0: return f"{self.cell()}.mat.density {cmp} {self.cell()}.mat.density"      # rank comparison
             if k == 1: return f"{self.cell()}.mat.density {cmp} {r.choice(FLITS)}"              # folded at code generation
-            if k == 2: return f"rand.{r.choice('xyzw')} {r.choice(['<', '<=', '>', '>='])} {r.choice(FLITS[:12])}"   # integer threshold
+            if k == 2: return f"rand.{'y' if self.eligible else r.choice('xyzw')} {r.choice(['<', '<=', '>', '>='])} {r.choice(FLITS[:12])}"   # integer threshold
             if k == 3: return f"isType_{r.choice(TYPES)}({self.cell()})"
             # (not EMPTY here: the reference replaces a compared material name GLOBALLY in the condition, rules.rs:246-260,
             #  which would turn isType_EMPTY / TYPE_EMPTY elsewhere in it into isType_MAT_EMPTY -- reproduced, but noise here)
@@ -135,13 +138,16 @@ class Gen:
         return f"(({self.B(d - 1)}) == ({self.B(d - 1)}))"
 
 
+ELIGIBLE = "eligible" in sys.argv[3:]
+
+
 def make_rules(seed):
     rng = random.Random(seed)
     n = rng.randint(3, 6)
     rules, names = [], []
     for k in range(n):
-        mirrored = rng.random() < 0.6
-        g = Gen(rng, ["SELF", "RIGHT", "DOWN", "DOWNRIGHT"])
+        mirrored = ELIGIBLE or rng.random() < 0.6
+        g = Gen(rng, ["SELF", "RIGHT", "DOWN", "DOWNRIGHT"], eligible=ELIGIBLE)
         name = f"q{k}"
         names.append(name)
 
