@@ -141,13 +141,14 @@ class Gen:
 ELIGIBLE = "eligible" in sys.argv[3:]
 
 
-def make_rules(seed):
+def make_rules(seed, eligible=None):
+    eligible = ELIGIBLE if eligible is None else eligible
     rng = random.Random(seed)
     n = rng.randint(3, 6)
     rules, names = [], []
     for k in range(n):
-        mirrored = ELIGIBLE or rng.random() < 0.6
-        g = Gen(rng, ["SELF", "RIGHT", "DOWN", "DOWNRIGHT"], eligible=ELIGIBLE)
+        mirrored = eligible or rng.random() < 0.6
+        g = Gen(rng, ["SELF", "RIGHT", "DOWN", "DOWNRIGHT"], eligible=eligible)
         name = f"q{k}"
         names.append(name)
 
@@ -186,8 +187,8 @@ def build_emu(rules, d):
     return lib
 
 
-def run_one(seed, steps=40, w=40, h=28):
-    text = make_rules(seed)
+def run_one(seed, steps=40, w=40, h=28, eligible=None):
+    text = make_rules(seed, eligible)
     try:
         rules = se.parse_string(text)                     # front end + CUDA code generation + NVRTC (sm_100a)
     except se.SandEngineError as e:

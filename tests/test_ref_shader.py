@@ -334,3 +334,18 @@ def test_colour_function_vs_reference_shader(native_lib, tmp_path_factory, defau
         lib.emu_shade(np.ascontiguousarray(ids).ctypes.data, w, h, got.ctypes.data)
         assert np.array_equal(got, want), float(np.abs(got - want).max())
         assert (ids != 0).mean() > 0.3 and np.abs(want[ids != 0][:, :3] - want[ids != 0][:, :3].round(2)).max() > 0   # noise was applied
+
+
+@needs_reference
+@pytest.mark.parametrize("seed,eligible", [(101, False), (117, False), (2001, True), (2007, True)])
+def test_random_expression_rule_sets_vs_reference_shader(native_lib, seed, eligible):
+    """Fixed slice of scripts/diff_expressions.py: random well-typed conditions (built-ins, bit operators, ?:, the density /
+    rand special forms); generated CUDA code (host) == transition table (eligible sets) == C oracle == the reference's shader
+    after every step."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("diff_expressions", REPO / "scripts" / "diff_expressions.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    status, info, text = mod.run_one(seed, eligible=eligible)
+    assert status == "ok", (status, info, text)
+    assert ("lut True" in info) == eligible
