@@ -219,6 +219,8 @@ struct FlowParser {
             ws();
             if (p < s.size() && s[p] == ']') { ++p; return v; }
             while (true) {
+                ws();
+                if (p < s.size() && s[p] == ',') fail(line, "empty entry in flow sequence");   // libyaml: "did not find expected node content"
                 v.seq.push_back(value());
                 ws();
                 if (p >= s.size()) fail(line, "unterminated flow sequence");
@@ -239,6 +241,8 @@ struct FlowParser {
             ws();
             if (p < s.size() && s[p] == '}') { ++p; return v; }
             while (true) {
+                ws();
+                if (p < s.size() && (s[p] == ':' || s[p] == ',')) fail(line, "empty key in flow mapping");
                 YamlValue key = scalar_from_text(token(true), line);
                 ws();
                 YamlValue val;
@@ -457,14 +461,38 @@ YamlValue yaml_parse(const std::string& text) {
             continue;
         }
         if (content == "..." && ind == 0) break;
-        int bal = flow_balance(content);
-        while (bal > 0) {
-            if (++k >= phys.size()) fail(no, "unterminated flow collection");
-            std::string more = trim(strip_comment(phys[k].first));
-            content += " " + more;
-            bal = flow_balance(content);
+        // Brackets are flow syntax only when the VALUE of the line starts with one (`key: [a,` / `- {x: 1,` / `[a,`); inside a
+        // plain scalar (`if: a[0] > b`) they are ordinary characters, as in libyaml.
+        size_t vstart = 0;
+        {
+            std::string rest = content;
+            while (rest.size() >= 2 && rest[0] == '-' && rest[1] == ' ') {        // "- - [..." / "- key: [..."
+                size_t skip = 2;
+                while (skip < rest.size() && rest[skip] == ' ') ++skip;
+                vstart += skip;
+                rest = rest.substr(skip);
+            }
+            if (!rest.empty() && rest[0] != '[' && rest[0] != '{') {
+                size_t sep = find_key_sep(rest);
+                if (sep != std::string::npos) {
+                    size_t v = sep + 1;
+                    while (v < rest.size() && rest[v] == ' ') ++v;
+                    vstart += v;
+                    rest = rest.substr(v);
+                }
+            }
+            if (rest.empty() || (rest[0] != '[' && rest[0] != '{')) vstart = std::string::npos;
         }
-        if (bal < 0) fail(no, "unbalanced ']' or '}'");
+        if (vstart != std::string::npos) {
+            int bal = flow_balance(content.substr(vstart));
+            while (bal > 0) {
+                if (++k >= phys.size()) fail(no, "unterminated flow collection");
+                std::string more = trim(strip_comment(phys[k].first));
+                content += " " + more;
+                bal = flow_balance(content.substr(vstart));
+            }
+            if (bal < 0) fail(no, "unbalanced ']' or '}'");
+        }
         bp.lines.push_back(Line{(int)ind, content, no});
     }
     if (bp.lines.empty()) return YamlValue();

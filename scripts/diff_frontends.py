@@ -3,9 +3,9 @@ behind the ABI and oracle/oracle_lang.py -- over line-level mutants of the rule 
 either fail with the same ParsingErr class or succeed with byte-identical gen/materials.glsl + gen/rules.glsl text.
    python scripts/diff_frontends.py <seed> <n_mutants> [indicators]
 `indicators` adds a mutation that drops YAML indicator characters ({ } [ ] : ? # & * ! | > % @ `) into the middle of values.
-That mode is exploratory, not a gate: ~1 % of its mutants get a different ERROR CLASS from the two YAML readers (stray
-brackets inside a plain scalar, empty flow entries `[a, , b]`, a bare `!` tag, `]#x`) -- malformed documents all, no valid
-rule file among them; see DESIGN.md section 7.
+That mode is exploratory, not a gate: ~0.3 % of its mutants get a different ERROR CLASS from the two YAML readers (`? ` /
+`- ` / `, ` indicators inside flow collections, a bare `!` tag, `]#x`) -- malformed documents all, no valid rule file among
+them; see DESIGN.md section 7.
 Mutations keep the YAML shape simple (the C++ reader is a YAML-1.2-core subset): delete / duplicate / swap lines, replace a
 scalar by another token of the same file, rename an identifier, tweak a number, toggle a bool."""
 import random
