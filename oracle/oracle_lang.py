@@ -674,7 +674,22 @@ _FLOATLIT_RE = re.compile(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][-+]?\d+)?|\d+[e
 _BUILTIN_RE = re.compile(r"\b(abs|min|max|clamp|mod|floor|ceil|fract|sign|step|sqrt|float|int)\(")
 
 
+# `X.mat.emission.rgb != vec3(0.0)`: GLSL compares vectors as a whole (one bool); written out per component for C
+_VECCMP_RE = re.compile(r"(\w+)\.mat\.(color|emission)\.([rgbaxyzw]{2,4})\s*(==|!=)\s*vec([234])\(([^()]*)\)")
+
+
+def _vec_compare_to_c(m) -> str:
+    cell, fld, swz, op, n, args = m.group(1), m.group(2), m.group(3), m.group(4), int(m.group(5)), [a.strip() for a in m.group(6).split(",")]
+    if len(args) == 1:
+        args = args * n
+    if len(args) != n or len(swz) != n:
+        return m.group(0)                      # left as it is: the C compiler rejects it, like the GLSL compiler would
+    body = " && ".join(f"({cell}.mat.{fld}.{c} == {a})" for c, a in zip(swz, args))
+    return f"({body})" if op == "==" else f"(!({body}))"
+
+
 def _to_c(text: str) -> str:
+    text = _VECCMP_RE.sub(_vec_compare_to_c, text)
     text = _BUILTIN_RE.sub(lambda m: f"se_{m.group(1)}(", text)
     text = _MATCMP_RE.sub(lambda m: f"({m.group(1)}.mat.id {m.group(2)} {m.group(3)}.id)", text)
     text = _SWAPCALL_RE.sub(lambda m: f"swap_cells(&{m.group(1)}, &{m.group(2)});", text)

@@ -40,7 +40,7 @@ std::string f32_lit(float v) {   // exact: hex-float (or bit pattern for inf/nan
 // ---------------------------------------------------------------------------------------------
 // Typed values produced while parsing a condition
 // ---------------------------------------------------------------------------------------------
-enum class VT { Bool, Int, Float, Mat, Cell, Vec4, RandVec, PosVec };
+enum class VT { Bool, Int, Float, Mat, Cell, Vec4, RandVec, PosVec, VecN };
 
 struct Val {
     VT type = VT::Bool;
@@ -54,6 +54,7 @@ struct Val {
     std::string cell;          // Mat: owning cell register ("" => constant material `mat_id`)
     int mat_id = -1;
     std::string vec_field;     // Vec4: "color" | "emission"
+    std::vector<std::string> comps;   // VecN: float code of each component (2..4): a swizzle of color / emission, or vecN(...)
 };
 
 struct Ctx {
@@ -230,6 +231,15 @@ struct Parser {
 
     Val compare(const Val& a, const std::string& op, const Val& b) {
         bool eqop = (op == "==" || op == "!=");
+        if (a.type == VT::VecN || b.type == VT::VecN) {
+            // GLSL: == / != on vectors compare the whole value and give one bool (e.g. `mat.emission.rgb != vec3(0.0)`,
+            // the reference's own isLightObstacle test, operations.glsl:68-70)
+            if (a.type != VT::VecN || b.type != VT::VecN || !eqop || a.comps.size() != b.comps.size())
+                bad("vectors can only be compared with == / != against a vector of the same size");
+            std::string all;
+            for (size_t k = 0; k < a.comps.size(); ++k) all += (k ? " && " : "") + std::string("(") + a.comps[k] + " == " + b.comps[k] + ")";
+            return mk_bool(op == "==" ? "(" + all + ")" : "(!(" + all + "))");
+        }
         if (a.type == VT::Mat || b.type == VT::Mat) {
             if (a.type != VT::Mat || b.type != VT::Mat || !eqop) bad("materials can only be compared with == / != against materials");
             auto idc = [&](const Val& v) { return v.cell.empty() ? std::to_string(v.mat_id) + "u" : "SE_ID(" + v.cell + ")"; };
@@ -392,6 +402,17 @@ struct Parser {
             if (m == "color" || m == "emission") { Val r = v; r.type = VT::Vec4; r.vec_field = m; return r; }
             bad("unknown material member '" + m + "'");
         }
+        if (v.type == VT::Vec4 && m.size() >= 2 && m.size() <= 4) {
+            Val r;
+            r.type = VT::VecN;
+            for (char c : m) {
+                int k = comp_index(std::string(1, c));
+                if (k < 0) bad("unknown vector component '" + m + "'");
+                if (v.cell.empty()) r.comps.push_back(f32_lit(v.vec_field == "color" ? cx.tb.color[v.mat_id][k] : cx.tb.emission[v.mat_id][k]));
+                else r.comps.push_back("__ldg(&se_" + v.vec_field + "_table[SE_ID(" + v.cell + ") * 4 + " + std::to_string(k) + "])");
+            }
+            return r;
+        }
         if (v.type == VT::Vec4) {
             int k = comp_index(m);
             if (k < 0) bad("unknown vector component '" + m + "'");
@@ -512,6 +533,29 @@ struct Parser {
             std::string id = lx.tok;
             lx.next();
             if (id == "true" || id == "false") return mk_bool(id);
+            if ((id == "vec2" || id == "vec3" || id == "vec4") && lx.is_op("(")) {
+                const size_t n = (size_t)(id[3] - '0');
+                lx.next();
+                Val r;
+                r.type = VT::VecN;
+                size_t n_args = 0;
+                if (!lx.is_op(")")) {
+                    for (;;) {
+                        Val a = parse_ternary();
+                        ++n_args;
+                        if (a.type == VT::VecN) r.comps.insert(r.comps.end(), a.comps.begin(), a.comps.end());
+                        else if (is_num(a)) r.comps.push_back(as_float_code(a));
+                        else bad(id + "() needs numbers or vectors");
+                        if (lx.is_op(",")) { lx.next(); continue; }
+                        break;
+                    }
+                }
+                if (!lx.is_op(")")) bad("missing ')' after the arguments of " + id + "()");
+                lx.next();
+                if (n_args == 1 && r.comps.size() == 1) r.comps.assign(n, r.comps[0]);       // vec3(0.0): one scalar fills every component
+                if (r.comps.size() != n) bad(id + "() needs 1 or " + std::to_string(n) + " components");
+                return r;
+            }
             if (is_builtin(id) && lx.is_op("(")) {
                 lx.next();
                 std::vector<Val> args;

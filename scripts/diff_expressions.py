@@ -1,6 +1,7 @@
 """Tooling (CPU, build container: needs /root/reference): differential test of the typed expression compiler.
 Random rule sets whose conditions are random, well-typed scalar GLSL expressions (comparisons of densities / colours /
-emissions / rand lanes / positions / frame / ids, arithmetic, the scalar built-ins, integer bit operators, ?:) are run
+emissions / rand lanes / positions / frame / ids, arithmetic, the scalar built-ins, integer bit operators, ?:, vector
+== / !=) are run
 through four evaluators and compared after every step:
    the product's generated CUDA rule code compiled for the host (tests/emu)      -- what NVRTC compiles for the device
    the transition table, when the rule set is table-eligible
@@ -117,7 +118,11 @@ class Gen:
         r = self.r
         cmp = r.choice(["<", "<=", ">", ">=", "==", "!="])
         if d <= 0 or r.random() < 0.3:
-            k = r.randrange(8)
+            k = r.randrange(9)
+            if k == 8:                                                                          # vector == / != (one bool)
+                sw = r.choice(["rgb", "rg", "rgba", "xyz"])
+                args = [r.choice(["0.0", "0.5", "1.0", "0.3", "0.9"]) for _ in range(len(sw))] if r.random() < 0.5 else [r.choice(["0.0", "1.0", "0.5"])]
+                return f"{self.cell()}.mat.{r.choice(['color', 'emission'])}.{sw} {r.choice(['==', '!='])} vec{len(sw)}({', '.join(args)})"
             if k == 0: return f"{self.cell()}.mat.density {cmp} {self.cell()}.mat.density"      # rank comparison
             if k == 1: return f"{self.cell()}.mat.density {cmp} {r.choice(FLITS)}"              # folded at code generation
             if k == 2: return f"rand.{'y' if self.eligible else r.choice('xyzw')} {r.choice(['<', '<=', '>', '>='])} {r.choice(FLITS[:12])}"   # integer threshold

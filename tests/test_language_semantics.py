@@ -30,13 +30,13 @@ def test_expression_grammar_three_way(native_lib, tmp_path_factory):
 
 def test_glsl_builtins_bit_operators_and_conditional_three_way(native_lib, tmp_path_factory):
     """The reference hands conditions to the GLSL compiler verbatim, so scalar built-ins (abs min max clamp mod floor ceil
-    fract sign step sqrt float() int()), integer & | ^ ~ << >> and ?: are legal in a rule file.  Generated CUDA code (host)
+    fract sign step sqrt float() int()), integer & | ^ ~ << >>, ?: and vector == / != (`mat.emission.rgb != vec3(0.0)`) are legal in a rule file.  Generated CUDA code (host)
     == C oracle step by step; with the reference present also == its own shader compiled for the CPU."""
     import sandengine_b200 as se
     from oracle import build_ref, oracle_lang
     rules = se.parse_string(Y.FUNC_YAML)                  # incl. NVRTC for sm_100a
     hdr = rules.cuda_header
-    for needle in ("floorf(", "ceilf(", "__fsqrt_rn(", " >> 1)", " & 1)", "(~px)", " ? "):
+    for needle in ("floorf(", "ceilf(", "__fsqrt_rn(", " >> 1)", " & 1)", "(~px)", " ? ", "se_emission_table[SE_ID(s) * 4 + 2]) == 0x0p+0f"):
         assert needle in hdr, needle
     lib = build_emu(tmp_path_factory, "func", rules)
     c_orc = load_oracle(Y.FUNC_YAML)
@@ -62,7 +62,9 @@ def test_glsl_builtins_bit_operators_and_conditional_three_way(native_lib, tmp_p
     ('"(pos.x > 1 ? 1 : true) == 1"', "NotRecognized"),       # (a ?: needs YAML quotes: ': ' cannot occur in a plain scalar)
     ("(pos.x > 1 ? 1 : true) == 1", "Yaml"),
     ("pos.x > 1 ? true", "NotRecognized"),
-    ("SELF.mat.emission.rgb != vec3(0.0)", "NotRecognized"),
+    ("SELF.mat.emission.rgb == vec2(0.0)", "NotRecognized"),   # sizes differ
+    ("SELF.mat.emission.rgb < vec3(0.0)", "NotRecognized"),    # only == / != have a scalar result
+    ("SELF.mat.emission.rgb", "NotRecognized"),
     ("SELF.mat.density +", "NotRecognized"),
     ("SELF.density < 1.0", "NotRecognized"),
     ("isType_movable_solid(SELF", "NotRecognized"),

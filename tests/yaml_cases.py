@@ -247,7 +247,7 @@ materials:
 EXPR_IDS = {"EMPTY": 0, "pebble": 3, "ash": 4, "ember": 5, "lamp": 6, "spark": 7}
 EXPR_MIX = (("EMPTY", 0.5), ("pebble", 0.15), ("ash", 0.15), ("ember", 0.08), ("lamp", 0.06), ("spark", 0.06))
 
-# Scalar GLSL built-ins, integer bit operators and the conditional operator in conditions (the reference passes
+# Scalar GLSL built-ins, integer bit operators, the conditional operator and vector == / != in conditions (the reference passes
 # conditions to the GLSL compiler verbatim, so all of this is legal there).  Same materials as EXPR_YAML.
 FUNC_YAML = """
 rules:
@@ -269,6 +269,11 @@ rules:
   fade:
     if: "(rand.w <= 0.4 ? frame % 2 == 0 : step(0.8, rand.x) > 0.5) or sign(float(pos.x) - 30.5) * sqrt(float(frame % 16)) > 3.0"   # ': ' needs quotes in YAML
     do: SET SELF EMPTY
+  glow_drop:
+    precondition: false
+    if: SELF.mat.emission.rgb != vec3(0.0) and DOWN.mat.color.rgba == vec4(0.0, 0.0, 0.0, 0.0) and RIGHT.mat.color.rg != vec2(0.5)
+    probability: 0.8
+    do: SWAP SELF DOWN
   sink_int:
     precondition: false
     if: int(SELF.mat.density * 2.0) >= 4 and DOWN.mat.id == 0 and ceil(SELF.mat.density) == 2.0 and (~pos.x | 1) != 0 and sign(pos.y - 5) >= 0
@@ -278,7 +283,7 @@ types:
   loose:
     base_rules: [band_fall, parity_drift]
   glowing:
-    base_rules: [heat]
+    base_rules: [heat, glow_drop]
   shortlived:
     base_rules: [fade]
 materials:
