@@ -7,7 +7,7 @@
 Definitions (DESIGN.md "Measurement"):
   step      one Margolus step (one `Simulation::run`, simulation.rs:195) over the whole S x S grid
   value     S*S*K / t, t = CUDA-event time of K steps issued through ONE se_sim_step(K) call, inputs resident in
-            HBM, max over ranks; default rule set (data/materials.yaml), lighting off, no modifications,
+            HBM, max over ranks, median of --reps repetitions; default rule set (data/materials.yaml), lighting off, no modifications,
             counter-hash initial grid seed 3, frames 2.. after W warm-up steps
   e2e       the same K steps through the public per-frame API with HOST buffers, every step: push the frame's
             modification record(s) from host memory (H2D), Simulation.run(), read the step's result -- the
@@ -48,9 +48,8 @@ def parse_args():
     ap.add_argument("--temporal-block", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--running-census", action="store_true", help="EXPERIMENTAL: SE_FLAG_RUNNING_CENSUS (census maintained by the per-frame kernel)")
-    ap.add_argument("--host-sync", action="store_true", help="order the ghost-row exchange with host barriers instead of device flags")
-    ap.add_argument("--debug-no-exchange", action="store_true", help="DIAGNOSTIC ONLY: skip ghost exchanges (wrong results) to time ranks uncoupled")
+    ap.add_argument("--reps", type=int, default=5, help="timed repetitions of --steps steps; the median is reported")
+    ap.add_argument("--no-running-census", action="store_true", help="e2e leg: recount the census every frame instead of SE_FLAG_RUNNING_CENSUS")
     return ap.parse_args()
 
 
@@ -258,8 +257,15 @@ def run_reference(args):
     cores = len(os.sched_getaffinity(0))
     K, Wm = max(1, args.steps), max(0, args.warmup)
     ref = load_ref_shader()
-    port_note = None
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: this arm uses every host core it is allowed to run on whatever
+    # the launcher says, so the N = 1 and the N > 1 lines measure the same baseline
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)
+    except Exception:
+        pass
     if ref is not None:
+        ref.set_threads(cores)
         kind = "reference"
         ladder = (2048, 1024, 512, 256, 128, 64)           # 256^2 is BASELINE configs[0], the reference's own CPU-sized case
 
@@ -308,13 +314,33 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(rate, 6), "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": Wm,
         "ms_per_step": round(dt / K * 1e3, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
-        "config": {"workload": f"bounded sample of the {args.size}^2 workload: {sample}x{sample} grid, same generator (seed {SEED}), "
+        "config": {"workload": f"bounded sample of the {args.size}^2 workload: {sample}x{sample} grid on {cores} host threads, same generator (seed {SEED}), "
                                "default rule set, no modifications" + (", lighting off" if kind == "port" else " (the shader relaxes light and shades colour every step)"),
                    "rules": "data/materials.yaml"},
         "cpu_baseline": cpu,
         "e2e": {"value": round(rate, 6), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def committed_checksum(S: int, total_steps: int):
+    """Checksum (sandengine_b200.grids.grid_checksum) of the ORACLE's grid after `total_steps` steps of the bench workload,
+    from tests/golden/bench_checksums.json (generator: tests/golden/make_bench_checksums.py); None when not committed."""
+    p = REPO / "tests" / "golden" / "bench_checksums.json"
+    try:
+        return json.loads(p.read_text()).get(f"{S}x{S}:seed{SEED}:steps{total_steps}")
+    except Exception:
+        return None
+
+
+def profile_traffic(S: int, world: int):
+    """Physical DRAM bytes per cell-update of se_step_tiles from the committed ncu capture of this configuration
+    (profiles/r2_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch / cell-updates of that launch)."""
+    try:
+        t = json.loads((REPO / "profiles" / "r2_traffic.json").read_text())
+        return t.get(f"{S}:gpus{world}")
+    except Exception:
+        return None
 
 
 def run_ours(args):
@@ -341,15 +367,11 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     S = args.size
-    K, Wm = args.steps, max(args.warmup, 3)
-    if args.running_census:
-        os.environ["SE_EXPERIMENTAL_KERNELS"] = "1"       # the experimental kernels are compiled only on request
+    K, Wm, R = args.steps, max(args.warmup, 3), max(1, args.reps)
     rules = se.parse_path(REPO / "data" / "materials.yaml")
     strip = StripSimulation(rules, (S, S), halo_rows=args.halo, device=local_rank, temporal_block=args.temporal_block,
-                            device_sync=not args.host_sync, running_census=args.running_census)
+                            running_census=not args.no_running_census)
     sim = strip.sim
-    if args.debug_no_exchange:
-        strip.exchange = lambda: None
     stream = torch.cuda.Stream()          # a real (non-legacy) stream: events below are recorded on the launching stream
     torch.cuda.set_stream(stream)
     sim.set_stream(stream.cuda_stream)
@@ -368,28 +390,54 @@ def run_ours(args):
         strip.upload_cells(host_np)
         sim.params.frame = 1
 
-    # ---------------- device-resident timing (value) ----------------
+    def reduce_max(values):
+        t = torch.tensor(values, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    # ---------------- device-resident timing (value): R repetitions of K steps, each timed on the device ----------------
     reset()
     strip.step(Wm)
     barrier()
     l0 = sim.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    reps = []
     sampler.mark_begin()
-    ev0.record(stream)
-    strip.step(K)
-    ev1.record(stream)
-    barrier()
+    for _ in range(R):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        strip.step(K)
+        ev1.record(stream)
+        barrier()
+        reps.append(ev0.elapsed_time(ev1) / 1e3)
     sampler.mark_end()
-    t_dev = ev0.elapsed_time(ev1) / 1e3
-    print(f"[bench] rank {rank}: device time {t_dev * 1e3:.3f} ms for {K} steps, rows {strip.row_begin}..{strip.row_end}", file=sys.stderr, flush=True)
-    launches = sim.launch_count - l0
+    launches = (sim.launch_count - l0) / R
+    print(f"[bench] rank {rank}: device times {[round(x * 1e3, 3) for x in reps]} ms for {K} steps each, rows {strip.row_begin}..{strip.row_end}", file=sys.stderr, flush=True)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([t_dev], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_dev = float(t.item())
+    reps = reduce_max(reps)                              # per repetition: the slowest rank
+    t_dev = sorted(reps)[len(reps) // 2]                 # median repetition
     value = S * S * K / t_dev / 1e9
+
+    # ---------------- parity: sharding-independent checksum + census of the grid after W + R*K steps ----------------
+    total_steps = Wm + R * K
+    cs_local = sim.checksum()
+    cs = torch.tensor([cs_local - (1 << 64) if cs_local >= (1 << 63) else cs_local], dtype=torch.int64, device="cuda")
+    census = torch.from_numpy(sim.census().astype(np.int64)).cuda()
+    if world > 1:
+        dist.all_reduce(cs, op=dist.ReduceOp.SUM)        # wraps modulo 2^64: the strips' checksums add up to the grid's
+        dist.all_reduce(census, op=dist.ReduceOp.SUM)
+    checksum = int(cs.item()) & 0xFFFFFFFFFFFFFFFF
+    want = committed_checksum(S, total_steps)
+    if want is None:
+        parity = {"status": "unchecked", "why": f"no committed oracle checksum for {S}x{S} after {total_steps} steps (tests/golden/bench_checksums.json)"}
+    else:
+        parity = {"status": "bit-exact" if int(want["checksum"]) == checksum else "MISMATCH",
+                  "against": "oracle (C restatement pinned by the reference's own shader), full grid, committed checksum"}
+        if "census" in want and [int(x) for x in want["census"]] != [int(x) for x in census.tolist()[:len(want["census"])]]:
+            parity["status"] = "MISMATCH"
+    parity.update({"checksum": f"{checksum:016x}", "after_steps": total_steps, "census": [int(x) for x in census.tolist()[:11]],
+                   "how": "sum over cells of mix(global index, id) mod 2^64 (se_sim_checksum), summed over ranks: independent of the sharding"})
 
     # ---------------- end to end through the per-frame API with host buffers ----------------
     reset()
@@ -408,69 +456,59 @@ def run_ours(args):
             census_log[k - 3:k + 1] = census_ring.numpy()[:, :11]
     sim.census_wait()
     barrier()
-    t_e2e = time.perf_counter() - t0
-    te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    t_e2e = float(te.item())
+    t_e2e = reduce_max([time.perf_counter() - t0])[0]
     e2e_value = S * S * K / t_e2e / 1e9
 
     # whole job from a host grid to a host grid (upload + K steps + download), reported beside e2e
     barrier()
     t0 = time.perf_counter()
     sim.upload_cells_ptr(host.data_ptr())
-    if world > 1:
-        strip.exchange()
     sim.params.frame = 1
     strip.step(K)
     sim.download_cells_ptr(host.data_ptr())            # download into the pinned buffer the grid was uploaded from
     barrier()
-    t_job = time.perf_counter() - t0
-    tj = torch.tensor([t_job], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tj, op=dist.ReduceOp.MAX)
-    t_job = float(tj.item())
+    t_job = reduce_max([time.perf_counter() - t0])[0]
 
     if rank == 0:
         peak, peak_src = measured_peak()
         # dominant kernel: se_step_tiles (K1b) fuses several Margolus steps per launch; algorithmic bytes of a
-        # launch = 8 B x cells of this rank's buffer x steps fused, i.e. 8 B x cells x K over the timed region
-        local_cells = S * (sim.owned_shape[0] + sum(strip.plan.ghosts(rank)))
+        # launch = 8 B x cells this rank owns x steps fused, i.e. 8 B x cells x K over one repetition
+        local_cells = S * sim.owned_shape[0]
         per_launch_s = t_dev / max(launches, 1)
         achieved = 8.0 * local_cells * K / t_dev / 1e9
-        # physical DRAM bytes of one se_step_tiles launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full,
-        # profiles/r1_k1b_ncu_full.txt): captured for exactly this configuration, null otherwise
-        # (captured on an 8-step T-block; a launch now carries K / launches steps = several T-blocks, same bytes per step)
-        traffic = (8.932404e9 + 8.540352e9) * (K / max(launches, 1)) / 64.0 if (S == 16384 and world == 1 and launches < K) else None
+        tr = profile_traffic(S, world) if launches < K else None
+        traffic = tr["dram_bytes_per_cell_update"] * local_cells * K / max(launches, 1) if tr else None
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": round(t_dev / K * 1e3, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"{S}x{S} grid, default rule set (data/materials.yaml), lighting off, no modifications, "
-                                   f"counter-hash initial grid seed {SEED}, frames {2 + Wm}..{1 + Wm + K}",
-                       "parallelism": f"strips{world}" + (f" halo{args.halo}" if world > 1 else ""),
+                                   f"counter-hash initial grid seed {SEED}, frames {2 + Wm}..{1 + Wm + R * K}",
+                       "parallelism": f"strips{world}" + (f" halo{args.halo}, ghost rows pushed by the boundary tiles of se_step_tiles over NVLink (peer st.global + per-tile flags)" if world > 1 else ""),
                        "l2": "inputs larger than L2 (1 GiB cell buffer at 16384^2); no explicit flush" if S * S * 4 > 2 * 126e6 else
                              "L2-RESIDENT workload: the cell buffer fits the 126 MB L2",
                        "cells_bytes": S * S * 4},
+            "timing": {"repetitions": R, "ms_per_repetition": [round(x * 1e3, 4) for x in reps], "reported": "median repetition (each repetition: max over ranks of the CUDA-event time of one se_sim_step(K) call)",
+                       "timed_region_ms": round(sum(reps) * 1e3, 3)},
+            "parity": parity,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": traffic, "traffic_unit": "bytes per launch, scaled from the ncu capture of a 64-step launch (dram read 8.93 GB + write 8.54 GB, profiles/r1_k1b_ncu_full.txt); "
-                                                             "algorithmic bytes per launch = 8 B x 268435456 cells x steps per launch",
+                         "traffic": traffic, "physical_frac": round(traffic / per_launch_s / 1e9 / peak, 4) if traffic else None,
+                         "traffic_unit": ("bytes per launch = (dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture in " + tr["source"] +
+                                          ") per cell-update x cell-updates of a timed launch") if tr else "null: no committed ncu capture of this configuration",
                          "kernel": "se_step_tiles" if launches < K else ("se_step_lut_global" if K == 1 else "se_step_inplace"), "peak_source": peak_src,
-                         "algorithmic_bytes_per_cell_update": 8, "launches_timed": launches,
+                         "algorithmic_bytes_per_cell_update": 8, "launches_per_repetition": launches,
                          "steps_per_launch": round(K / max(launches, 1), 2), "avg_launch_us": round(per_launch_s * 1e6, 2),
-                         "note": "temporal blocking: physical DRAM bytes per launch are ~8/T per cell-update (see profiles/), "
-                                 "so the algorithmic fraction can exceed 1.0; the kernel is ALU-pipe bound, not HBM bound"},
+                         "note": "temporal blocking: physical DRAM bytes are ~8/T per cell-update (physical_frac), so the algorithmic "
+                                 "fraction can exceed 1.0; the kernel is instruction-issue bound, not HBM bound"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": 32, "d2h_bytes_per_step": 2048,
                     "what": "per frame: push modification record (H2D) + Simulation.run() + per-material census (D2H, asynchronous: "
-                            "read on the host every 4 frames, all inside the timed region)",
+                            "read on the host every 4 frames, all inside the timed region)" + ("" if args.no_running_census else "; census kept up to date by the step kernel (SE_FLAG_RUNNING_CENSUS)"),
                     "job_roundtrip": {"value": round(S * S * K / t_job / 1e9, 2), "unit": UNIT,
                                       "what": f"upload grid from pinned host memory + {K} steps + download grid",
                                       "h2d_bytes": S * rows * 4, "d2h_bytes": S * rows * 4}},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(round(launches * R)),
             "clocks": clocks,
         }
-        if args.running_census:
-            line["config"]["experimental"] = "SE_FLAG_RUNNING_CENSUS"
         if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
             try:
                 # the reference's own shader compiled for the CPU when oracle/_ref exists ("reference"), with the

@@ -38,6 +38,7 @@ pub mod ffi {
         pub row_end: u32,
         pub halo_rows: u32,
         pub temporal_block: u32,
+        pub device_share: u32,
     }
     pub const SE_FLAG_LIGHTING: u32 = 1;
 
@@ -61,6 +62,7 @@ pub mod ffi {
         pub fn se_sim_download_color(s: *mut se_sim, host_rgba_f32: *mut f32, host_rgba8: *mut u32) -> c_int;
         pub fn se_sim_device_cells(s: *mut se_sim, dptr: *mut *mut c_void, pitch_bytes: *mut usize) -> c_int;
         pub fn se_sim_census(s: *mut se_sim, counts256: *mut u64) -> c_int;
+        pub fn se_sim_checksum(s: *mut se_sim, sum: *mut u64) -> c_int;
         pub fn se_sim_synchronize(s: *mut se_sim) -> c_int;
         pub fn se_last_error() -> *const c_char;
     }

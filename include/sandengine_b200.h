@@ -55,20 +55,17 @@ typedef struct se_modification {
 #define SE_MAX_MODIFICATIONS 256 /* simulation.rs:43 */
 
 #define SE_FLAG_LIGHTING 1u      /* evaluate the lighting relaxation every step (operations.glsl:114-169) */
-/* EXPERIMENTAL, off by default: keep the per-material census of the owned rows up to date inside the per-frame
- * step kernel (population deltas of the blocks where a SET fired) so that se_sim_census[_async] after a
- * se_sim_step(sim, 1) needs no pass over the grid.  Results are identical to the recount; only table-eligible
- * rule sets with lighting off use it, elsewhere the flag is ignored.  Its kernels (and those of
- * SE_FLAG_FUSED_LIGHT_EXPERIMENTAL) are compiled only when the rules are compiled with env SE_EXPERIMENTAL_KERNELS=1;
- * otherwise se_sim_create refuses the flag with SE_ERR_INVALID_ARG. */
+/* Keep the per-material census of the owned rows up to date inside the per-frame step kernel (population deltas of the
+ * blocks where a SET fired) so that se_sim_census[_async] after a se_sim_step(sim, 1) needs no pass over the grid.
+ * Results are identical to the recount; only rule sets with a single shared-memory transition table and lighting off
+ * use it, elsewhere the flag is ignored. */
 #define SE_FLAG_RUNNING_CENSUS 2u
-/* EXPERIMENTAL opt-in: allow SE_FLAG_LIGHTING on a strip.  The light field then gets ghost rows too: attach the
- * neighbours' light buffers (se_sim_ipc_export_light / _attach_light, or se_sim_attach_local) and exchange every
- * `halo_rows` steps (the light stencil uses up one ghost row per step).  Without this flag lighting on a strip is
- * refused with SE_ERR_UNSUPPORTED. */
+/* Accepted for compatibility (round 1 gated lighting on a strip behind it): lit strips are always allowed now.  The
+ * light field gets ghost rows too: attach the neighbours' light buffers (se_sim_ipc_export_light / _attach_light, or
+ * se_sim_attach_local); the light stencil uses up one ghost row per step and se_sim_step exchanges when they run out. */
 #define SE_FLAG_LIT_STRIP_EXPERIMENTAL 4u
-/* EXPERIMENTAL, off by default: with SE_FLAG_LIGHTING and a table-eligible rule set, run the Margolus step, the
- * modification override and the lighting relaxation as ONE kernel (se_light_fused) instead of two.  Same results. */
+/* With SE_FLAG_LIGHTING and a table-eligible rule set, run the Margolus step, the modification override and the
+ * lighting relaxation as ONE kernel instead of two.  Same results.  Ignored where it does not apply. */
 #define SE_FLAG_FUSED_LIGHT_EXPERIMENTAL 8u
 
 typedef struct se_create_params {
@@ -78,11 +75,16 @@ typedef struct se_create_params {
     int32_t device;          /* CUDA device ordinal */
     /* Strip decomposition (multi-GPU): this sim owns global rows [row_begin, row_end) and keeps
      * `halo_rows` ghost rows towards each neighbour.  Single GPU: row_begin = 0, row_end = 0 (= height),
-     * halo_rows = 0.  row_begin/row_end must be even (Margolus blocks are 2 rows).  Strips carry ghost rows of
-     * the id buffer only: SE_FLAG_LIGHTING on a strip returns SE_ERR_UNSUPPORTED (but see
-     * SE_FLAG_LIT_STRIP_EXPERIMENTAL). */
+     * halo_rows = 0.  row_begin/row_end and halo_rows must be even (Margolus blocks are 2 rows).  With neighbours
+     * attached se_sim_step keeps the ghost rows current by itself: the tile kernel pushes its boundary rows into the
+     * neighbours' ghost rows as part of its store phase, the per-step kernels exchange on the stream when the ghost rows
+     * are used up.  Every strip of a grid must be given the same sequence of se_sim_step calls. */
     uint32_t row_begin, row_end, halo_rows;
     uint32_t temporal_block; /* Margolus steps fused per launch by the tiled kernel; 0 = library default */
+    /* Number of sims that share this CUDA device AND are stepped concurrently (several strips of one grid on one GPU,
+     * the single-process test set-up): the persistent tile kernel then takes 1/device_share of the SMs so that the
+     * strips' kernels, which wait for each other's boundary tiles, are co-resident.  0 or 1: the device is this sim's. */
+    uint32_t device_share;
 } se_create_params;
 
 /* ---- codegen seam: replaces sandengine_lang::parse_string + create_glsl_from_parser ------------
@@ -131,6 +133,10 @@ int se_sim_download_color(se_sim* s, float* host_rgba_f32, uint32_t* host_rgba8)
 int se_sim_device_cells(se_sim* s, void** dptr, size_t* pitch_bytes);
 /* Per-material population of the owned rows (256 bins), computed on the device. */
 int se_sim_census(se_sim* s, uint64_t* counts256);
+/* Checksum of the owned rows: sum over cells of mix(global cell index, id) modulo 2^64 (mix: see static_kernels.cu).
+ * Order- and sharding-independent: the values of the strips of a grid add up (mod 2^64) to the value of the whole grid,
+ * which is how a sharded run is compared with an unsharded one without gathering the grid. */
+int se_sim_checksum(se_sim* s, uint64_t* sum);
 /* Asynchronous census: enqueued after everything issued so far, runs on the sim's side stream CONCURRENTLY with
  * later steps (a later step that would overwrite the buffer being counted waits for it on the device).
  * host_counts256 (256 x uint64; pinned memory for a truly asynchronous copy) is valid after
@@ -158,7 +164,8 @@ int se_sim_ipc_attach_light(se_sim* s, int which, const void* handles_2x64);
  * reference's single-process model); peer access is enabled when the devices differ. */
 int se_sim_attach_local(se_sim* s, int which, se_sim* neighbour);
 /* Push this sim's boundary rows into the attached neighbours' ghost rows (device-to-device over NVLink).
- * The caller is responsible for ordering against the neighbours' kernels (host barriers). */
+ * The caller is responsible for ordering against the neighbours' kernels (host barriers).  se_sim_step does its own
+ * exchanges; these two entry points remain for callers that want to drive the exchange themselves. */
 int se_sim_halo_push(se_sim* s);
 /* The same exchange with the ordering done ON THE DEVICE, no host synchronisation: stream-ordered flag
  * writes / waits on peer-mapped words (cuStreamWriteValue32 / cuStreamWaitValue32):

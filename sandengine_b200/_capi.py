@@ -33,7 +33,7 @@ EXPORTS = [
     "se_rules_material", "se_rules_material_id", "se_rules_rule",
     "se_sim_create", "se_sim_destroy", "se_sim_step", "se_sim_push_modifications", "se_sim_set_frame", "se_sim_get_frame",
     "se_sim_upload_cells", "se_sim_download_cells", "se_sim_upload_light", "se_sim_download_light", "se_sim_download_color", "se_sim_device_cells",
-    "se_sim_census", "se_sim_census_async", "se_sim_census_wait", "se_sim_set_stream", "se_sim_synchronize", "se_sim_launch_count",
+    "se_sim_census", "se_sim_checksum", "se_sim_census_async", "se_sim_census_wait", "se_sim_set_stream", "se_sim_synchronize", "se_sim_launch_count",
     "se_sim_ipc_export", "se_sim_ipc_attach", "se_sim_ipc_export_light", "se_sim_ipc_attach_light", "se_sim_attach_local", "se_sim_halo_push", "se_sim_halo_exchange_async", "se_last_error", "se_version",
 ]
 
@@ -45,7 +45,8 @@ class se_modification(C.Structure):  # == simulation.rs:45-56
 
 class se_create_params(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("flags", C.c_uint32), ("device", C.c_int32),
-                ("row_begin", C.c_uint32), ("row_end", C.c_uint32), ("halo_rows", C.c_uint32), ("temporal_block", C.c_uint32)]
+                ("row_begin", C.c_uint32), ("row_end", C.c_uint32), ("halo_rows", C.c_uint32), ("temporal_block", C.c_uint32),
+                ("device_share", C.c_uint32)]
 
 
 _lib = None
@@ -86,6 +87,7 @@ def lib() -> C.CDLL:
     L.se_sim_download_color.argtypes = [vp, vp, vp]
     L.se_sim_device_cells.argtypes = [vp, P(vp), P(sz)]
     L.se_sim_census.argtypes = [vp, vp]
+    L.se_sim_checksum.argtypes = [vp, vp]
     L.se_sim_census_async.argtypes = [vp, vp]
     L.se_sim_census_wait.argtypes = [vp]
     L.se_sim_set_stream.argtypes = [vp, vp]

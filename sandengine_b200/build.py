@@ -87,11 +87,8 @@ def inspect_default() -> Path:
     cu = out_dir / "sand_kernels_default.cu"
     cu.write_text((CSRC / "kernels" / "sand_kernels.cuh").read_text())
     cubin = out_dir / "sand_kernels_default.cubin"
-    # same defines as the NVRTC compile in api.cpp::compile_front (SE_TILE_THREADS: CTA size of the tile kernel)
-    tile_threads = os.environ.get("SE_TILE_THREADS", "1024")
-    if tile_threads not in ("256", "512", "768", "1024"):
-        tile_threads = "1024"
-    cmd = [NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-fmad=false", f"-DSE_TILE_THREADS={tile_threads}", "-Xptxas", "-v", "-cubin",
+    # same options as the NVRTC compile in api.cpp::compile_front
+    cmd = [NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xptxas", "-v", "-cubin",
            "-I", str(out_dir), str(cu), "-o", str(cubin)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     (out_dir / "ptxas_default.log").write_text(r.stdout + r.stderr)

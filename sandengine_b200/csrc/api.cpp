@@ -133,14 +133,26 @@ struct SeStepParams {
 struct SeTileParams {
     unsigned* buf0;
     unsigned* buf1;
+    unsigned* nbr_buf0[2];
+    unsigned* nbr_buf1[2];
+    unsigned* nbr_flags[2];
+    const unsigned* in_flags[2];
+    int nbr_gy0[2];
     int W, Hl, gy0, Hg;
+    int own_y0, own_y1;
     int frame0, nblk, tsteps, nsub_last;
     unsigned seq_base;
     unsigned* done;
-    int HY, HX, PH;
+    unsigned* status;
+    unsigned* queue;
+    unsigned queue_base;
+    int HY, HX, PH, THo;
     int tiles_x, tiles_y;
-    int lut_words, pool_offset, tile_offset;
+    int push_rows;
+    int table_bytes, pool_offset, tile_offset, tile_stride;
     const unsigned* lut;
+    const unsigned* pool;
+    unsigned spin_limit;
 };
 struct SeShadeParams {
     const unsigned* cells;
@@ -152,8 +164,9 @@ struct SeLutStepParams {
     unsigned* cells;
     int W, Hl, gy0, Hg;
     int frame;
-    int lut_words, pool_offset;
+    int table_bytes, pool_offset;
     const unsigned* lut;
+    const unsigned* pool;
 };
 struct SeLutCensusParams {
     unsigned long long* census;
@@ -168,15 +181,13 @@ struct SeLightParams {
     float4* light_out;
     int W, Hl, gy0, Hg;
 };
-struct SeFusedParams {
-    SeLightParams lp;
-    int frame;
-    int n_mods;
-    const SeMod* mods;
-    int lut_words, pool_offset;
-    int tile_offset;
-    const unsigned* lut;
-    int tiles_x, tiles_y;
+
+// words of the per-sim flag block that sits behind cells[0] in the same allocation (one IPC handle maps both)
+enum : int {
+    FLAG_EPOCH = 0,       // [0]/[1] "done computing" epoch of the strip above/below, [2]/[3] "ghost rows delivered" from above/below
+    FLAG_STATUS = 8,      // != 0: a tile of se_step_tiles gave up waiting for a flag (results invalid)
+    FLAG_QUEUE = 9,       // work queue of se_step_tiles (never reset: the host knows its value at every launch)
+    FLAG_TILE_IN = 64,    // [64, 64 + cap): sequence numbers of the boundary tiles of the strip ABOVE, [64 + cap, 64 + 2 cap): of the strip BELOW
 };
 
 }  // namespace
@@ -187,8 +198,6 @@ struct se_rules {
     std::vector<char> cubin;
     std::string nvrtc_log;
     bool compiled = false;
-    int tile_threads = 1024;   // CTA size of the tile kernel (compile-time launch bound; tunable: env SE_TILE_THREADS)
-    bool experimental_kernels = false;   // compiled with env SE_EXPERIMENTAL_KERNELS=1
     int light_rows = 4;        // rows per thread of se_light => tile height 8 * light_rows (tunable: env SE_LT_ROWS)
 };
 
@@ -233,21 +242,29 @@ struct se_sim {
     cudaEvent_t ev_main = nullptr, census_done[2] = {nullptr, nullptr};
     bool census_pending[2] = {false, false};
     unsigned census_slot = 0;
-    // transition-table tile kernel (K1b)
+    // transition-table kernels (K1b tiles, K1c per frame)
     bool tiled = false;
     CUfunction f_tiles = nullptr, f_build_lut = nullptr, f_lut_global = nullptr;
-    unsigned* d_lut = nullptr;
+    unsigned* d_lut = nullptr;         // table image: N^4 * tables entries, then (mode 1, same allocation) the pool
+    unsigned* d_pool = nullptr;        // mode 2: pool entries {thr, A, B} in global memory
     unsigned* d_tile_done = nullptr;   // per-tile sequence numbers (dataflow between the T-blocks of one launch)
+    int tile_done_cap = 0;
     unsigned tile_seq = 0;             // T-blocks completed so far
+    unsigned tile_queue = 0;           // value of the device-side work queue counter when the next launch starts
     // se_step_tiles spins on flags written by other CTAs of the same grid, so all of its CTAs must be resident
     // together: it is launched cooperatively (the driver then places the whole grid at once, even when another
-    // stream's kernels share the device).  False only on a device / context that reports no support.
+    // stream's kernels share the device).  Without cooperative launch support every launch carries ONE T-block
+    // (its tiles wait on no flag of the same grid), so partial residency cannot deadlock.
     bool coop = false;
-    int T = 0, HY = 0, HX = 0, PH = 0, tiles_x = 0, tiles_y = 0, lut_words = 0, pool_offset = 0, tile_offset = 0, tile_smem = 0, tile_grid = 0, tile_grid_max = 0, k1c_grid = 0;
-    // fused step + modifications + lighting (SE_FLAG_FUSED_LIGHT_EXPERIMENTAL)
-    bool fused_light = false;
-    CUfunction f_light_fused = nullptr;
-    int lf_smem = 0, lf_grid = 0, lf_tiles_x = 0, lf_tiles_y = 0;
+    int lut_mode = 0;
+    int T = 0, HY = 0, HX = 0, PH_max = 0, tiles_x = 0, table_bytes = 0, pool_offset = 0, tile_offset = 0, tile_grid = 0, k1c_grid = 0, k1c_smem = 0;
+    int smem_budget = 0;
+    int device_share = 1;
+    // ghost rows (strips): rows of each ghost zone, counted from the owned rows outwards, that hold the neighbour's
+    // current state.  The per-step kernels recompute the ghost rows redundantly and use the zone up from the outside
+    // (one row every other frame; one row per frame with lighting); the tile kernel refreshes `push_rows` of them
+    // in every T-block.  se_sim_step exchanges (device-ordered) whenever the next launch needs more than there is.
+    int ghost_valid = 0;
     // running census (SE_FLAG_RUNNING_CENSUS, experimental): d_running is valid only between K1c-census steps
     bool running = false, running_valid = false, running_copy_pending = false;
     CUfunction f_lut_global_census = nullptr, f_build_popbits = nullptr;
@@ -262,6 +279,11 @@ struct se_sim {
     unsigned* flags = nullptr;
     unsigned epoch = 0;
     static size_t flags_offset(size_t W_, size_t Hl_) { return ((W_ * Hl_ * sizeof(unsigned)) + 255) / 256 * 256; }
+    static size_t tile_flag_cap(size_t W_) { return W_ / 192 + 2; }             // tiles per row for the widest halo (HX <= 32)
+    static size_t flags_bytes(size_t W_) { return (((size_t)FLAG_TILE_IN + 2 * tile_flag_cap(W_)) * sizeof(unsigned) + 255) / 256 * 256; }
+    bool is_strip() const { return ghost_top > 0 || ghost_bottom > 0; }
+    bool has_neighbours() const { return nb[0].attached || nb[1].attached; }
+    int ghost_rows() const { return ghost_top > 0 && ghost_bottom > 0 ? std::min(ghost_top, ghost_bottom) : std::max(ghost_top, ghost_bottom); }
     size_t cells_bytes() const { return (size_t)W * Hl * sizeof(unsigned); }
     size_t owned_offset() const { return (size_t)ghost_top * W; }
     size_t owned_cells() const { return (size_t)W * (row_end - row_begin); }
@@ -299,15 +321,7 @@ int compile_front(const char* yaml, size_t len, se_rules** out, bool with_nvrtc)
         }
         // -fmad=false: the lighting sums and any float arithmetic in rule conditions are evaluated as
         // written (no FMA contraction), matching the reference expression tree.
-        if (const char* tt = std::getenv("SE_TILE_THREADS")) {
-            int v = std::atoi(tt);
-            if (v == 256 || v == 512 || v == 768 || v == 1024) r->tile_threads = v;
-        }
-        const std::string def_threads = "-DSE_TILE_THREADS=" + std::to_string(r->tile_threads);
         std::vector<std::string> extra;                       // experiments only: SE_NVRTC_DEFS="-DX=1 -DY=2"
-        if (const char* ek = std::getenv("SE_EXPERIMENTAL_KERNELS")) {   // the kernels behind the experimental SE_FLAG_*s
-            if (std::string(ek) == "1") { extra.push_back("-DSE_EXPERIMENTAL_KERNELS=1"); r->experimental_kernels = true; }
-        }
         if (const char* lr = std::getenv("SE_LT_ROWS")) {     // experiments only: se_light tile height
             const int v = std::atoi(lr);
             if (v == 2 || v == 4 || v == 8) { r->light_rows = v; extra.push_back("-DSE_LT_ROWS=" + std::to_string(v)); }
@@ -323,7 +337,7 @@ int compile_front(const char* yaml, size_t len, se_rules** out, bool with_nvrtc)
                 else tok.push_back(d[i]);
             }
         }
-        std::vector<const char*> opts = {"-arch=sm_100a", "-std=c++17", "-lineinfo", "-fmad=false", def_threads.c_str()};
+        std::vector<const char*> opts = {"-arch=sm_100a", "-std=c++17", "-lineinfo", "-fmad=false"};
         for (auto& e : extra) opts.push_back(e.c_str());
         nvrtcResult res = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
         size_t log_size = 0;
@@ -366,28 +380,50 @@ int guard_buffer_write(se_sim* s, int buf) {
 }
 
 int launch(se_sim* s, CUfunction f, dim3 grid, dim3 block, void** args, unsigned smem = 0, bool cooperative = false) {
-    if (cooperative) {
-        CUresult r = driver().LaunchCooperativeKernel(f, grid.x, grid.y, grid.z, block.x, block.y, block.z, smem, (CUstream)s->stream, args);
-        if (r != CUDA_SUCCESS) {
-            // e.g. CUDA_ERROR_COOPERATIVE_LAUNCH_TOO_LARGE when the context can hold fewer CTAs than the occupancy
-            // query promised (an MPS partition), or a driver without support: the grid is still <= occupancy x SMs,
-            // so the same grid is launched normally from now on; a real launch error then surfaces from that call.
-            s->coop = false;
-            cooperative = false;
-        }
-    }
-    if (!cooperative)
+    if (cooperative)
+        SE_CU(driver().LaunchCooperativeKernel(f, grid.x, grid.y, grid.z, block.x, block.y, block.z, smem, (CUstream)s->stream, args));
+    else
         SE_CU(driver().LaunchKernel(f, grid.x, grid.y, grid.z, block.x, block.y, block.z, smem, (CUstream)s->stream, args, nullptr));
     s->launches++;
     return SE_OK;
 }
 
+int halo_exchange_async(se_sim* s);
+
+// Strips: make sure at least `need` ghost rows per side hold the neighbours' current rows before the next launch
+// (device-ordered exchange, no host synchronisation).  A strip without attached neighbours (a stand-alone probe of one
+// strip) is left alone: its ghost rows are then simply the caller's business.
+// A tile of se_step_tiles that gave up waiting for a neighbour strip's flag leaves a mark instead of hanging the device.
+// Call with the stream idle.
+int check_status(se_sim* s) {
+    if (!s->tiled || !s->is_strip()) return SE_OK;
+    unsigned st = 0;
+    SE_CUDA(cudaMemcpy(&st, s->flags + FLAG_STATUS, sizeof st, cudaMemcpyDeviceToHost));
+    if (st == 0) return SE_OK;
+    SE_CUDA(cudaMemset(s->flags + FLAG_STATUS, 0, sizeof st));
+    return fail(SE_ERR_CUDA, "a strip waited in vain for a neighbour strip (step every strip of the grid before synchronising any of them); the cell state is invalid");
+}
+
+int ensure_ghosts(se_sim* s, int need) {
+    if (!s->is_strip() || !s->has_neighbours() || s->ghost_valid >= need) return SE_OK;
+    return halo_exchange_async(s);
+}
+
 int one_step(se_sim* s, bool use_mods, int n_mods) {
     { int rc = guard_buffer_write(s, 0); if (rc) return rc; rc = guard_buffer_write(s, 1); if (rc) return rc; }
-    s->frame += 1;
-    const int frame = s->frame;
+    const int frame = s->frame + 1;
     const int ox = ((frame & 3) == 1 || (frame & 3) == 3) ? 1 : 0;
     const int oy = ((frame & 3) == 1 || (frame & 3) == 2) ? 1 : 0;
+    // Ghost rows: a step keeps the outermost valid ghost row valid only when that row's block lies inside the valid
+    // zone (the strip boundaries are even rows, so the row is a block's inner row iff ghost_valid + oy is even); the
+    // 8-neighbour light stencil (operations.glsl:114-160) uses up one more row every frame.
+    if (s->is_strip() && frame != 1) {
+        const int after = s->lighting ? s->ghost_valid - 1 : s->ghost_valid - ((s->ghost_valid + oy) & 1);
+        if (after < 0) { int rc = ensure_ghosts(s, s->ghost_rows()); if (rc) return rc; }
+    } else if (s->is_strip() && s->lighting) {
+        int rc = ensure_ghosts(s, 1); if (rc) return rc;
+    }
+    s->frame = frame;
     if (frame == 1) {
         // falling_sand.glsl:743-746: every cell becomes EMPTY; modifications are ignored this frame.
         size_t n = (size_t)s->W * s->Hl;
@@ -395,6 +431,7 @@ int one_step(se_sim* s, bool use_mods, int n_mods) {
         if (!s->lighting) {
             unsigned* buf = s->cells[s->cur];
             void* args[] = {&buf, &n, &zero};
+            s->ghost_valid = s->ghost_rows();               // the ghost rows are EMPTY like everything else
             return launch(s, s->f_fill, dim3(148 * 8), dim3(256), args);
         }
         unsigned* outb = s->cells[s->cur ^ 1];
@@ -407,8 +444,10 @@ int one_step(se_sim* s, bool use_mods, int n_mods) {
         if (rc) return rc;
         s->cur ^= 1;
         s->lcur ^= 1;
+        if (s->is_strip()) s->ghost_valid = std::max(0, s->ghost_valid - 1);
         return SE_OK;
     }
+    if (s->is_strip()) s->ghost_valid = std::max(0, s->lighting ? s->ghost_valid - 1 : s->ghost_valid - ((s->ghost_valid + oy) & 1));
     const int jb0 = (s->gy0 + oy) >> 1;
     const int y_end = std::min(s->Hg, s->gy0 + s->Hl);
     const int nby = ((y_end + oy + 1) >> 1) - jb0;
@@ -424,19 +463,6 @@ int one_step(se_sim* s, bool use_mods, int n_mods) {
         p.out = s->cells[s->cur];
         return launch(s, p.n_mods ? s->f_inplace_mods : s->f_inplace, grid, block, args);
     }
-    if (s->fused_light) {
-        SeFusedParams fp;
-        fp.lp = SeLightParams{s->cells[s->cur], s->cells[s->cur ^ 1], s->light[s->lcur], s->light[s->lcur ^ 1], s->W, s->Hl, s->gy0, s->Hg};
-        fp.frame = frame; fp.n_mods = p.n_mods; fp.mods = s->d_mods;
-        fp.lut_words = s->lut_words; fp.pool_offset = s->pool_offset; fp.tile_offset = s->tile_offset; fp.lut = s->d_lut;
-        fp.tiles_x = s->lf_tiles_x; fp.tiles_y = s->lf_tiles_y;
-        void* fargs[] = {&fp};
-        int rcf = launch(s, s->f_light_fused, dim3(s->lf_grid), dim3(256), fargs, (unsigned)s->lf_smem);
-        if (rcf) return rcf;
-        s->cur ^= 1;
-        s->lcur ^= 1;
-        return SE_OK;
-    }
     p.in = s->cells[s->cur];
     p.out = s->cells[s->cur ^ 1];
     int rc = launch(s, p.n_mods ? s->f_pingpong_mods : s->f_pingpong, grid, block, args);
@@ -448,6 +474,43 @@ int one_step(se_sim* s, bool use_mods, int n_mods) {
     s->cur ^= 1;
     s->lcur ^= 1;
     return SE_OK;
+}
+
+// ---- K1b geometry: tile rows of one launch ------------------------------------------------------------------
+// The tiles' interiors partition the OWNED rows into tiles_y rows of THo rows (the last one may be shorter).  Every
+// half-CTA processes ceil(items / workers) tiles of PH = THo + 2 HY rows, so the launch costs about
+// rounds * (PH + c): pick the tiles_y that minimises it (avoids a nearly empty last round, which is what costs
+// strong scaling: at 16384 x 2048 rows per GPU a fixed PH would spend 9 rounds on 8.4 rounds of work).
+struct TileGeom { int tiles_y, THo, PH; };
+
+TileGeom choose_tile_geometry(const se_sim* s, int nblk, int owned) {
+    const int workers = 2 * s->tile_grid;
+    const int push_min = s->is_strip() ? s->HY : 2;
+    TileGeom best{0, 0, 0};
+    double best_cost = -1;
+    const int tho_max = (s->PH_max - 2 * s->HY) & ~1;
+    const int ty_min = std::max(1, (owned + tho_max - 1) / tho_max);
+    for (int ty = ty_min; ty <= ty_min + 4 * workers; ++ty) {
+        int tho = ((owned + ty - 1) / ty + 1) & ~1;
+        if (tho > tho_max) continue;
+        if (tho < 2 * s->T + 8 && ty > ty_min) break;                // tiles this flat are mostly halo
+        const int last = owned - (ty - 1) * tho;
+        if (last <= 0 || (ty > 1 && last < push_min)) continue;
+        const long long items = (long long)nblk * s->tiles_x * ty;
+        const long long rounds = (items + workers - 1) / workers;
+        // + 24: per-tile fixed work (flag waits, barriers, exposed load/store) expressed in rows (fitted on B200)
+        const double cost = (double)rounds * (tho + 2 * s->HY + 24);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = TileGeom{ty, tho, tho + 2 * s->HY}; }
+    }
+    if (best.tiles_y == 0) {                                          // cannot happen for owned >= 2; keep a safe answer anyway
+        const int tho = std::min(tho_max, (owned + 1) & ~1);
+        best = TileGeom{(owned + tho - 1) / tho, tho, tho + 2 * s->HY};
+    }
+    if (const char* ov = std::getenv("SE_TILE_PH")) {                // experiments only: fix the tile height
+        const int v = (std::atoi(ov) & ~1) - 2 * s->HY;
+        if (v >= 2 && v <= tho_max) best = TileGeom{(owned + v - 1) / v, v, v + 2 * s->HY};
+    }
+    return best;
 }
 
 }  // namespace
@@ -557,6 +620,7 @@ int se_sim_destroy(se_sim* s) try {
     if (s->ev_main) cudaEventDestroy(s->ev_main);
     for (auto& ev : s->census_done) if (ev) cudaEventDestroy(ev);
     if (s->d_lut) cudaFree(s->d_lut);
+    if (s->d_pool) cudaFree(s->d_pool);
     if (s->d_tile_done) cudaFree(s->d_tile_done);
     if (s->d_popbits) cudaFree(s->d_popbits);
     if (s->d_running) cudaFree(s->d_running);
@@ -576,15 +640,11 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
     uint32_t rb = prm->row_begin, re = prm->row_end ? prm->row_end : prm->height;
     if (rb >= re || re > prm->height) return fail(SE_ERR_INVALID_ARG, "bad row range");
     if ((rb & 1u) || ((re & 1u) && re != prm->height)) return fail(SE_ERR_INVALID_ARG, "strip boundaries must be even rows");
-    // Strips exchange ghost rows of the id buffer only; the light field of a strip would need its own ghost rows
-    // (one row per step, operations.glsl:114-160).  Not implemented: refuse instead of relaxing stale light.
-    if ((prm->flags & SE_FLAG_LIGHTING) && (rb > 0 || re < prm->height) && !(prm->flags & SE_FLAG_LIT_STRIP_EXPERIMENTAL))
-        return fail(SE_ERR_UNSUPPORTED, "(Unsupported) lighting on a strip (row_begin/row_end) is not implemented: run lighting on one device");
     // per-step kernels index block rows with gridDim.y (<= 65535 CTAs of 4 block rows / 8 light rows)
     if ((uint64_t)(re - rb) + 2ull * prm->halo_rows > 65535ull * 8ull)
         return fail(SE_ERR_INVALID_ARG, "more than 524280 rows per device are not supported (shard the grid into strips)");
-    if ((prm->flags & (SE_FLAG_RUNNING_CENSUS | SE_FLAG_FUSED_LIGHT_EXPERIMENTAL)) && !rules->experimental_kernels)
-        return fail(SE_ERR_INVALID_ARG, "experimental flag: compile the rules with env SE_EXPERIMENTAL_KERNELS=1 (the kernels are not built by default)");
+    if ((prm->halo_rows & 1u) != 0u) return fail(SE_ERR_INVALID_ARG, "halo_rows must be even (strip buffers start on even rows)");
+    if (prm->device_share > 64u) return fail(SE_ERR_INVALID_ARG, "device_share out of range");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -630,9 +690,11 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
     // Simulation::new allocates zero-filled textures (simulation.rs:145,177-181)
     const bool two = s->lighting;
     const size_t flags_off = se_sim::flags_offset((size_t)s->W, (size_t)s->Hl);
-    SE_CUDA_S(cudaMalloc(&s->cells[0], flags_off + 256));
-    SE_CUDA_S(cudaMemsetAsync(s->cells[0], 0, flags_off + 256, s->stream));
+    const size_t flags_len = se_sim::flags_bytes((size_t)s->W);
+    SE_CUDA_S(cudaMalloc(&s->cells[0], flags_off + flags_len));
+    SE_CUDA_S(cudaMemsetAsync(s->cells[0], 0, flags_off + flags_len, s->stream));
     s->flags = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(s->cells[0]) + flags_off);
+    s->device_share = prm->device_share ? (int)prm->device_share : 1;
     if (two) {
         SE_CUDA_S(cudaMalloc(&s->cells[1], s->cells_bytes()));
         SE_CUDA_S(cudaMemsetAsync(s->cells[1], 0, s->cells_bytes(), s->stream));
@@ -649,164 +711,120 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
     SE_CUDA_S(cudaEventCreateWithFlags(&s->ev_main, cudaEventDisableTiming));
     for (auto& ev : s->census_done) SE_CUDA_S(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 
-    // ---- K1b: transition table + shared-memory tiles with temporal blocking -------------------------
-    // Used for runs of steps without modifications when lighting is off, the rule set is table-eligible
-    // (codegen.h) and rows are 16-byte aligned.  temporal_block == 1 forces the per-step kernel K1a.
+    // ---- transition-table kernels: K1b (tiles + temporal blocking) and K1c (one step, per frame) ----------------
+    // Used for steps without modifications when lighting is off, the rule set is table-eligible (codegen.h) and rows
+    // are 16-byte aligned.  temporal_block == 1 forces the per-step generated-code kernel K1a.
     if (rules->cr.lut_eligible && !s->lighting && (s->W % 4) == 0 && prm->temporal_block != 1) {
-        const int N = rules->cr.tables.n_materials, NCLS = (int)rules->cr.lut_thresholds.size() + 1;
-        const int N4 = N * N * N * N;
-        const int NE = N4 * rules->cr.lut_tables;                 // table entries (two tables for Left/Right rule sets, experimental)
-        const int POOL_MAX = 4095;
-        (void)NCLS;
-        const size_t pool_off = ((size_t)NE * 2 + 7) / 8 * 8;     // pool entries are 8 bytes {thr, A, B}
-        const size_t lut_cap = pool_off + (size_t)POOL_MAX * 8 + 16;
-        unsigned* d_counter = nullptr;
+        const int N = rules->cr.tables.n_materials;
+        const size_t N4 = (size_t)N * N * N * N;
+        const size_t NE = N4 * (size_t)rules->cr.lut_tables;            // table entries (one table per view for Left/Right rule sets and in mode 2)
+        s->lut_mode = rules->cr.lut_mode;
+        int smem_optin = 0, n_sm = 0, coop_attr = 0;
+        SE_CUDA_S(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
+        SE_CUDA_S(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device));
+        SE_CUDA_S(cudaDeviceGetAttribute(&coop_attr, cudaDevAttrCooperativeLaunch, s->device));
+        s->smem_budget = smem_optin - 1024 - 64;                        // static shared memory of the kernels: 1 KB fat table
+        int T = prm->temporal_block ? (int)prm->temporal_block : 8;
+        T = std::min(64, std::max(2, T + (T & 1)));
+        // rows: the Margolus row offset changes every other frame, so T fused steps need only T/2+1 halo rows
+        s->T = T;
+        s->HY = ((T / 2 + 1) + 1) & ~1;
+        s->HX = (T + 3) & ~3;
+        const int min_tile = 2 * 256 * (4 * T + 16);                    // both halves must hold a tile of at least 4T+16 rows
         SE_CU_S(driver().ModuleGetFunction(&s->f_tiles, s->mod, "se_step_tiles"));
         SE_CU_S(driver().ModuleGetFunction(&s->f_build_lut, s->mod, "se_build_lut"));
         SE_CU_S(driver().ModuleGetFunction(&s->f_lut_global, s->mod, "se_step_lut_global"));
-        SE_CUDA_S(cudaMalloc(&s->d_lut, lut_cap));
+        unsigned* d_counter = nullptr;
         SE_CUDA_S(cudaMalloc(&d_counter, sizeof(unsigned)));
-        SE_CUDA_S(cudaMemsetAsync(s->d_lut, 0, lut_cap, s->stream));
         SE_CUDA_S(cudaMemsetAsync(d_counter, 0, sizeof(unsigned), s->stream));
-        unsigned short* base = reinterpret_cast<unsigned short*>(s->d_lut);
-        void* pool = reinterpret_cast<char*>(s->d_lut) + pool_off;
-        void* bargs[] = {&base, &pool, &d_counter};
-        SE_TRY(launch(s, s->f_build_lut, dim3((NE + 255) / 256), dim3(256), bargs));
         unsigned n_pool = 0;
-        SE_CUDA_S(cudaMemcpyAsync(&n_pool, d_counter, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
-        SE_CUDA_S(cudaStreamSynchronize(s->stream));
-        cudaFree(d_counter);
-        int smem_sm = 0, smem_optin = 0;
-        SE_CUDA_S(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, s->device));
-        SE_CUDA_S(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
-        if ((int)n_pool <= POOL_MAX) {
-            const size_t lut_bytes = pool_off + (size_t)n_pool * 8;
-            s->pool_offset = (int)pool_off;
-            s->lut_words = (int)((lut_bytes + 3) / 4);
-            s->tile_offset = (int)((lut_bytes + 15) / 16 * 16);
-            // two CTAs per SM: each gets half of the SM's shared memory minus the per-CTA reservation (1 KB)
-            // and the kernel's static shared memory (1 KB fat table)
-            const int budget = std::min(smem_optin, smem_sm / 2 - 2048 - 256);
-            int T = prm->temporal_block ? (int)prm->temporal_block : 8;
-            T = std::max(2, T + (T & 1));
-            int PH_max = ((budget - s->tile_offset) / 256) & ~1;
-            PH_max = std::min(PH_max, 256);   // measured: taller tiles (up to the 276 rows that fit) are slower (less load/compute overlap)
-            // rows: the Margolus row offset changes every other frame, so T fused steps need only T/2+1 halo rows
-            const int HY = ((T / 2 + 1) + 1) & ~1;
-            if (PH_max >= 4 * T + 16) {
-                int n_sm = 0;
-                SE_CUDA_S(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device));
-                const int grid_max = 2 * n_sm;                       // persistent: 2 CTAs per SM
-                s->T = T;
-                s->HY = HY;
-                s->HX = (T + 3) & ~3;
-                s->tiles_x = (s->W + (256 - 2 * s->HX) - 1) / (256 - 2 * s->HX);
-                // Tile height: every CTA processes ceil(tiles / grid) tiles of PH rows, so the launch costs
-                // rounds * (PH + c).  Pick the PH that minimises it (avoids a nearly empty last round: at
-                // 16384 x 2176 rows per GPU a fixed PH = 256 would spend 3 rounds on 2.3 rounds of work).
-                long best_cost = -1;
-                int best_PH = PH_max;
-                for (int PH = PH_max; PH >= 4 * T + 16; PH -= 2) {
-                    const int ty = (s->Hl + (PH - 2 * HY) - 1) / (PH - 2 * HY);
-                    const long tiles = (long)s->tiles_x * ty;
-                    // launches usually carry several T-blocks whose tiles are dealt to the CTAs as one sequence
-                    // (dataflow inside the kernel), so the round count is taken over a typical 8-T-block launch
-                    const long rounds = (8 * tiles + grid_max - 1) / grid_max;
-                    // useful rows per tile shrink with PH: account for the halo rows recomputed by every tile
-                    // + 24: per-tile fixed work (table/phase set-up, barriers, exposed load/store) expressed in rows;
-                    // fitted on B200 (16384 x 2116 rows: 3 rounds of PH 190 beat 4 rounds of PH 138)
-                    const long cost = rounds * (PH + 24);
-                    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_PH = PH; }
-                }
-                int PH = best_PH;
-                if (const char* ov = std::getenv("SE_TILE_PH")) {      // experiments only: override the search
-                    const int v = std::atoi(ov) & ~1;
-                    if (v >= 4 * T + 16 && v <= PH_max) PH = v;
-                }
-                s->PH = PH;
-                s->tile_smem = s->tile_offset + 256 * PH;
-                s->tiles_y = (s->Hl + (PH - 2 * HY) - 1) / (PH - 2 * HY);
-                s->tile_grid = std::min(grid_max, s->tiles_x * s->tiles_y);
-                s->tile_grid_max = grid_max;
-                s->k1c_grid = grid_max;
-                if (const char* kg = std::getenv("SE_K1C_GRID")) s->k1c_grid = std::max(1, std::atoi(kg));   // experiments only
-                SE_CU_S(driver().FuncSetAttribute(s->f_tiles, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->tile_smem));
-                SE_CU_S(driver().FuncSetAttribute(s->f_lut_global, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->tile_offset));
-                // the dataflow between T-blocks needs every CTA of the grid to be resident: size the grid from the
-                // occupancy the driver reports for this kernel / block size / shared-memory footprint
-                int occ = 0;
-                SE_CU_S(driver().OccupancyMaxActiveBlocks(&occ, s->f_tiles, rules->tile_threads, (size_t)s->tile_smem));
-                if (occ < 1) { fail(SE_ERR_CUDA, "se_step_tiles does not fit on an SM"); return bail(SE_ERR_CUDA); }
-                s->tile_grid_max = std::min(grid_max, occ * n_sm);
-                int coop_attr = 0;
-                SE_CUDA_S(cudaDeviceGetAttribute(&coop_attr, cudaDevAttrCooperativeLaunch, s->device));
-                s->coop = coop_attr != 0 && !std::getenv("SE_NO_COOP_LAUNCH");   // env: experiments only
-                SE_CUDA_S(cudaMalloc(&s->cells[1], s->cells_bytes()));
-                SE_CUDA_S(cudaMemsetAsync(s->cells[1], 0, s->cells_bytes(), s->stream));
-                SE_CUDA_S(cudaMalloc(&s->d_tile_done, (size_t)s->tiles_x * s->tiles_y * sizeof(unsigned)));
-                SE_CUDA_S(cudaMemsetAsync(s->d_tile_done, 0, (size_t)s->tiles_x * s->tiles_y * sizeof(unsigned), s->stream));
-                s->tiled = true;
-                if ((prm->flags & SE_FLAG_RUNNING_CENSUS) && rules->cr.lut_tables == 1) {
-                    SE_CU_S(driver().ModuleGetFunction(&s->f_lut_global_census, s->mod, "se_step_lut_global_census"));
-                    SE_CU_S(driver().ModuleGetFunction(&s->f_build_popbits, s->mod, "se_build_popbits"));
-                    s->pop_words = (N4 + 31) / 32;
-                    s->pop_offset = s->tile_offset;                       // behind the staged table (16-aligned)
-                    SE_CUDA_S(cudaMalloc(&s->d_popbits, (size_t)s->pop_words * sizeof(unsigned)));
-                    SE_CUDA_S(cudaMemsetAsync(s->d_popbits, 0, (size_t)s->pop_words * sizeof(unsigned), s->stream));
-                    SE_CUDA_S(cudaMalloc(&s->d_running, 256 * sizeof(unsigned long long)));
-                    SE_CUDA_S(cudaEventCreateWithFlags(&s->running_copy_done, cudaEventDisableTiming));
-                    void* pargs[] = {&s->d_popbits};
-                    SE_TRY(launch(s, s->f_build_popbits, dim3((N4 + 255) / 256), dim3(256), pargs));
-                    SE_CU_S(driver().FuncSetAttribute(s->f_lut_global_census, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
-                                                      s->pop_offset + ((s->pop_words * 4 + 15) & ~15)));
-                    s->running = true;
+        bool ok = false;
+        if (s->lut_mode == 1) {
+            // mode 1: table + pool in one image that every CTA stages into shared memory
+            const size_t pool_off = (NE * 4 + 15) / 16 * 16;                // pool entries are read with 128-bit loads
+            const long long cap = ((long long)s->smem_budget - (long long)pool_off - min_tile) / 16;
+            if (cap >= 0) {
+                const size_t image = pool_off + (size_t)cap * 16 + 16;
+                SE_CUDA_S(cudaMalloc(&s->d_lut, image));
+                SE_CUDA_S(cudaMemsetAsync(s->d_lut, 0, image, s->stream));
+                unsigned* base = s->d_lut;
+                unsigned* pool = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(s->d_lut) + pool_off);
+                unsigned ucap = (unsigned)cap;
+                void* bargs[] = {&base, &pool, &d_counter, &ucap};
+                SE_TRY(launch(s, s->f_build_lut, dim3((unsigned)((NE + 255) / 256)), dim3(256), bargs));
+                SE_CUDA_S(cudaMemcpyAsync(&n_pool, d_counter, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
+                SE_CUDA_S(cudaStreamSynchronize(s->stream));
+                if ((long long)n_pool <= cap) {
+                    s->pool_offset = (int)pool_off;
+                    s->table_bytes = (int)(pool_off + (size_t)n_pool * 16);
+                    s->tile_offset = (s->table_bytes + 15) / 16 * 16;
+                    ok = true;
                 }
             }
+        } else {
+            // mode 2: the table stays in global memory.  Pass 1 counts the pool entries, pass 2 fills them.
+            SE_CUDA_S(cudaMalloc(&s->d_lut, NE * 4));
+            unsigned* base = s->d_lut;
+            unsigned* pool = nullptr;
+            unsigned ucap = 0;
+            void* bargs[] = {&base, &pool, &d_counter, &ucap};
+            SE_TRY(launch(s, s->f_build_lut, dim3((unsigned)((NE + 255) / 256)), dim3(256), bargs));
+            SE_CUDA_S(cudaMemcpyAsync(&n_pool, d_counter, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
+            SE_CUDA_S(cudaStreamSynchronize(s->stream));
+            if (n_pool < 0x3FFFFFFFu) {
+                SE_CUDA_S(cudaMalloc(&s->d_pool, (size_t)std::max(1u, n_pool) * 16));
+                SE_CUDA_S(cudaMemsetAsync(d_counter, 0, sizeof(unsigned), s->stream));
+                pool = s->d_pool;
+                ucap = n_pool;
+                SE_TRY(launch(s, s->f_build_lut, dim3((unsigned)((NE + 255) / 256)), dim3(256), bargs));
+                SE_CUDA_S(cudaStreamSynchronize(s->stream));
+                s->pool_offset = 0;
+                s->table_bytes = 0;
+                s->tile_offset = 0;
+                ok = true;
+            }
         }
-    }
-    // ---- K3f (experimental): table step + override + lighting in one kernel --------------------------------
-    if ((prm->flags & SE_FLAG_FUSED_LIGHT_EXPERIMENTAL) && s->lighting && rules->cr.lut_eligible) {
-        // the table is built exactly as for K1b above (kept separate so that the default path is untouched)
-        const int N = rules->cr.tables.n_materials;
-        const int N4 = N * N * N * N * rules->cr.lut_tables;
-        const int POOL_MAX = 4095;
-        const size_t pool_off = ((size_t)N4 * 2 + 7) / 8 * 8;
-        const size_t lut_cap = pool_off + (size_t)POOL_MAX * 8 + 16;
-        unsigned* d_counter = nullptr;
-        CUfunction f_build = nullptr;
-        SE_CU_S(driver().ModuleGetFunction(&f_build, s->mod, "se_build_lut"));
-        SE_CU_S(driver().ModuleGetFunction(&s->f_light_fused, s->mod, "se_light_fused"));
-        SE_CUDA_S(cudaMalloc(&s->d_lut, lut_cap));
-        SE_CUDA_S(cudaMalloc(&d_counter, sizeof(unsigned)));
-        SE_CUDA_S(cudaMemsetAsync(s->d_lut, 0, lut_cap, s->stream));
-        SE_CUDA_S(cudaMemsetAsync(d_counter, 0, sizeof(unsigned), s->stream));
-        unsigned short* base = reinterpret_cast<unsigned short*>(s->d_lut);
-        void* pool = reinterpret_cast<char*>(s->d_lut) + pool_off;
-        void* bargs[] = {&base, &pool, &d_counter};
-        SE_TRY(launch(s, f_build, dim3((N4 + 255) / 256), dim3(256), bargs));
-        unsigned n_pool = 0;
-        SE_CUDA_S(cudaMemcpyAsync(&n_pool, d_counter, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
-        SE_CUDA_S(cudaStreamSynchronize(s->stream));
         cudaFree(d_counter);
-        if ((int)n_pool <= POOL_MAX) {
-            const size_t lut_bytes = pool_off + (size_t)n_pool * 8;
-            const int tile_h = 8 * rules->light_rows;
-            s->pool_offset = (int)pool_off;
-            s->lut_words = (int)((lut_bytes + 3) / 4);
-            s->tile_offset = (int)((lut_bytes + 15) / 16 * 16);
-            s->lf_smem = s->tile_offset + (tile_h + 2) * 34 * 16 + (tile_h + 2) * 36;     // table + term[] + ids[] (SE_LT_TERMS, SE_LF_IDS_BYTES)
-            s->lf_tiles_x = (s->W + 31) / 32;
-            s->lf_tiles_y = (s->Hl + tile_h - 1) / tile_h;
-            int n_sm = 0, occ = 0, smem_optin = 0;
-            SE_CUDA_S(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device));
-            SE_CUDA_S(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
-            if (s->lf_smem <= smem_optin) {
-                SE_CU_S(driver().FuncSetAttribute(s->f_light_fused, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->lf_smem));
-                SE_CU_S(driver().OccupancyMaxActiveBlocks(&occ, s->f_light_fused, 256, (size_t)s->lf_smem));
-                if (occ >= 1) {
-                    s->lf_grid = (int)std::min<long long>((long long)occ * n_sm, (long long)s->lf_tiles_x * s->lf_tiles_y);
-                    s->fused_light = true;
-                }
+        const int owned = s->row_end - s->row_begin;
+        // strips: the tile kernel reads HY ghost rows and pushes as many into the neighbours
+        if (ok && s->is_strip() && ((int)prm->halo_rows < s->HY || owned < 2 * s->HY)) ok = false;
+        if (ok) {
+            int PH_max = (((s->smem_budget - s->tile_offset) / 2) / 256) & ~1;
+            PH_max = std::min(PH_max, 320);                            // taller tiles: fewer, coarser work items for the same bytes
+            if (const char* pm = std::getenv("SE_TILE_PH_MAX")) PH_max = std::min(PH_max, std::max(4 * T + 16, std::atoi(pm) & ~1));   // experiments only
+            s->PH_max = PH_max;
+            s->tiles_x = (s->W + (256 - 2 * s->HX) - 1) / (256 - 2 * s->HX);
+            s->tile_grid = std::max(1, n_sm / s->device_share);        // persistent: one CTA (two halves) per SM
+            s->k1c_grid = std::max(1, 2 * n_sm / s->device_share);
+            if (const char* kg = std::getenv("SE_K1C_GRID")) s->k1c_grid = std::max(1, std::atoi(kg));   // experiments only
+            s->k1c_smem = s->tile_offset;
+            const int tile_smem_max = s->tile_offset + 2 * 256 * PH_max;
+            SE_CU_S(driver().FuncSetAttribute(s->f_tiles, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, tile_smem_max));
+            if (s->k1c_smem > 0) SE_CU_S(driver().FuncSetAttribute(s->f_lut_global, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->k1c_smem));
+            int occ = 0;
+            SE_CU_S(driver().OccupancyMaxActiveBlocks(&occ, s->f_tiles, 1024, (size_t)tile_smem_max));
+            if (occ < 1) { fail(SE_ERR_CUDA, "se_step_tiles does not fit on an SM"); return bail(SE_ERR_CUDA); }
+            s->coop = coop_attr != 0 && !std::getenv("SE_NO_COOP_LAUNCH");   // env: experiments only
+            SE_CUDA_S(cudaMalloc(&s->cells[1], s->cells_bytes()));
+            SE_CUDA_S(cudaMemsetAsync(s->cells[1], 0, s->cells_bytes(), s->stream));
+            s->tile_done_cap = s->tiles_x * (owned / 8 + 2);
+            SE_CUDA_S(cudaMalloc(&s->d_tile_done, (size_t)s->tile_done_cap * sizeof(unsigned)));
+            SE_CUDA_S(cudaMemsetAsync(s->d_tile_done, 0, (size_t)s->tile_done_cap * sizeof(unsigned), s->stream));
+            s->tiled = true;
+            if ((prm->flags & SE_FLAG_RUNNING_CENSUS) && rules->cr.lut_tables == 1) {
+                SE_CU_S(driver().ModuleGetFunction(&s->f_lut_global_census, s->mod, "se_step_lut_global_census"));
+                SE_CU_S(driver().ModuleGetFunction(&s->f_build_popbits, s->mod, "se_build_popbits"));
+                s->pop_words = (int)((N4 + 31) / 32);
+                s->pop_offset = s->tile_offset;                       // behind the staged table (16-aligned)
+                SE_CUDA_S(cudaMalloc(&s->d_popbits, (size_t)s->pop_words * sizeof(unsigned)));
+                SE_CUDA_S(cudaMemsetAsync(s->d_popbits, 0, (size_t)s->pop_words * sizeof(unsigned), s->stream));
+                SE_CUDA_S(cudaMalloc(&s->d_running, 256 * sizeof(unsigned long long)));
+                SE_CUDA_S(cudaEventCreateWithFlags(&s->running_copy_done, cudaEventDisableTiming));
+                void* pargs[] = {&s->d_popbits};
+                SE_TRY(launch(s, s->f_build_popbits, dim3((unsigned)((N4 + 255) / 256)), dim3(256), pargs));
+                SE_CU_S(driver().FuncSetAttribute(s->f_lut_global_census, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                                  s->pop_offset + ((s->pop_words * 4 + 15) & ~15)));
+                s->running = true;
             }
         }
     }
@@ -851,15 +869,19 @@ int se_sim_step(se_sim* s, uint32_t n_steps) try {
     for (uint32_t k = 0; k < n_steps;) {
         const bool mods_now = (k == 0 && n_mods > 0);
         if (s->tiled && !mods_now && s->frame + 1 != 1) {
-            // a run of plain steps: fuse up to T of them per launch (ping-pong buffers)
-            const int nsub = (int)std::min<uint32_t>((uint32_t)s->T, n_steps - k);
-            if (nsub == 1) {
+            if (n_steps - k == 1) {
                 // a lone step (the per-frame path): K1c, table transitions straight from global memory, in place
                 { int rc = guard_buffer_write(s, s->cur); if (rc) return rc; }
+                const int frame = s->frame + 1;
+                const int oy = ((frame & 3) == 1 || (frame & 3) == 2) ? 1 : 0;
+                if (s->is_strip()) {
+                    if (s->ghost_valid - ((s->ghost_valid + oy) & 1) < 0) { int rc = ensure_ghosts(s, s->ghost_rows()); if (rc) return rc; }
+                    s->ghost_valid = std::max(0, s->ghost_valid - ((s->ghost_valid + oy) & 1));
+                }
                 SeLutStepParams lp;
                 lp.cells = s->cells[s->cur];
-                lp.W = s->W; lp.Hl = s->Hl; lp.gy0 = s->gy0; lp.Hg = s->Hg; lp.frame = s->frame + 1;
-                lp.lut_words = s->lut_words; lp.pool_offset = s->pool_offset; lp.lut = s->d_lut;
+                lp.W = s->W; lp.Hl = s->Hl; lp.gy0 = s->gy0; lp.Hg = s->Hg; lp.frame = frame;
+                lp.table_bytes = s->table_bytes; lp.pool_offset = s->pool_offset; lp.lut = s->d_lut; lp.pool = s->d_pool;
                 void* largs[] = {&lp};
                 int rc;
                 if (s->running && s->running_valid) {
@@ -867,34 +889,66 @@ int se_sim_step(se_sim* s, uint32_t n_steps) try {
                     void* cargs[] = {&lp, &cx};
                     rc = launch(s, s->f_lut_global_census, dim3(s->k1c_grid), dim3(512), cargs, (unsigned)(s->pop_offset + ((s->pop_words * 4 + 15) & ~15)));
                 } else {
-                    rc = launch(s, s->f_lut_global, dim3(s->k1c_grid), dim3(512), largs, (unsigned)s->tile_offset);   // SE_K1C_THREADS
+                    rc = launch(s, s->f_lut_global, dim3(s->k1c_grid), dim3(512), largs, (unsigned)s->k1c_smem);   // SE_K1C_THREADS
                 }
                 if (rc) return rc;
                 s->frame += 1;
                 k += 1;
                 continue;
             }
-            // a run of plain steps: ONE launch of ceil(run / T) T-blocks (dataflow between them inside the kernel)
+            // a run of plain steps: ONE launch of nblk T-blocks of (nearly) equal length -- 20 steps are 7 + 7 + 6, not
+            // 8 + 8 + 4 -- with dataflow between them inside the kernel.  Without cooperative launch: one T-block per launch.
             s->running_valid = false;
             { int rc = guard_buffer_write(s, 0); if (rc) return rc; rc = guard_buffer_write(s, 1); if (rc) return rc; }
-            const uint32_t run = std::min<uint32_t>(n_steps - k, 64u * (uint32_t)s->T);     // bound the kernel duration
+            uint32_t run = std::min<uint32_t>(n_steps - k, 64u * (uint32_t)s->T);     // bound the kernel duration
+            if (!s->coop) run = std::min<uint32_t>(run, (uint32_t)s->T);
             const int nblk = (int)((run + (uint32_t)s->T - 1) / (uint32_t)s->T);
+            const int tsteps = (int)((run + (uint32_t)nblk - 1) / (uint32_t)nblk);
+            { int rc = ensure_ghosts(s, s->HY); if (rc) return rc; }
+            const TileGeom g = choose_tile_geometry(s, nblk, s->row_end - s->row_begin);
+            if ((long long)s->tiles_x * g.tiles_y > s->tile_done_cap) return fail(SE_ERR_INTERNAL, "tile flag array too small");
             SeTileParams tp;
+            std::memset(&tp, 0, sizeof tp);
             tp.buf0 = s->cells[s->cur]; tp.buf1 = s->cells[s->cur ^ 1];
+            const size_t cap = se_sim::tile_flag_cap((size_t)s->W);
+            int push_rows = 0;
+            for (int w = 0; w < 2; ++w) {
+                const Neighbour& nb = s->nb[w];
+                const int nb_ghost = (int)(w == 0 ? nb.ghost_bottom : nb.ghost_top);      // the neighbour's ghost zone that my rows fill
+                if (!nb.attached || nb_ghost == 0) continue;
+                tp.nbr_buf0[w] = nb.cells[s->cur]; tp.nbr_buf1[w] = nb.cells[s->cur ^ 1];
+                // my tiles publish in the neighbour's "from below" (w == 0: I am below it) / "from above" array
+                tp.nbr_flags[w] = nb.flags + FLAG_TILE_IN + (w == 0 ? cap : 0);
+                tp.in_flags[w] = s->flags + FLAG_TILE_IN + (w == 0 ? 0 : cap);
+                tp.nbr_gy0[w] = (w == 0) ? (s->row_begin - ((int)nb.local_rows - (int)nb.ghost_bottom)) : (s->row_end - (int)nb.ghost_top);
+                push_rows = push_rows ? std::min(push_rows, nb_ghost) : nb_ghost;
+            }
+            // rows pushed per boundary tile: the whole ghost zone of the neighbour when the boundary tile rows hold that many
+            const int last_rows = (s->row_end - s->row_begin) - (g.tiles_y - 1) * g.THo;
+            push_rows = std::min(push_rows, std::min(g.THo, last_rows));
             tp.W = s->W; tp.Hl = s->Hl; tp.gy0 = s->gy0; tp.Hg = s->Hg;
-            tp.frame0 = s->frame + 1; tp.nblk = nblk; tp.tsteps = s->T; tp.nsub_last = (int)(run - (uint32_t)(nblk - 1) * (uint32_t)s->T);
-            tp.seq_base = s->tile_seq; tp.done = s->d_tile_done;
-            tp.HY = s->HY; tp.HX = s->HX; tp.PH = s->PH;
-            tp.tiles_x = s->tiles_x; tp.tiles_y = s->tiles_y; tp.lut_words = s->lut_words; tp.pool_offset = s->pool_offset; tp.tile_offset = s->tile_offset;
-            tp.lut = s->d_lut;
+            tp.own_y0 = s->row_begin; tp.own_y1 = s->row_end;
+            tp.frame0 = s->frame + 1; tp.nblk = nblk; tp.tsteps = tsteps; tp.nsub_last = (int)(run - (uint32_t)(nblk - 1) * (uint32_t)tsteps);
+            tp.seq_base = s->tile_seq; tp.done = s->d_tile_done; tp.status = s->flags + FLAG_STATUS;
+            tp.queue = s->flags + FLAG_QUEUE; tp.queue_base = s->tile_queue;
+            tp.HY = s->HY; tp.HX = s->HX; tp.PH = g.PH; tp.THo = g.THo;
+            tp.tiles_x = s->tiles_x; tp.tiles_y = g.tiles_y; tp.push_rows = push_rows;
+            tp.table_bytes = s->table_bytes; tp.pool_offset = s->pool_offset; tp.tile_offset = s->tile_offset; tp.tile_stride = 256 * g.PH;
+            tp.lut = s->d_lut; tp.pool = s->d_pool;
+            tp.spin_limit = 4000000u;                                   // ~2 s of polling before a tile gives up on a flag
             void* targs[] = {&tp};
-            const long long items = (long long)nblk * s->tiles_x * s->tiles_y;
-            const int grid = (int)std::min<long long>((long long)s->tile_grid_max, items);
-            int rc = launch(s, s->f_tiles, dim3(grid), dim3(s->rules->tile_threads), targs, (unsigned)s->tile_smem, s->coop);
+            const long long items = (long long)nblk * s->tiles_x * g.tiles_y;
+            const int grid = (int)std::min<long long>((long long)s->tile_grid, (items + 1) / 2);
+            int rc = launch(s, s->f_tiles, dim3(grid), dim3(1024), targs, (unsigned)(s->tile_offset + 2 * 256 * g.PH), s->coop);
             if (rc) return rc;
             s->frame += (int)run;
             s->tile_seq += (unsigned)nblk;
+            s->tile_queue += (unsigned)items + 2u * (unsigned)grid;      // every half draws exactly one number past the end
             s->cur ^= (nblk & 1);
+            // Every neighbour pushed at least HY rows (its boundary tile rows are at least that high).  HY and not the
+            // actual count: the figure must be the same on every strip of the grid, because it decides when the
+            // stream-ordered exchange of the per-step kernels happens, and that exchange runs in lock-step epochs.
+            if (s->is_strip()) s->ghost_valid = s->has_neighbours() ? s->HY : 0;
             k += run;
             continue;
         }
@@ -931,6 +985,7 @@ int se_sim_upload_cells(se_sim* s, const uint32_t* host) try {
     SE_CUDA(cudaSetDevice(s->device));
     { int rc = guard_buffer_write(s, s->cur); if (rc) return rc; }
     s->running_valid = false;
+    s->ghost_valid = 0;                                   // the neighbours' copies of my rows and mine of theirs are stale now
     SE_CUDA(cudaMemcpyAsync(s->cells[s->cur] + s->owned_offset(), host, s->owned_cells() * sizeof(unsigned), cudaMemcpyHostToDevice, s->stream));
     SE_CUDA(cudaStreamSynchronize(s->stream));
     return SE_OK;
@@ -941,13 +996,14 @@ int se_sim_download_cells(se_sim* s, uint32_t* host) try {
     SE_CUDA(cudaSetDevice(s->device));
     SE_CUDA(cudaMemcpyAsync(host, s->cells[s->cur] + s->owned_offset(), s->owned_cells() * sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
     SE_CUDA(cudaStreamSynchronize(s->stream));
-    return SE_OK;
+    return check_status(s);
 } SE_ABI_CATCH("se_sim_download_cells")
 
 int se_sim_upload_light(se_sim* s, const float* host) try {
     if (!s || !host) return fail(SE_ERR_INVALID_ARG, "null argument");
     if (!s->lighting) return fail(SE_ERR_INVALID_ARG, "sim was created without SE_FLAG_LIGHTING");
     SE_CUDA(cudaSetDevice(s->device));
+    s->ghost_valid = 0;
     SE_CUDA(cudaMemcpyAsync(s->light[s->lcur] + s->owned_offset(), host, s->owned_cells() * sizeof(float4), cudaMemcpyHostToDevice, s->stream));
     SE_CUDA(cudaStreamSynchronize(s->stream));
     return SE_OK;
@@ -1022,6 +1078,20 @@ int se_sim_census(se_sim* s, uint64_t* counts256) try {
     return SE_OK;
 } SE_ABI_CATCH("se_sim_census")
 
+int se_sim_checksum(se_sim* s, uint64_t* sum) try {
+    if (!s || !sum) return fail(SE_ERR_INVALID_ARG, "null argument");
+    SE_CUDA(cudaSetDevice(s->device));
+    SE_CUDA(cudaMemsetAsync(s->d_census, 0, sizeof(unsigned long long), s->stream));
+    se_static::launch_checksum(s->cells[s->cur] + s->owned_offset(), s->owned_cells(), (unsigned long long)s->row_begin * (unsigned long long)s->W, s->d_census, s->stream);
+    s->launches++;
+    SE_CUDA(cudaGetLastError());
+    unsigned long long v = 0;
+    SE_CUDA(cudaMemcpyAsync(&v, s->d_census, sizeof v, cudaMemcpyDeviceToHost, s->stream));
+    SE_CUDA(cudaStreamSynchronize(s->stream));
+    *sum = v;
+    return check_status(s);
+} SE_ABI_CATCH("se_sim_checksum")
+
 int se_sim_census_async(se_sim* s, uint64_t* host_counts256) try {
     if (!s || !host_counts256) return fail(SE_ERR_INVALID_ARG, "null argument");
     SE_CUDA(cudaSetDevice(s->device));
@@ -1076,7 +1146,7 @@ int se_sim_synchronize(se_sim* s) try {
     if (!s) return fail(SE_ERR_INVALID_ARG, "null sim");
     SE_CUDA(cudaSetDevice(s->device));
     SE_CUDA(cudaStreamSynchronize(s->stream));
-    return SE_OK;
+    return check_status(s);
 } SE_ABI_CATCH("se_sim_synchronize")
 
 int se_sim_launch_count(const se_sim* s, uint64_t* n) try {
@@ -1195,6 +1265,7 @@ int se_sim_halo_push(se_sim* s) try {
             SE_CUDA(cudaMemcpyAsync(dst, src, lrowb * g, cudaMemcpyDeviceToDevice, s->stream));
         }
     }
+    s->ghost_valid = s->ghost_rows();   // every strip pushes in this protocol: the neighbours refresh this strip's ghost rows alike
     return SE_OK;
 } SE_ABI_CATCH("se_sim_halo_push")
 
@@ -1232,26 +1303,34 @@ int se_sim_ipc_attach_light(se_sim* s, int which, const void* handles) try {
 
 int se_sim_halo_exchange_async(se_sim* s) try {
     if (!s) return fail(SE_ERR_INVALID_ARG, "null sim");
+    return halo_exchange_async(s);
+} SE_ABI_CATCH("se_sim_halo_exchange_async")
+
+}  // extern "C"
+
+namespace {
+int halo_exchange_async(se_sim* s) {
     SE_CUDA(cudaSetDevice(s->device));
     if (!driver().ok) return fail(SE_ERR_CUDA, driver().why);
     const unsigned e = ++s->epoch;
     CUstream st = (CUstream)s->stream;
     // (a) tell both neighbours that this strip has finished every step enqueued so far
     for (int w = 0; w < 2; ++w)
-        if (s->nb[w].attached) SE_CU(driver().StreamWriteValue32(st, (CUdeviceptr)(s->nb[w].flags + (w == 0 ? 1 : 0)), e, CU_STREAM_WRITE_VALUE_DEFAULT));
+        if (s->nb[w].attached) SE_CU(driver().StreamWriteValue32(st, (CUdeviceptr)(s->nb[w].flags + FLAG_EPOCH + (w == 0 ? 1 : 0)), e, CU_STREAM_WRITE_VALUE_DEFAULT));
     // (b) wait until the neighbours have finished theirs: only then may their ghost rows be overwritten
     for (int w = 0; w < 2; ++w)
-        if (s->nb[w].attached) SE_CU(driver().StreamWaitValue32(st, (CUdeviceptr)(s->flags + (w == 0 ? 0 : 1)), e, CU_STREAM_WAIT_VALUE_GEQ));
+        if (s->nb[w].attached) SE_CU(driver().StreamWaitValue32(st, (CUdeviceptr)(s->flags + FLAG_EPOCH + (w == 0 ? 0 : 1)), e, CU_STREAM_WAIT_VALUE_GEQ));
     // (c) push boundary rows over NVLink
     int rc = se_sim_halo_push(s);
     if (rc) return rc;
     // (d) publish "delivered"
     for (int w = 0; w < 2; ++w)
-        if (s->nb[w].attached) SE_CU(driver().StreamWriteValue32(st, (CUdeviceptr)(s->nb[w].flags + (w == 0 ? 3 : 2)), e, CU_STREAM_WRITE_VALUE_DEFAULT));
+        if (s->nb[w].attached) SE_CU(driver().StreamWriteValue32(st, (CUdeviceptr)(s->nb[w].flags + FLAG_EPOCH + (w == 0 ? 3 : 2)), e, CU_STREAM_WRITE_VALUE_DEFAULT));
     // (e) later work of this stream starts once this strip's own ghost rows have been delivered
     for (int w = 0; w < 2; ++w)
-        if (s->nb[w].attached) SE_CU(driver().StreamWaitValue32(st, (CUdeviceptr)(s->flags + (w == 0 ? 2 : 3)), e, CU_STREAM_WAIT_VALUE_GEQ));
+        if (s->nb[w].attached) SE_CU(driver().StreamWaitValue32(st, (CUdeviceptr)(s->flags + FLAG_EPOCH + (w == 0 ? 2 : 3)), e, CU_STREAM_WAIT_VALUE_GEQ));
+    s->ghost_valid = s->ghost_rows();
     return SE_OK;
-} SE_ABI_CATCH("se_sim_halo_exchange_async")
+}
+}  // namespace
 
-}  // extern "C"

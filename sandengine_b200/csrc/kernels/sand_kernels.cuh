@@ -484,58 +484,56 @@ extern "C" __global__ void __launch_bounds__(256) se_fill_cells(unsigned* cells,
 #endif  // SE_HOST_EMU
 
 // =============================================================================================
-// K1b: transition-table kernel with shared-memory tiles and temporal blocking.
+// Transition tables.
 //
-// Eligible rule sets (SE_LUT_ELIGIBLE, decided by the code generator): the block transition is a pure
-// function of (4 material ids, mirror bit, rand.y) with rand.y used only against literal thresholds --
-// no pos/frame/other rand use -- there are no non-mirrored rules and N = SE_N_MATERIALS <= 12.  Then
-//     T0[idx],  idx = ((a*N + b)*N + c)*N + d            (N^4 entries, 16 bit)
-// holds the UNMIRRORED transition of every block state, nibble-packed (a | b<<4 | c<<8 | d<<12), built on
-// the device by se_build_lut from the very rule code generated for the generic path.  Entry kinds:
-//     0x0000..0xEFFF  the result (ids < 15)
-//     0xF000 | k      result depends on rand.y: pool[k] = {thr, A, B}: result = (u1 <= thr) ? A : B, where A/B
-//                     are again entries (B may chain to another pool entry for states with several thresholds)
-//     0xFFFF          the state or its result holds WALL / NULL (guarded swaps, operations.glsl:16-23):
-//                     take the generic path (same generated code as K1a)
-// The mirrored transition is  swap_pairs(T0[swap_pairs(state)])  -- exact when no cell of the block
-// refuses to swap, which is precisely when the table is used.
-//
-// One persistent CTA loops over tiles: load (uint4 global -> u8 shared), nsub Margolus sub-steps in
-// shared memory with a halo of T columns / T/2+1 rows, store the interior (u8 shared -> uint4 global, ping-pong buffer).
-// HBM traffic per cell-update ~ (4 * tile/interior + 4) / T bytes instead of 8.
+// Eligible rule sets (SE_LUT_MODE != 0, decided by the code generator): the block transition is a pure function of
+// (4 material ids, mirror bit, rand.y) with rand.y used only against literal thresholds -- no pos / frame / other
+// rand use -- and at most 127 materials.  Then
+//     T[idx],  idx = ((a*N + b)*N + c)*N + d            (N^4 32-bit entries per view)
+// holds the transition of every block state, built on the device by se_build_lut from the very rule code generated
+// for the generic path (se_block_with_rand).  Entry kinds:
+//     bit 31 clear          the result: four id bytes a | b<<8 | c<<16 | d<<24 (ids < 128)
+//     SE_E_SPECIAL | k      the result depends on rand.y: pool[k] = {thr, A, B, 0}: result = (u1 <= thr) ? A : B, where A / B
+//                           are again entries (B may chain to another pool entry for states with several thresholds)
+//     SE_E_SPECIAL|SE_E_SLOW  one-table mode only: the state or its result holds WALL / NULL (guarded swaps,
+//                           operations.glsl:16-23): take the generic path (same generated code as K1a)
+// One-table mode (no Left/Right rules): the table holds the UNMIRRORED evaluation; the mirrored transition is
+// swap_pairs(T[swap_pairs(state)]) -- exact when no cell of the block refuses to swap, which is precisely when the
+// table is used.  Two-table mode: entries [N^4, 2 N^4) hold the finished MIRRORED evaluation (guarded swap, mirrored +
+// left rules, guarded swap back) of the same state, so there are neither byte swaps nor a slow path.
+//   SE_LUT_MODE 1: the table is staged in shared memory (N^4 * tables * 4 B <= 60 KB: the default rule set)
+//   SE_LUT_MODE 2: the table stays in global memory (L2 / HBM resident), always two views: up to 127 materials
 // =============================================================================================
 #if SE_LUT_ELIGIBLE
 #define SE_N4 (SE_N_MATERIALS * SE_N_MATERIALS * SE_N_MATERIALS * SE_N_MATERIALS)
-// SE_LUT_TWO_TABLES (rule sets with Left/Right rules, EXPERIMENTAL): entries [0, N^4) hold the unmirrored view, entries
-// [N^4, 2 N^4) the final result of the MIRRORED evaluation (swap, mirrored + left rules, swap back) of the same state,
-// so the lookup needs no byte swaps; without Left/Right rules one table serves both views through the mirror symmetry.
 #define SE_LUT_ENTRIES (SE_N4 * (SE_LUT_TWO_TABLES ? 2 : 1))
-#define SE_TILE_PW 256          // tile width in cells (= bytes); 64 words per row
-#define SE_LUT_POOL_MAX 4095
-#define SE_LUT_SLOW 0xFFFFu
-#ifndef SE_TILE_THREADS
-#define SE_TILE_THREADS 512
-#endif
+#define SE_E_SPECIAL 0x80000000u
+#define SE_E_SLOW 0x40000000u
+#define SE_E_INDEX 0x3FFFFFFFu
+#define SE_TILE_PW 256          // tile width in cells (= bytes): one warp walks a tile row, 8 cells per lane
 
-struct SePoolEntry { unsigned thr; unsigned short a, b; };   // 8 bytes
+static __device__ __forceinline__ unsigned se_ids4(unsigned s, unsigned r, unsigned d, unsigned dr) {
+    return SE_ID(s) | (SE_ID(r) << 8) | (SE_ID(d) << 16) | (SE_ID(dr) << 24);
+}
 
-// one block state: evaluate every rand.y class with the generated rule code, then encode
-static __device__ __forceinline__ void se_build_lut_entry(int idx, unsigned short* __restrict__ base, SePoolEntry* __restrict__ pool,
-                                                          unsigned* __restrict__ counter) {
-    const int N = SE_N_MATERIALS;
+// one block state: evaluate every rand.y class with the generated rule code, then encode.  pool == nullptr: count only.
+static __device__ __forceinline__ void se_build_lut_entry(unsigned entry, unsigned* __restrict__ base, unsigned* __restrict__ pool,
+                                                          unsigned* __restrict__ counter, unsigned pool_cap) {
+    const unsigned N = SE_N_MATERIALS;
 #if SE_LUT_TWO_TABLES
-    const int entry = idx;
-    const bool mirror_table = entry >= SE_N4;
-    idx = entry - (mirror_table ? SE_N4 : 0);
+    const bool mirror_table = entry >= (unsigned)SE_N4;
+    const unsigned idx = entry - (mirror_table ? (unsigned)SE_N4 : 0u);
+#else
+    const unsigned idx = entry;
 #endif
     const unsigned ia = idx / (N * N * N), ib = (idx / (N * N)) % N, ic = (idx / N) % N, id = idx % N;
-    unsigned short res[SE_LUT_NCLS];
+    unsigned res[SE_LUT_NCLS];
     // class c <=> rand.y hash lane u1 in (U_{c-1}, U_c]  (U_{-1} = -1, U_{NCLS-1} = 2^32-1)
     bool noswap = ((se_fat_table[ia] | se_fat_table[ib] | se_fat_table[ic] | se_fat_table[id]) & SE_F_NOSWAP) != 0u;
 #pragma unroll
     for (int cls = 0; cls < SE_LUT_NCLS; ++cls) {
         unsigned s = se_fat_table[ia], r = se_fat_table[ib], d = se_fat_table[ic], dr = se_fat_table[id];
-        if (idx != 0) {
+        if (idx != 0) {                                                   // all-EMPTY early-out (falling_sand.glsl:692-694): T[0] == 0
             SeRand rnd;
 #if SE_LUT_TWO_TABLES
             rnd.u[0] = mirror_table ? 0u : 0xFFFFFFFFu;                   // rand.x < 0.5: the mirrored evaluation, start to finish
@@ -547,148 +545,151 @@ static __device__ __forceinline__ void se_build_lut_entry(int idx, unsigned shor
             se_block_with_rand(s, r, d, dr, rnd, 0, 0, 0);
         }
         if ((s | r | d | dr) & SE_F_NOSWAP) noswap = true;
-        res[cls] = (unsigned short)(SE_ID(s) | (SE_ID(r) << 4) | (SE_ID(d) << 8) | (SE_ID(dr) << 12));
+        res[cls] = se_ids4(s, r, d, dr);
     }
-#if SE_LUT_TWO_TABLES
-    idx = entry;                                                          // the slot written below
+#if !SE_LUT_TWO_TABLES
+    if (noswap) { base[entry] = SE_E_SPECIAL | SE_E_SLOW; return; }
+#else
+    (void)noswap;
 #endif
-    if (noswap) { base[idx] = SE_LUT_SLOW; return; }
     int n_breaks = 0;
 #pragma unroll
     for (int cls = 1; cls < SE_LUT_NCLS; ++cls) n_breaks += (res[cls] != res[cls - 1]) ? 1 : 0;
-    if (n_breaks == 0) { base[idx] = res[0]; return; }
+    if (n_breaks == 0) { base[entry] = res[0]; return; }
     const unsigned k0 = atomicAdd(counter, (unsigned)n_breaks);
-    if (k0 + n_breaks > SE_LUT_POOL_MAX) { base[idx] = SE_LUT_SLOW; return; }   // overflow: the host refuses the table
-    base[idx] = (unsigned short)(0xF000u | k0);
+    base[entry] = SE_E_SPECIAL | (k0 & SE_E_INDEX);
+    if (!pool || k0 + (unsigned)n_breaks > pool_cap) return;              // counting pass / overflow: the host looks at the counter
     unsigned k = k0;
     int left = n_breaks;
     for (int cls = 1; cls < SE_LUT_NCLS; ++cls) {
         if (res[cls] != res[cls - 1]) {
             --left;
-            SePoolEntry e;
-            e.thr = se_lut_thresholds[cls - 1];            // u1 <= U_{cls-1}  <=>  class < cls
-            e.a = res[cls - 1];
-            e.b = left ? (unsigned short)(0xF000u | (k + 1)) : res[cls];
-            pool[k] = e;
+            pool[4u * k + 0u] = se_lut_thresholds[cls - 1];              // u1 <= U_{cls-1}  <=>  class < cls
+            pool[4u * k + 1u] = res[cls - 1];
+            pool[4u * k + 2u] = left ? (SE_E_SPECIAL | (k + 1u)) : res[cls];
+            pool[4u * k + 3u] = 0u;                                       // 16-byte entries: one 128-bit read
             ++k;
         }
     }
 }
 
 #ifndef SE_HOST_EMU
-extern "C" __global__ void __launch_bounds__(256) se_build_lut(unsigned short* __restrict__ base, SePoolEntry* __restrict__ pool,
-                                                               unsigned* __restrict__ counter) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < SE_LUT_ENTRIES) se_build_lut_entry(idx, base, pool, counter);
+extern "C" __global__ void __launch_bounds__(256) se_build_lut(unsigned* __restrict__ base, unsigned* __restrict__ pool,
+                                                               unsigned* __restrict__ counter, unsigned pool_cap) {
+    const unsigned entry = blockIdx.x * blockDim.x + threadIdx.x;
+    if (entry < (unsigned)SE_LUT_ENTRIES) se_build_lut_entry(entry, base, pool, counter, pool_cap);
 }
 #endif
 
-struct SeTileParams {
-    unsigned* buf0;         // local buffer (row 0 == global row gy0) read by the first T-block of the launch
-    unsigned* buf1;         // the other ping-pong buffer; T-block k reads buf[k & 1] and writes buf[(k + 1) & 1]
-    int W, Hl, gy0, Hg;
-    int frame0;             // frame number of the first sub-step of this launch
-    int nblk;               // T-blocks in this launch (>= 1)
-    int tsteps;             // sub-steps of every T-block but the last (<= the halo allows)
-    int nsub_last;          // sub-steps of the last T-block, 1..tsteps
-    unsigned seq_base;      // T-blocks completed by earlier launches (the per-tile flags count in this sequence)
-    unsigned* done;         // per tile: sequence number of its last completed T-block (dataflow between T-blocks)
-    int HY;                 // halo depth in rows (even, >= nsub/2 + 1: the row offset changes every OTHER frame,
-                            // operations.glsl:25-34, so validity shrinks by at most floor(n/2)+1 rows in n steps)
-    int HX;                 // halo depth in columns (multiple of 4, >= nsub: the column offset alternates every frame)
-    int PH;                 // tile height in cells (even)
-    int tiles_x, tiles_y;
-    int lut_words;          // 32-bit words of (base + pad + pool) to stage in shared memory
-    int pool_offset;        // byte offset of the pool inside the staged table (8-aligned)
-    int tile_offset;        // byte offset of the tile inside dynamic shared memory (16-aligned)
-    const unsigned* lut;
-};
-
-static __device__ __forceinline__ unsigned se_pack_ids(uint4 v) {
-    const unsigned a = v.x < SE_N_MATERIALS ? v.x : 1u, b = v.y < SE_N_MATERIALS ? v.y : 1u;
-    const unsigned c = v.z < SE_N_MATERIALS ? v.z : 1u, d = v.w < SE_N_MATERIALS ? v.w : 1u;
-    return a | (b << 8) | (c << 16) | (d << 24);
-}
-
-static __device__ __forceinline__ unsigned se_nibbles_to_bytes(unsigned e) {
-    unsigned x = (e | (e << 8)) & 0x00FF00FFu;
-    return (x | (x << 4)) & 0x0F0F0F0Fu;
-}
-
-// Table access: on the device the table lives in shared memory and is addressed with 32-bit shared
-// addresses (explicit ld.shared keeps the compiler from re-deriving the shared window base per access);
-// the host emulation reads the same layout through plain pointers.
+// ---- table access: shared-space addresses (mode 1), global pointers (mode 2), plain pointers on the host ----
 #ifdef SE_HOST_EMU
-typedef const unsigned char* se_tab_t;
-static inline unsigned se_tab_u16(se_tab_t t, unsigned byte_off) { unsigned short v; std::memcpy(&v, t + byte_off, 2); return v; }
-static inline void se_tab_pool(se_tab_t t, unsigned byte_off, unsigned& thr, unsigned& ab) { std::memcpy(&thr, t + byte_off, 4); std::memcpy(&ab, t + byte_off + 4, 4); }
-static inline unsigned se_idx4(unsigned vv) {
-    return (((vv & 0xFFu) * SE_N_MATERIALS + ((vv >> 8) & 0xFFu)) * SE_N_MATERIALS + ((vv >> 16) & 0xFFu)) * SE_N_MATERIALS + (vv >> 24);
+struct SeTab { const unsigned* base; const unsigned* pool; };
+static inline unsigned se_tab_entry(const SeTab& t, unsigned idx) { return t.base[idx]; }
+static inline void se_tab_pool(const SeTab& t, unsigned k, unsigned& thr, unsigned& a, unsigned& b) { thr = t.pool[4u * k]; a = t.pool[4u * k + 1u]; b = t.pool[4u * k + 2u]; }
+static inline unsigned se_dp4a(unsigned x, unsigned w) {
+    return (x & 0xFFu) * (w & 0xFFu) + ((x >> 8) & 0xFFu) * ((w >> 8) & 0xFFu) + ((x >> 16) & 0xFFu) * ((w >> 16) & 0xFFu) + (x >> 24) * (w >> 24);
 }
 #else
-typedef unsigned se_tab_t;   // shared-space address
 static __device__ __forceinline__ unsigned se_lds_u8(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 static __device__ __forceinline__ unsigned se_lds_u16(unsigned a) { unsigned v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 static __device__ __forceinline__ unsigned se_lds_u32(unsigned a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+static __device__ __forceinline__ void se_lds_u64(unsigned a, unsigned& x, unsigned& y) { asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(a)); }
 static __device__ __forceinline__ void se_sts_u8(unsigned a, unsigned v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 static __device__ __forceinline__ void se_sts_u16(unsigned a, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 static __device__ __forceinline__ void se_sts_u32(unsigned a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
-static __device__ __forceinline__ unsigned se_tab_u16(se_tab_t t, unsigned byte_off) { return se_lds_u16(t + byte_off); }
-static __device__ __forceinline__ void se_tab_pool(se_tab_t t, unsigned byte_off, unsigned& thr, unsigned& ab) {
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(thr), "=r"(ab) : "r"(t + byte_off));
+static __device__ __forceinline__ void se_sts_u64(unsigned a, unsigned x, unsigned y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(a), "r"(x), "r"(y) : "memory"); }
+static __device__ __forceinline__ unsigned se_dp4a(unsigned x, unsigned w) { return __dp4a(x, w, 0u); }
+#if SE_LUT_MODE == 1
+struct SeTab { unsigned base; unsigned pool; };            // shared-space byte addresses
+static __device__ __forceinline__ unsigned se_tab_entry(const SeTab& t, unsigned idx) { return se_lds_u32(t.base + 4u * idx); }
+static __device__ __forceinline__ void se_tab_pool(const SeTab& t, unsigned k, unsigned& thr, unsigned& a, unsigned& b) {
+    unsigned pad;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(thr), "=r"(a), "=r"(b), "=r"(pad) : "r"(t.pool + 16u * k));
 }
-// idx = ((a*N + b)*N + c)*N + d from the four id bytes: one dp4a for a*N^2 + b*N + c
-static __device__ __forceinline__ unsigned se_idx4(unsigned vv) {
-    return __dp4a(vv, (unsigned)(SE_N_MATERIALS * SE_N_MATERIALS) | ((unsigned)SE_N_MATERIALS << 8) | (1u << 16), 0u) * SE_N_MATERIALS + (vv >> 24);
+#else
+struct SeTab { const unsigned* base; const unsigned* pool; };   // global memory, read-only for the whole launch
+static __device__ __forceinline__ unsigned se_tab_entry(const SeTab& t, unsigned idx) {
+    unsigned v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(t.base + idx));
+    return v;
+}
+static __device__ __forceinline__ void se_tab_pool(const SeTab& t, unsigned k, unsigned& thr, unsigned& a, unsigned& b) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(t.pool) + k);
+    thr = q.x; a = q.y; b = q.z;
 }
 #endif
+#endif
 
-// one block: v = a | b<<8 | c<<16 | d<<24 (material ids), returns the new ids in the same packing
-static __device__ __forceinline__ unsigned se_block_lut(unsigned v, unsigned seed, int px, int py, int frame,
-                                                        se_tab_t tab, unsigned pool_off, const unsigned* __restrict__ fat_sm) {
+// idx = ((a*N + b)*N + c)*N + d from the four id bytes: two byte dot products (weights <= 255 for every N)
+static __device__ __forceinline__ unsigned se_idx4(unsigned v) {
+    const unsigned w = (unsigned)SE_N_MATERIALS | (1u << 8);
+    return se_dp4a(v, w) * (unsigned)(SE_N_MATERIALS * SE_N_MATERIALS) + se_dp4a(v, w << 16);
+}
+
+// The rare ways out of the table: rand.y-dependent states walk their pool chain, slow states run the generated code.
+// `e` is the special entry, `v` the block as stored (unpermuted); the result is returned in the TABLE's view (the
+// caller undoes the mirror permutation in one-table mode, so the slow path applies it once more: an involution).
+#ifndef SE_HOST_EMU
+static __device__ __noinline__ unsigned se_block_special(unsigned e, unsigned v, unsigned seed, unsigned mirror_sel, int px, int py, int frame,
+                                                         const SeTab tab, const unsigned* __restrict__ fat_sm)
+#else
+static inline unsigned se_block_special(unsigned e, unsigned v, unsigned seed, unsigned mirror_sel, int px, int py, int frame,
+                                        const SeTab tab, const unsigned* fat_sm)
+#endif
+{
+    const unsigned u1 = se_hashi(seed * 2131u);
+#if !SE_LUT_TWO_TABLES
+    if (e & SE_E_SLOW) {
+        unsigned s = fat_sm[v & 0xFFu], r = fat_sm[(v >> 8) & 0xFFu], d = fat_sm[(v >> 16) & 0xFFu], dr = fat_sm[v >> 24];
+        SeRand rnd;
+        rnd.u[0] = (mirror_sel == 0x2301u) ? 0u : 0xFFFFFFFFu;
+        rnd.u[1] = u1; rnd.u[2] = 0u; rnd.u[3] = 0u;
+        se_block_with_rand(s, r, d, dr, rnd, px, py, frame);
+        return __byte_perm(se_ids4(s, r, d, dr), 0u, mirror_sel);
+    }
+#else
+    (void)v; (void)mirror_sel; (void)px; (void)py; (void)frame; (void)fat_sm;
+#endif
+    do {
+        unsigned thr, a, b;
+        se_tab_pool(tab, e & SE_E_INDEX, thr, a, b);
+        e = (u1 <= thr) ? a : b;
+    } while (e & SE_E_SPECIAL);
+    return e;
+}
+
+// one block: v = a | b<<8 | c<<16 | d<<24 (material ids < N), returns the new ids in the same packing.
+// No branch for the all-EMPTY early-out (falling_sand.glsl:692-694): T[0] == 0 in both views by construction.
+static __device__ __forceinline__ unsigned se_block_lut(unsigned v, unsigned seed, int px, int py, int frame, const SeTab tab,
+                                                        const unsigned* __restrict__ fat_sm) {
     const unsigned u0 = se_hashi(seed * 213u);
     const bool mirror = u0 <= SE_MIRROR_UMAX;
 #if SE_LUT_TWO_TABLES
-    unsigned e = se_tab_u16(tab, (se_idx4(v) + (mirror ? (unsigned)SE_N4 : 0u)) * 2u);
+    unsigned e = se_tab_entry(tab, se_idx4(v) + (mirror ? (unsigned)SE_N4 : 0u));
+    if (e & SE_E_SPECIAL) e = se_block_special(e, v, seed, 0x3210u, px, py, frame, tab, fat_sm);
+    return e;
 #else
-    const unsigned vv = mirror ? __byte_perm(v, 0u, 0x2301) : v;
-    unsigned e = se_tab_u16(tab, se_idx4(vv) * 2u);
-#endif
-    if (e >= 0xF000u) {
-        if (e != SE_LUT_SLOW) {
-            const unsigned u1 = se_hashi(seed * 2131u);
-            do {
-                unsigned thr, ab;
-                se_tab_pool(tab, pool_off + (e & 0xFFFu) * 8u, thr, ab);
-                e = (u1 <= thr) ? (ab & 0xFFFFu) : (ab >> 16);
-            } while (e >= 0xF000u);
-        } else {
-            // generic path (the block touches WALL / NULL): same generated code as K1a
-            unsigned s = fat_sm[v & 0xFFu], r = fat_sm[(v >> 8) & 0xFFu], d = fat_sm[(v >> 16) & 0xFFu], dr = fat_sm[v >> 24];
-            SeRand rnd;
-            rnd.u[0] = u0;
-            rnd.u[1] = (SE_RAND_LANES & 2u) ? se_hashi(seed * 2131u) : 0u;
-            rnd.u[2] = 0u; rnd.u[3] = 0u;
-            se_block_with_rand(s, r, d, dr, rnd, px, py, frame);
-            return SE_ID(s) | (SE_ID(r) << 8) | (SE_ID(d) << 16) | (SE_ID(dr) << 24);
-        }
-    }
-#if SE_LUT_TWO_TABLES
-    return se_nibbles_to_bytes(e);
-#else
-    const unsigned rr = se_nibbles_to_bytes(e);
-    return mirror ? __byte_perm(rr, 0u, 0x2301) : rr;
+    const unsigned sel = mirror ? 0x2301u : 0x3210u;
+    unsigned e = se_tab_entry(tab, se_idx4(__byte_perm(v, 0u, sel)));
+    if (e & SE_E_SPECIAL) e = se_block_special(e, v, seed, sel, px, py, frame, tab, fat_sm);
+    return __byte_perm(e, 0u, sel);
 #endif
 }
 
+static __device__ __forceinline__ unsigned se_clamp_id(unsigned id) { return id < SE_N_MATERIALS ? id : 1u; }   // unknown ids read as NULL (gen/materials.glsl:79-86)
+static __device__ __forceinline__ unsigned se_pack_ids(uint4 v) {
+    return se_clamp_id(v.x) | (se_clamp_id(v.y) << 8) | (se_clamp_id(v.z) << 16) | (se_clamp_id(v.w) << 24);
+}
+
 // ---------------------------------------------------------------------------------------------
-// Running census (EXPERIMENTAL, SE_FLAG_RUNNING_CENSUS; off by default): the per-material population of the
-// owned rows is kept up to date by the per-frame kernel K1c instead of being recounted by a pass over the grid.
+// Running census (SE_FLAG_RUNNING_CENSUS, one-table mode): the per-material population of the owned rows is kept up
+// to date by the per-frame kernel K1c instead of being recounted by a pass over the grid.
 // Guarded swaps only permute the cells of a block, so the population changes only where a SET fired (or where a
 // block straddles the first/last owned row of a strip, or holds an id the table does not know).  `popbits` is
 // a bit per block state: 1 = some outcome of the state (any rand.y class, either mirror view) is not a
 // permutation of its four ids.  It is only a filter: blocks that pass it are compared cell by cell.
 // ---------------------------------------------------------------------------------------------
+#if !SE_LUT_TWO_TABLES
 static __device__ __forceinline__ unsigned se_sorted4(unsigned a, unsigned b, unsigned c, unsigned d) {
     unsigned t;
     if (a > b) { t = a; a = b; b = t; }
@@ -735,14 +736,10 @@ typedef const unsigned* se_pop_t;
 static inline unsigned se_popbit(se_pop_t pop, unsigned idx) { return (pop[idx >> 5] >> (idx & 31)) & 1u; }
 #else
 typedef unsigned se_pop_t;   // shared-space address
-static __device__ __forceinline__ unsigned se_popbit(se_pop_t pop, unsigned idx) {
-    unsigned w;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(pop + 4u * (idx >> 5)));
-    return (w >> (idx & 31)) & 1u;
-}
+static __device__ __forceinline__ unsigned se_popbit(se_pop_t pop, unsigned idx) { return (se_lds_u32(pop + 4u * (idx >> 5)) >> (idx & 31)) & 1u; }
 #endif
 
-// One block of K1c: v = clamped ids (what the table saw), raw* = the words read from memory, nv = new ids,
+// One block of K1c: v = clamped ids (what the table saw), r* = the words read from memory, nv = new ids,
 // cm = bit k set when cell k (a, b, c, d) is inside the grid AND in an owned row.  Adds the population deltas of
 // the counted cells to hist[256] (CTA-local, flushed once per launch).
 static __device__ __forceinline__ void se_census_block(int* hist, se_pop_t pop, unsigned v, unsigned ra, unsigned rb, unsigned rc, unsigned rd,
@@ -757,276 +754,341 @@ static __device__ __forceinline__ void se_census_block(int* hist, se_pop_t pop, 
     if ((cm & 4u) && nc != rc) { atomicAdd(hist + (rc < 255u ? rc : 255u), -1); atomicAdd(hist + nc, 1); }
     if ((cm & 8u) && nd != rd) { atomicAdd(hist + (rd < 255u ? rd : 255u), -1); atomicAdd(hist + nd, 1); }
 }
-
-// ---------------------------------------------------------------------------------------------
-// K3f (EXPERIMENTAL, SE_FLAG_FUSED_LIGHT_EXPERIMENTAL; off by default): Margolus step + modification override +
-// lighting relaxation in ONE pass over the grid for table-eligible rule sets.  se_light already stages the old ids
-// of its 32 x SE_LT_H tile and a one-cell ring; every 2x2 block that covers a tile cell lies inside tile + ring
-// (the block offset is 0 or 1), so the CTA can run the transition table on those ids in shared memory, apply the
-// modification override per cell, and feed the new ids straight into the light combine: the separate step kernel
-// (K1a ping-pong) and one read of the id buffer disappear (48 -> 40 physical bytes per cell).
-// Blocks cut by a tile edge are evaluated by both CTAs (deterministic: RAND depends on position and frame only).
-// Three per-thread phases, run CTA by CTA on the host by tests/emu:
-//   stage  : old id (clamped; WALL outside the grid; MISSING inside the grid but outside the local buffer) and
-//            the light term of every tile + ring cell
-//   blocks : transition table on the blocks covering the tile, in place in the shared id array
-//   compute: override, store the new id, combine the eight neighbour terms (se_light_compute)
-// ---------------------------------------------------------------------------------------------
-#define SE_LF_IDS_STRIDE (SE_LT_W + 4)
-#define SE_LF_IDS_BYTES ((SE_LT_H + 2) * SE_LF_IDS_STRIDE)
-#define SE_LF_MISSING 0xFFu
-
-struct SeFusedParams {
-    SeLightParams lp;        // old_cells: ids before the step; new_cells: ids after the step (WRITTEN by this kernel)
-    int frame;
-    int n_mods;              // already cut at the first mod_size == 0
-    const SeMod* mods;
-    int lut_words, pool_offset;
-    int tile_offset;         // byte offset of term[] in dynamic shared memory (behind the staged table, 16-aligned)
-    const unsigned* lut;
-    int tiles_x, tiles_y;
-};
-
-// can record m touch a cell of the rectangle?  (both shapes lie inside the square |dx|,|dy| <= size; negative sizes never match)
-static __device__ __forceinline__ bool se_mod_touches(const SeMod& m, int x_lo, int x_hi, int y_lo, int y_hi) {
-    return m.size >= 0 && m.px + m.size >= x_lo && m.px - m.size <= x_hi && m.py + m.size >= y_lo && m.py - m.size <= y_hi;
-}
-
-template <bool INTERIOR>
-static __device__ __forceinline__ void se_fused_stage_one(const SeLightParams& p, const unsigned* fat, float4* term, unsigned char* ids,
-                                                          int bx, int by, int i, int j) {
-    const int nx = bx * SE_LT_W - 1 + j, nyl = by * SE_LT_H - 1 + i, ny = p.gy0 + nyl;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    unsigned idb;
-    const bool in_grid = INTERIOR || (nx >= 0 && nx < p.W && ny >= 0 && ny < p.Hg);
-    if (INTERIOR || (in_grid && nyl >= 0 && nyl < p.Hl)) {
-        const size_t nidx = (size_t)nyl * p.W + nx;
-        const unsigned id = p.old_cells[nidx];
-        const float4 li = p.light_in[nidx];
-        const unsigned nf = fat[id < 255u ? id : 255u];
-        const float keep = (nf & SE_F_OBSTACLE) ? 0.0f : 1.0f;
-        const float la = li.w;
-        v = make_float4((li.x * keep) * la, (li.y * keep) * la, (li.z * keep) * la, la);
-        idb = id < SE_N_MATERIALS ? id : 1u;                       // unknown ids read as NULL (gen/materials.glsl:79-86)
-    } else {
-        idb = in_grid ? SE_LF_MISSING : 2u;                        // WALL outside the grid (operations.glsl:45-51)
-    }
-    term[i * SE_LT_STRIDE + j] = v;
-    ids[i * SE_LF_IDS_STRIDE + j] = (unsigned char)idb;
-}
-
-template <bool INTERIOR>
-static __device__ __forceinline__ void se_fused_stage(const SeLightParams& p, const unsigned* fat, float4* term, unsigned char* ids, int bx, int by, int tid) {
-    const int warp = tid >> 5, lane = tid & 31;
-#pragma unroll
-    for (int it = 0; it < (SE_LT_H + 2 + 7) / 8; ++it) {
-        const int i = warp + 8 * it;
-        if (i < SE_LT_H + 2) se_fused_stage_one<INTERIOR>(p, fat, term, ids, bx, by, i, lane + 1);
-    }
-    if (tid < 2 * (SE_LT_H + 2)) se_fused_stage_one<INTERIOR>(p, fat, term, ids, bx, by, tid >> 1, (tid & 1) * (SE_LT_W + 1));
-}
-
-// the blocks that cover the tile: (SE_LT_W/2 + ox) x (SE_LT_H/2 + oy) of them, in place in ids[]
-static __device__ __forceinline__ void se_fused_blocks(const SeLightParams& p, int frame, se_tab_t tab, unsigned pool_off, const unsigned* fat,
-                                                       unsigned char* ids, int bx, int by, int tid) {
-    int ox, oy;
-    se_margolus_offset(frame, ox, oy);
-    const int nbx = SE_LT_W / 2 + ox, nby = SE_LT_H / 2 + oy;
-    const unsigned fterm = (unsigned)frame * (2131u * 2131u);
-    for (int b = tid; b < nbx * nby; b += 256) {
-        const int bj = b / nbx, bi = b - bj * nbx;
-        const int cx = 2 * bi + 1 - ox, cy = 2 * bj + 1 - oy;      // ring coordinates of the block's top-left cell
-        const int x0 = bx * SE_LT_W - 1 + cx, y0 = p.gy0 + by * SE_LT_H - 1 + cy;
-        unsigned char* q = ids + cy * SE_LF_IDS_STRIDE + cx;
-        const unsigned a = q[0], bb = q[1], c = q[SE_LF_IDS_STRIDE], d = q[SE_LF_IDS_STRIDE + 1];
-        if ((a | bb | c | d) & 0x80u) continue;                    // a row of the block is not in the local buffer: skipped (see K1a)
-        const unsigned v = a | (bb << 8) | (c << 16) | (d << 24);
-        const unsigned seed = (unsigned)x0 * 461u + (unsigned)y0 * 2131u + fterm;
-        const unsigned nv = se_block_lut(v, seed, x0, y0, frame, tab, pool_off, fat);
-        q[0] = (unsigned char)(nv & 0xFFu); q[1] = (unsigned char)((nv >> 8) & 0xFFu);
-        q[SE_LF_IDS_STRIDE] = (unsigned char)((nv >> 16) & 0xFFu); q[SE_LF_IDS_STRIDE + 1] = (unsigned char)(nv >> 24);
-    }
-}
-
-// new id of a tile cell: the table's result, overridden by the (culled) modification list, stored to the id buffer
-template <bool HAS_MODS>
-struct SeNewIdFused {
-    const unsigned char* ids;
-    unsigned* new_cells;
-    const SeMod* mods;
-    int n_mods;
-    __device__ __forceinline__ unsigned operator()(size_t idx, int x, int y, int tile_row, int tile_col) const {
-        unsigned id = ids[(tile_row + 1) * SE_LF_IDS_STRIDE + tile_col + 1];
-        if (HAS_MODS) {
-            unsigned m;
-            if (se_mod_lookup(mods, n_mods, x, y, m)) id = m;
-        }
-        new_cells[idx] = id;
-        return id;
-    }
-};
+#endif  // !SE_LUT_TWO_TABLES
 
 #ifndef SE_HOST_EMU
-// one Margolus sub-step over the whole tile; OX (column phase) is a template parameter so that the
-// aligned 16-bit and the byte access variants are separate straight-line loops
+// =============================================================================================
+// K1b: transition table + shared-memory tiles + temporal blocking + (strips) the ghost-row push.
+//
+// Launch shape: one CTA of 1024 threads per SM.  The CTA stages the table once (mode 1) and then runs as TWO
+// independent halves of 16 warps, each with its own tile buffer and its own named barrier: while one half waits
+// for HBM (tile load / store) the other one computes, and both share the one copy of the table.
+// A tile is 256 cells wide (one byte per cell in shared memory), PH rows high.  Per Margolus sub-step a warp walks
+// block rows; a lane owns 8 consecutive cells of both rows of the block row (two 8-byte shared loads), i.e. four
+// blocks in the even column phase; in the odd phase its four blocks are shifted by one cell and the straddling byte
+// pair travels through one shuffle each way.  The block itself is: lowbias32 hash -> mirror bit -> byte permute ->
+// two byte dot products -> one table read -> permute back (se_block_lut).
+//
+// Work items (k, t) = (T-block, tile), numbered k * n_tiles + position(t), are drawn by the 2 x gridDim.x halves from
+// one device-wide queue (atomicAdd), in order.  A tile of T-block k needs the
+// results of T-block k-1 in its 3x3 tile neighbourhood only, so instead of a grid-wide barrier (or a launch)
+// between T-blocks every tile publishes a sequence number when its interior is stored and consumers wait on the
+// flags they need.  Deadlock-free because every dependency has a smaller index and all CTAs are co-resident
+// (cooperative launch, grid <= SMs).
+//
+// Strips: the tiles cover the rows this device OWNS.  A tile in the first / last tile row also
+// stores the `push_rows` rows next to the strip boundary into the neighbour device's ghost rows (peer st.global
+// over NVLink, same ping-pong parity) and publishes its sequence number in the neighbour's memory (st.release.sys);
+// the neighbour's boundary tiles acquire those flags exactly like the local ones, which also covers the
+// write-after-read hazard on the ghost rows.  The boundary tile rows are dealt first, so the push overlaps the
+// interior of the same T-block.  No host synchronisation and no separate copy: the exchange is part of the store.
+// A wait that outlives `spin_limit` polls (a neighbour that was never launched) raises status[0] and lets the
+// kernel run to its end instead of hanging the device; the host reports it.
+// =============================================================================================
+struct SeTileParams {
+    unsigned* buf0;         // local buffer (row 0 == global row gy0) read by the first T-block of the launch
+    unsigned* buf1;         // the other ping-pong buffer; T-block k reads buf[k & 1] and writes buf[(k + 1) & 1]
+    unsigned* nbr_buf0[2];  // [0] strip above, [1] strip below: the neighbour's buffers of the same parity (null: none)
+    unsigned* nbr_buf1[2];
+    unsigned* nbr_flags[2]; // per tile column, in the NEIGHBOUR's memory: sequence numbers of my boundary tiles
+    const unsigned* in_flags[2];   // per tile column, in MY memory: sequence numbers of the neighbours' boundary tiles
+    int nbr_gy0[2];         // global row of row 0 of the neighbour's buffers
+    int W, Hl, gy0, Hg;
+    int own_y0, own_y1;     // owned global rows: the tiles' interiors partition [own_y0, own_y1)
+    int frame0;             // frame number of the first sub-step of this launch
+    int nblk;               // T-blocks in this launch (>= 1)
+    int tsteps;             // sub-steps of every T-block but the last
+    int nsub_last;          // sub-steps of the last T-block, 1..tsteps
+    unsigned seq_base;      // T-blocks completed by earlier launches (the flags count in this sequence)
+    unsigned* done;         // per tile: sequence number of its last completed T-block
+    unsigned* status;       // [0] != 0: a flag wait timed out (results invalid)
+    unsigned* queue;        // work queue: the halves draw item numbers with atomicAdd (in order: dependencies always have a smaller number)
+    unsigned queue_base;    // value of *queue when this launch starts (it is never reset: every half overshoots exactly once)
+    int HY;                 // halo depth in rows (even, >= nsub/2 + 1: the row offset changes every OTHER frame,
+                            // operations.glsl:25-34, so validity shrinks by at most floor(n/2)+1 rows in n steps)
+    int HX;                 // halo depth in columns (multiple of 4, >= nsub: the column offset alternates every frame)
+    int PH;                 // tile height in cells (even) = THo + 2 HY
+    int THo;                // interior rows per tile (even)
+    int tiles_x, tiles_y;
+    int push_rows;          // rows pushed into a neighbour's ghost rows (>= HY of the neighbour)
+    int table_bytes;        // mode 1: bytes of (table + pool) to stage in shared memory
+    int pool_offset;        // mode 1: byte offset of the pool inside the staged image
+    int tile_offset;        // byte offset of the first tile buffer in dynamic shared memory (16-aligned)
+    int tile_stride;        // bytes between the two halves' tile buffers
+    const unsigned* lut;    // table image in global memory (mode 1: staged; mode 2: read in place)
+    const unsigned* pool;   // mode 2: pool in global memory
+    unsigned spin_limit;
+};
+
+#define SE_HALF_WARPS 16
+#ifndef SE_LOAD_ROWS
+#define SE_LOAD_ROWS 2          // tile rows whose 128-bit loads a lane keeps in flight together (registers: 8 per row)
+#endif
+#define SE_HALF_THREADS (32 * SE_HALF_WARPS)
+static __device__ __forceinline__ void se_half_sync(int half) { asm volatile("bar.sync %0, %1;" :: "r"(half + 1), "n"(SE_HALF_THREADS) : "memory"); }
+
+// one Margolus sub-step over the whole tile; OX (column phase) is a template parameter: separate straight-line loops
+// one Margolus sub-step over the whole tile; OX (column phase) is a template parameter: separate straight-line loops
 template <int OX>
-static __device__ __forceinline__ void se_tile_substep(unsigned tile_sa, se_tab_t tab, unsigned pool_off, const unsigned* __restrict__ fat_sm,
-                                                       int PH, int oy, int frame, int gx_org, int gy_org, int warp, int nwarps, int lane) {
-    const int PW = SE_TILE_PW;
-    const int nbx = (PW - OX) >> 1, nby = (PH - oy) >> 1;
-    const unsigned fterm = (unsigned)frame * (2131u * 2131u) + (unsigned)(gx_org + OX) * 461u;
-    for (int j = warp; j < nby; j += nwarps) {
+static __device__ __forceinline__ void se_tile_substep(unsigned tile_sa, const SeTab tab, const unsigned* __restrict__ fat_sm,
+                                                       int PH, int oy, int frame, int gx_org, int gy_org, int W, int Hg, int hw, int lane) {
+    // block rows whose two cell rows both lie outside the grid hold WALL only (re-imposed after every sub-step): skipped
+    const int j_lo = max(0, (-gy_org - oy) >> 1);                      // first j with gy_org + 2j + oy >= -1
+    const int j_hi = min((PH - oy) >> 1, ((Hg - 1 - gy_org - oy) >> 1) + 1);   // one past the last j with gy_org + 2j + oy <= Hg - 1
+    const int lane_x = gx_org + 8 * lane + OX;                         // global x of the left cell of the lane's first block
+    // lanes whose four blocks lie outside the grid (the unused part of the last tile column) only take part in the shuffles
+    const bool lane_in = lane_x + 7 >= 0 && lane_x < W;
+    const unsigned fterm = (unsigned)frame * (2131u * 2131u) + (unsigned)lane_x * 461u;
+    for (int j = j_lo + hw; j < j_hi; j += SE_HALF_WARPS) {
         const int ly = 2 * j + oy;
         const unsigned rowseed = (unsigned)(gy_org + ly) * 2131u + fterm;
-        const unsigned row_sa = tile_sa + (unsigned)(ly * PW + OX);
+        const unsigned a0 = tile_sa + (unsigned)(ly * SE_TILE_PW + 8 * lane);
+        unsigned X0, Y0, X1, Y1;
+        se_lds_u64(a0, X0, Y0);
+        se_lds_u64(a0 + SE_TILE_PW, X1, Y1);
+        unsigned v[4], n[4];
+        if (OX == 0) {
+            v[0] = __byte_perm(X0, X1, 0x5410); v[1] = __byte_perm(X0, X1, 0x7632);
+            v[2] = __byte_perm(Y0, Y1, 0x5410); v[3] = __byte_perm(Y0, Y1, 0x7632);
+        } else {
+            // blocks at cells (1,2) (3,4) (5,6) (7, 8 = the next lane's cell 0)
+            const unsigned q = __shfl_down_sync(0xFFFFFFFFu, __byte_perm(X0, X1, 0x0040), 1);
+            const unsigned S0 = __funnelshift_r(X0, Y0, 24), S1 = __funnelshift_r(X1, Y1, 24);
+            v[0] = __byte_perm(X0, X1, 0x6521);
+            v[1] = __byte_perm(S0, S1, 0x5410); v[2] = __byte_perm(S0, S1, 0x7632);
+            v[3] = __byte_perm(__byte_perm(Y0, Y1, 0x0703), q, 0x5240);
+        }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int i = lane + 32 * k;
-            if (OX == 0 || i < nbx) {
-                const unsigned c0 = row_sa + 2u * (unsigned)i;
-                unsigned v;
-                if (OX == 0) v = se_lds_u16(c0) | (se_lds_u16(c0 + PW) << 16);
-                else v = se_lds_u8(c0) | (se_lds_u8(c0 + 1) << 8) | (se_lds_u8(c0 + PW) << 16) | (se_lds_u8(c0 + PW + 1) << 24);
-                // No branch for the all-EMPTY early-out (falling_sand.glsl:692-694): T0[0] == 0 by construction
-                // (se_build_lut_entry skips the rules for state 0), so an empty block maps to itself.
-                {
-                    const unsigned seed = rowseed + (unsigned)(2 * i) * 461u;
-                    const unsigned nv = se_block_lut(v, seed, gx_org + OX + 2 * i, gy_org + ly, frame, tab, pool_off, fat_sm);
-                    if (nv != v) {
-                        if (OX == 0) {
-                            se_sts_u16(c0, nv & 0xFFFFu);
-                            se_sts_u16(c0 + PW, nv >> 16);
-                        } else {
-                            se_sts_u8(c0, nv & 0xFFu); se_sts_u8(c0 + 1, (nv >> 8) & 0xFFu);
-                            se_sts_u8(c0 + PW, (nv >> 16) & 0xFFu); se_sts_u8(c0 + PW + 1, nv >> 24);
-                        }
-                    }
-                }
+        for (int k = 0; k < 4; ++k) n[k] = v[k];
+        if (lane_in) {
+            // the four table reads are issued back to back; the entries that need more than the table (rand.y-dependent
+            // states, WALL / NULL blocks in one-table mode) are picked up afterwards behind ONE test.
+            // (Measured and rejected: deferring those blocks to a per-warp list in shared memory and working them off 32 at a
+            // time -- the ballots and list bookkeeping cost more than the divergence: 15.5 ms against 13.0 ms per 64 steps.)
+            unsigned e[4], mir = 0u;                                   // mir bit k: block k is evaluated in the mirrored view
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool mirror = se_hashi((rowseed + (unsigned)(2 * k) * 461u) * 213u) <= SE_MIRROR_UMAX;
+                mir |= mirror ? (1u << k) : 0u;
+#if SE_LUT_TWO_TABLES
+                e[k] = se_tab_entry(tab, se_idx4(v[k]) + (mirror ? (unsigned)SE_N4 : 0u));
+#else
+                e[k] = se_tab_entry(tab, se_idx4(__byte_perm(v[k], 0u, mirror ? 0x2301u : 0x3210u)));
+#endif
             }
+            if ((e[0] | e[1] | e[2] | e[3]) & SE_E_SPECIAL) {
+                // rand.y-dependent states: the second hash lane, then the pool chain (one 128-bit read per threshold), inline
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if ((e[k] & (SE_E_SPECIAL | SE_E_SLOW)) == SE_E_SPECIAL) {
+                        const unsigned u1 = se_hashi((rowseed + (unsigned)(2 * k) * 461u) * 2131u);
+                        do {
+                            unsigned thr, a, b;
+                            se_tab_pool(tab, e[k] & SE_E_INDEX, thr, a, b);
+                            e[k] = (u1 <= thr) ? a : b;
+                        } while (e[k] & SE_E_SPECIAL);
+                    }
+#if !SE_LUT_TWO_TABLES
+                // what is left in one-table mode: blocks that hold WALL / NULL (generated code, out of line; table-eligible
+                // rule sets never read pos / frame, so the generated code gets zeros for them)
+                if ((e[0] | e[1] | e[2] | e[3]) & SE_E_SPECIAL) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (e[k] & SE_E_SPECIAL)
+                            e[k] = se_block_special(e[k], v[k], rowseed + (unsigned)(2 * k) * 461u, ((mir >> k) & 1u) ? 0x2301u : 0x3210u, 0, 0, 0, tab, fat_sm);
+                }
+#endif
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) n[k] = SE_LUT_TWO_TABLES ? e[k] : __byte_perm(e[k], 0u, ((mir >> k) & 1u) ? 0x2301u : 0x3210u);
+        }
+        if (OX == 0) {
+            se_sts_u64(a0, __byte_perm(n[0], n[1], 0x5410), __byte_perm(n[2], n[3], 0x5410));
+            se_sts_u64(a0 + SE_TILE_PW, __byte_perm(n[0], n[1], 0x7632), __byte_perm(n[2], n[3], 0x7632));
+        } else {
+            // cell 0 of the lane is cell 8 of the lane to the left.  Lane 0 / lane 31 have no partner: their edge
+            // cells take a (valid-id) byte that is never used -- the outermost tile columns are inside the halo that
+            // an odd-phase sub-step invalidates anyway.
+            const unsigned ld = __shfl_up_sync(0xFFFFFFFFu, n[3], 1);
+            se_sts_u64(a0, __byte_perm(__byte_perm(n[0], n[1], 0x4100), ld, 0x3215), __byte_perm(__byte_perm(n[1], n[2], 0x0541), n[3], 0x4210));
+            se_sts_u64(a0 + SE_TILE_PW, __byte_perm(__byte_perm(n[0], n[1], 0x6320), ld, 0x3217), __byte_perm(__byte_perm(n[1], n[2], 0x0763), n[3], 0x6210));
         }
     }
 }
 
-extern "C" __global__ void __launch_bounds__(SE_TILE_THREADS, 2) se_step_tiles(const SeTileParams p) {
+// wait until *flag has reached `want`; false (and status raised) when the wait is abandoned
+static __device__ __forceinline__ bool se_wait_flag(const unsigned* flag, unsigned want, bool sys_scope, unsigned* status, unsigned spin_limit) {
+    unsigned spins = 0;
+    while (true) {
+        unsigned v;
+        if (sys_scope) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        else asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - want) >= 0) return true;
+        if ((++spins & 63u) == 0u) {
+            unsigned st;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(st) : "l"(status) : "memory");
+            if (st != 0u || spins > spin_limit) { atomicExch(status, 1u); return false; }
+        }
+        __nanosleep(spins < 64u ? 40 : 400);
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(2 * SE_HALF_THREADS, 1) se_step_tiles(const SeTileParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned fat_sm[256];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    unsigned smem_sa;   // laundered through asm so the compiler keeps it in a register instead of re-deriving it (S2R) per access
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int half = warp / SE_HALF_WARPS, hw = warp - half * SE_HALF_WARPS, htid = tid - half * SE_HALF_THREADS;
+    unsigned smem_sa;   // laundered through asm so the compiler keeps it in a register instead of re-deriving it per access
     asm volatile("mov.u32 %0, %1;" : "=r"(smem_sa) : "r"((unsigned)__cvta_generic_to_shared(smem)));
-    const se_tab_t tab = smem_sa;
-    const unsigned pool_off = (unsigned)p.pool_offset;
-    const unsigned tile_sa = smem_sa + (unsigned)p.tile_offset;
-
-    // stage the table with 16-byte loads (it is re-read by every CTA of every launch: keep this prologue short)
-    {
+    const unsigned tile_sa = smem_sa + (unsigned)p.tile_offset + (unsigned)half * (unsigned)p.tile_stride;
+#if SE_LUT_MODE == 1
+    {   // stage table + pool with 16-byte loads (the image is padded to a multiple of 16 bytes)
         const uint4* lut4 = reinterpret_cast<const uint4*>(p.lut);
-        const int n4 = (p.lut_words + 3) >> 2;           // the device buffer is padded to a multiple of 16 bytes
+        const int n4 = (p.table_bytes + 15) >> 4;
         for (int i = tid; i < n4; i += blockDim.x) {
             const uint4 v = __ldg(lut4 + i);
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(smem_sa + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
         }
     }
+    const SeTab tab{smem_sa, smem_sa + (unsigned)p.pool_offset};
+#else
+    const SeTab tab{p.lut, p.pool};
+#endif
     if (tid < 256) fat_sm[tid] = se_fat_table[tid];
     __syncthreads();
 
     const int PW = SE_TILE_PW, PH = p.PH;
-    const int TWo = PW - 2 * p.HX, THo = PH - 2 * p.HY;
+    const int TWo = PW - 2 * p.HX;
     const int n_tiles = p.tiles_x * p.tiles_y;
-    // Work items (k, t) = (T-block, tile), ordered by w = k * n_tiles + t and dealt round-robin to the persistent
-    // CTAs, each taking its items in increasing order.  A tile of T-block k needs the results of T-block k-1 in
-    // its 3x3 tile neighbourhood only, so instead of a grid-wide barrier (or a launch) between T-blocks every
-    // tile publishes a sequence number when its interior is stored and consumers wait on the nine flags they
-    // need.  CTAs that run out of work in T-block k move on to k+1: no launch gap, no table re-staging, and
-    // the partially filled last round of one T-block is filled with tiles of the next.  Deadlock-free because
-    // every dependency has a smaller w and all CTAs are co-resident (grid <= occupancy x SMs).
-    const long long total_items = (long long)p.nblk * n_tiles;
-    for (long long w = blockIdx.x; w < total_items; w += gridDim.x) {
-        const int k = (int)(w / n_tiles), t = (int)(w - (long long)k * n_tiles);
-        const unsigned* in = (k & 1) ? p.buf1 : p.buf0;
+    const bool has_above = p.nbr_flags[0] != nullptr, has_below = p.nbr_flags[1] != nullptr;
+    const unsigned total_items = (unsigned)p.nblk * (unsigned)n_tiles;
+    __shared__ unsigned next_item[2];
+    while (true) {
+        // Work items are drawn from one device-wide queue, in order: a half that was held up (a tile at the grid's edge, a
+        // slow flag) does not hold up the tiles dealt to it in advance, and the two halves of a CTA drift apart so that one
+        // computes while the other waits for HBM.
+        if (htid == 0) next_item[half] = atomicAdd(p.queue, 1u) - p.queue_base;
+        se_half_sync(half);
+        const unsigned w = next_item[half];
+        if (w >= total_items) break;
+        const int k = (int)(w / (unsigned)n_tiles), pos = (int)(w - (unsigned)k * (unsigned)n_tiles);
+        // boundary tile rows first (row 0, then the last row when a strip below depends on it), interior after
+        const int ry = pos / p.tiles_x, tx = pos - ry * p.tiles_x;
+        int ty = ry;
+        if (has_below && p.tiles_y > 2) ty = (ry == 0) ? 0 : (ry == 1 ? p.tiles_y - 1 : ry - 1);
+        const int t = ty * p.tiles_x + tx;
+        unsigned* in = (k & 1) ? p.buf1 : p.buf0;
         unsigned* out = (k & 1) ? p.buf0 : p.buf1;
         const int nsub = (k == p.nblk - 1) ? p.nsub_last : p.tsteps;
         const int tframe0 = p.frame0 + k * p.tsteps;
-        const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
-        if (k > 0) {
-            if (tid < 9) {
-                const int ntx = tx + (tid % 3) - 1, nty = ty + (tid / 3) - 1;
-                if (ntx >= 0 && ntx < p.tiles_x && nty >= 0 && nty < p.tiles_y) {
-                    const unsigned* flag = p.done + (nty * p.tiles_x + ntx);
-                    const unsigned want = p.seq_base + (unsigned)k;
-                    unsigned v;
-                    while (true) {
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-                        if ((int)(v - want) >= 0) break;
-                        __nanosleep(100);
-                    }
-                }
+        const bool top_row = ty == 0, bottom_row = ty == p.tiles_y - 1;
+        // ---- dependencies: 3x3 tile neighbourhood of T-block k-1, across the strip boundary too ----
+        if (htid < 15) {
+            const unsigned want = p.seq_base + (unsigned)k;
+            if (htid < 9) {
+                const int ntx = tx + (htid % 3) - 1, nty = ty + (htid / 3) - 1;
+                if (k > 0 && ntx >= 0 && ntx < p.tiles_x && nty >= 0 && nty < p.tiles_y)
+                    se_wait_flag(p.done + (nty * p.tiles_x + ntx), want, false, p.status, p.spin_limit);
+            } else {
+                const int side = (htid - 9) / 3, ntx = tx + ((htid - 9) % 3) - 1;
+                const bool need = side == 0 ? (has_above && top_row) : (has_below && bottom_row);
+                if (need && ntx >= 0 && ntx < p.tiles_x)
+                    se_wait_flag(p.in_flags[side] + ntx, want, true, p.status, p.spin_limit);
             }
-            __syncthreads();
         }
-        const int gx_org = tx * TWo - p.HX;              // global x of tile column 0 (multiple of 4)
-        const int gy_org = p.gy0 + ty * THo - p.HY;      // global y of tile row 0 (even)
+        se_half_sync(half);
+        const int gx_org = tx * TWo - p.HX;                 // global x of tile column 0 (multiple of 4)
+        const int y_int0 = p.own_y0 + ty * p.THo;           // first interior row (global, even)
+        const int gy_org = y_int0 - p.HY;                   // global y of tile row 0 (even)
+        const int y_int1 = min(y_int0 + p.THo, p.own_y1);   // end of the interior rows
         const bool border = gx_org < 0 || gx_org + PW > p.W || gy_org < 0 || gy_org + PH > p.Hg;
 
-        // ---- load: uint4 of packed-u32 cells -> 4 id bytes ----
-        for (int r = warp; r < PH; r += nwarps) {
-            const int gy = gy_org + r, lr = gy - p.gy0;
-            const bool row_ok = gy >= 0 && gy < p.Hg && lr >= 0 && lr < p.Hl;
-            const uint4* src = reinterpret_cast<const uint4*>(in + (size_t)(row_ok ? lr : 0) * p.W);
+        // ---- load: 2 x uint4 of packed-u32 cells -> 8 id bytes per lane; SE_LOAD_ROWS rows (two 128-bit loads each) in flight per lane ----
+        for (int r0 = hw; r0 < PH; r0 += SE_LOAD_ROWS * SE_HALF_WARPS) {
+            uint4 q0[SE_LOAD_ROWS], q1[SE_LOAD_ROWS];
+            bool ok0[SE_LOAD_ROWS], ok1[SE_LOAD_ROWS];
+            const int gx = gx_org + 8 * lane;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int q = lane + 32 * h;
-                const int gx = gx_org + 4 * q;
-                // __ldcg (L2 only): the data may have been written by another SM earlier in this very launch
-                unsigned wv = 0x02020202u;               // WALL outside the grid (operations.glsl:45-51)
-                if (row_ok && gx >= 0 && gx < p.W) wv = se_pack_ids(__ldcg(src + (gx >> 2)));
-                se_sts_u32(tile_sa + 4u * (unsigned)(r * (PW / 4) + q), wv);
+            for (int u = 0; u < SE_LOAD_ROWS; ++u) {
+                const int r = r0 + u * SE_HALF_WARPS;
+                const int gy = gy_org + r, lr = gy - p.gy0;
+                const bool row_ok = r < PH && gy >= 0 && gy < p.Hg && lr >= 0 && lr < p.Hl;
+                const uint4* src = reinterpret_cast<const uint4*>(in + (size_t)(row_ok ? lr : 0) * p.W);
+                ok0[u] = row_ok && gx >= 0 && gx < p.W;
+                ok1[u] = row_ok && gx + 4 >= 0 && gx + 4 < p.W;
+                // __ldcg (L2 only): the data may have been written by another SM (or a peer device) earlier in this very launch
+                if (ok0[u]) q0[u] = __ldcg(src + (gx >> 2));
+                if (ok1[u]) q1[u] = __ldcg(src + ((gx + 4) >> 2));
+            }
+#pragma unroll
+            for (int u = 0; u < SE_LOAD_ROWS; ++u) {
+                const int r = r0 + u * SE_HALF_WARPS;
+                if (r < PH)                                  // WALL outside the grid (operations.glsl:45-51)
+                    se_sts_u64(tile_sa + (unsigned)(r * PW + 8 * lane), ok0[u] ? se_pack_ids(q0[u]) : 0x02020202u, ok1[u] ? se_pack_ids(q1[u]) : 0x02020202u);
             }
         }
-        __syncthreads();
+        se_half_sync(half);
 
         // ---- nsub Margolus sub-steps in shared memory ----
         for (int sub = 0; sub < nsub; ++sub) {
             const int frame = tframe0 + sub;
             int ox, oy;
             se_margolus_offset(frame, ox, oy);
-            if (ox == 0) se_tile_substep<0>(tile_sa, tab, pool_off, fat_sm, PH, oy, frame, gx_org, gy_org, warp, nwarps, lane);
-            else se_tile_substep<1>(tile_sa, tab, pool_off, fat_sm, PH, oy, frame, gx_org, gy_org, warp, nwarps, lane);
-            __syncthreads();
+            if (ox == 0) se_tile_substep<0>(tile_sa, tab, fat_sm, PH, oy, frame, gx_org, gy_org, p.W, p.Hg, hw, lane);
+            else se_tile_substep<1>(tile_sa, tab, fat_sm, PH, oy, frame, gx_org, gy_org, p.W, p.Hg, hw, lane);
+            se_half_sync(half);
             if (border) {
                 // cells outside the grid are WALL at every step, whatever a SET wrote into them
-                for (int r = warp; r < PH; r += nwarps) {
+                for (int r = hw; r < PH; r += SE_HALF_WARPS) {
                     const int gy = gy_org + r;
                     const bool row_out = gy < 0 || gy >= p.Hg;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int q = lane + 32 * h;
-                        const int gx = gx_org + 4 * q;
-                        if (row_out || gx < 0 || gx >= p.W) se_sts_u32(tile_sa + 4u * (unsigned)(r * (PW / 4) + q), 0x02020202u);
-                    }
+                    const int gx = gx_org + 8 * lane;
+                    if (row_out || gx < 0 || gx >= p.W) se_sts_u32(tile_sa + (unsigned)(r * PW + 8 * lane), 0x02020202u);
+                    if (row_out || gx + 4 < 0 || gx + 4 >= p.W) se_sts_u32(tile_sa + (unsigned)(r * PW + 8 * lane + 4), 0x02020202u);
                 }
-                __syncthreads();
+                se_half_sync(half);
             }
         }
 
-        // ---- store the interior: 4 id bytes -> uint4 of packed-u32 cells ----
-        for (int r = p.HY + warp; r < PH - p.HY; r += nwarps) {
-            const int gy = gy_org + r, lr = gy - p.gy0;
-            if (gy >= p.Hg || lr >= p.Hl) break;
-            uint4* dst = reinterpret_cast<uint4*>(out + (size_t)lr * p.W);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int q = lane + 32 * h;
-                const int gx = gx_org + 4 * q;
-                if (4 * q >= p.HX && 4 * q < PW - p.HX && gx < p.W) {
-                    const unsigned wv = se_lds_u32(tile_sa + 4u * (unsigned)(r * (PW / 4) + q));
-                    dst[gx >> 2] = make_uint4(wv & 0xFFu, (wv >> 8) & 0xFFu, (wv >> 16) & 0xFFu, wv >> 24);
-                }
+        // ---- store the interior: 8 id bytes -> 2 x uint4 of packed-u32 cells; boundary rows also into the neighbours' ghost rows ----
+        unsigned* nb_out[2];
+        nb_out[0] = (has_above && top_row) ? ((k & 1) ? p.nbr_buf0[0] : p.nbr_buf1[0]) : nullptr;
+        nb_out[1] = (has_below && bottom_row) ? ((k & 1) ? p.nbr_buf0[1] : p.nbr_buf1[1]) : nullptr;
+        for (int r = p.HY + hw; r < PH - p.HY; r += SE_HALF_WARPS) {
+            const int gy = gy_org + r;
+            if (gy >= y_int1) break;
+            const int gx = gx_org + 8 * lane;
+            unsigned w0, w1;
+            se_lds_u64(tile_sa + (unsigned)(r * PW + 8 * lane), w0, w1);
+            const bool ok0 = 8 * lane >= p.HX && 8 * lane < PW - p.HX && gx < p.W;
+            const bool ok1 = 8 * lane + 4 >= p.HX && 8 * lane + 4 < PW - p.HX && gx + 4 < p.W;
+            const uint4 c0 = make_uint4(w0 & 0xFFu, (w0 >> 8) & 0xFFu, (w0 >> 16) & 0xFFu, w0 >> 24);
+            const uint4 c1 = make_uint4(w1 & 0xFFu, (w1 >> 8) & 0xFFu, (w1 >> 16) & 0xFFu, w1 >> 24);
+            uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(gy - p.gy0) * p.W);
+            if (ok0) dst[gx >> 2] = c0;
+            if (ok1) dst[(gx + 4) >> 2] = c1;
+            if (nb_out[0] && gy < p.own_y0 + p.push_rows) {
+                uint4* nd = reinterpret_cast<uint4*>(nb_out[0] + (size_t)(gy - p.nbr_gy0[0]) * p.W);
+                if (ok0) nd[gx >> 2] = c0;
+                if (ok1) nd[(gx + 4) >> 2] = c1;
+            }
+            if (nb_out[1] && gy >= p.own_y1 - p.push_rows) {
+                uint4* nd = reinterpret_cast<uint4*>(nb_out[1] + (size_t)(gy - p.nbr_gy0[1]) * p.W);
+                if (ok0) nd[gx >> 2] = c0;
+                if (ok1) nd[(gx + 4) >> 2] = c1;
             }
         }
-        __syncthreads();                                  // every thread's stores are issued ...
-        if (tid == 0) {                                   // ... and made visible before the tile is published
-            __threadfence();
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p.done + t), "r"(p.seq_base + (unsigned)k + 1u) : "memory");
+        se_half_sync(half);                               // every thread's stores are issued ...
+        if (htid == 0) {                                  // ... and made visible before the tile is published
+            const unsigned seq = p.seq_base + (unsigned)k + 1u;
+            if ((has_above && top_row) || (has_below && bottom_row)) {
+                __threadfence_system();
+                if (has_above && top_row) asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p.nbr_flags[0] + tx), "r"(seq) : "memory");
+                if (has_below && bottom_row) asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p.nbr_flags[1] + tx), "r"(seq) : "memory");
+            } else {
+                __threadfence();
+            }
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p.done + t), "r"(seq) : "memory");
         }
     }
 }
@@ -1036,7 +1098,7 @@ extern "C" __global__ void __launch_bounds__(SE_TILE_THREADS, 2) se_step_tiles(c
 // This is the per-frame path (`Simulation::run()` called once per frame): a single step cannot amortise the
 // tile load/store of K1b, so blocks are read directly (two 8-byte loads per block when the column phase is
 // even, four 4-byte loads otherwise), pushed through se_block_lut and only the cells that changed are
-// written back.  Persistent CTAs keep the table in shared memory; a warp walks 32 consecutive blocks of
+// written back.  Persistent CTAs keep the table in shared memory (mode 1); a warp walks 32 consecutive blocks of
 // one block row, a CTA walks block rows grid-stride.  HBM-bound: ~4 B read + (changed fraction) x 4 B
 // written per cell.
 // ---------------------------------------------------------------------------------------------
@@ -1044,20 +1106,21 @@ struct SeLutStepParams {
     unsigned* cells;        // local buffer, updated in place
     int W, Hl, gy0, Hg;
     int frame;
-    int lut_words, pool_offset;
+    int table_bytes, pool_offset;
     const unsigned* lut;
+    const unsigned* pool;
 };
 
 #define SE_K1C_THREADS 512
 #define SE_K1C_SPAN 8           // a work item = one block row x SPAN chunks of 32 blocks (amortises the row set-up)
 #ifndef SE_K1C_BATCH
 #define SE_K1C_BATCH 4          // chunks whose loads are issued together (the update is in place, so the compiler
-#endif                          // cannot hoist loads over the previous chunk's stores by itself); 4: 425 us, 2: 461 us @16384^2
+#endif                          // cannot hoist loads over the previous chunk's stores by itself)
 #ifndef SE_K1C_MINCTAS
 #define SE_K1C_MINCTAS 2
 #endif
 
-// running census (EXPERIMENTAL): extra arguments of se_step_lut_global_census
+// running census: extra arguments of se_step_lut_global_census
 struct SeLutCensusParams {
     unsigned long long* census;   // 256 bins: population of the owned rows, updated in place
     const unsigned* popbits;      // ceil(N^4 / 32) words
@@ -1073,23 +1136,27 @@ static __device__ __forceinline__ void se_k1c_body(const SeLutStepParams& p, con
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     unsigned smem_sa;
     asm volatile("mov.u32 %0, %1;" : "=r"(smem_sa) : "r"((unsigned)__cvta_generic_to_shared(smem)));
+#if !SE_LUT_TWO_TABLES
     if (CENSUS) {
-        for (int i = tid; i < cx.pop_words; i += blockDim.x)
-            asm volatile("st.shared.u32 [%0], %1;" :: "r"(smem_sa + (unsigned)cx.pop_offset + 4u * i), "r"(__ldg(cx.popbits + i)) : "memory");
+        for (int i = tid; i < cx.pop_words; i += blockDim.x) se_sts_u32(smem_sa + (unsigned)cx.pop_offset + 4u * i, __ldg(cx.popbits + i));
         for (int i = tid; i < 256; i += blockDim.x) hist_sm[i] = 0;
     }
+#endif
+#if SE_LUT_MODE == 1
     {
         const uint4* lut4 = reinterpret_cast<const uint4*>(p.lut);
-        const int n4 = (p.lut_words + 3) >> 2;
+        const int n4 = (p.table_bytes + 15) >> 4;
         for (int i = tid; i < n4; i += blockDim.x) {
             const uint4 v = __ldg(lut4 + i);
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(smem_sa + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
         }
     }
+    const SeTab tab{smem_sa, smem_sa + (unsigned)p.pool_offset};
+#else
+    const SeTab tab{p.lut, p.pool};
+#endif
     if (tid < 256) fat_sm[tid] = se_fat_table[tid];
     __syncthreads();
-    const se_tab_t tab = smem_sa;
-    const unsigned pool_off = (unsigned)p.pool_offset;
 
     int ox, oy;
     se_margolus_offset(p.frame, ox, oy);
@@ -1139,16 +1206,16 @@ static __device__ __forceinline__ void se_k1c_body(const SeLutStepParams& p, con
                 const int bx = (cb + u) * 32 + lane;
                 const int x0 = 2 * bx - ox;
                 if (cb + u < c_end && bx < nbx) {
-                    const unsigned ia = a[u] < SE_N_MATERIALS ? a[u] : 1u, ib = b[u] < SE_N_MATERIALS ? b[u] : 1u;
-                    const unsigned ic = c[u] < SE_N_MATERIALS ? c[u] : 1u, id = d[u] < SE_N_MATERIALS ? d[u] : 1u;
-                    const unsigned v = ia | (ib << 8) | (ic << 16) | (id << 24);
+                    const unsigned v = se_clamp_id(a[u]) | (se_clamp_id(b[u]) << 8) | (se_clamp_id(c[u]) << 16) | (se_clamp_id(d[u]) << 24);
                     const unsigned seed = (unsigned)x0 * 461u + rowseed;
-                    const unsigned nv = se_block_lut(v, seed, x0, y0, p.frame, tab, pool_off, fat_sm);
+                    const unsigned nv = se_block_lut(v, seed, x0, y0, p.frame, tab, fat_sm);
                     const unsigned na = nv & 0xFFu, nb = (nv >> 8) & 0xFFu, nc = (nv >> 16) & 0xFFu, nd = nv >> 24;
+#if !SE_LUT_TWO_TABLES
                     if (CENSUS) {
                         const unsigned cm_cols = (x0 >= 0 ? 5u : 0u) | ((x0 + 1) < p.W ? 10u : 0u);
                         se_census_block(hist_sm, smem_sa + (unsigned)cx.pop_offset, v, a[u], b[u], c[u], d[u], nv, cm_rows & cm_cols);
                     }
+#endif
                     if (vec_ok) {
                         if (st0 == 0 && (na != a[u] || nb != b[u])) *reinterpret_cast<uint2*>(base0 + x0) = make_uint2(na, nb);
                         if (st1 == 0 && (nc != c[u] || nd != d[u])) *reinterpret_cast<uint2*>(base1 + x0) = make_uint2(nc, nd);
@@ -1163,6 +1230,7 @@ static __device__ __forceinline__ void se_k1c_body(const SeLutStepParams& p, con
             }
         }
     }
+#if !SE_LUT_TWO_TABLES
     if (CENSUS) {
         __syncthreads();
         for (int i = tid; i < 256; i += blockDim.x) {
@@ -1170,80 +1238,23 @@ static __device__ __forceinline__ void se_k1c_body(const SeLutStepParams& p, con
             if (dlt != 0) atomicAdd(cx.census + i, (unsigned long long)(long long)dlt);   // two's complement: negative deltas wrap correctly
         }
     }
+#endif
 }
 
 extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_step_lut_global(const SeLutStepParams p) {
     se_k1c_body<false>(p, SeLutCensusParams{}, nullptr);
 }
 
-#if SE_EXPERIMENTAL_KERNELS      // compiled only on request (env SE_EXPERIMENTAL_KERNELS=1 when the rules are compiled)
+#if !SE_LUT_TWO_TABLES
 extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_step_lut_global_census(const SeLutStepParams p, const SeLutCensusParams cx) {
     __shared__ int hist_sm[256];
     se_k1c_body<true>(p, cx, hist_sm);
-}
-
-#ifndef SE_LF_MINCTAS
-#define SE_LF_MINCTAS 3
-#endif
-extern "C" __global__ void __launch_bounds__(256, SE_LF_MINCTAS) se_light_fused(const SeFusedParams p) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ unsigned fat_sm[256];
-    __shared__ SeMod mods_sm[256];
-    __shared__ int warp_counts[8];
-    const int tid = threadIdx.x;
-    unsigned smem_sa;
-    asm volatile("mov.u32 %0, %1;" : "=r"(smem_sa) : "r"((unsigned)__cvta_generic_to_shared(smem)));
-    {
-        const uint4* lut4 = reinterpret_cast<const uint4*>(p.lut);
-        const int n4 = (p.lut_words + 3) >> 2;
-        for (int i = tid; i < n4; i += blockDim.x) {
-            const uint4 v = __ldg(lut4 + i);
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(smem_sa + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-        }
-    }
-    fat_sm[tid] = se_fat_table[tid];
-    __syncthreads();
-    const se_tab_t tab = smem_sa;
-    float4* term = reinterpret_cast<float4*>(smem + p.tile_offset);
-    unsigned char* ids = reinterpret_cast<unsigned char*>(term + SE_LT_TERMS);
-    const int n_tiles = p.tiles_x * p.tiles_y;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {        // persistent: the table is staged once per CTA
-        const int by = t / p.tiles_x, bx = t - by * p.tiles_x;
-        int n_cull = 0;
-        if (p.n_mods > 0) {
-            // cull the modification list against this tile, keeping the order (last match wins, falling_sand.glsl:764-773)
-            const int x_lo = bx * SE_LT_W, y_lo = p.lp.gy0 + by * SE_LT_H;
-            bool keep = false;
-            SeMod m;
-            if (tid < p.n_mods) { m = p.mods[tid]; keep = se_mod_touches(m, x_lo, x_lo + SE_LT_W - 1, y_lo, y_lo + SE_LT_H - 1); }
-            const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
-            const int warp = tid >> 5, lane = tid & 31;
-            if (lane == 0) warp_counts[warp] = __popc(ballot);
-            __syncthreads();
-            int base = 0;
-            for (int w = 0; w < 8; ++w) { if (w < warp) base += warp_counts[w]; n_cull += warp_counts[w]; }
-            if (keep) mods_sm[base + __popc(ballot & ((1u << lane) - 1u))] = m;
-        }
-        if (se_light_tile_is_interior(p.lp, bx, by)) se_fused_stage<true>(p.lp, fat_sm, term, ids, bx, by, tid);
-        else se_fused_stage<false>(p.lp, fat_sm, term, ids, bx, by, tid);
-        __syncthreads();
-        se_fused_blocks(p.lp, p.frame, tab, (unsigned)p.pool_offset, fat_sm, ids, bx, by, tid);
-        __syncthreads();
-        if (se_light_tile_is_interior(p.lp, bx, by)) {
-            if (n_cull) se_light_compute<true>(p.lp, fat_sm, term, bx, by, tid, SeNewIdFused<true>{ids, const_cast<unsigned*>(p.lp.new_cells), mods_sm, n_cull});
-            else se_light_compute<true>(p.lp, fat_sm, term, bx, by, tid, SeNewIdFused<false>{ids, const_cast<unsigned*>(p.lp.new_cells), mods_sm, 0});
-        } else {
-            if (n_cull) se_light_compute<false>(p.lp, fat_sm, term, bx, by, tid, SeNewIdFused<true>{ids, const_cast<unsigned*>(p.lp.new_cells), mods_sm, n_cull});
-            else se_light_compute<false>(p.lp, fat_sm, term, bx, by, tid, SeNewIdFused<false>{ids, const_cast<unsigned*>(p.lp.new_cells), mods_sm, 0});
-        }
-        __syncthreads();                                           // the next tile overwrites term[] / ids[] / mods_sm[]
-    }
 }
 
 extern "C" __global__ void __launch_bounds__(256) se_build_popbits(unsigned* __restrict__ popbits) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < SE_N4) se_build_popbits_entry(idx, popbits);
 }
-#endif  // SE_EXPERIMENTAL_KERNELS
+#endif
 #endif  // SE_HOST_EMU
 #endif  // SE_LUT_ELIGIBLE

@@ -794,19 +794,32 @@ CompiledRules compile_rules(const ParsingResult& parsed) {
 
     std::sort(y_thr.begin(), y_thr.end());
     y_thr.erase(std::unique(y_thr.begin(), y_thr.end()), y_thr.end());
-    // table budget: 2 mirror variants x N^4 states x 2 B must leave room for a tile in shared memory
-    // Left/Right rules break the mirror symmetry the single table relies on; with SE_LUT_LR=1 (EXPERIMENTAL, read when
-    // the rules are compiled) such sets get one table per view instead of falling back to the generated code.
+    // Transition-table modes (kernels/sand_kernels.cuh, "transition tables"):
+    //   1  the table (N^4 32-bit entries per view) fits beside the tiles in shared memory
+    //   2  the table lives in global memory (L2 / HBM resident): rule sets with up to 127 materials
+    // Left/Right rules break the mirror symmetry a single table relies on: such sets get one table per view
+    // (unmirrored / mirrored evaluation); the global-memory mode always keeps both views (no slow path at all).
     const bool lr = out.have_left || out.have_right;
-    const char* lr_env = std::getenv("SE_LUT_LR");
-    const bool allow_lr = lr_env && std::string(lr_env) == "1";
-    out.lut_eligible = lut_ok && tb.n_materials <= 12 && y_thr.size() <= 15 && (!lr || allow_lr);
-    out.lut_tables = (out.lut_eligible && lr) ? 2 : 1;
+    const size_t n4 = (size_t)tb.n_materials * tb.n_materials * tb.n_materials * tb.n_materials;
+    int mode = 0, tables = lr ? 2 : 1;
+    if (lut_ok && tb.n_materials <= 127 && y_thr.size() <= 15) {
+        if ((size_t)tables * n4 * 4 <= 60u * 1024u) mode = 1;
+        else { mode = 2; tables = 2; }
+    }
+    if (const char* fm = std::getenv("SE_LUT_FORCE_MODE")) {       // experiments / tests: "0" (generated code only) or "2"
+        const int v = std::atoi(fm);
+        if (v == 0) mode = 0;
+        if (v == 2 && mode == 1) { mode = 2; tables = 2; }
+    }
+    out.lut_eligible = mode != 0;
+    out.lut_mode = mode;
+    out.lut_tables = out.lut_eligible ? tables : 1;
     out.lut_thresholds = y_thr;
 
     std::ostringstream h;
     h << "// GENERATED by sandengine_b200 (CUDA C back end of the rule language). Do not edit.\n";
     h << "#define SE_LUT_ELIGIBLE " << (out.lut_eligible ? 1 : 0) << "\n";
+    h << "#define SE_LUT_MODE " << out.lut_mode << "\n";
     h << "#define SE_LUT_TWO_TABLES " << (out.lut_tables == 2 ? 1 : 0) << "\n";
     h << "#define SE_LUT_NCLS " << (y_thr.size() + 1) << "\n";
     h << "// class c of a block = number of thresholds its rand.y hash lane exceeds (u1 > U_i)\n";

@@ -51,7 +51,8 @@ struct CompiledRules {
     // (4 material ids, mirror bit, which of the sorted rand.y thresholds the hash lane clears):
     // no pos / frame / other rand lanes / generic float use of rand, and few enough materials.
     bool lut_eligible = false;
-    int lut_tables = 1;          // 2: separate tables for the unmirrored and the mirrored view (rule sets with Left/Right rules; EXPERIMENTAL, env SE_LUT_LR=1)
+    int lut_mode = 0;            // 0: generated code only; 1: table in shared memory; 2: table in global memory (up to 127 materials)
+    int lut_tables = 1;          // 2: separate tables for the unmirrored and the mirrored view (rule sets with Left/Right rules, and always in mode 2)
     std::vector<uint32_t> lut_thresholds;   // sorted distinct U: condition i is `u1 <= U_i`
 };
 

@@ -1,6 +1,14 @@
 """Strip sharding of one grid over the GPUs of a node: one process per GPU,
 `torch.distributed` for the plumbing (rendezvous, IPC-handle exchange, barriers), ghost rows pushed
-device-to-device over NVLink by the native library (se_sim_halo_push) -- no data-path collective.
+device-to-device over NVLink by the native library -- no data-path collective.
+
+The exchange itself lives in the library: the tile kernel (K1b) stores the rows next to a strip boundary into the
+neighbour's ghost rows as part of its store phase and publishes per-tile flags in the neighbour's memory, so a run of
+steps needs neither a separate copy nor a host synchronisation; the per-step kernels (modifications, lighting, rule
+sets without a transition table) recompute the ghost rows redundantly and `se_sim_step` exchanges on the stream
+(cuStreamWriteValue32 / cuStreamWaitValue32) when they are used up.  `StripSimulation.step(n)` is therefore just
+`Simulation.step(n)` on every rank.  `StripPlan` holds the row arithmetic and the schedule of the redundant-ghost scheme
+and is shared with the CPU (gloo) emulation the tests use.
 
 The grid is cut into horizontal strips on EVEN rows.  A strip keeps `halo_rows` ghost rows towards each
 neighbour and re-computes them redundantly: the Margolus update is block-local and its RAND depends
@@ -70,7 +78,7 @@ class StripSimulation:
     the light field gets ghost rows too and the exchange happens every `halo_rows` steps."""
 
     def __init__(self, rules, size, halo_rows: int = 32, device=None, temporal_block: int = 0, device_sync: bool = True,
-                 running_census: bool = False, lighting: bool = False):
+                 running_census: bool = False, lighting: bool = False, device_share: int = 1):
         import torch
         import torch.distributed as dist
 
@@ -84,7 +92,8 @@ class StripSimulation:
         self.row_begin, self.row_end = self.plan.rows(self.rank)
         dev = torch.cuda.current_device() if device is None else device
         self.sim = Simulation(rules, size, lighting=bool(lighting), lit_strip=bool(lighting) and self.world > 1, device=dev, row_begin=self.row_begin, row_end=self.row_end,
-                              halo_rows=self.plan.halo_rows, temporal_block=temporal_block, running_census=running_census)
+                              halo_rows=self.plan.halo_rows, temporal_block=temporal_block, running_census=running_census,
+                              device_share=device_share)
         if self.world > 1:
             mine = self.sim.ipc_export()
             everyone = [None] * self.world
@@ -109,23 +118,21 @@ class StripSimulation:
         return self.sim.params
 
     def upload_cells(self, owned_rows) -> None:
-        self.sim.upload_cells(owned_rows)
-        self.exchange()
+        self.sim.upload_cells(owned_rows)       # marks the ghost rows stale: the next step exchanges first
 
     def download_cells(self, out=None):
         return self.sim.download_cells(out)
 
     def upload_light(self, owned_rows) -> None:
         self.sim.upload_light(owned_rows)
-        self.exchange()
 
     def download_light(self):
         return self.sim.download_light()
 
     def exchange(self) -> None:
-        """Everyone has finished computing -> push boundary rows into the neighbours' ghosts -> everyone has landed.
-        device_sync: the ordering is enforced by stream-ordered flag writes/waits on peer memory (no host in
-        the loop); otherwise by two host barriers."""
+        """Explicit exchange (not needed around step()): everyone has finished computing -> push boundary rows into the
+        neighbours' ghosts -> everyone has landed.  device_sync: the ordering is enforced by stream-ordered flag
+        writes/waits on peer memory (no host in the loop); otherwise by two host barriers."""
         if self.world == 1:
             return
         if self.device_sync:
@@ -138,9 +145,8 @@ class StripSimulation:
         self.dist.barrier()
 
     def step(self, n_steps: int) -> None:
-        for k in self.plan.chunks(int(n_steps)):
-            self.sim.step(k)
-            self.exchange()
+        """Every rank calls this with the same n_steps; the library keeps the ghost rows current (see the module text)."""
+        self.sim.step(int(n_steps))
 
     def census(self):
         return self.sim.census()

@@ -59,3 +59,20 @@ def kat_grid(n: int) -> np.ndarray:
     pal = np.array([0, 3, 5, 7, 4, 10, 0, 0], dtype=np.uint32)
     y, x = np.mgrid[0:n, 0:n]
     return pal[(7 * x + 13 * y + ((x * y) % 5)) % 8]
+
+
+def grid_checksum(cells: np.ndarray, width: int | None = None, row_begin: int = 0) -> int:
+    """numpy twin of se_sim_checksum (csrc/static_kernels.cu): sum over cells of mix(global index, id) mod 2^64."""
+    cells = np.asarray(cells, dtype=np.uint32)
+    w = int(width if width is not None else cells.shape[1])
+    total = 0
+    with np.errstate(over="ignore"):
+        for r0 in range(0, cells.shape[0], 1024):            # bounded temporaries
+            blk = cells[r0:r0 + 1024].astype(np.uint64).ravel()
+            idx = np.uint64((row_begin + r0) * w) + np.arange(blk.size, dtype=np.uint64)
+            h = idx * np.uint64(0x9E3779B97F4A7C15) + blk * np.uint64(0xD6E8FEB86659FD93)
+            h ^= h >> np.uint64(32)
+            h *= np.uint64(0xD6E8FEB86659FD93)
+            h ^= h >> np.uint64(32)
+            total = (total + int(h.sum(dtype=np.uint64))) & 0xFFFFFFFFFFFFFFFF
+    return total

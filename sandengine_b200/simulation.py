@@ -55,7 +55,7 @@ class Simulation:
 
     def __init__(self, rules: ParsingResult, size: Tuple[int, int], lighting: bool = False, device: int = 0,
                  row_begin: int = 0, row_end: int = 0, halo_rows: int = 0, temporal_block: int = 0,
-                 running_census: bool = False, lit_strip: bool = False, fused_light: bool = False):
+                 running_census: bool = False, lit_strip: bool = False, fused_light: bool = False, device_share: int = 1):
         if not rules.compiled:
             raise ValueError("rules must be compiled (parse_string(..., compile=True))")
         self.rules = rules
@@ -68,7 +68,7 @@ class Simulation:
         flags = ((_capi.SE_FLAG_LIGHTING if lighting else 0) | (_capi.SE_FLAG_RUNNING_CENSUS if running_census else 0)
                  | (_capi.SE_FLAG_LIT_STRIP_EXPERIMENTAL if lit_strip else 0) | (_capi.SE_FLAG_FUSED_LIGHT_EXPERIMENTAL if fused_light else 0))   # the last two: experimental, see the header
         prm = _capi.se_create_params(self.size[0], self.size[1], flags, device,
-                                     self.row_begin, self.row_end, int(halo_rows), int(temporal_block))
+                                     self.row_begin, self.row_end, int(halo_rows), int(temporal_block), int(device_share))
         h = C.c_void_p()
         _capi.check(_capi.lib().se_sim_create(rules._h, C.byref(prm), C.byref(h)))
         self._h = h
@@ -170,6 +170,12 @@ class Simulation:
         out = np.zeros(256, np.uint64)
         _capi.check(_capi.lib().se_sim_census(self._h, out.ctypes.data))
         return out
+
+    def checksum(self) -> int:
+        """Sharding-independent checksum of the owned rows (se_sim_checksum): the strips' values add up mod 2^64."""
+        v = C.c_uint64()
+        _capi.check(_capi.lib().se_sim_checksum(self._h, C.byref(v)))
+        return v.value
 
     def census_async(self, host_ptr: int) -> None:
         """Enqueue a census whose 256 x uint64 result lands at `host_ptr` (pinned memory) after census_wait();

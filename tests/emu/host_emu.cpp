@@ -106,20 +106,25 @@ extern "C" void emu_light(const uint32_t* old_cells, const uint32_t* new_cells, 
 extern "C" int emu_lut_eligible(void) { return SE_LUT_ELIGIBLE; }
 
 #if SE_LUT_ELIGIBLE
-// table image exactly as the kernel stages it: base[N^4] u16, padding to 8 bytes, pool[] of 8-byte entries
-static std::vector<unsigned char> g_table;
-static unsigned g_pool_off = 0, g_pool_entries = 0;
+// table image as the kernels see it: base[N^4 * tables] u32 entries and pool[] of {thr, A, B} triples
+static std::vector<unsigned> g_base, g_pool;
+static unsigned g_pool_entries = 0;
+static SeTab g_tab{nullptr, nullptr};
 
-// returns the number of pool entries, or -1 on pool overflow
+// returns the number of pool entries (two passes like se_sim_create in mode 2: count, then fill)
 extern "C" int emu_build_lut(void) {
-    g_pool_off = ((unsigned)SE_LUT_ENTRIES * 2u + 7u) / 8u * 8u;
-    g_table.assign(g_pool_off + (size_t)SE_LUT_POOL_MAX * 8, 0);
-    g_pool_entries = 0;
-    unsigned short* base = reinterpret_cast<unsigned short*>(g_table.data());
-    SePoolEntry* pool = reinterpret_cast<SePoolEntry*>(g_table.data() + g_pool_off);
-    for (int idx = 0; idx < SE_LUT_ENTRIES; ++idx) se_build_lut_entry(idx, base, pool, &g_pool_entries);
-    return g_pool_entries > SE_LUT_POOL_MAX ? -1 : (int)g_pool_entries;
+    g_base.assign((size_t)SE_LUT_ENTRIES, 0u);
+    unsigned counter = 0;
+    for (unsigned idx = 0; idx < (unsigned)SE_LUT_ENTRIES; ++idx) se_build_lut_entry(idx, g_base.data(), nullptr, &counter, 0u);
+    g_pool_entries = counter;
+    g_pool.assign((size_t)4 * (counter + 1), 0u);
+    counter = 0;
+    for (unsigned idx = 0; idx < (unsigned)SE_LUT_ENTRIES; ++idx) se_build_lut_entry(idx, g_base.data(), g_pool.data(), &counter, g_pool_entries);
+    g_tab = SeTab{g_base.data(), g_pool.data()};
+    return (int)g_pool_entries;
 }
+extern "C" int emu_lut_mode(void) { return SE_LUT_MODE; }
+extern "C" int emu_lut_two_tables(void) { return SE_LUT_TWO_TABLES; }
 
 // one in-place Margolus step through the transition table (se_block_lut), ids packed as in the tile kernel
 extern "C" void emu_step_lut_inplace(uint32_t* cells, int W, int H, int frame) {
@@ -137,7 +142,7 @@ extern "C" void emu_step_lut_inplace(uint32_t* cells, int W, int H, int frame) {
             unsigned nv = v;
             {   // like the tile kernel: no all-EMPTY branch, T0[0] == 0
                 const unsigned seed = (unsigned)x0 * 461u + (unsigned)y0 * 2131u + (unsigned)frame * (2131u * 2131u);
-                nv = se_block_lut(v, seed, x0, y0, frame, g_table.data(), g_pool_off, se_fat_table);
+                nv = se_block_lut(v, seed, x0, y0, frame, g_tab, se_fat_table);
             }
             for (int k = 0; k < 4; ++k) {
                 int x = x0 + (k & 1), y = y0 + (k >> 1);
@@ -146,39 +151,7 @@ extern "C" void emu_step_lut_inplace(uint32_t* cells, int W, int H, int frame) {
         }
 }
 
-// ---- K3f (experimental fused step + modifications + lighting): the three per-thread phases, CTA by CTA ----
-extern "C" void emu_light_fused(const uint32_t* old_cells, uint32_t* new_cells, const float* light_in, float* light_out,
-                                int W, int Hl, int gy0, int Hg, int frame, const SeMod* mods, int n_mods) {
-    SeLightParams p{old_cells, new_cells, reinterpret_cast<const float4*>(light_in), reinterpret_cast<float4*>(light_out), W, Hl, gy0, Hg};
-    std::vector<float4> term(SE_LT_TERMS);
-    std::vector<unsigned char> ids(SE_LF_IDS_BYTES);
-    std::vector<SeMod> culled(256);
-    for (int by = 0; by < (Hl + SE_LT_H - 1) / SE_LT_H; ++by)
-        for (int bx = 0; bx < (W + SE_LT_W - 1) / SE_LT_W; ++bx) {
-            for (auto& t : term) t = make_float4(NAN, NAN, NAN, NAN);
-            for (auto& b : ids) b = 0xEE;                                       // poison: must be staged before use
-            int n_cull = 0;
-            const int x_lo = bx * SE_LT_W, y_lo = gy0 + by * SE_LT_H;
-            for (int i = 0; i < n_mods; ++i)
-                if (se_mod_touches(mods[i], x_lo, x_lo + SE_LT_W - 1, y_lo, y_lo + SE_LT_H - 1)) culled[n_cull++] = mods[i];
-            const bool interior = se_light_tile_is_interior(p, bx, by);
-            for (int tid = 0; tid < 256; ++tid) {
-                if (interior) se_fused_stage<true>(p, se_fat_table, term.data(), ids.data(), bx, by, tid);
-                else se_fused_stage<false>(p, se_fat_table, term.data(), ids.data(), bx, by, tid);
-            }
-            for (int tid = 0; tid < 256; ++tid) se_fused_blocks(p, frame, g_table.data(), g_pool_off, se_fat_table, ids.data(), bx, by, tid);
-            for (int tid = 0; tid < 256; ++tid) {
-                if (interior) {
-                    if (n_cull) se_light_compute<true>(p, se_fat_table, term.data(), bx, by, tid, SeNewIdFused<true>{ids.data(), new_cells, culled.data(), n_cull});
-                    else se_light_compute<true>(p, se_fat_table, term.data(), bx, by, tid, SeNewIdFused<false>{ids.data(), new_cells, culled.data(), 0});
-                } else {
-                    if (n_cull) se_light_compute<false>(p, se_fat_table, term.data(), bx, by, tid, SeNewIdFused<true>{ids.data(), new_cells, culled.data(), n_cull});
-                    else se_light_compute<false>(p, se_fat_table, term.data(), bx, by, tid, SeNewIdFused<false>{ids.data(), new_cells, culled.data(), 0});
-                }
-            }
-        }
-}
-
+#if !SE_LUT_TWO_TABLES
 // ---- running census (experimental): popbits filter + per-block deltas, decisions exactly as in se_k1c_body<true> ----
 static std::vector<unsigned> g_pop;
 extern "C" int emu_build_popbits(void) {
@@ -208,7 +181,7 @@ extern "C" void emu_step_lut_census(uint32_t* cells, int W, int H, int frame, in
             unsigned v = 0;
             for (int k = 0; k < 4; ++k) v |= (raw[k] < SE_N_MATERIALS ? raw[k] : 1u) << (8 * k);
             const unsigned seed = (unsigned)x0 * 461u + (unsigned)y0 * 2131u + (unsigned)frame * (2131u * 2131u);
-            const unsigned nv = se_block_lut(v, seed, x0, y0, frame, g_table.data(), g_pool_off, se_fat_table);
+            const unsigned nv = se_block_lut(v, seed, x0, y0, frame, g_tab, se_fat_table);
             const unsigned cm_rows = ((st0 == 0 && y0 >= own_y0 && y0 < own_y1) ? 3u : 0u) | ((st1 == 0 && y1 >= own_y0 && y1 < own_y1) ? 12u : 0u);
             const unsigned cm_cols = (cx0 ? 5u : 0u) | (cx1 ? 10u : 0u);
             const unsigned cm = cm_rows & cm_cols;
@@ -223,7 +196,12 @@ extern "C" void emu_step_lut_census(uint32_t* cells, int W, int H, int frame, in
     for (int i = 0; i < 256; ++i) census256[i] += hist[i];
 }
 #else
-extern "C" void emu_light_fused(const uint32_t*, uint32_t*, const float*, float*, int, int, int, int, int, const void*, int) {}
+extern "C" int emu_build_popbits(void) { return -2; }
+extern "C" void emu_step_lut_census(uint32_t*, int, int, int, int, int, long long*, long long*) {}
+#endif
+#else
+extern "C" int emu_lut_mode(void) { return 0; }
+extern "C" int emu_lut_two_tables(void) { return 0; }
 extern "C" int emu_build_popbits(void) { return -2; }
 extern "C" void emu_step_lut_census(uint32_t*, int, int, int, int, int, long long*, long long*) {}
 extern "C" int emu_build_lut(void) { return -2; }

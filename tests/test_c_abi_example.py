@@ -31,8 +31,6 @@ def test_c_example_fails_loudly_without_a_device(example_binary):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("SE_TEST_EXPERIMENTAL") != "1",
-                    reason="written without a GPU at hand: first run it with SE_TEST_EXPERIMENTAL=1 (scripts/gpu_experiments.sh)")
 def test_c_example_runs(example_binary, oracle):
     import numpy as np
 
@@ -65,7 +63,7 @@ def test_abi_rejects_null_arguments(native_lib):
                      (L.se_sim_create, (null, None, None)), (L.se_sim_step, (null, 1)), (L.se_sim_push_modifications, (null, None, 0)),
                      (L.se_sim_set_frame, (null, 0)), (L.se_sim_get_frame, (null, None)), (L.se_sim_upload_cells, (null, None)),
                      (L.se_sim_download_cells, (null, None)), (L.se_sim_upload_light, (null, None)), (L.se_sim_download_light, (null, None)),
-                     (L.se_sim_download_color, (null, None, None)), (L.se_sim_device_cells, (null, None, None)), (L.se_sim_census, (null, None)),
+                     (L.se_sim_download_color, (null, None, None)), (L.se_sim_device_cells, (null, None, None)), (L.se_sim_census, (null, None)), (L.se_sim_checksum, (null, None)),
                      (L.se_sim_census_async, (null, None)), (L.se_sim_census_wait, (null,)), (L.se_sim_set_stream, (null, None)),
                      (L.se_sim_synchronize, (null,)), (L.se_sim_launch_count, (null, None)), (L.se_sim_ipc_export, (null, None, None, None, None)),
                      (L.se_sim_ipc_attach, (null, 0, None, 0, 0, 0)), (L.se_sim_ipc_export_light, (null, None)),

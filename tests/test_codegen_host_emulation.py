@@ -236,83 +236,32 @@ def _stage_mods(se, mods, n_materials):
     return out[:n]
 
 
-@pytest.mark.parametrize("rows", [4, 8])
-def test_fused_step_light_kernel_phases_on_host(native_lib, tmp_path_factory, default_rules, oracle, rows):
-    """EXPERIMENTAL K3f (se_light_fused): table step + modification override + lighting in one pass, its three per-thread
-    phases run CTA by CTA on the host: ids AND light bit-identical to the oracle's per-cell form -- all Margolus phases,
-    ragged sizes, WALL / NULL / unknown ids, modifications (incl. unknown material, size 0 mid-list), strips."""
-    import sandengine_b200 as se
-    lib = build_emu(tmp_path_factory, f"fused{rows}", default_rules, defs=(f"-DSE_LT_ROWS={rows}",))
-    lib.emu_light_fused.argtypes = [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p, C.c_int]
-    assert lib.emu_build_lut() > 0
-    n_mat = len(default_rules.materials)
-    rng = np.random.default_rng(17)
-    for (w, h, seed, steps, with_mods) in [(160, 128, 1, 9, True), (33, 17, 2, 6, True), (97, 99, 3, 5, False), (2, 2, 4, 4, False),
-                                           (100, 200, 7, 5, True), (64, 64, 8, 8, True)]:
-        cells = synthetic_grid(w, h, seed)
-        if seed == 8:
-            cells[rng.integers(0, h, 40), rng.integers(0, w, 40)] = 2
-            cells[rng.integers(0, h, 15), rng.integers(0, w, 15)] = 1
-            cells[3, 3] = 77; cells[9, 5] = 4000000000
-        light = rng.random((h, w, 4), dtype=np.float32)
-        light[rng.random((h, w)) < 0.2, 3] = 0.0
-        frame = 1
-        for s in range(steps):
-            frame += 1
-            mods = np.zeros(0, se.MOD_DTYPE)
-            if with_mods and s % 2 == 0:
-                mods = np.zeros(6, se.MOD_DTYPE)
-                for i in range(6):
-                    mods[i]["position"] = (int(rng.integers(-5, w + 5)), int(rng.integers(-5, h + 5)))
-                    mods[i]["mod_shape"] = int(rng.integers(0, 2)); mods[i]["mod_size"] = int(rng.integers(1, 12))
-                    mods[i]["mod_matID"] = int(rng.integers(0, n_mat))
-                mods[2]["mod_matID"] = 99                       # unknown id: NULL cancels an earlier hit
-                if s % 4 == 0:
-                    mods[4]["mod_size"] = 0                     # the shader stops at the first size-0 record
-            want_c, want_l, _ = oracle.step_cells(cells, frame, light, mods)
-            staged = _stage_mods(se, mods, n_mat)
-            got_c = np.full_like(cells, 12345)
-            got_l = np.full_like(light, np.nan)
-            lib.emu_light_fused(cells.ctypes.data, got_c.ctypes.data, light.ctypes.data, got_l.ctypes.data, w, h, 0, h, frame,
-                                staged.ctypes.data if len(staged) else None, len(staged))
-            assert np.array_equal(got_c, want_c), f"{w}x{h} step {s + 1}: ids"
-            assert np.array_equal(got_l.view(np.uint32), want_l.view(np.uint32)), f"{w}x{h} step {s + 1}: light"
-            if w == 160 and s == 1:
-                # a strip: local rows [32, 102); ids two rows in and light one row in from the buffer edges equal the full grid
-                gy0, hl = 32, 70
-                pc = np.full((hl, w), 12345, np.uint32); pl = np.full((hl, w, 4), np.nan, np.float32)
-                lib.emu_light_fused(np.ascontiguousarray(cells[gy0:gy0 + hl]).ctypes.data, pc.ctypes.data,
-                                    np.ascontiguousarray(light[gy0:gy0 + hl]).ctypes.data, pl.ctypes.data, w, hl, gy0, h, frame,
-                                    staged.ctypes.data if len(staged) else None, len(staged))
-                assert np.array_equal(pc[2:-2], want_c[gy0 + 2:gy0 + hl - 2])
-                assert np.array_equal(pl[2:-2].view(np.uint32), want_l[gy0 + 2:gy0 + hl - 2].view(np.uint32))
-            cells, light = want_c, want_l
-
-
 @pytest.mark.parametrize("seed,n_mat,n_rules,kinds", [(201, 7, 23, ("mirrored",)), (216, 12, 22, ("mirrored",)), (110, 20, 28, None)])
 def test_random_rule_sets_differential(native_lib, tmp_path_factory, seed, n_mat, n_rules, kinds):
     """Random rule sets (scripts/diff_campaign.py runs many more): oracle == generated code on the host == transition
-    table (when the set is eligible: mirrored-only, <= 12 materials)."""
+    table (one shared-memory table for small mirrored-only sets, one table per view otherwise; mode 2 = table in global
+    memory for the 20-material Left/Right set)."""
     import sandengine_b200 as se
     from oracle.build_oracle import load_oracle
     from sandengine_b200.synth_rules import synthetic_rule_set
     text, ids, mix = synthetic_rule_set(n_mat, n_rules, seed=seed, **({"kinds": kinds} if kinds else {}))
     rules = se.parse_string(text)
-    assert ("#define SE_LUT_ELIGIBLE 1" in rules.cuda_header) == (kinds is not None)
+    assert "#define SE_LUT_ELIGIBLE 1" in rules.cuda_header
+    assert ("#define SE_LUT_TWO_TABLES 1" in rules.cuda_header) == (kinds is None or n_mat > 11)
     orc = load_oracle(text)
     lib = build_emu(tmp_path_factory, f"rand{seed}", rules)
     g = synthetic_grid(48, 40, seed, mix=mix, ids=ids)
     ref = compare(lib, orc, g, 60)
     assert (ref != g).sum() > 500
-    if kinds is not None:
-        assert lib.emu_lut_eligible() == 1 and lib.emu_build_lut() >= 0
-        compare(lib, orc, g, 60, lut=True)
+    assert lib.emu_lut_eligible() == 1 and lib.emu_build_lut() >= 0
+    assert lib.emu_lut_mode() == (1 if n_mat <= 11 and kinds is not None else 2)
+    compare(lib, orc, g, 60, lut=True)
 
 
 def test_two_table_lut_for_left_right_rule_sets(native_lib, tmp_path_factory, monkeypatch):
-    """EXPERIMENTAL (env SE_LUT_LR=1 when the rules are compiled): rule sets with Left/Right rules get one transition
-    table per view instead of falling back to the generated code.  Table build + lookup on the host vs the oracle for
-    random mixed rule sets (<= 12 materials) and for the Left/Right test YAMLs that use no pos / rand.x."""
+    """Rule sets with Left/Right rules get one transition table per view (unmirrored / mirrored evaluation) instead of
+    falling back to the generated code.  Table build + lookup on the host vs the oracle for random mixed rule sets and
+    for the Left/Right test YAMLs that use no pos / rand.x; SE_LUT_FORCE_MODE=0 switches the tables off."""
     import sandengine_b200 as se
     from oracle.build_oracle import load_oracle
     from sandengine_b200.synth_rules import synthetic_rule_set
@@ -321,9 +270,10 @@ def test_two_table_lut_for_left_right_rule_sets(native_lib, tmp_path_factory, mo
         text, ids, mix = synthetic_rule_set(n_mat, n_rules, seed=seed)      # mirrored + right + left rules
         cases.append((f"synth{seed}", text, dict(mix=mix, ids=ids)))
     cases.append(("base_ok", Y.BASE_OK, {}))
+    monkeypatch.setenv("SE_LUT_FORCE_MODE", "0")
     off = se.parse_string(cases[0][1])
-    assert "#define SE_LUT_ELIGIBLE 0" in off.cuda_header                     # default: not eligible
-    monkeypatch.setenv("SE_LUT_LR", "1")
+    assert "#define SE_LUT_ELIGIBLE 0" in off.cuda_header                     # tables switched off: generated code only
+    monkeypatch.delenv("SE_LUT_FORCE_MODE")
     n_two = 0
     for name, text, gk in cases:
         rules = se.parse_string(text)

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(native_lib):
 def test_abi_struct_layout():
     from sandengine_b200 import _capi
     assert C.sizeof(_capi.se_modification) == 32      # simulation.rs:45-56, std140 stride of the UBO
-    assert C.sizeof(_capi.se_create_params) == 32
+    assert C.sizeof(_capi.se_create_params) == 36     # 9 x uint32 (device_share appended in round 2)
 
 
 def test_glsl_known_answer(default_rules):
@@ -173,13 +173,11 @@ def test_create_rejects_bad_geometry_before_touching_a_device(default_rules):
     for size, kw in (((0, 64), {}), ((64, 0), {}), ((4, 600_000), {}),
                      ((64, 64), dict(row_begin=3, row_end=33)),        # odd strip boundary
                      ((64, 64), dict(row_begin=32, row_end=16)),       # empty strip
-                     ((64, 64), dict(row_begin=0, row_end=128))):      # beyond the grid
+                     ((64, 64), dict(row_begin=0, row_end=128)),       # beyond the grid
+                     ((64, 64), dict(row_begin=0, row_end=32, halo_rows=3))):   # ghost zones start on even rows
         with pytest.raises(se.SandEngineError) as ei:
             se.Simulation(default_rules, size, **kw)
         assert ei.value.kind == "InvalidArg", (size, kw, str(ei.value))
-    with pytest.raises(se.SandEngineError) as ei:       # strips carry no light ghost rows: refused, not silently wrong
-        se.Simulation(default_rules, (64, 64), lighting=True, row_begin=0, row_end=32, halo_rows=4)
-    assert ei.value.kind == "Unsupported"
 
 
 def test_yaml_syntax_variants_parse_identically(native_lib):

@@ -254,7 +254,7 @@ def test_synthetic_64_material_rules_1024(se):
     assert np.array_equal(got, ref) and not np.array_equal(got, g)
 
 
-def _strip_pair_run(se, rules, g, steps, halo, n_strips, device_sync=False, per_step=False):
+def _strip_pair_run(se, rules, g, steps, halo, n_strips, device_sync=False, per_step=False, auto=False):
     """n strips of one grid on ONE device in ONE process (se_sim_attach_local): exercises ghost rows, the
     missing-row logic and se_sim_halo_push without torch.distributed."""
     from sandengine_b200.distributed import StripPlan
@@ -263,7 +263,7 @@ def _strip_pair_run(se, rules, g, steps, halo, n_strips, device_sync=False, per_
     sims = []
     for r in range(n_strips):
         b, e = plan.rows(r)
-        s = se.Simulation(rules, (W, H), row_begin=b, row_end=e, halo_rows=halo)
+        s = se.Simulation(rules, (W, H), row_begin=b, row_end=e, halo_rows=halo, device_share=n_strips)
         s.upload_cells(g[b:e])
         s.params.frame = 1
         sims.append(s)
@@ -280,14 +280,18 @@ def _strip_pair_run(se, rules, g, steps, halo, n_strips, device_sync=False, per_
         for s in sims: s.synchronize()
         for s in sims: s.halo_push()
         for s in sims: s.synchronize()
-    exchange()
-    for k in plan.chunks(steps):
-        for s in sims:
-            if per_step:            # one se_sim_step(1) per frame: the K1c (single-step table kernel) path
-                for _ in range(k): s.step(1)
-            else:
-                s.step(k)
+    if auto:                # no explicit exchange at all: se_sim_step keeps the ghost rows current (fused push / stream exchange)
+        for k in ([1] * steps if per_step else [steps // 3, steps - steps // 3]):
+            for s in sims: s.step(k)
+    else:
         exchange()
+        for k in plan.chunks(steps):
+            for s in sims:
+                if per_step:            # one se_sim_step(1) per frame: the K1c (single-step table kernel) path
+                    for _ in range(k): s.step(1)
+                else:
+                    s.step(k)
+            exchange()
     out = np.concatenate([s.download_cells() for s in sims], axis=0)
     for s in sims: s.close()
     return out
@@ -303,6 +307,10 @@ def test_strips_equal_single_grid(se, default_rules, oracle, n_strips, halo, h):
     got = _strip_pair_run(se, default_rules, g, steps, halo, n_strips, device_sync=True)
     assert np.array_equal(got, ref)
     got = _strip_pair_run(se, default_rules, g, steps, halo, n_strips, device_sync=True, per_step=True)
+    assert np.array_equal(got, ref)
+    got = _strip_pair_run(se, default_rules, g, steps, halo, n_strips, auto=True)
+    assert np.array_equal(got, ref)
+    got = _strip_pair_run(se, default_rules, g, steps, halo, n_strips, auto=True, per_step=True)
     assert np.array_equal(got, ref)
 
 
@@ -488,13 +496,10 @@ def test_gpu_matches_committed_state_hashes(se):
         assert hashlib.sha256(got.astype(np.uint32).tobytes()).hexdigest() == want[name]["final"], name
 
 
-@pytest.mark.skipif(os.environ.get("SE_TEST_EXPERIMENTAL") != "1",
-                    reason="EXPERIMENTAL SE_FLAG_RUNNING_CENSUS: off by default, not yet validated on a GPU (SE_TEST_EXPERIMENTAL=1 runs it)")
-def test_running_census_experimental(se, oracle, monkeypatch):
+def test_running_census(se, oracle, monkeypatch):
     """SE_FLAG_RUNNING_CENSUS: cells stay bit-exact and every census (sync and async, after K1c steps, after runs that
     fall back to a recount, with WALL / NULL / unknown ids, odd widths) equals a host recount."""
     import torch
-    monkeypatch.setenv("SE_EXPERIMENTAL_KERNELS", "1")          # the experimental kernels are not compiled by default
     default_rules = se.parse_path(DEFAULT_YAML)
     for (w, h, seed) in [(516, 130, 41), (1024, 768, 42), (260, 258, 43)]:
         g = synthetic_grid(w, h, seed)
@@ -520,10 +525,8 @@ def test_running_census_experimental(se, oracle, monkeypatch):
         sim.close()
 
 
-@pytest.mark.skipif(os.environ.get("SE_TEST_EXPERIMENTAL") != "1",
-                    reason="EXPERIMENTAL lit strips (SE_FLAG_LIT_STRIP_EXPERIMENTAL): not yet validated on a GPU (SE_TEST_EXPERIMENTAL=1 runs it)")
 @pytest.mark.parametrize("n_strips,halo,w,h", [(2, 4, 96, 64), (3, 6, 200, 150), (4, 2, 64, 64)])
-def test_lit_strips_experimental(se, default_rules, oracle, n_strips, halo, w, h):
+def test_lit_strips(se, default_rules, oracle, n_strips, halo, w, h):
     """Strips with lighting in one process (se_sim_attach_local): ids bit-exact, light bit-exact against the oracle's
     full-grid run; ghost rows of ids AND light are exchanged every `halo` steps (StripPlan(lighting=True))."""
     from sandengine_b200.distributed import StripPlan
@@ -537,7 +540,7 @@ def test_lit_strips_experimental(se, default_rules, oracle, n_strips, halo, w, h
     sims = []
     for r in range(n_strips):
         b, e = plan.rows(r)
-        s = se.Simulation(default_rules, (w, h), lighting=True, lit_strip=True, row_begin=b, row_end=e, halo_rows=halo)
+        s = se.Simulation(default_rules, (w, h), lighting=True, lit_strip=True, row_begin=b, row_end=e, halo_rows=halo, device_share=n_strips)
         s.upload_cells(g[b:e]); s.upload_light(np.ascontiguousarray(L0[b:e])); s.params.frame = 1
         sims.append(s)
     for r, s in enumerate(sims):
@@ -559,11 +562,8 @@ def test_lit_strips_experimental(se, default_rules, oracle, n_strips, halo, w, h
     assert np.abs(gotL - refL).max() <= LIGHT_ATOL
 
 
-@pytest.mark.skipif(os.environ.get("SE_TEST_EXPERIMENTAL") != "1",
-                    reason="EXPERIMENTAL fused step + lighting kernel (SE_FLAG_FUSED_LIGHT_EXPERIMENTAL): not yet validated on a GPU")
-def test_fused_light_experimental(se, oracle, monkeypatch):
+def test_fused_light(se, oracle, monkeypatch):
     """se_light_fused: ids bit-exact and light within tolerance against the oracle, with modifications, frame 1 included."""
-    monkeypatch.setenv("SE_EXPERIMENTAL_KERNELS", "1")          # the experimental kernels are not compiled by default
     default_rules = se.parse_path(DEFAULT_YAML)
     rng = np.random.default_rng(29)
     for (w, h, steps, frame0) in [(200, 150, 24, 1), (80, 64, 30, 1), (33, 17, 10, 0), (516, 130, 12, 1)]:
@@ -585,8 +585,6 @@ def test_fused_light_experimental(se, oracle, monkeypatch):
         assert np.abs(gotL - refL).max() <= LIGHT_ATOL, (w, h)
 
 
-@pytest.mark.skipif(os.environ.get("SE_TEST_EXPERIMENTAL") != "1",
-                    reason="added without a GPU at hand: run once with SE_TEST_EXPERIMENTAL=1 (scripts/gpu_experiments.sh), then un-gate")
 @pytest.mark.parametrize("seed,n_mat,n_rules", [(201, 7, 23), (216, 12, 22)])
 def test_table_kernels_on_random_eligible_rule_sets(se, seed, n_mat, n_rules):
     """K1b / K1c with table-eligible rule sets OTHER than the default one (different material count, table size,
@@ -609,13 +607,10 @@ def test_table_kernels_on_random_eligible_rule_sets(se, seed, n_mat, n_rules):
         sim.close()
 
 
-@pytest.mark.skipif(os.environ.get("SE_TEST_EXPERIMENTAL") != "1",
-                    reason="EXPERIMENTAL two-table transition tables for Left/Right rule sets (env SE_LUT_LR=1): not yet validated on a GPU")
-def test_two_table_lut_experimental(se, monkeypatch):
+def test_two_table_lut(se, monkeypatch):
     """K1b / K1c for rule sets with Left/Right rules through one table per view (SE_LUT_LR=1 at rule-compile time)."""
     from oracle.build_oracle import load_oracle
     from sandengine_b200.synth_rules import synthetic_rule_set
-    monkeypatch.setenv("SE_LUT_LR", "1")
     for seed, n_mat, n_rules in [(401, 9, 20), (505, 11, 21)]:
         text, ids, mix = synthetic_rule_set(n_mat, n_rules, seed=seed)
         rules = se.parse_string(text)
@@ -633,8 +628,6 @@ def test_two_table_lut_experimental(se, monkeypatch):
             sim.close()
 
 
-@pytest.mark.skipif(os.environ.get("SE_TEST_EXPERIMENTAL") != "1",
-                    reason="added without a GPU at hand: run once with SE_TEST_EXPERIMENTAL=1 (scripts/gpu_experiments.sh), then un-gate")
 @pytest.mark.parametrize("n_strips,halo", [(2, 4), (3, 8)])
 def test_strips_with_modifications(se, default_rules, oracle, n_strips, halo):
     """modifications are broadcast to every strip (global coordinates, clipped by the kernels); the
@@ -649,7 +642,7 @@ def test_strips_with_modifications(se, default_rules, oracle, n_strips, halo):
     sims = []
     for r in range(n_strips):
         b, e = plan.rows(r)
-        s = se.Simulation(default_rules, (w, h), row_begin=b, row_end=e, halo_rows=halo)
+        s = se.Simulation(default_rules, (w, h), row_begin=b, row_end=e, halo_rows=halo, device_share=n_strips)
         s.upload_cells(g[b:e]); s.params.frame = 1
         sims.append(s)
     for r, s in enumerate(sims):
