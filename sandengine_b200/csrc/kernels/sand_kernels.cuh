@@ -821,6 +821,30 @@ struct SeTileParams {
 };
 
 #define SE_HALF_WARPS 16
+// The sub-step loops are bound by the ALU pipe (LOP3 / SHF / ISETP / PRMT / SEL issue every other cycle per scheduler),
+// the FMA pipe (IMAD) idles: wherever it costs nothing, integer work is phrased as a multiply-add.
+// (seed + offset) * factor as ONE multiply-add per block instead of one multiply per row and an ALU add per block:
+static __device__ __forceinline__ unsigned se_seed_mul(unsigned seed, unsigned offset, unsigned factor) {
+    unsigned r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(seed), "r"(factor), "r"(offset * factor));
+    return r;
+}
+// rand.x < 0.5 from the hash lane WITHOUT its last xor-shift.  With y the value before `x ^= x >> 16`:
+//   u0 = y ^ (y >> 16) <= SE_MIRROR_UMAX = 2^31 - 65   <=>   y < 2^31  and not  0x7FFF8000 <= y <= 0x7FFF803F
+// (the high half-word of u0 is that of y; for y >> 16 == 0x7FFF the low half-word of u0 is that of y xor 0x7FFF, and
+// u0 >= 0x7FFFFFC0 means that low half-word lies in [0xFFC0, 0xFFFF], i.e. y's in [0x8000, 0x803F]).  Two compares
+// instead of shift + xor + compare; checked exhaustively around every boundary by tests/test_codegen_host_emulation.py.
+static __device__ __forceinline__ bool se_mirror_bit(unsigned x) {
+#if SE_MIRROR_UMAX == 0x7fffffbfu
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU;
+    // y < 0x7FFF8000 (unsigned)  or  y > 0x7FFF803F as a SIGNED number (i.e. 0x7FFF8040 .. 0x7FFFFFFF): two chained SETPs
+    unsigned r;
+    asm("{\n\t.reg .pred p, q;\n\tsetp.lt.u32 p, %1, 0x7FFF8000;\n\tsetp.gt.or.s32 q, %1, 0x7FFF803F, p;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(r) : "r"(x));
+    return r != 0u;
+#else
+    return se_hashi(x) <= SE_MIRROR_UMAX;
+#endif
+}
 #ifndef SE_LOAD_ROWS
 #define SE_LOAD_ROWS 2          // tile rows whose 128-bit loads a lane keeps in flight together (registers: 8 per row)
 #endif
@@ -868,7 +892,7 @@ static __device__ __forceinline__ void se_tile_substep(unsigned tile_sa, const S
             unsigned e[4], mir = 0u;                                   // mir bit k: block k is evaluated in the mirrored view
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const bool mirror = se_hashi((rowseed + (unsigned)(2 * k) * 461u) * 213u) <= SE_MIRROR_UMAX;
+                const bool mirror = se_mirror_bit(se_seed_mul(rowseed, (unsigned)(2 * k) * 461u, 213u));
                 mir |= mirror ? (1u << k) : 0u;
 #if SE_LUT_TWO_TABLES
                 e[k] = se_tab_entry(tab, se_idx4(v[k]) + (mirror ? (unsigned)SE_N4 : 0u));
@@ -881,7 +905,7 @@ static __device__ __forceinline__ void se_tile_substep(unsigned tile_sa, const S
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if ((e[k] & (SE_E_SPECIAL | SE_E_SLOW)) == SE_E_SPECIAL) {
-                        const unsigned u1 = se_hashi((rowseed + (unsigned)(2 * k) * 461u) * 2131u);
+                        const unsigned u1 = se_hashi(se_seed_mul(rowseed, (unsigned)(2 * k) * 461u, 2131u));
                         do {
                             unsigned thr, a, b;
                             se_tab_pool(tab, e[k] & SE_E_INDEX, thr, a, b);
@@ -972,10 +996,14 @@ extern "C" __global__ void __launch_bounds__(2 * SE_HALF_THREADS, 1) se_step_til
         const unsigned w = next_item[half];
         if (w >= total_items) break;
         const int k = (int)(w / (unsigned)n_tiles), pos = (int)(w - (unsigned)k * (unsigned)n_tiles);
-        // boundary tile rows first (row 0, then the last row when a strip below depends on it), interior after
+        // Strips: tile rows from the outside in (0, last, 1, last - 1, ...).  The boundary rows come first, so their push
+        // overlaps the interior of the same T-block and the neighbours never wait for the end of a T-block; and a tile's
+        // dependencies (its own row and the two next to it, one T-block earlier) are at most two rows behind it in this
+        // order, i.e. nearly a whole T-block of items ahead in the queue.  (Rows top to bottom would make the strip below
+        // wait for the LAST row of every T-block; "boundary rows first, then top to bottom" would make the own last row wait
+        // for its upper neighbour, the last one drawn: 0.5 rounds of stall per T-block at 8 GPUs.)
         const int ry = pos / p.tiles_x, tx = pos - ry * p.tiles_x;
-        int ty = ry;
-        if (has_below && p.tiles_y > 2) ty = (ry == 0) ? 0 : (ry == 1 ? p.tiles_y - 1 : ry - 1);
+        const int ty = (has_above || has_below) ? ((ry & 1) ? p.tiles_y - 1 - (ry >> 1) : (ry >> 1)) : ry;
         const int t = ty * p.tiles_x + tx;
         unsigned* in = (k & 1) ? p.buf1 : p.buf0;
         unsigned* out = (k & 1) ? p.buf0 : p.buf1;
@@ -1201,30 +1229,79 @@ static __device__ __forceinline__ void se_k1c_body(const SeLutStepParams& p, con
                     }
                 }
             }
+            // ---- transitions: the table reads of the whole batch back to back, the rare entries behind one test ----
+            unsigned v[SE_K1C_BATCH], e[SE_K1C_BATCH], mir = 0u, unknown = 0u;   // unknown bit u: a raw id the table does not know (reads as NULL)
 #pragma unroll
-            for (int u = 0; u < SE_K1C_BATCH; ++u) {                       // ---- transitions + write-back
+            for (int u = 0; u < SE_K1C_BATCH; ++u) {
+                const unsigned vmax = max(max(a[u], b[u]), max(c[u], d[u]));
+                if (!(cb + u < c_end && (cb + u) * 32 + lane < nbx)) {
+                    v[u] = 0u;                                             // no block here: entry 0 (all EMPTY), nothing written
+                } else if (vmax >= (unsigned)SE_N_MATERIALS) {
+                    unknown |= 1u << u;
+                    v[u] = se_clamp_id(a[u]) | (se_clamp_id(b[u]) << 8) | (se_clamp_id(c[u]) << 16) | (se_clamp_id(d[u]) << 24);
+                } else {
+                    v[u] = __byte_perm(__byte_perm(a[u], b[u], 0x0040), __byte_perm(c[u], d[u], 0x0040), 0x5410);
+                }
+                const unsigned seed = (unsigned)(2 * ((cb + u) * 32 + lane) - ox) * 461u + rowseed;
+                const bool mirror = se_mirror_bit(seed * 213u);
+                mir |= mirror ? (1u << u) : 0u;
+#if SE_LUT_TWO_TABLES
+                e[u] = se_tab_entry(tab, se_idx4(v[u]) + (mirror ? (unsigned)SE_N4 : 0u));
+#else
+                e[u] = se_tab_entry(tab, se_idx4(__byte_perm(v[u], 0u, mirror ? 0x2301u : 0x3210u)));
+#endif
+            }
+            unsigned any = 0u;
+#pragma unroll
+            for (int u = 0; u < SE_K1C_BATCH; ++u) any |= e[u];
+            if (any & SE_E_SPECIAL) {
+#pragma unroll
+                for (int u = 0; u < SE_K1C_BATCH; ++u)
+                    if ((e[u] & (SE_E_SPECIAL | SE_E_SLOW)) == SE_E_SPECIAL) {
+                        const unsigned seed = (unsigned)(2 * ((cb + u) * 32 + lane) - ox) * 461u + rowseed;
+                        const unsigned u1 = se_hashi(seed * 2131u);
+                        do {
+                            unsigned thr, ea, eb;
+                            se_tab_pool(tab, e[u] & SE_E_INDEX, thr, ea, eb);
+                            e[u] = (u1 <= thr) ? ea : eb;
+                        } while (e[u] & SE_E_SPECIAL);
+                    }
+#if !SE_LUT_TWO_TABLES
+#pragma unroll
+                for (int u = 0; u < SE_K1C_BATCH; ++u)
+                    if (e[u] & SE_E_SPECIAL) {
+                        const unsigned seed = (unsigned)(2 * ((cb + u) * 32 + lane) - ox) * 461u + rowseed;
+                        e[u] = se_block_special(e[u], v[u], seed, ((mir >> u) & 1u) ? 0x2301u : 0x3210u, 0, 0, 0, tab, fat_sm);
+                    }
+#endif
+            }
+#pragma unroll
+            for (int u = 0; u < SE_K1C_BATCH; ++u) {                       // ---- write-back of the cells that changed
                 const int bx = (cb + u) * 32 + lane;
                 const int x0 = 2 * bx - ox;
                 if (cb + u < c_end && bx < nbx) {
-                    const unsigned v = se_clamp_id(a[u]) | (se_clamp_id(b[u]) << 8) | (se_clamp_id(c[u]) << 16) | (se_clamp_id(d[u]) << 24);
-                    const unsigned seed = (unsigned)x0 * 461u + rowseed;
-                    const unsigned nv = se_block_lut(v, seed, x0, y0, p.frame, tab, fat_sm);
-                    const unsigned na = nv & 0xFFu, nb = (nv >> 8) & 0xFFu, nc = (nv >> 16) & 0xFFu, nd = nv >> 24;
+                    const unsigned nv = SE_LUT_TWO_TABLES ? e[u] : __byte_perm(e[u], 0u, ((mir >> u) & 1u) ? 0x2301u : 0x3210u);
 #if !SE_LUT_TWO_TABLES
                     if (CENSUS) {
                         const unsigned cm_cols = (x0 >= 0 ? 5u : 0u) | ((x0 + 1) < p.W ? 10u : 0u);
-                        se_census_block(hist_sm, smem_sa + (unsigned)cx.pop_offset, v, a[u], b[u], c[u], d[u], nv, cm_rows & cm_cols);
+                        se_census_block(hist_sm, smem_sa + (unsigned)cx.pop_offset, v[u], a[u], b[u], c[u], d[u], nv, cm_rows & cm_cols);
                     }
 #endif
-                    if (vec_ok) {
-                        if (st0 == 0 && (na != a[u] || nb != b[u])) *reinterpret_cast<uint2*>(base0 + x0) = make_uint2(na, nb);
-                        if (st1 == 0 && (nc != c[u] || nd != d[u])) *reinterpret_cast<uint2*>(base1 + x0) = make_uint2(nc, nd);
-                    } else {
-                        const bool cx0 = x0 >= 0, cx1 = (x0 + 1) < p.W;
-                        if (st0 == 0 && cx0 && na != a[u]) base0[x0] = na;
-                        if (st0 == 0 && cx1 && nb != b[u]) base0[x0 + 1] = nb;
-                        if (st1 == 0 && cx0 && nc != c[u]) base1[x0] = nc;
-                        if (st1 == 0 && cx1 && nd != d[u]) base1[x0 + 1] = nd;
+                    // a cell is written when its id changed -- or when the raw word was an id the table does not know (it is
+                    // NULL from now on, like in the reference: operations.glsl:111 stores the id of what getCell returned)
+                    const unsigned diff = ((unknown >> u) & 1u) ? 0xFFFFFFFFu : (nv ^ v[u]);
+                    if (diff != 0u) {
+                        const unsigned na = nv & 0xFFu, nb = (nv >> 8) & 0xFFu, nc = (nv >> 16) & 0xFFu, nd = nv >> 24;
+                        if (vec_ok) {
+                            if (st0 == 0 && (diff & 0xFFFFu)) *reinterpret_cast<uint2*>(base0 + x0) = make_uint2(na, nb);
+                            if (st1 == 0 && (diff >> 16)) *reinterpret_cast<uint2*>(base1 + x0) = make_uint2(nc, nd);
+                        } else {
+                            const bool cx0 = x0 >= 0, cx1 = (x0 + 1) < p.W;
+                            if (st0 == 0 && cx0 && na != a[u]) base0[x0] = na;
+                            if (st0 == 0 && cx1 && nb != b[u]) base0[x0 + 1] = nb;
+                            if (st1 == 0 && cx0 && nc != c[u]) base1[x0] = nc;
+                            if (st1 == 0 && cx1 && nd != d[u]) base1[x0 + 1] = nd;
+                        }
                     }
                 }
             }
@@ -1256,5 +1333,265 @@ extern "C" __global__ void __launch_bounds__(256) se_build_popbits(unsigned* __r
     if (idx < SE_N4) se_build_popbits_entry(idx, popbits);
 }
 #endif
+
+// =============================================================================================
+// K3f: Margolus step + modification override + lighting relaxation in ONE pass over the grid (the reference's single
+// dispatch, falling_sand.glsl:737-799 + operations.glsl:99-171), for table-eligible rule sets.  HBM-bound by design:
+// 4 B old id + 16 B old light in, 4 B new id + 16 B new light out per cell = the 40 algorithmic bytes.
+//
+// Persistent CTAs (one per SM, 512 threads) walk 64 x 32 tiles.  The inputs of a tile -- light and ids of the tile and
+// its one-cell ring -- arrive by TMA (cp.async.bulk.tensor: one 3-D box of float4 light, one 2-D box of ids, out-of-grid
+// elements zero-filled) into one of two shared-memory buffers, signalled by an mbarrier; the loads of tile i+1 are
+// issued before tile i is touched, so HBM latency is hidden by a whole tile of work without a single register staged.
+// Per tile, three phases:
+//   A  every ring + tile cell: old id -> one byte (unknown ids NULL, WALL outside the grid, MISSING inside the grid but
+//      outside a strip's buffer) and the reader-independent neighbour term (rgb * keep * a, a) written over the light
+//   B  the 2x2 blocks that cover the tile (they lie inside tile + ring: the block offset is 0 or 1) through the
+//      transition table, in place in the byte array; blocks cut by a tile edge are evaluated by both CTAs
+//      (deterministic: RAND depends on position and frame only)
+//   C  every tile cell: new id (table result, overridden by the culled modification list), stored; the eight
+//      neighbour terms combined in the shader's order with a sliding 3 x 3 window (as in se_light), stored
+// =============================================================================================
+#define SE_LF_TW 64
+#define SE_LF_TH 32
+#define SE_LF_LSTRIDE (SE_LF_TW + 2)                 // light / term row stride (float4)
+#define SE_LF_ISTRIDE (SE_LF_TW + 4)                 // id row stride (elements): the TMA box row must be a multiple of 16 bytes
+#define SE_LF_LIGHT_BYTES ((SE_LF_TH + 2) * SE_LF_LSTRIDE * 16)
+#define SE_LF_IDS_BYTES ((SE_LF_TH + 2) * SE_LF_ISTRIDE * 4)
+#define SE_LF_IDS_OFFSET ((SE_LF_LIGHT_BYTES + 127) / 128 * 128)
+#define SE_LF_BUF_BYTES ((SE_LF_IDS_OFFSET + SE_LF_IDS_BYTES + 127) / 128 * 128)
+#define SE_LF_MISSING 0xFFu
+#define SE_LF_THREADS 512
+
+struct alignas(64) SeTensorMap { unsigned long long opaque[16]; };   // CUtensorMap (cuda.h), encoded by the host
+
+struct SeLitParams {
+    unsigned* new_cells;     // ids after the step (the other ping-pong buffer), local rows
+    float4* light_out;
+    int W, Hl, gy0, Hg;
+    int frame;
+    int n_mods;              // already cut at the first mod_size == 0
+    const SeMod* mods;
+    int table_bytes, pool_offset;
+    const unsigned* lut;
+    const unsigned* pool;
+    int tiles_x, tiles_y;
+    int buf_offset;          // byte offset of the first input buffer in dynamic shared memory (128-aligned, behind the staged table)
+};
+
+// can record m touch a cell of the rectangle?  (both shapes lie inside the square |dx|,|dy| <= size; negative sizes never
+// match; 64-bit sums: a position near INT_MAX must not wrap around)
+static __device__ __forceinline__ bool se_mod_touches(const SeMod& m, int x_lo, int x_hi, int y_lo, int y_hi) {
+    const long long px = m.px, py = m.py, sz = m.size;
+    return m.size >= 0 && px + sz >= x_lo && px - sz <= x_hi && py + sz >= y_lo && py - sz <= y_hi;
+}
+
+static __device__ __forceinline__ void se_mbar_init(unsigned mbar_sa, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar_sa), "r"(count) : "memory"); }
+static __device__ __forceinline__ void se_mbar_expect_tx(unsigned mbar_sa, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar_sa), "r"(bytes) : "memory");
+}
+static __device__ __forceinline__ void se_mbar_wait(unsigned mbar_sa, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" :: "r"(mbar_sa), "r"(parity) : "memory");
+}
+static __device__ __forceinline__ void se_tma_load_2d(unsigned dst_sa, const SeTensorMap* tm, int c0, int c1, unsigned mbar_sa) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst_sa), "l"(reinterpret_cast<unsigned long long>(tm)), "r"(c0), "r"(c1), "r"(mbar_sa) : "memory");
+}
+static __device__ __forceinline__ void se_tma_load_3d(unsigned dst_sa, const SeTensorMap* tm, int c0, int c1, int c2, unsigned mbar_sa) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(dst_sa), "l"(reinterpret_cast<unsigned long long>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(mbar_sa) : "memory");
+}
+
+extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const __grid_constant__ SeTensorMap tm_cells, const __grid_constant__ SeTensorMap tm_light,
+                                                                              const SeLitParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ unsigned fat_sm[256];
+    __shared__ SeMod mods_sm[256];
+    __shared__ int warp_counts[SE_LF_THREADS / 32];
+    __shared__ __align__(8) unsigned long long mbar[2];
+    __shared__ __align__(4) unsigned char ids8[(SE_LF_TH + 2) * SE_LF_ISTRIDE];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned smem_sa;
+    asm volatile("mov.u32 %0, %1;" : "=r"(smem_sa) : "r"((unsigned)__cvta_generic_to_shared(smem)));
+#if SE_LUT_MODE == 1
+    {
+        const uint4* lut4 = reinterpret_cast<const uint4*>(p.lut);
+        const int n4 = (p.table_bytes + 15) >> 4;
+        for (int i = tid; i < n4; i += blockDim.x) {
+            const uint4 v = __ldg(lut4 + i);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(smem_sa + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        }
+    }
+    const SeTab tab{smem_sa, smem_sa + (unsigned)p.pool_offset};
+#else
+    const SeTab tab{p.lut, p.pool};
+#endif
+    if (tid < 256) fat_sm[tid] = se_fat_table[tid];
+    const unsigned mbar_sa = (unsigned)__cvta_generic_to_shared(mbar);
+    if (tid == 0) {
+        se_mbar_init(mbar_sa, 1u);
+        se_mbar_init(mbar_sa + 8u, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int n_tiles = p.tiles_x * p.tiles_y;
+    const unsigned buf0_sa = smem_sa + (unsigned)p.buf_offset;
+    auto issue = [&](int t, int buf) {                       // one thread: both boxes of tile t into buffer `buf`
+        const int by = t / p.tiles_x, bx = t - by * p.tiles_x;
+        const unsigned dst = buf0_sa + (unsigned)buf * SE_LF_BUF_BYTES, mb = mbar_sa + 8u * (unsigned)buf;
+        se_mbar_expect_tx(mb, SE_LF_LIGHT_BYTES + SE_LF_IDS_BYTES);
+        se_tma_load_3d(dst, &tm_light, 0, bx * SE_LF_TW - 1, by * SE_LF_TH - 1, mb);
+        se_tma_load_2d(dst + SE_LF_IDS_OFFSET, &tm_cells, bx * SE_LF_TW - 1, by * SE_LF_TH - 1, mb);
+    };
+    if (tid == 0 && (int)blockIdx.x < n_tiles) issue((int)blockIdx.x, 0);
+
+    int ox, oy;
+    se_margolus_offset(p.frame, ox, oy);
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int by = t / p.tiles_x, bx = t - by * p.tiles_x;
+        const int x_org = bx * SE_LF_TW - 1, yl_org = by * SE_LF_TH - 1;      // ring cell (0, 0): column / local row
+        // the next tile's loads go out before this tile is touched (its buffer was released by the barrier that ended the
+        // previous iteration; the proxy fence orders that iteration's generic writes before the async ones)
+        if (tid == 0 && t + (int)gridDim.x < n_tiles) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(t + (int)gridDim.x, buf ^ 1);
+        }
+        // modification list culled against this tile, order kept (last match wins, falling_sand.glsl:764-773)
+        int n_cull = 0;
+        if (p.n_mods > 0) {
+            const int x_lo = bx * SE_LF_TW, y_lo = p.gy0 + by * SE_LF_TH;
+            bool keep = false;
+            SeMod m;
+            if (tid < p.n_mods) { m = p.mods[tid]; keep = se_mod_touches(m, x_lo, x_lo + SE_LF_TW - 1, y_lo, y_lo + SE_LF_TH - 1); }
+            const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
+            if (lane == 0) warp_counts[warp] = __popc(ballot);
+            __syncthreads();
+            int base = 0;
+            for (int w = 0; w < SE_LF_THREADS / 32; ++w) { if (w < warp) base += warp_counts[w]; n_cull += warp_counts[w]; }
+            if (keep) mods_sm[base + __popc(ballot & ((1u << lane) - 1u))] = m;
+        }
+        se_mbar_wait(mbar_sa + 8u * (unsigned)buf, (unsigned)(it >> 1) & 1u);
+        const unsigned light_sa = buf0_sa + (unsigned)buf * SE_LF_BUF_BYTES, ids_sa = light_sa + SE_LF_IDS_OFFSET;
+
+        // ---- phase A: id bytes and neighbour terms of every ring + tile cell ----
+        for (int c = tid; c < (SE_LF_TH + 2) * SE_LF_LSTRIDE; c += SE_LF_THREADS) {
+            const int i = c / SE_LF_LSTRIDE, j = c - i * SE_LF_LSTRIDE;
+            const int x = x_org + j, yl = yl_org + i, y = p.gy0 + yl;
+            const bool in_grid = x >= 0 && x < p.W && y >= 0 && y < p.Hg;
+            const bool local = in_grid && yl >= 0 && yl < p.Hl;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            unsigned idb = in_grid ? SE_LF_MISSING : 2u;                     // WALL outside the grid (operations.glsl:45-51)
+            if (local) {
+                const unsigned id = se_lds_u32(ids_sa + 4u * (unsigned)(i * SE_LF_ISTRIDE + j));
+                float4 li;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(li.x), "=f"(li.y), "=f"(li.z), "=f"(li.w) : "r"(light_sa + 16u * (unsigned)c));
+                const unsigned nf = fat_sm[id < 255u ? id : 255u];
+                const float keep = (nf & SE_F_OBSTACLE) ? 0.0f : 1.0f;     // vec4(vec3(float(!obstacle)), 1.0), :498
+                const float la = li.w;
+                v = make_float4((li.x * keep) * la, (li.y * keep) * la, (li.z * keep) * la, la);
+                idb = se_clamp_id(id);
+            }
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(light_sa + 16u * (unsigned)c), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            ids8[i * SE_LF_ISTRIDE + j] = (unsigned char)idb;
+        }
+        __syncthreads();
+
+        // ---- phase B: the blocks that cover the tile, in place in ids8 ----
+        {
+            const int nbx = SE_LF_TW / 2 + ox, nby = SE_LF_TH / 2 + oy;
+            const unsigned fterm = (unsigned)p.frame * (2131u * 2131u);
+            for (int b = tid; b < nbx * nby; b += SE_LF_THREADS) {
+                const int bj = b / nbx, bi = b - bj * nbx;
+                const int cx = 2 * bi + 1 - ox, cy = 2 * bj + 1 - oy;      // ring coordinates of the block's top-left cell
+                unsigned char* q = ids8 + cy * SE_LF_ISTRIDE + cx;
+                const unsigned a = q[0], bb = q[1], c = q[SE_LF_ISTRIDE], d = q[SE_LF_ISTRIDE + 1];
+                if ((a | bb | c | d) & 0x80u) continue;                    // a row of the block is not in the local buffer: skipped (see K1a)
+                const unsigned v = a | (bb << 8) | (c << 16) | (d << 24);
+                const unsigned seed = (unsigned)(x_org + cx) * 461u + (unsigned)(p.gy0 + yl_org + cy) * 2131u + fterm;
+                const unsigned nv = se_block_lut(v, seed, 0, 0, 0, tab, fat_sm);
+                q[0] = (unsigned char)(nv & 0xFFu); q[1] = (unsigned char)((nv >> 8) & 0xFFu);
+                q[SE_LF_ISTRIDE] = (unsigned char)((nv >> 16) & 0xFFu); q[SE_LF_ISTRIDE + 1] = (unsigned char)(nv >> 24);
+            }
+        }
+        __syncthreads();
+
+        // ---- phase C: new id + light of every tile cell: column tid & 31 of half (warp & 1), rows 4 * (warp >> 1) .. + 3 ----
+        {
+            const bool interior = x_org >= 0 && x_org + SE_LF_TW + 1 < p.W && yl_org >= 0 && yl_org + SE_LF_TH + 1 < p.Hl &&
+                                  p.gy0 + yl_org >= 0 && p.gy0 + yl_org + SE_LF_TH + 1 < p.Hg;
+            const int tx = lane + 32 * (warp & 1), row0 = (warp >> 1) * 4;
+            const int x = bx * SE_LF_TW + tx;
+            if (x < p.W) {
+                const unsigned tp = light_sa + 16u * (unsigned)(row0 * SE_LF_LSTRIDE + tx);      // term (row0 - 1, tx - 1) of the tile
+#define SE_LF_LDT(dst, off) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dst.x), "=f"(dst.y), "=f"(dst.z), "=f"(dst.w) : "r"(tp + 16u * (unsigned)(off)))
+                float4 a0, a1, a2, b0, b1, b2;
+                SE_LF_LDT(a0, 0); SE_LF_LDT(a1, 1); SE_LF_LDT(a2, 2);
+                SE_LF_LDT(b0, SE_LF_LSTRIDE); SE_LF_LDT(b1, SE_LF_LSTRIDE + 1); SE_LF_LDT(b2, SE_LF_LSTRIDE + 2);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int yl = by * SE_LF_TH + row0 + i;
+                    if (yl >= p.Hl) break;
+                    float4 c0, c1, c2;
+                    SE_LF_LDT(c0, (i + 2) * SE_LF_LSTRIDE); SE_LF_LDT(c1, (i + 2) * SE_LF_LSTRIDE + 1); SE_LF_LDT(c2, (i + 2) * SE_LF_LSTRIDE + 2);
+                    const int y = p.gy0 + yl;
+                    const size_t idx = (size_t)yl * p.W + x;
+                    unsigned id = ids8[(row0 + i + 1) * SE_LF_ISTRIDE + tx + 1];
+                    if (n_cull) {
+                        unsigned m;
+                        if (se_mod_lookup(mods_sm, n_cull, x, y, m)) id = m;
+                    }
+                    if (id != SE_LF_MISSING) p.new_cells[idx] = id;        // (a MISSING cell lies in a block row the strip cannot compute: left alone, see K1a)
+                    const unsigned me = id < 255u ? id : 255u;
+                    float4 light;
+                    if (fat_sm[me] & SE_F_EMISSIVE) {                       // operations.glsl:126-127
+                        light = make_float4(se_emission_table[me * 4 + 0], se_emission_table[me * 4 + 1], se_emission_table[me * 4 + 2], se_emission_table[me * 4 + 3]);
+                    } else if (y == 0) {                                    // :128-129
+                        light = make_float4(1.0f, 1.0f, 1.0f, 0.999999f);
+                    } else {
+                        float4 avg = make_float4(0.f, 0.f, 0.f, 0.f), mx = make_float4(0.f, 0.f, 0.f, 0.f);
+                        float max_falloff = 0.0f;
+                        if (interior) {
+                            // DOWN, UP, DOWNLEFT, UPLEFT, DOWNRIGHT, UPRIGHT, RIGHT, LEFT (math.glsl:154-166)
+                            SE_LIGHT_ACC(c1) SE_LIGHT_ACC(a1) SE_LIGHT_ACC(c0) SE_LIGHT_ACC(a0)
+                            SE_LIGHT_ACC(c2) SE_LIGHT_ACC(a2) SE_LIGHT_ACC(b2) SE_LIGHT_ACC(b0)
+                            avg.x *= 0.125f; avg.y *= 0.125f; avg.z *= 0.125f; avg.w *= 0.125f;    // num == 8: exact
+                        } else {
+                            const bool up = yl - 1 >= 0 && y - 1 >= 0, down = yl + 1 < p.Hl && y + 1 < p.Hg;
+                            const bool left = x - 1 >= 0, right = x + 1 < p.W;
+                            int num = 0;
+                            if (down) { SE_LIGHT_ACC(c1) ++num; }
+                            if (up) { SE_LIGHT_ACC(a1) ++num; }
+                            if (down && left) { SE_LIGHT_ACC(c0) ++num; }
+                            if (up && left) { SE_LIGHT_ACC(a0) ++num; }
+                            if (down && right) { SE_LIGHT_ACC(c2) ++num; }
+                            if (up && right) { SE_LIGHT_ACC(a2) ++num; }
+                            if (right) { SE_LIGHT_ACC(b2) ++num; }
+                            if (left) { SE_LIGHT_ACC(b0) ++num; }
+                            if (num > 0) {                                  // :516-518
+                                const float dn = (float)num;
+                                avg.x = __fdiv_rn(avg.x, dn); avg.y = __fdiv_rn(avg.y, dn); avg.z = __fdiv_rn(avg.z, dn); avg.w = __fdiv_rn(avg.w, dn);
+                            }
+                        }
+                        light = make_float4(avg.x * 0.5f + mx.x * 0.5f, avg.y * 0.5f + mx.y * 0.5f, avg.z * 0.5f + mx.z * 0.5f, avg.w);   // mix(avg.rgb, max.rgb, 0.5), :521
+                    }
+                    p.light_out[idx] = light;
+                    a0 = b0; a1 = b1; a2 = b2;
+                    b0 = c0; b1 = c1; b2 = c2;
+                }
+#undef SE_LF_LDT
+            }
+        }
+        __syncthreads();                                   // the buffers, ids8 and mods_sm are free for the next tile
+    }
+}
 #endif  // SE_HOST_EMU
 #endif  // SE_LUT_ELIGIBLE

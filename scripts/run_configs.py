@@ -2,7 +2,8 @@
   python scripts/run_configs.py 1        # 256^2, 1000 steps (BASELINE configs[0]): timing + comparison with the reference shader's output
   python scripts/run_configs.py 2        # 4096^2, lighting off, 10k steps (L2-resident)
   python scripts/run_configs.py 4        # 4096^2, brush stamps + explosion every frame, lighting on
-  torchrun ... scripts/run_configs.py 5  # synthetic 64-material rule set, 65536^2 over the ranks (K1a path)
+  torchrun ... scripts/run_configs.py 5  # synthetic 64-material rule set, 65536^2 over the ranks (table in global memory; env SE_LUT_FORCE_MODE=0: generated code)
+  SE_CFG5_SIZE=16384 python scripts/run_configs.py 5      # the same rule set on one GPU
 """
 import json
 import os
@@ -133,24 +134,31 @@ def config5():
     K = 64
     text, ids, mix = synthetic_rule_set(64, 28, seed=5)
     rules = se.parse_string(text)
-    strip = StripSimulation(rules, (S, S), halo_rows=32, device=local)
+    mode = int(rules.cuda_header.split("#define SE_LUT_MODE ")[1].split()[0])
+    strip = StripSimulation(rules, (S, S), halo_rows=34, device=local)
     st = torch.cuda.Stream(); torch.cuda.set_stream(st); strip.sim.set_stream(st.cuda_stream)
     rows = strip.row_end - strip.row_begin
     g = synthetic_grid(S, S, 5, mix=mix, ids=ids, row_begin=strip.row_begin, row_end=strip.row_end)
     strip.upload_cells(g); strip.params.frame = 1
     strip.step(32)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    if world > 1: dist.barrier()
-    e0.record(st); strip.step(K); e1.record(st); torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device="cuda")
+    times = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if world > 1: dist.barrier()
+        e0.record(st); strip.step(K); e1.record(st); torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1) / 1e3)
+    t = torch.tensor(times, dtype=torch.float64, device="cuda")
     if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t = t.median()
     census = torch.from_numpy(strip.census().astype(np.int64)).cuda()
     if world > 1: dist.all_reduce(census)
     if rank == 0:
         tt = float(t.item())
         print(json.dumps({"config": 5, "workload": f"synthetic 64-material rule set (28 rules, LEFT/RIGHT, depth-6 types), {S}x{S} over {world} GPU(s), seed 5",
-                          "kernel": "se_step_inplace (generated code; 64 materials are not table-eligible)", "steps": K, "gcell_per_s": round(S * S * K / tt / 1e9, 1),
+                          "kernel": {0: "se_step_inplace (generated code, one step per launch)", 1: "se_step_tiles (table in shared memory)",
+                                     2: "se_step_tiles (one transition table per view in global memory: 2 x 64^4 x 4 B = 134 MB, L2 / HBM resident)"}[mode],
+                          "steps": K, "repetitions": 3, "gcell_per_s": round(S * S * K / tt / 1e9, 1),
                           "ms_per_step": round(tt / K * 1e3, 4), "roofline_frac_8B_per_gpu": round(8.0 * S * S * K / tt / 1e9 / 6549.8 / world, 4),
                           "cells_total": int(census.sum().item()), "cells_expected": S * S}), flush=True)
     strip.close()
