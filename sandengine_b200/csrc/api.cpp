@@ -75,6 +75,7 @@ struct Driver {
     decltype(&cuStreamWriteValue32) StreamWriteValue32 = nullptr;
     decltype(&cuStreamWaitValue32) StreamWaitValue32 = nullptr;
     decltype(&cuOccupancyMaxActiveBlocksPerMultiprocessor) OccupancyMaxActiveBlocks = nullptr;
+    decltype(&cuTensorMapEncodeTiled) TensorMapEncodeTiled = nullptr;
     bool ok = false;
     std::string why;
 };
@@ -98,7 +99,8 @@ Driver& driver() {
                get("cuLaunchCooperativeKernel", (void**)&d.LaunchCooperativeKernel) &&
                get("cuFuncSetAttribute", (void**)&d.FuncSetAttribute) && get("cuGetErrorString", (void**)&d.GetErrorString) &&
                get("cuStreamWriteValue32", (void**)&d.StreamWriteValue32) && get("cuStreamWaitValue32", (void**)&d.StreamWaitValue32) &&
-               get("cuOccupancyMaxActiveBlocksPerMultiprocessor", (void**)&d.OccupancyMaxActiveBlocks);
+               get("cuOccupancyMaxActiveBlocksPerMultiprocessor", (void**)&d.OccupancyMaxActiveBlocks) &&
+               get("cuTensorMapEncodeTiled", (void**)&d.TensorMapEncodeTiled);
     });
     return d;
 }
@@ -170,8 +172,6 @@ struct SeLutStepParams {
 };
 struct SeLutCensusParams {
     unsigned long long* census;
-    const unsigned* popbits;
-    int pop_words, pop_offset;
     int own_y0, own_y1;
 };
 struct SeLightParams {
@@ -181,6 +181,24 @@ struct SeLightParams {
     float4* light_out;
     int W, Hl, gy0, Hg;
 };
+
+struct SeLitParams {
+    unsigned* new_cells;
+    float4* light_out;
+    int W, Hl, gy0, Hg;
+    int frame;
+    int n_mods;
+    const SeMod* mods;
+    int table_bytes, pool_offset;
+    const unsigned* lut;
+    const unsigned* pool;
+    int tiles_x, tiles_y;
+    int buf_offset;
+};
+// geometry of se_step_lit (kernels/sand_kernels.cuh: SE_LF_*)
+constexpr int LF_TW = 64, LF_TH = 32;
+constexpr int LF_LIGHT_BYTES = (LF_TH + 2) * (LF_TW + 2) * 16, LF_IDS_BYTES = (LF_TH + 2) * (LF_TW + 8) * 4;
+constexpr int LF_IDS_OFFSET = (LF_LIGHT_BYTES + 127) / 128 * 128, LF_BUF_BYTES = (LF_IDS_OFFSET + LF_IDS_BYTES + 127) / 128 * 128;
 
 // words of the per-sim flag block that sits behind cells[0] in the same allocation (one IPC handle maps both)
 enum : int {
@@ -265,12 +283,16 @@ struct se_sim {
     // (one row every other frame; one row per frame with lighting); the tile kernel refreshes `push_rows` of them
     // in every T-block.  se_sim_step exchanges (device-ordered) whenever the next launch needs more than there is.
     int ghost_valid = 0;
+    // fused step + modifications + lighting (K3f, se_step_lit): tensor maps of the two id buffers and the two light buffers
+    bool fused_light = false;
+    CUfunction f_step_lit = nullptr;
+    CUtensorMap tm_cells[2], tm_light[2];
+    int lf_smem = 0, lf_grid = 0, lf_tiles_x = 0, lf_tiles_y = 0, lf_buf_offset = 0;
     // running census (SE_FLAG_RUNNING_CENSUS, experimental): d_running is valid only between K1c-census steps
     bool running = false, running_valid = false, running_copy_pending = false;
-    CUfunction f_lut_global_census = nullptr, f_build_popbits = nullptr;
-    unsigned* d_popbits = nullptr;
+    CUfunction f_lut_global_census = nullptr;
+    unsigned* d_lut_census = nullptr;      // copy of the table image whose outcomes carry SE_E_POPFLAG (kernels/sand_kernels.cuh)
     unsigned long long* d_running = nullptr;
-    int pop_words = 0, pop_offset = 0;
     cudaEvent_t running_copy_done = nullptr;
     Neighbour nb[2];
     // Device-side exchange protocol: 4 flag words live right behind cells[0] (same allocation, so that one
@@ -463,6 +485,22 @@ int one_step(se_sim* s, bool use_mods, int n_mods) {
         p.out = s->cells[s->cur];
         return launch(s, p.n_mods ? s->f_inplace_mods : s->f_inplace, grid, block, args);
     }
+    if (s->fused_light) {
+        // K3f: one TMA-fed pass reads ids + light of the current buffers and writes the other pair
+        SeLitParams lp;
+        lp.new_cells = s->cells[s->cur ^ 1]; lp.light_out = s->light[s->lcur ^ 1];
+        lp.W = s->W; lp.Hl = s->Hl; lp.gy0 = s->gy0; lp.Hg = s->Hg; lp.frame = frame;
+        lp.n_mods = p.n_mods; lp.mods = s->d_mods;
+        lp.table_bytes = s->table_bytes; lp.pool_offset = s->pool_offset; lp.lut = s->d_lut;
+        lp.pool = s->d_pool ? s->d_pool : s->d_lut + s->pool_offset / 4;      // mode 1: the pool sits behind the table in one image
+        lp.tiles_x = s->lf_tiles_x; lp.tiles_y = s->lf_tiles_y; lp.buf_offset = s->lf_buf_offset;
+        void* fargs[] = {&s->tm_cells[s->cur], &s->tm_light[s->lcur], &lp};
+        int rcf = launch(s, s->f_step_lit, dim3(s->lf_grid), dim3(512), fargs, (unsigned)s->lf_smem);
+        if (rcf) return rcf;
+        s->cur ^= 1;
+        s->lcur ^= 1;
+        return SE_OK;
+    }
     p.in = s->cells[s->cur];
     p.out = s->cells[s->cur ^ 1];
     int rc = launch(s, p.n_mods ? s->f_pingpong_mods : s->f_pingpong, grid, block, args);
@@ -622,7 +660,7 @@ int se_sim_destroy(se_sim* s) try {
     if (s->d_lut) cudaFree(s->d_lut);
     if (s->d_pool) cudaFree(s->d_pool);
     if (s->d_tile_done) cudaFree(s->d_tile_done);
-    if (s->d_popbits) cudaFree(s->d_popbits);
+    if (s->d_lut_census) cudaFree(s->d_lut_census);
     if (s->d_running) cudaFree(s->d_running);
     if (s->running_copy_done) cudaEventDestroy(s->running_copy_done);
     if (s->mod && driver().ok) driver().ModuleUnload(s->mod);
@@ -714,7 +752,7 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
     // ---- transition-table kernels: K1b (tiles + temporal blocking) and K1c (one step, per frame) ----------------
     // Used for steps without modifications when lighting is off, the rule set is table-eligible (codegen.h) and rows
     // are 16-byte aligned.  temporal_block == 1 forces the per-step generated-code kernel K1a.
-    if (rules->cr.lut_eligible && !s->lighting && (s->W % 4) == 0 && prm->temporal_block != 1) {
+    if (rules->cr.lut_eligible && (s->W % 4) == 0 && prm->temporal_block != 1) {
         const int N = rules->cr.tables.n_materials;
         const size_t N4 = (size_t)N * N * N * N;
         const size_t NE = N4 * (size_t)rules->cr.lut_tables;            // table entries (one table per view for Left/Right rule sets and in mode 2)
@@ -749,8 +787,8 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
                 SE_CUDA_S(cudaMemsetAsync(s->d_lut, 0, image, s->stream));
                 unsigned* base = s->d_lut;
                 unsigned* pool = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(s->d_lut) + pool_off);
-                unsigned ucap = (unsigned)cap;
-                void* bargs[] = {&base, &pool, &d_counter, &ucap};
+                unsigned ucap = (unsigned)cap, flag_pop = 0;
+                void* bargs[] = {&base, &pool, &d_counter, &ucap, &flag_pop};
                 SE_TRY(launch(s, s->f_build_lut, dim3((unsigned)((NE + 255) / 256)), dim3(256), bargs));
                 SE_CUDA_S(cudaMemcpyAsync(&n_pool, d_counter, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
                 SE_CUDA_S(cudaStreamSynchronize(s->stream));
@@ -766,8 +804,8 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
             SE_CUDA_S(cudaMalloc(&s->d_lut, NE * 4));
             unsigned* base = s->d_lut;
             unsigned* pool = nullptr;
-            unsigned ucap = 0;
-            void* bargs[] = {&base, &pool, &d_counter, &ucap};
+            unsigned ucap = 0, flag_pop = 0;
+            void* bargs[] = {&base, &pool, &d_counter, &ucap, &flag_pop};
             SE_TRY(launch(s, s->f_build_lut, dim3((unsigned)((NE + 255) / 256)), dim3(256), bargs));
             SE_CUDA_S(cudaMemcpyAsync(&n_pool, d_counter, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
             SE_CUDA_S(cudaStreamSynchronize(s->stream));
@@ -786,9 +824,39 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
         }
         cudaFree(d_counter);
         const int owned = s->row_end - s->row_begin;
+        // ---- K3f: with lighting on, step + override + lighting in one TMA-fed kernel (se_step_lit) ----
+        if (ok && s->lighting && !std::getenv("SE_NO_FUSED_LIT")) {     // env: A/B against the two-kernel path
+            s->lf_buf_offset = 0;                                        // the table is read from global memory: shared memory holds the two input buffers only
+            s->lf_smem = 2 * LF_BUF_BYTES + 128;                         // + 128: the kernel aligns its buffers itself
+            if (2 * (s->lf_smem + 13 * 1024) <= smem_optin) {            // two CTAs per SM (+ static: modification list, id bytes, fat table)
+                SE_CU_S(driver().ModuleGetFunction(&s->f_step_lit, s->mod, "se_step_lit"));
+                SE_CU_S(driver().FuncSetAttribute(s->f_step_lit, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->lf_smem));
+                s->lf_tiles_x = (s->W + LF_TW - 1) / LF_TW;
+                s->lf_tiles_y = (s->Hl + LF_TH - 1) / LF_TH;
+                s->lf_grid = (int)std::min<long long>((long long)std::max(1, 2 * n_sm / s->device_share), (long long)s->lf_tiles_x * s->lf_tiles_y);
+                bool maps_ok = true;
+                for (int b = 0; b < 2 && maps_ok; ++b) {
+                    // ids: 3-D [Hl][W/4][4] u32 (groups of four cells = 16 bytes, like a float4), box 4 x 18 x 34: the box starts
+                    // four columns left of the tile; out-of-range elements read 0.  (A 2-D box with a 272-byte row is accepted
+                    // by the encoder and then faults as an illegal instruction: box rows stay at 16 bytes.)
+                    const cuuint64_t cdim[3] = {4, (cuuint64_t)s->W / 4, (cuuint64_t)s->Hl}, cstr[2] = {16, (cuuint64_t)s->W * 4};
+                    const cuuint32_t cbox[3] = {4, (LF_TW + 8) / 4, LF_TH + 2}, cel[3] = {1, 1, 1};
+                    maps_ok = driver().TensorMapEncodeTiled(&s->tm_cells[b], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, s->cells[b], cdim, cstr, cbox, cel,
+                                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                    // light: 3-D [Hl][W][4] f32, box 4 x 66 x 34 (a float4 per cell)
+                    const cuuint64_t ldim[3] = {4, (cuuint64_t)s->W, (cuuint64_t)s->Hl}, lstr[2] = {16, (cuuint64_t)s->W * 16};
+                    const cuuint32_t lbox[3] = {4, LF_TW + 2, LF_TH + 2}, lel[3] = {1, 1, 1};
+                    maps_ok = maps_ok && driver().TensorMapEncodeTiled(&s->tm_light[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s->light[b], ldim, lstr, lbox, lel,
+                                                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                }
+                s->fused_light = maps_ok;
+            }
+        }
         // strips: the tile kernel reads HY ghost rows and pushes as many into the neighbours
         if (ok && s->is_strip() && ((int)prm->halo_rows < s->HY || owned < 2 * s->HY)) ok = false;
-        if (ok) {
+        if (ok && !s->lighting) {
             int PH_max = (((s->smem_budget - s->tile_offset) / 2) / 256) & ~1;
             PH_max = std::min(PH_max, 320);                            // taller tiles: fewer, coarser work items for the same bytes
             if (const char* pm = std::getenv("SE_TILE_PH_MAX")) PH_max = std::min(PH_max, std::max(4 * T + 16, std::atoi(pm) & ~1));   // experiments only
@@ -811,19 +879,25 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
             SE_CUDA_S(cudaMalloc(&s->d_tile_done, (size_t)s->tile_done_cap * sizeof(unsigned)));
             SE_CUDA_S(cudaMemsetAsync(s->d_tile_done, 0, (size_t)s->tile_done_cap * sizeof(unsigned), s->stream));
             s->tiled = true;
-            if ((prm->flags & SE_FLAG_RUNNING_CENSUS) && rules->cr.lut_tables == 1) {
+            if ((prm->flags & SE_FLAG_RUNNING_CENSUS) && rules->cr.lut_tables == 1 && s->lut_mode == 1) {
+                // the census variant of K1c stages a second image of the table: same entries, population-changing outcomes flagged
                 SE_CU_S(driver().ModuleGetFunction(&s->f_lut_global_census, s->mod, "se_step_lut_global_census"));
-                SE_CU_S(driver().ModuleGetFunction(&s->f_build_popbits, s->mod, "se_build_popbits"));
-                s->pop_words = (int)((N4 + 31) / 32);
-                s->pop_offset = s->tile_offset;                       // behind the staged table (16-aligned)
-                SE_CUDA_S(cudaMalloc(&s->d_popbits, (size_t)s->pop_words * sizeof(unsigned)));
-                SE_CUDA_S(cudaMemsetAsync(s->d_popbits, 0, (size_t)s->pop_words * sizeof(unsigned), s->stream));
+                const size_t image = (size_t)s->tile_offset + 16;
+                SE_CUDA_S(cudaMalloc(&s->d_lut_census, image));
+                SE_CUDA_S(cudaMemsetAsync(s->d_lut_census, 0, image, s->stream));
+                unsigned* d_cnt = nullptr;
+                SE_CUDA_S(cudaMalloc(&d_cnt, sizeof(unsigned)));
+                SE_CUDA_S(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned), s->stream));
+                unsigned* base = s->d_lut_census;
+                unsigned* pool = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(s->d_lut_census) + s->pool_offset);
+                unsigned ucap = (unsigned)((s->table_bytes - s->pool_offset) / 16), flag_pop = 1;
+                void* cargs[] = {&base, &pool, &d_cnt, &ucap, &flag_pop};
+                SE_TRY(launch(s, s->f_build_lut, dim3((unsigned)((NE + 255) / 256)), dim3(256), cargs));
+                SE_CUDA_S(cudaStreamSynchronize(s->stream));
+                cudaFree(d_cnt);
                 SE_CUDA_S(cudaMalloc(&s->d_running, 256 * sizeof(unsigned long long)));
                 SE_CUDA_S(cudaEventCreateWithFlags(&s->running_copy_done, cudaEventDisableTiming));
-                void* pargs[] = {&s->d_popbits};
-                SE_TRY(launch(s, s->f_build_popbits, dim3((unsigned)((N4 + 255) / 256)), dim3(256), pargs));
-                SE_CU_S(driver().FuncSetAttribute(s->f_lut_global_census, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
-                                                  s->pop_offset + ((s->pop_words * 4 + 15) & ~15)));
+                SE_CU_S(driver().FuncSetAttribute(s->f_lut_global_census, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->k1c_smem));
                 s->running = true;
             }
         }
@@ -885,9 +959,10 @@ int se_sim_step(se_sim* s, uint32_t n_steps) try {
                 void* largs[] = {&lp};
                 int rc;
                 if (s->running && s->running_valid) {
-                    SeLutCensusParams cx{s->d_running, s->d_popbits, s->pop_words, s->pop_offset, s->row_begin, s->row_end};
+                    SeLutCensusParams cx{s->d_running, s->row_begin, s->row_end};
+                    lp.lut = s->d_lut_census;
                     void* cargs[] = {&lp, &cx};
-                    rc = launch(s, s->f_lut_global_census, dim3(s->k1c_grid), dim3(512), cargs, (unsigned)(s->pop_offset + ((s->pop_words * 4 + 15) & ~15)));
+                    rc = launch(s, s->f_lut_global_census, dim3(s->k1c_grid), dim3(512), cargs, (unsigned)s->k1c_smem);
                 } else {
                     rc = launch(s, s->f_lut_global, dim3(s->k1c_grid), dim3(512), largs, (unsigned)s->k1c_smem);   // SE_K1C_THREADS
                 }
@@ -939,8 +1014,22 @@ int se_sim_step(se_sim* s, uint32_t n_steps) try {
             void* targs[] = {&tp};
             const long long items = (long long)nblk * s->tiles_x * g.tiles_y;
             const int grid = (int)std::min<long long>((long long)s->tile_grid, (items + 1) / 2);
-            int rc = launch(s, s->f_tiles, dim3(grid), dim3(1024), targs, (unsigned)(s->tile_offset + 2 * 256 * g.PH), s->coop);
-            if (rc) return rc;
+            const unsigned smem_bytes = (unsigned)(s->tile_offset + 2 * 256 * g.PH);
+            if (s->coop) {
+                // A cooperative launch can be refused (CUDA_ERROR_COOPERATIVE_LAUNCH_TOO_LARGE under an MPS partition that holds
+                // fewer CTAs than the device).  The same grid launched normally could deadlock on its own flags, so from then
+                // on every launch carries ONE T-block: its tiles wait on no flag of the same grid.
+                const CUresult cr = driver().LaunchCooperativeKernel(s->f_tiles, (unsigned)grid, 1, 1, 1024, 1, 1, smem_bytes, (CUstream)s->stream, targs);
+                if (cr != CUDA_SUCCESS) {
+                    s->coop = false;
+                    (void)cudaGetLastError();
+                    continue;                                           // plan this run again, one T-block per launch
+                }
+                s->launches++;
+            } else {
+                int rc = launch(s, s->f_tiles, dim3(grid), dim3(1024), targs, smem_bytes, false);
+                if (rc) return rc;
+            }
             s->frame += (int)run;
             s->tile_seq += (unsigned)nblk;
             s->tile_queue += (unsigned)items + 2u * (unsigned)grid;      // every half draws exactly one number past the end

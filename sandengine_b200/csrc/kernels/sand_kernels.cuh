@@ -196,8 +196,10 @@ static __device__ __forceinline__ int se_cull_mods(const SeStepParams& p, SeMod*
     SeMod m;
     if (t < p.n_mods) {
         m = p.mods[t];
-        // both shapes are contained in the square |dx| <= size, |dy| <= size (negative sizes never match)
-        keep = m.size >= 0 && m.px + m.size >= x_lo && m.px - m.size <= x_hi && m.py + m.size >= y_lo && m.py - m.size <= y_hi;
+        // both shapes are contained in the square |dx| <= size, |dy| <= size (negative sizes never match); 64-bit sums: a
+        // position near INT_MAX must not wrap around and drop a record the shader's per-cell test would still match
+        const long long px = m.px, py = m.py, sz = m.size;
+        keep = m.size >= 0 && px + sz >= x_lo && px - sz <= x_hi && py + sz >= y_lo && py - sz <= y_hi;
     }
     const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
     const int warp = t >> 5, lane = t & 31;
@@ -515,10 +517,23 @@ extern "C" __global__ void __launch_bounds__(256) se_fill_cells(unsigned* cells,
 static __device__ __forceinline__ unsigned se_ids4(unsigned s, unsigned r, unsigned d, unsigned dr) {
     return SE_ID(s) | (SE_ID(r) << 8) | (SE_ID(d) << 16) | (SE_ID(dr) << 24);
 }
+// the four ids of a block as a sorted tuple: two blocks hold the same population iff these are equal
+static __device__ __forceinline__ unsigned se_sorted4(unsigned a, unsigned b, unsigned c, unsigned d) {
+    unsigned t;
+    if (a > b) { t = a; a = b; b = t; }
+    if (c > d) { t = c; c = d; d = t; }
+    if (a > c) { t = a; a = c; c = t; }
+    if (b > d) { t = b; b = d; d = t; }
+    if (b > c) { t = b; b = c; c = t; }
+    return a | (b << 8) | (c << 16) | (d << 24);
+}
+#define SE_E_POPFLAG 0x80u      // census tables only: bit 7 of the first id byte = "this outcome is not a permutation of the state"
 
 // one block state: evaluate every rand.y class with the generated rule code, then encode.  pool == nullptr: count only.
+// flag_pop: build the table of the running census (se_step_lut_global_census): outcomes that change the population of
+// the block (a SET fired) carry SE_E_POPFLAG, so the kernel knows from the entry it has read anyway when to look closer.
 static __device__ __forceinline__ void se_build_lut_entry(unsigned entry, unsigned* __restrict__ base, unsigned* __restrict__ pool,
-                                                          unsigned* __restrict__ counter, unsigned pool_cap) {
+                                                          unsigned* __restrict__ counter, unsigned pool_cap, unsigned flag_pop) {
     const unsigned N = SE_N_MATERIALS;
 #if SE_LUT_TWO_TABLES
     const bool mirror_table = entry >= (unsigned)SE_N4;
@@ -546,6 +561,7 @@ static __device__ __forceinline__ void se_build_lut_entry(unsigned entry, unsign
         }
         if ((s | r | d | dr) & SE_F_NOSWAP) noswap = true;
         res[cls] = se_ids4(s, r, d, dr);
+        if (flag_pop && se_sorted4(SE_ID(s), SE_ID(r), SE_ID(d), SE_ID(dr)) != se_sorted4(ia, ib, ic, id)) res[cls] |= SE_E_POPFLAG;
     }
 #if !SE_LUT_TWO_TABLES
     if (noswap) { base[entry] = SE_E_SPECIAL | SE_E_SLOW; return; }
@@ -575,9 +591,9 @@ static __device__ __forceinline__ void se_build_lut_entry(unsigned entry, unsign
 
 #ifndef SE_HOST_EMU
 extern "C" __global__ void __launch_bounds__(256) se_build_lut(unsigned* __restrict__ base, unsigned* __restrict__ pool,
-                                                               unsigned* __restrict__ counter, unsigned pool_cap) {
+                                                               unsigned* __restrict__ counter, unsigned pool_cap, unsigned flag_pop) {
     const unsigned entry = blockIdx.x * blockDim.x + threadIdx.x;
-    if (entry < (unsigned)SE_LUT_ENTRIES) se_build_lut_entry(entry, base, pool, counter, pool_cap);
+    if (entry < (unsigned)SE_LUT_ENTRIES) se_build_lut_entry(entry, base, pool, counter, pool_cap, flag_pop);
 }
 #endif
 
@@ -599,24 +615,26 @@ static __device__ __forceinline__ void se_sts_u16(unsigned a, unsigned v) { asm 
 static __device__ __forceinline__ void se_sts_u32(unsigned a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 static __device__ __forceinline__ void se_sts_u64(unsigned a, unsigned x, unsigned y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(a), "r"(x), "r"(y) : "memory"); }
 static __device__ __forceinline__ unsigned se_dp4a(unsigned x, unsigned w) { return __dp4a(x, w, 0u); }
-#if SE_LUT_MODE == 1
-struct SeTab { unsigned base; unsigned pool; };            // shared-space byte addresses
-static __device__ __forceinline__ unsigned se_tab_entry(const SeTab& t, unsigned idx) { return se_lds_u32(t.base + 4u * idx); }
-static __device__ __forceinline__ void se_tab_pool(const SeTab& t, unsigned k, unsigned& thr, unsigned& a, unsigned& b) {
-    unsigned pad;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(thr), "=r"(a), "=r"(b), "=r"(pad) : "r"(t.pool + 16u * k));
-}
-#else
-struct SeTab { const unsigned* base; const unsigned* pool; };   // global memory, read-only for the whole launch
-static __device__ __forceinline__ unsigned se_tab_entry(const SeTab& t, unsigned idx) {
+struct SeTabG { const unsigned* base; const unsigned* pool; };   // table in global memory, read-only for the whole launch
+static __device__ __forceinline__ unsigned se_tab_entry(const SeTabG& t, unsigned idx) {
     unsigned v;
     asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(t.base + idx));
     return v;
 }
-static __device__ __forceinline__ void se_tab_pool(const SeTab& t, unsigned k, unsigned& thr, unsigned& a, unsigned& b) {
+static __device__ __forceinline__ void se_tab_pool(const SeTabG& t, unsigned k, unsigned& thr, unsigned& a, unsigned& b) {
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(t.pool) + k);
     thr = q.x; a = q.y; b = q.z;
 }
+#if SE_LUT_MODE == 1
+struct SeTabS { unsigned base; unsigned pool; };            // table staged in shared memory: shared-space byte addresses
+static __device__ __forceinline__ unsigned se_tab_entry(const SeTabS& t, unsigned idx) { return se_lds_u32(t.base + 4u * idx); }
+static __device__ __forceinline__ void se_tab_pool(const SeTabS& t, unsigned k, unsigned& thr, unsigned& a, unsigned& b) {
+    unsigned pad;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(thr), "=r"(a), "=r"(b), "=r"(pad) : "r"(t.pool + 16u * k));
+}
+typedef SeTabS SeTab;
+#else
+typedef SeTabG SeTab;
 #endif
 #endif
 
@@ -629,12 +647,13 @@ static __device__ __forceinline__ unsigned se_idx4(unsigned v) {
 // The rare ways out of the table: rand.y-dependent states walk their pool chain, slow states run the generated code.
 // `e` is the special entry, `v` the block as stored (unpermuted); the result is returned in the TABLE's view (the
 // caller undoes the mirror permutation in one-table mode, so the slow path applies it once more: an involution).
+template <class Tab>
 #ifndef SE_HOST_EMU
 static __device__ __noinline__ unsigned se_block_special(unsigned e, unsigned v, unsigned seed, unsigned mirror_sel, int px, int py, int frame,
-                                                         const SeTab tab, const unsigned* __restrict__ fat_sm)
+                                                         const Tab tab, const unsigned* __restrict__ fat_sm)
 #else
 static inline unsigned se_block_special(unsigned e, unsigned v, unsigned seed, unsigned mirror_sel, int px, int py, int frame,
-                                        const SeTab tab, const unsigned* fat_sm)
+                                        const Tab tab, const unsigned* fat_sm)
 #endif
 {
     const unsigned u1 = se_hashi(seed * 2131u);
@@ -660,7 +679,8 @@ static inline unsigned se_block_special(unsigned e, unsigned v, unsigned seed, u
 
 // one block: v = a | b<<8 | c<<16 | d<<24 (material ids < N), returns the new ids in the same packing.
 // No branch for the all-EMPTY early-out (falling_sand.glsl:692-694): T[0] == 0 in both views by construction.
-static __device__ __forceinline__ unsigned se_block_lut(unsigned v, unsigned seed, int px, int py, int frame, const SeTab tab,
+template <class Tab>
+static __device__ __forceinline__ unsigned se_block_lut(unsigned v, unsigned seed, int px, int py, int frame, const Tab tab,
                                                         const unsigned* __restrict__ fat_sm) {
     const unsigned u0 = se_hashi(seed * 213u);
     const bool mirror = u0 <= SE_MIRROR_UMAX;
@@ -685,70 +705,18 @@ static __device__ __forceinline__ unsigned se_pack_ids(uint4 v) {
 // Running census (SE_FLAG_RUNNING_CENSUS, one-table mode): the per-material population of the owned rows is kept up
 // to date by the per-frame kernel K1c instead of being recounted by a pass over the grid.
 // Guarded swaps only permute the cells of a block, so the population changes only where a SET fired (or where a
-// block straddles the first/last owned row of a strip, or holds an id the table does not know).  `popbits` is
-// a bit per block state: 1 = some outcome of the state (any rand.y class, either mirror view) is not a
-// permutation of its four ids.  It is only a filter: blocks that pass it are compared cell by cell.
+// block straddles the first/last owned row of a strip, or holds an id the table does not know).  The census variant of
+// K1c reads a copy of the table whose outcomes carry SE_E_POPFLAG when they are not a permutation of the state (the
+// generated-code path for WALL / NULL blocks always counts as flagged): one bit test per block, and only flagged or
+// partly counted blocks are compared cell by cell.
 // ---------------------------------------------------------------------------------------------
 #if !SE_LUT_TWO_TABLES
-static __device__ __forceinline__ unsigned se_sorted4(unsigned a, unsigned b, unsigned c, unsigned d) {
-    unsigned t;
-    if (a > b) { t = a; a = b; b = t; }
-    if (c > d) { t = c; c = d; d = t; }
-    if (a > c) { t = a; a = c; c = t; }
-    if (b > d) { t = b; b = d; d = t; }
-    if (b > c) { t = b; b = c; c = t; }
-    return a | (b << 8) | (c << 16) | (d << 24);
-}
-
-// same evaluation as se_build_lut_entry: every rand.y class of the unmirrored view
-static __device__ __forceinline__ bool se_popchange_entry(int idx) {
-    const int N = SE_N_MATERIALS;
-    const unsigned ia = idx / (N * N * N), ib = (idx / (N * N)) % N, ic = (idx / N) % N, id = idx % N;
-    if ((se_fat_table[ia] | se_fat_table[ib] | se_fat_table[ic] | se_fat_table[id]) & SE_F_NOSWAP) return true;   // generic path
-    if (idx == 0) return false;
-    const unsigned before = se_sorted4(ia, ib, ic, id);
-#pragma unroll
-    for (int cls = 0; cls < SE_LUT_NCLS; ++cls) {
-        unsigned s = se_fat_table[ia], r = se_fat_table[ib], d = se_fat_table[ic], dr = se_fat_table[id];
-        SeRand rnd;
-        rnd.u[0] = 0xFFFFFFFFu;
-        rnd.u[1] = cls == 0 ? 0u : se_lut_thresholds[cls - 1] + 1u;
-        rnd.u[2] = 0u; rnd.u[3] = 0u;
-        se_block_with_rand(s, r, d, dr, rnd, 0, 0, 0);
-        if ((s | r | d | dr) & SE_F_NOSWAP) return true;
-        if (se_sorted4(SE_ID(s), SE_ID(r), SE_ID(d), SE_ID(dr)) != before) return true;
-    }
-    return false;
-}
-
-// sets the bit of state idx and of its mirror image (the lookup uses the unmirrored block whatever rand.x says)
-static __device__ __forceinline__ void se_build_popbits_entry(int idx, unsigned* __restrict__ popbits) {
-    if (!se_popchange_entry(idx)) return;
-    const int N = SE_N_MATERIALS;
-    const int ia = idx / (N * N * N), ib = (idx / (N * N)) % N, ic = (idx / N) % N, id = idx % N;
-    const int mirrored = ((ib * N + ia) * N + id) * N + ic;
-    atomicOr(popbits + (idx >> 5), 1u << (idx & 31));
-    atomicOr(popbits + (mirrored >> 5), 1u << (mirrored & 31));
-}
-
-#ifdef SE_HOST_EMU
-typedef const unsigned* se_pop_t;
-static inline unsigned se_popbit(se_pop_t pop, unsigned idx) { return (pop[idx >> 5] >> (idx & 31)) & 1u; }
-#else
-typedef unsigned se_pop_t;   // shared-space address
-static __device__ __forceinline__ unsigned se_popbit(se_pop_t pop, unsigned idx) { return (se_lds_u32(pop + 4u * (idx >> 5)) >> (idx & 31)) & 1u; }
-#endif
-
-// One block of K1c: v = clamped ids (what the table saw), r* = the words read from memory, nv = new ids,
-// cm = bit k set when cell k (a, b, c, d) is inside the grid AND in an owned row.  Adds the population deltas of
-// the counted cells to hist[256] (CTA-local, flushed once per launch).
-static __device__ __forceinline__ void se_census_block(int* hist, se_pop_t pop, unsigned v, unsigned ra, unsigned rb, unsigned rc, unsigned rd,
-                                                       unsigned nv, unsigned cm) {
+// One block of K1c: r* = the words read from memory, nv = new ids (flag removed), cm = bit k set when cell k (a, b, c, d)
+// is inside the grid AND in an owned row, `look` = the outcome was flagged / generated code / a raw id was unknown.
+// Adds the population deltas of the counted cells to hist[256] (CTA-local, flushed once per launch).
+static __device__ __forceinline__ void se_census_block(int* hist, bool look, unsigned ra, unsigned rb, unsigned rc, unsigned rd, unsigned nv, unsigned cm) {
+    if (cm == 0u || (cm == 0xFu && !look)) return;      // all four cells counted and the outcome is a permutation: nothing to do
     const unsigned na = nv & 0xFFu, nb = (nv >> 8) & 0xFFu, nc = (nv >> 16) & 0xFFu, nd = nv >> 24;
-    if (cm == 0u || (na == ra && nb == rb && nc == rc && nd == rd)) return;
-    // all four cells counted and every outcome of this state is a permutation: nothing to do.  (A raw id the
-    // table does not know reads as NULL, NULL states have their bit set, so v is what decides.)
-    if (cm == 0xFu && !se_popbit(pop, se_idx4(v))) return;
     if ((cm & 1u) && na != ra) { atomicAdd(hist + (ra < 255u ? ra : 255u), -1); atomicAdd(hist + na, 1); }
     if ((cm & 2u) && nb != rb) { atomicAdd(hist + (rb < 255u ? rb : 255u), -1); atomicAdd(hist + nb, 1); }
     if ((cm & 4u) && nc != rc) { atomicAdd(hist + (rc < 255u ? rc : 255u), -1); atomicAdd(hist + nc, 1); }
@@ -1151,9 +1119,6 @@ struct SeLutStepParams {
 // running census: extra arguments of se_step_lut_global_census
 struct SeLutCensusParams {
     unsigned long long* census;   // 256 bins: population of the owned rows, updated in place
-    const unsigned* popbits;      // ceil(N^4 / 32) words
-    int pop_words;
-    int pop_offset;               // byte offset of the staged popbits in dynamic shared memory (16-aligned, behind the table)
     int own_y0, own_y1;           // owned global rows [own_y0, own_y1)
 };
 
@@ -1166,7 +1131,6 @@ static __device__ __forceinline__ void se_k1c_body(const SeLutStepParams& p, con
     asm volatile("mov.u32 %0, %1;" : "=r"(smem_sa) : "r"((unsigned)__cvta_generic_to_shared(smem)));
 #if !SE_LUT_TWO_TABLES
     if (CENSUS) {
-        for (int i = tid; i < cx.pop_words; i += blockDim.x) se_sts_u32(smem_sa + (unsigned)cx.pop_offset + 4u * i, __ldg(cx.popbits + i));
         for (int i = tid; i < 256; i += blockDim.x) hist_sm[i] = 0;
     }
 #endif
@@ -1272,6 +1236,7 @@ static __device__ __forceinline__ void se_k1c_body(const SeLutStepParams& p, con
                     if (e[u] & SE_E_SPECIAL) {
                         const unsigned seed = (unsigned)(2 * ((cb + u) * 32 + lane) - ox) * 461u + rowseed;
                         e[u] = se_block_special(e[u], v[u], seed, ((mir >> u) & 1u) ? 0x2301u : 0x3210u, 0, 0, 0, tab, fat_sm);
+                        if (CENSUS) unknown |= 1u << u;                    // generated code: no flag to go by, compare the cells
                     }
 #endif
             }
@@ -1280,11 +1245,15 @@ static __device__ __forceinline__ void se_k1c_body(const SeLutStepParams& p, con
                 const int bx = (cb + u) * 32 + lane;
                 const int x0 = 2 * bx - ox;
                 if (cb + u < c_end && bx < nbx) {
+#if !SE_LUT_TWO_TABLES
+                    const bool look = CENSUS && ((e[u] & SE_E_POPFLAG) || ((unknown >> u) & 1u));
+                    if (CENSUS) e[u] &= ~SE_E_POPFLAG;
+#endif
                     const unsigned nv = SE_LUT_TWO_TABLES ? e[u] : __byte_perm(e[u], 0u, ((mir >> u) & 1u) ? 0x2301u : 0x3210u);
 #if !SE_LUT_TWO_TABLES
                     if (CENSUS) {
                         const unsigned cm_cols = (x0 >= 0 ? 5u : 0u) | ((x0 + 1) < p.W ? 10u : 0u);
-                        se_census_block(hist_sm, smem_sa + (unsigned)cx.pop_offset, v[u], a[u], b[u], c[u], d[u], nv, cm_rows & cm_cols);
+                        se_census_block(hist_sm, look, a[u], b[u], c[u], d[u], nv, cm_rows & cm_cols);
                     }
 #endif
                     // a cell is written when its id changed -- or when the raw word was an id the table does not know (it is
@@ -1328,10 +1297,6 @@ extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_
     se_k1c_body<true>(p, cx, hist_sm);
 }
 
-extern "C" __global__ void __launch_bounds__(256) se_build_popbits(unsigned* __restrict__ popbits) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < SE_N4) se_build_popbits_entry(idx, popbits);
-}
 #endif
 
 // =============================================================================================
@@ -1340,8 +1305,8 @@ extern "C" __global__ void __launch_bounds__(256) se_build_popbits(unsigned* __r
 // 4 B old id + 16 B old light in, 4 B new id + 16 B new light out per cell = the 40 algorithmic bytes.
 //
 // Persistent CTAs (one per SM, 512 threads) walk 64 x 32 tiles.  The inputs of a tile -- light and ids of the tile and
-// its one-cell ring -- arrive by TMA (cp.async.bulk.tensor: one 3-D box of float4 light, one 2-D box of ids, out-of-grid
-// elements zero-filled) into one of two shared-memory buffers, signalled by an mbarrier; the loads of tile i+1 are
+// its one-cell ring -- arrive by TMA (cp.async.bulk.tensor: one 3-D box of float4 light, one 3-D box of ids in groups of
+// four, out-of-grid elements zero-filled) into one of two shared-memory buffers, signalled by an mbarrier; the loads of tile i+1 are
 // issued before tile i is touched, so HBM latency is hidden by a whole tile of work without a single register staged.
 // Per tile, three phases:
 //   A  every ring + tile cell: old id -> one byte (unknown ids NULL, WALL outside the grid, MISSING inside the grid but
@@ -1355,7 +1320,8 @@ extern "C" __global__ void __launch_bounds__(256) se_build_popbits(unsigned* __r
 #define SE_LF_TW 64
 #define SE_LF_TH 32
 #define SE_LF_LSTRIDE (SE_LF_TW + 2)                 // light / term row stride (float4)
-#define SE_LF_ISTRIDE (SE_LF_TW + 4)                 // id row stride (elements): the TMA box row must be a multiple of 16 bytes
+#define SE_LF_ISTRIDE (SE_LF_TW + 8)                 // id row stride (elements): the id box starts 4 columns left of the tile (16-byte groups)
+#define SE_LF_ICOL0 3                                // ring column j is element j + 3 of an id row
 #define SE_LF_LIGHT_BYTES ((SE_LF_TH + 2) * SE_LF_LSTRIDE * 16)
 #define SE_LF_IDS_BYTES ((SE_LF_TH + 2) * SE_LF_ISTRIDE * 4)
 #define SE_LF_IDS_OFFSET ((SE_LF_LIGHT_BYTES + 127) / 128 * 128)
@@ -1408,30 +1374,43 @@ static __device__ __forceinline__ void se_tma_load_3d(unsigned dst_sa, const SeT
                  :: "r"(dst_sa), "l"(reinterpret_cast<unsigned long long>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(mbar_sa) : "memory");
 }
 
-extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const __grid_constant__ SeTensorMap tm_cells, const __grid_constant__ SeTensorMap tm_light,
+// phase A for one ring / tile cell c = i * SE_LF_LSTRIDE + j
+template <bool INTERIOR>
+static __device__ __forceinline__ void se_lit_stage_cell(const SeLitParams& p, const unsigned* fat_sm, unsigned light_sa, unsigned ids_sa, unsigned char* ids8,
+                                                         int x_org, int yl_org, int c, int i, int j) {
+    const int x = x_org + j, yl = yl_org + i, y = p.gy0 + yl;
+    const bool in_grid = INTERIOR || (x >= 0 && x < p.W && y >= 0 && y < p.Hg);
+    const bool local = INTERIOR || (in_grid && yl >= 0 && yl < p.Hl);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    unsigned idb = in_grid ? SE_LF_MISSING : 2u;                             // WALL outside the grid (operations.glsl:45-51)
+    if (local) {
+        const unsigned id = se_lds_u32(ids_sa + 4u * (unsigned)(i * SE_LF_ISTRIDE + j + SE_LF_ICOL0));
+        float4 li;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(li.x), "=f"(li.y), "=f"(li.z), "=f"(li.w) : "r"(light_sa + 16u * (unsigned)c));
+        const unsigned nf = fat_sm[id < 255u ? id : 255u];
+        const float keep = (nf & SE_F_OBSTACLE) ? 0.0f : 1.0f;             // vec4(vec3(float(!obstacle)), 1.0), :498
+        const float la = li.w;
+        v = make_float4((li.x * keep) * la, (li.y * keep) * la, (li.z * keep) * la, la);
+        idb = se_clamp_id(id);
+    }
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(light_sa + 16u * (unsigned)c), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    ids8[i * SE_LF_ISTRIDE + j] = (unsigned char)idb;
+}
+
+extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 2) se_step_lit(const __grid_constant__ SeTensorMap tm_cells, const __grid_constant__ SeTensorMap tm_light,
                                                                               const SeLitParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ unsigned fat_sm[256];
     __shared__ SeMod mods_sm[256];
-    __shared__ int warp_counts[SE_LF_THREADS / 32];
+    __shared__ int n_cull_sm;
     __shared__ __align__(8) unsigned long long mbar[2];
     __shared__ __align__(4) unsigned char ids8[(SE_LF_TH + 2) * SE_LF_ISTRIDE];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned smem_sa;
     asm volatile("mov.u32 %0, %1;" : "=r"(smem_sa) : "r"((unsigned)__cvta_generic_to_shared(smem)));
-#if SE_LUT_MODE == 1
-    {
-        const uint4* lut4 = reinterpret_cast<const uint4*>(p.lut);
-        const int n4 = (p.table_bytes + 15) >> 4;
-        for (int i = tid; i < n4; i += blockDim.x) {
-            const uint4 v = __ldg(lut4 + i);
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(smem_sa + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-        }
-    }
-    const SeTab tab{smem_sa, smem_sa + (unsigned)p.pool_offset};
-#else
-    const SeTab tab{p.lut, p.pool};
-#endif
+    // the table is read where it lies in global memory (L1 / L2 resident: 561 blocks per tile against 2048 lit cells),
+    // which leaves the shared memory to two CTAs per SM: one stages / transitions while the other relaxes light
+    const SeTabG tab{p.lut, p.pool};
     if (tid < 256) fat_sm[tid] = se_fat_table[tid];
     const unsigned mbar_sa = (unsigned)__cvta_generic_to_shared(mbar);
     if (tid == 0) {
@@ -1442,13 +1421,13 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
     __syncthreads();
 
     const int n_tiles = p.tiles_x * p.tiles_y;
-    const unsigned buf0_sa = smem_sa + (unsigned)p.buf_offset;
+    const unsigned buf0_sa = (smem_sa + 127u) & ~127u;       // TMA destinations are 128-byte aligned whatever the base of dynamic shared memory is
     auto issue = [&](int t, int buf) {                       // one thread: both boxes of tile t into buffer `buf`
         const int by = t / p.tiles_x, bx = t - by * p.tiles_x;
         const unsigned dst = buf0_sa + (unsigned)buf * SE_LF_BUF_BYTES, mb = mbar_sa + 8u * (unsigned)buf;
         se_mbar_expect_tx(mb, SE_LF_LIGHT_BYTES + SE_LF_IDS_BYTES);
         se_tma_load_3d(dst, &tm_light, 0, bx * SE_LF_TW - 1, by * SE_LF_TH - 1, mb);
-        se_tma_load_2d(dst + SE_LF_IDS_OFFSET, &tm_cells, bx * SE_LF_TW - 1, by * SE_LF_TH - 1, mb);
+        se_tma_load_3d(dst + SE_LF_IDS_OFFSET, &tm_cells, 0, bx * (SE_LF_TW / 4) - 1, by * SE_LF_TH - 1, mb);
     };
     if (tid == 0 && (int)blockIdx.x < n_tiles) issue((int)blockIdx.x, 0);
 
@@ -1465,45 +1444,38 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue(t + (int)gridDim.x, buf ^ 1);
         }
-        // modification list culled against this tile, order kept (last match wins, falling_sand.glsl:764-773)
-        int n_cull = 0;
-        if (p.n_mods > 0) {
+        // modification list culled against this tile by ONE warp, order kept (last match wins, falling_sand.glsl:764-773)
+        if (warp == 1) {
+            int n = 0;
             const int x_lo = bx * SE_LF_TW, y_lo = p.gy0 + by * SE_LF_TH;
-            bool keep = false;
-            SeMod m;
-            if (tid < p.n_mods) { m = p.mods[tid]; keep = se_mod_touches(m, x_lo, x_lo + SE_LF_TW - 1, y_lo, y_lo + SE_LF_TH - 1); }
-            const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
-            if (lane == 0) warp_counts[warp] = __popc(ballot);
-            __syncthreads();
-            int base = 0;
-            for (int w = 0; w < SE_LF_THREADS / 32; ++w) { if (w < warp) base += warp_counts[w]; n_cull += warp_counts[w]; }
-            if (keep) mods_sm[base + __popc(ballot & ((1u << lane) - 1u))] = m;
+            for (int m0 = 0; m0 < p.n_mods; m0 += 32) {
+                bool keep = false;
+                SeMod m;
+                if (m0 + lane < p.n_mods) { m = p.mods[m0 + lane]; keep = se_mod_touches(m, x_lo, x_lo + SE_LF_TW - 1, y_lo, y_lo + SE_LF_TH - 1); }
+                const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
+                if (keep) mods_sm[n + __popc(ballot & ((1u << lane) - 1u))] = m;
+                n += __popc(ballot);
+            }
+            if (lane == 0) n_cull_sm = n;
         }
+        const bool interior = x_org >= 0 && x_org + SE_LF_TW + 1 < p.W && yl_org >= 0 && yl_org + SE_LF_TH + 1 < p.Hl &&
+                              p.gy0 + yl_org >= 0 && p.gy0 + yl_org + SE_LF_TH + 1 < p.Hg;
         se_mbar_wait(mbar_sa + 8u * (unsigned)buf, (unsigned)(it >> 1) & 1u);
         const unsigned light_sa = buf0_sa + (unsigned)buf * SE_LF_BUF_BYTES, ids_sa = light_sa + SE_LF_IDS_OFFSET;
 
-        // ---- phase A: id bytes and neighbour terms of every ring + tile cell ----
-        for (int c = tid; c < (SE_LF_TH + 2) * SE_LF_LSTRIDE; c += SE_LF_THREADS) {
-            const int i = c / SE_LF_LSTRIDE, j = c - i * SE_LF_LSTRIDE;
-            const int x = x_org + j, yl = yl_org + i, y = p.gy0 + yl;
-            const bool in_grid = x >= 0 && x < p.W && y >= 0 && y < p.Hg;
-            const bool local = in_grid && yl >= 0 && yl < p.Hl;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            unsigned idb = in_grid ? SE_LF_MISSING : 2u;                     // WALL outside the grid (operations.glsl:45-51)
-            if (local) {
-                const unsigned id = se_lds_u32(ids_sa + 4u * (unsigned)(i * SE_LF_ISTRIDE + j));
-                float4 li;
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(li.x), "=f"(li.y), "=f"(li.z), "=f"(li.w) : "r"(light_sa + 16u * (unsigned)c));
-                const unsigned nf = fat_sm[id < 255u ? id : 255u];
-                const float keep = (nf & SE_F_OBSTACLE) ? 0.0f : 1.0f;     // vec4(vec3(float(!obstacle)), 1.0), :498
-                const float la = li.w;
-                v = make_float4((li.x * keep) * la, (li.y * keep) * la, (li.z * keep) * la, la);
-                idb = se_clamp_id(id);
+        // ---- phase A: id bytes and neighbour terms of every ring + tile cell ((i, j) stepped without a division) ----
+        {
+            int c = tid, i = tid / SE_LF_LSTRIDE, j = tid - i * SE_LF_LSTRIDE;
+            const int di = SE_LF_THREADS / SE_LF_LSTRIDE, dj = SE_LF_THREADS - di * SE_LF_LSTRIDE;
+            for (; c < (SE_LF_TH + 2) * SE_LF_LSTRIDE; c += SE_LF_THREADS) {
+                if (interior) se_lit_stage_cell<true>(p, fat_sm, light_sa, ids_sa, ids8, x_org, yl_org, c, i, j);
+                else se_lit_stage_cell<false>(p, fat_sm, light_sa, ids_sa, ids8, x_org, yl_org, c, i, j);
+                i += di; j += dj;
+                if (j >= SE_LF_LSTRIDE) { j -= SE_LF_LSTRIDE; ++i; }
             }
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(light_sa + 16u * (unsigned)c), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-            ids8[i * SE_LF_ISTRIDE + j] = (unsigned char)idb;
         }
         __syncthreads();
+        const int n_cull = n_cull_sm;
 
         // ---- phase B: the blocks that cover the tile, in place in ids8 ----
         {
@@ -1526,8 +1498,6 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
 
         // ---- phase C: new id + light of every tile cell: column tid & 31 of half (warp & 1), rows 4 * (warp >> 1) .. + 3 ----
         {
-            const bool interior = x_org >= 0 && x_org + SE_LF_TW + 1 < p.W && yl_org >= 0 && yl_org + SE_LF_TH + 1 < p.Hl &&
-                                  p.gy0 + yl_org >= 0 && p.gy0 + yl_org + SE_LF_TH + 1 < p.Hg;
             const int tx = lane + 32 * (warp & 1), row0 = (warp >> 1) * 4;
             const int x = bx * SE_LF_TW + tx;
             if (x < p.W) {
@@ -1549,7 +1519,7 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
                         unsigned m;
                         if (se_mod_lookup(mods_sm, n_cull, x, y, m)) id = m;
                     }
-                    if (id != SE_LF_MISSING) p.new_cells[idx] = id;        // (a MISSING cell lies in a block row the strip cannot compute: left alone, see K1a)
+                    p.new_cells[idx] = id;
                     const unsigned me = id < 255u ? id : 255u;
                     float4 light;
                     if (fat_sm[me] & SE_F_EMISSIVE) {                       // operations.glsl:126-127

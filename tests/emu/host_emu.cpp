@@ -110,16 +110,17 @@ extern "C" int emu_lut_eligible(void) { return SE_LUT_ELIGIBLE; }
 static std::vector<unsigned> g_base, g_pool;
 static unsigned g_pool_entries = 0;
 static SeTab g_tab{nullptr, nullptr};
+static unsigned g_flag_pop = 0;      // 1: build the census variant of the table (population-changing outcomes flagged)
 
 // returns the number of pool entries (two passes like se_sim_create in mode 2: count, then fill)
 extern "C" int emu_build_lut(void) {
     g_base.assign((size_t)SE_LUT_ENTRIES, 0u);
     unsigned counter = 0;
-    for (unsigned idx = 0; idx < (unsigned)SE_LUT_ENTRIES; ++idx) se_build_lut_entry(idx, g_base.data(), nullptr, &counter, 0u);
+    for (unsigned idx = 0; idx < (unsigned)SE_LUT_ENTRIES; ++idx) se_build_lut_entry(idx, g_base.data(), nullptr, &counter, 0u, g_flag_pop);
     g_pool_entries = counter;
     g_pool.assign((size_t)4 * (counter + 1), 0u);
     counter = 0;
-    for (unsigned idx = 0; idx < (unsigned)SE_LUT_ENTRIES; ++idx) se_build_lut_entry(idx, g_base.data(), g_pool.data(), &counter, g_pool_entries);
+    for (unsigned idx = 0; idx < (unsigned)SE_LUT_ENTRIES; ++idx) se_build_lut_entry(idx, g_base.data(), g_pool.data(), &counter, g_pool_entries, g_flag_pop);
     g_tab = SeTab{g_base.data(), g_pool.data()};
     return (int)g_pool_entries;
 }
@@ -152,13 +153,14 @@ extern "C" void emu_step_lut_inplace(uint32_t* cells, int W, int H, int frame) {
 }
 
 #if !SE_LUT_TWO_TABLES
-// ---- running census (experimental): popbits filter + per-block deltas, decisions exactly as in se_k1c_body<true> ----
-static std::vector<unsigned> g_pop;
-extern "C" int emu_build_popbits(void) {
-    g_pop.assign((SE_N4 + 31) / 32, 0u);
-    for (int idx = 0; idx < SE_N4; ++idx) se_build_popbits_entry(idx, g_pop.data());
+// ---- running census: flagged table + per-block deltas, decisions exactly as in se_k1c_body<true> ----
+// (re)builds the table with SE_E_POPFLAG on the outcomes that are not permutations; returns how many plain entries carry it
+extern "C" int emu_build_census_lut(void) {
+    g_flag_pop = 1;
+    emu_build_lut();
+    g_flag_pop = 0;
     int n = 0;
-    for (int idx = 0; idx < SE_N4; ++idx) n += (int)se_popbit(g_pop.data(), (unsigned)idx);
+    for (unsigned e : g_base) n += (!(e & SE_E_SPECIAL) && (e & SE_E_POPFLAG)) ? 1 : 0;
     return n;
 }
 
@@ -181,12 +183,24 @@ extern "C" void emu_step_lut_census(uint32_t* cells, int W, int H, int frame, in
             unsigned v = 0;
             for (int k = 0; k < 4; ++k) v |= (raw[k] < SE_N_MATERIALS ? raw[k] : 1u) << (8 * k);
             const unsigned seed = (unsigned)x0 * 461u + (unsigned)y0 * 2131u + (unsigned)frame * (2131u * 2131u);
-            const unsigned nv = se_block_lut(v, seed, x0, y0, frame, g_tab, se_fat_table);
+            // as in the kernel: the entry's flag decides whether the block is looked at; generated-code blocks always are
+            const bool mirror = se_hashi(seed * 213u) <= SE_MIRROR_UMAX;
+            const unsigned sel = mirror ? 0x2301u : 0x3210u;
+            unsigned e = se_tab_entry(g_tab, se_idx4(__byte_perm(v, 0u, sel)));
+            bool look = false;
+            for (int k = 0; k < 4; ++k) look = look || raw[k] >= (unsigned)SE_N_MATERIALS;
+            if (e & SE_E_SPECIAL) {
+                if (e & SE_E_SLOW) look = true;
+                e = se_block_special(e, v, seed, sel, 0, 0, 0, g_tab, se_fat_table);
+            }
+            if (e & SE_E_POPFLAG) look = true;
+            e &= ~SE_E_POPFLAG;
+            const unsigned nv = __byte_perm(e, 0u, sel);
             const unsigned cm_rows = ((st0 == 0 && y0 >= own_y0 && y0 < own_y1) ? 3u : 0u) | ((st1 == 0 && y1 >= own_y0 && y1 < own_y1) ? 12u : 0u);
             const unsigned cm_cols = (cx0 ? 5u : 0u) | (cx1 ? 10u : 0u);
             const unsigned cm = cm_rows & cm_cols;
-            if (n_filtered && cm == 0xFu && nv != v && !se_popbit(g_pop.data(), se_idx4(v))) ++*n_filtered;
-            se_census_block(hist, g_pop.data(), v, raw[0], raw[1], raw[2], raw[3], nv, cm);
+            if (n_filtered && cm == 0xFu && nv != v && !look) ++*n_filtered;
+            se_census_block(hist, look, raw[0], raw[1], raw[2], raw[3], nv, cm);
             const unsigned nn[4] = {nv & 0xFFu, (nv >> 8) & 0xFFu, (nv >> 16) & 0xFFu, nv >> 24};
             if (st0 == 0 && cx0 && nn[0] != raw[0]) cells[(size_t)y0 * W + x0] = nn[0];
             if (st0 == 0 && cx1 && nn[1] != raw[1]) cells[(size_t)y0 * W + x0 + 1] = nn[1];
@@ -196,13 +210,13 @@ extern "C" void emu_step_lut_census(uint32_t* cells, int W, int H, int frame, in
     for (int i = 0; i < 256; ++i) census256[i] += hist[i];
 }
 #else
-extern "C" int emu_build_popbits(void) { return -2; }
+extern "C" int emu_build_census_lut(void) { return -2; }
 extern "C" void emu_step_lut_census(uint32_t*, int, int, int, int, int, long long*, long long*) {}
 #endif
 #else
 extern "C" int emu_lut_mode(void) { return 0; }
 extern "C" int emu_lut_two_tables(void) { return 0; }
-extern "C" int emu_build_popbits(void) { return -2; }
+extern "C" int emu_build_census_lut(void) { return -2; }
 extern "C" void emu_step_lut_census(uint32_t*, int, int, int, int, int, long long*, long long*) {}
 extern "C" int emu_build_lut(void) { return -2; }
 extern "C" void emu_step_lut_inplace(uint32_t*, int, int, int) {}
