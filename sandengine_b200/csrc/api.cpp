@@ -519,34 +519,38 @@ int one_step(se_sim* s, bool use_mods, int n_mods) {
 // half-CTA processes ceil(items / workers) tiles of PH = THo + 2 HY rows, so the launch costs about
 // rounds * (PH + c): pick the tiles_y that minimises it (avoids a nearly empty last round, which is what costs
 // strong scaling: at 16384 x 2048 rows per GPU a fixed PH would spend 9 rounds on 8.4 rounds of work).
-struct TileGeom { int tiles_y, THo, PH; };
+// The halo is sized for the sub-steps a T-block of THIS launch really has (20 steps with T = 12 are two T-blocks of 10: a halo
+// of 12 columns and 6 rows, not the 8 rows a T-block of 12 would need): HX = sub-steps rounded up to 4, HY = even >= n/2 + 1.
+struct TileGeom { int tiles_y, THo, PH, HX, HY, tiles_x; };
 
-TileGeom choose_tile_geometry(const se_sim* s, int nblk, int owned) {
+TileGeom choose_tile_geometry(const se_sim* s, int nblk, int tsteps, int owned) {
     const int workers = 2 * s->tile_grid;
+    const int HY = ((tsteps / 2 + 1) + 1) & ~1, HX = (tsteps + 3) & ~3;
+    const int tiles_x = (s->W + (256 - 2 * HX) - 1) / (256 - 2 * HX);
     const int push_min = s->is_strip() ? s->HY : 2;
     TileGeom best{0, 0, 0};
     double best_cost = -1;
-    const int tho_max = (s->PH_max - 2 * s->HY) & ~1;
+    const int tho_max = (s->PH_max - 2 * HY) & ~1;
     const int ty_min = std::max(1, (owned + tho_max - 1) / tho_max);
     for (int ty = ty_min; ty <= ty_min + 4 * workers; ++ty) {
         int tho = ((owned + ty - 1) / ty + 1) & ~1;
         if (tho > tho_max) continue;
-        if (tho < 2 * s->T + 8 && ty > ty_min) break;                // tiles this flat are mostly halo
+        if (tho < 2 * tsteps + 8 && ty > ty_min) break;              // tiles this flat are mostly halo
         const int last = owned - (ty - 1) * tho;
         if (last <= 0 || (ty > 1 && last < push_min)) continue;
-        const long long items = (long long)nblk * s->tiles_x * ty;
+        const long long items = (long long)nblk * tiles_x * ty;
         const long long rounds = (items + workers - 1) / workers;
         // + 24: per-tile fixed work (flag waits, barriers, exposed load/store) expressed in rows (fitted on B200)
-        const double cost = (double)rounds * (tho + 2 * s->HY + 24);
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = TileGeom{ty, tho, tho + 2 * s->HY}; }
+        const double cost = (double)rounds * (tho + 2 * HY + 24);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = TileGeom{ty, tho, tho + 2 * HY, HX, HY, tiles_x}; }
     }
     if (best.tiles_y == 0) {                                          // cannot happen for owned >= 2; keep a safe answer anyway
         const int tho = std::min(tho_max, (owned + 1) & ~1);
-        best = TileGeom{(owned + tho - 1) / tho, tho, tho + 2 * s->HY};
+        best = TileGeom{(owned + tho - 1) / tho, tho, tho + 2 * HY, HX, HY, tiles_x};
     }
     if (const char* ov = std::getenv("SE_TILE_PH")) {                // experiments only: fix the tile height
-        const int v = (std::atoi(ov) & ~1) - 2 * s->HY;
-        if (v >= 2 && v <= tho_max) best = TileGeom{(owned + v - 1) / v, v, v + 2 * s->HY};
+        const int v = (std::atoi(ov) & ~1) - 2 * HY;
+        if (v >= 2 && v <= tho_max) best = TileGeom{(owned + v - 1) / v, v, v + 2 * HY, HX, HY, tiles_x};
     }
     return best;
 }
@@ -762,8 +766,10 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
         SE_CUDA_S(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device));
         SE_CUDA_S(cudaDeviceGetAttribute(&coop_attr, cudaDevAttrCooperativeLaunch, s->device));
         s->smem_budget = smem_optin - 1024 - 64;                        // static shared memory of the kernels: 1 KB fat table
-        int T = prm->temporal_block ? (int)prm->temporal_block : 8;
-        T = std::min(64, std::max(2, T + (T & 1)));
+        // default 12: load + store of a tile cost about three sub-steps, the halo grows with T; measured at 16384^2 over 20
+        // steps: T = 6 / 8 / 10 -> 1110 / 1212 / 1308 Gcell/s, and by that model 12 .. 16 are best for long runs
+        int T = prm->temporal_block ? (int)prm->temporal_block : 12;
+        T = std::min(32, std::max(2, T + (T & 1)));
         // rows: the Margolus row offset changes every other frame, so T fused steps need only T/2+1 halo rows
         s->T = T;
         s->HY = ((T / 2 + 1) + 1) & ~1;
@@ -861,7 +867,7 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
             PH_max = std::min(PH_max, 320);                            // taller tiles: fewer, coarser work items for the same bytes
             if (const char* pm = std::getenv("SE_TILE_PH_MAX")) PH_max = std::min(PH_max, std::max(4 * T + 16, std::atoi(pm) & ~1));   // experiments only
             s->PH_max = PH_max;
-            s->tiles_x = (s->W + (256 - 2 * s->HX) - 1) / (256 - 2 * s->HX);
+            s->tiles_x = (s->W + (256 - 2 * 4) - 1) / (256 - 2 * 4);      // the most tile columns any launch can have (HX >= 4)
             s->tile_grid = std::max(1, n_sm / s->device_share);        // persistent: one CTA (two halves) per SM
             s->k1c_grid = std::max(1, 2 * n_sm / s->device_share);
             if (const char* kg = std::getenv("SE_K1C_GRID")) s->k1c_grid = std::max(1, std::atoi(kg));   // experiments only
@@ -980,8 +986,8 @@ int se_sim_step(se_sim* s, uint32_t n_steps) try {
             const int nblk = (int)((run + (uint32_t)s->T - 1) / (uint32_t)s->T);
             const int tsteps = (int)((run + (uint32_t)nblk - 1) / (uint32_t)nblk);
             { int rc = ensure_ghosts(s, s->HY); if (rc) return rc; }
-            const TileGeom g = choose_tile_geometry(s, nblk, s->row_end - s->row_begin);
-            if ((long long)s->tiles_x * g.tiles_y > s->tile_done_cap) return fail(SE_ERR_INTERNAL, "tile flag array too small");
+            const TileGeom g = choose_tile_geometry(s, nblk, tsteps, s->row_end - s->row_begin);
+            if ((long long)g.tiles_x * g.tiles_y > s->tile_done_cap) return fail(SE_ERR_INTERNAL, "tile flag array too small");
             SeTileParams tp;
             std::memset(&tp, 0, sizeof tp);
             tp.buf0 = s->cells[s->cur]; tp.buf1 = s->cells[s->cur ^ 1];
@@ -1006,13 +1012,13 @@ int se_sim_step(se_sim* s, uint32_t n_steps) try {
             tp.frame0 = s->frame + 1; tp.nblk = nblk; tp.tsteps = tsteps; tp.nsub_last = (int)(run - (uint32_t)(nblk - 1) * (uint32_t)tsteps);
             tp.seq_base = s->tile_seq; tp.done = s->d_tile_done; tp.status = s->flags + FLAG_STATUS;
             tp.queue = s->flags + FLAG_QUEUE; tp.queue_base = s->tile_queue;
-            tp.HY = s->HY; tp.HX = s->HX; tp.PH = g.PH; tp.THo = g.THo;
-            tp.tiles_x = s->tiles_x; tp.tiles_y = g.tiles_y; tp.push_rows = push_rows;
+            tp.HY = g.HY; tp.HX = g.HX; tp.PH = g.PH; tp.THo = g.THo;
+            tp.tiles_x = g.tiles_x; tp.tiles_y = g.tiles_y; tp.push_rows = push_rows;
             tp.table_bytes = s->table_bytes; tp.pool_offset = s->pool_offset; tp.tile_offset = s->tile_offset; tp.tile_stride = 256 * g.PH;
             tp.lut = s->d_lut; tp.pool = s->d_pool;
             tp.spin_limit = 4000000u;                                   // ~2 s of polling before a tile gives up on a flag
             void* targs[] = {&tp};
-            const long long items = (long long)nblk * s->tiles_x * g.tiles_y;
+            const long long items = (long long)nblk * g.tiles_x * g.tiles_y;
             const int grid = (int)std::min<long long>((long long)s->tile_grid, (items + 1) / 2);
             const unsigned smem_bytes = (unsigned)(s->tile_offset + 2 * 256 * g.PH);
             if (s->coop) {

@@ -962,7 +962,20 @@ extern "C" __global__ void __launch_bounds__(2 * SE_HALF_THREADS, 1) se_step_til
         if (htid == 0) next_item[half] = atomicAdd(p.queue, 1u) - p.queue_base;
         se_half_sync(half);
         const unsigned w = next_item[half];
-        if (w >= total_items) break;
+        if (w >= total_items) {
+            // Strips: the half that draws the first number past the end keeps the kernel alive until the neighbours' pushes of
+            // the LAST T-block have landed in this strip's ghost rows (their boundary tiles come first in every T-block, so
+            // this is rarely a wait).  A kernel that runs after this one -- a per-step kernel, which looks at no flags -- then
+            // finds the ghost rows of the final buffer complete.
+            if (w == total_items && (has_above || has_below)) {
+                const unsigned want = p.seq_base + (unsigned)p.nblk;
+                for (int i = htid; i < 2 * p.tiles_x; i += SE_HALF_THREADS) {
+                    const int side = i / p.tiles_x, ntx = i - side * p.tiles_x;
+                    if (side == 0 ? has_above : has_below) se_wait_flag(p.in_flags[side] + ntx, want, true, p.status, p.spin_limit);
+                }
+            }
+            break;
+        }
         const int k = (int)(w / (unsigned)n_tiles), pos = (int)(w - (unsigned)k * (unsigned)n_tiles);
         // Strips: tile rows from the outside in (0, last, 1, last - 1, ...).  The boundary rows come first, so their push
         // overlaps the interior of the same T-block and the neighbours never wait for the end of a T-block; and a tile's
@@ -986,8 +999,11 @@ extern "C" __global__ void __launch_bounds__(2 * SE_HALF_THREADS, 1) se_step_til
                 if (k > 0 && ntx >= 0 && ntx < p.tiles_x && nty >= 0 && nty < p.tiles_y)
                     se_wait_flag(p.done + (nty * p.tiles_x + ntx), want, false, p.status, p.spin_limit);
             } else {
+                // (k == 0 waits for nothing, here as above: every launch ends only when the neighbours' boundary tiles of its
+                // last T-block are complete -- the final wait below -- so what the first T-block reads has been delivered and
+                // what it overwrites has been read.  The flags of an earlier launch may belong to another tile geometry.)
                 const int side = (htid - 9) / 3, ntx = tx + ((htid - 9) % 3) - 1;
-                const bool need = side == 0 ? (has_above && top_row) : (has_below && bottom_row);
+                const bool need = k > 0 && (side == 0 ? (has_above && top_row) : (has_below && bottom_row));
                 if (need && ntx >= 0 && ntx < p.tiles_x)
                     se_wait_flag(p.in_flags[side] + ntx, want, true, p.status, p.spin_limit);
             }
@@ -1251,7 +1267,8 @@ static __device__ __forceinline__ void se_k1c_body(const SeLutStepParams& p, con
 #endif
                     const unsigned nv = SE_LUT_TWO_TABLES ? e[u] : __byte_perm(e[u], 0u, ((mir >> u) & 1u) ? 0x2301u : 0x3210u);
 #if !SE_LUT_TWO_TABLES
-                    if (CENSUS) {
+                    // only flagged outcomes and blocks cut by the grid's / the strip's edge are looked at
+                    if (CENSUS && (look || cm_rows != 0xFu || x0 < 0 || x0 + 1 >= p.W)) {
                         const unsigned cm_cols = (x0 >= 0 ? 5u : 0u) | ((x0 + 1) < p.W ? 10u : 0u);
                         se_census_block(hist_sm, look, a[u], b[u], c[u], d[u], nv, cm_rows & cm_cols);
                     }

@@ -281,7 +281,10 @@ def _strip_pair_run(se, rules, g, steps, halo, n_strips, device_sync=False, per_
         for s in sims: s.halo_push()
         for s in sims: s.synchronize()
     if auto:                # no explicit exchange at all: se_sim_step keeps the ghost rows current (fused push / stream exchange)
-        for k in ([1] * steps if per_step else [steps // 3, steps - steps // 3]):
+        # runs of steps (tile kernel, fused push), single steps (K1c / K1a, stream-ordered exchange) and mixtures of both:
+        # a per-step kernel right after a run must find the neighbours' last push complete
+        sched = [1] * steps if per_step else [steps // 3, 1, 1, steps - steps // 3 - 3, 1]
+        for k in sched:
             for s in sims: s.step(k)
     else:
         exchange()
