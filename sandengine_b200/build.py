@@ -4,7 +4,7 @@ Steps
   1. embed kernels/sand_kernels.cuh as a C++ raw string (csrc/_gen/sand_kernels_embed.inc): it is the
      NVRTC translation unit that is compiled together with the generated rules header at rule-compile time.
   2. nvcc -gencode arch=compute_100a,code=sm_100a: api.cpp + lang/*.cpp + static_kernels.cu -> .so
-     (static cudart, dynamic libnvrtc; no libcuda link dependency).
+     (static cudart; libnvrtc opened at run time by path; no libcuda link dependency).
   3. (inspect=True) run the front end on data/materials.yaml, dump the generated CUDA header and
      compile the rule kernels ahead of time with `-Xptxas -v` into build/ so registers/spills/SASS can be
      checked without a GPU (cuobjdump -sass build/sand_kernels_default.cubin).
@@ -61,7 +61,9 @@ def build(force: bool = False, inspect: bool = False, verbose: bool = True) -> P
         cmd = [NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
                "-cudart", "static", "-I", str(CSRC), "-I", str(REPO / "include")]
         cmd += [str(CSRC / s) for s in SOURCES]
-        cmd += ["-o", str(LIB), "-lnvrtc"]
+        # NVRTC is opened at run time by path (csrc/api.cpp: struct Nvrtc): the toolkit's own, next to this nvcc
+        nvrtc_dir = Path(NVCC).resolve().parent.parent / "lib64"
+        cmd += [f'-DSE_NVRTC_DIR="{nvrtc_dir}"', "-o", str(LIB), "-ldl"]
         if verbose:
             print("[build]", " ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -8,6 +8,7 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <nvrtc.h>
 
 #include <algorithm>
@@ -17,6 +18,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "lang/codegen.h"
@@ -62,6 +64,55 @@ int map_kind(se::ErrKind k) {
 const char* const KERNEL_SOURCE =
 #include "_gen/sand_kernels_embed.inc"
     ;
+
+// ---- NVRTC, loaded by path ---------------------------------------------------------------------
+// The kernels are compiled by the NVRTC of the toolkit this library was built against (CUDA 12.9: its ptxas knows the
+// three-input max and the packed f32 adds the lit kernel uses).  A process that imported PyTorch first already has torch's
+// own, older libnvrtc.so.12 mapped, and a plain link dependency would silently bind to that one -- so the library is
+// opened by absolute path (a path never matches an already loaded SONAME), with the default search as the fallback; the
+// kernel source compiles with either (it checks __CUDACC_VER_MINOR__).  SE_NVRTC_LIB overrides the choice.
+struct Nvrtc {
+    decltype(&nvrtcCreateProgram) CreateProgram = nullptr;
+    decltype(&nvrtcCompileProgram) CompileProgram = nullptr;
+    decltype(&nvrtcGetProgramLogSize) GetProgramLogSize = nullptr;
+    decltype(&nvrtcGetProgramLog) GetProgramLog = nullptr;
+    decltype(&nvrtcGetErrorString) GetErrorString = nullptr;
+    decltype(&nvrtcGetCUBINSize) GetCUBINSize = nullptr;
+    decltype(&nvrtcGetCUBIN) GetCUBIN = nullptr;
+    decltype(&nvrtcDestroyProgram) DestroyProgram = nullptr;
+    decltype(&nvrtcVersion) Version = nullptr;
+    bool ok = false;
+    std::string why, path;
+    Nvrtc() {
+        std::vector<std::string> candidates;
+        if (const char* e = std::getenv("SE_NVRTC_LIB")) candidates.push_back(e);
+#ifdef SE_NVRTC_DIR
+        candidates.push_back(std::string(SE_NVRTC_DIR) + "/libnvrtc.so.12");
+#endif
+        candidates.push_back("/usr/local/cuda/lib64/libnvrtc.so.12");
+        candidates.push_back("libnvrtc.so.12");
+        candidates.push_back("libnvrtc.so");
+        void* h = nullptr;
+        for (const auto& c : candidates) {
+            h = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL | RTLD_DEEPBIND);
+            if (h) { path = c; break; }
+            why += c + ": " + (dlerror() ? "not loadable" : "?") + "; ";
+        }
+        if (!h) return;
+        auto get = [&](auto& fn, const char* name) {
+            fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(dlsym(h, name));
+            if (!fn) why += std::string("missing ") + name + "; ";
+            return fn != nullptr;
+        };
+        ok = get(CreateProgram, "nvrtcCreateProgram") & get(CompileProgram, "nvrtcCompileProgram") & get(GetProgramLogSize, "nvrtcGetProgramLogSize") &
+             get(GetProgramLog, "nvrtcGetProgramLog") & get(GetErrorString, "nvrtcGetErrorString") & get(GetCUBINSize, "nvrtcGetCUBINSize") &
+             get(GetCUBIN, "nvrtcGetCUBIN") & get(DestroyProgram, "nvrtcDestroyProgram") & get(Version, "nvrtcVersion");
+    }
+};
+Nvrtc& nvrtc() {
+    static Nvrtc n;
+    return n;
+}
 
 // ---- driver API through the runtime (no libcuda link dependency) -----------------------------
 struct Driver {
@@ -194,9 +245,10 @@ struct SeLitParams {
     const unsigned* pool;
     int tiles_x, tiles_y;
     int buf_offset;
+    unsigned tiles_x_magic;
 };
 // geometry of se_step_lit (kernels/sand_kernels.cuh: SE_LF_*)
-constexpr int LF_TW = 64, LF_TH = 32;
+constexpr int LF_TW = 64, LF_TH = 16;
 constexpr int LF_LIGHT_BYTES = (LF_TH + 2) * (LF_TW + 2) * 16, LF_IDS_BYTES = (LF_TH + 2) * (LF_TW + 8) * 4;
 constexpr int LF_IDS_OFFSET = (LF_LIGHT_BYTES + 127) / 128 * 128, LF_BUF_BYTES = (LF_IDS_OFFSET + LF_IDS_BYTES + 127) / 128 * 128;
 
@@ -334,10 +386,14 @@ int compile_front(const char* yaml, size_t len, se_rules** out, bool with_nvrtc)
         return fail(SE_ERR_INVALID_ARG, msg);
     }
     if (with_nvrtc) {
+        if (!nvrtc().ok) {
+            delete r;
+            return fail(SE_ERR_COMPILE, "NVRTC not available: " + nvrtc().why);
+        }
         nvrtcProgram prog;
         const char* hdr_src[1] = {r->cr.cuda_header.c_str()};
         const char* hdr_name[1] = {"rules_gen.cuh"};
-        if (nvrtcCreateProgram(&prog, KERNEL_SOURCE, "sand_kernels.cu", 1, hdr_src, hdr_name) != NVRTC_SUCCESS) {
+        if (nvrtc().CreateProgram(&prog, KERNEL_SOURCE, "sand_kernels.cu", 1, hdr_src, hdr_name) != NVRTC_SUCCESS) {
             delete r;
             return fail(SE_ERR_COMPILE, "nvrtcCreateProgram failed");
         }
@@ -361,30 +417,35 @@ int compile_front(const char* yaml, size_t len, se_rules** out, bool with_nvrtc)
         }
         std::vector<const char*> opts = {"-arch=sm_100a", "-std=c++17", "-lineinfo", "-fmad=false"};
         for (auto& e : extra) opts.push_back(e.c_str());
-        nvrtcResult res = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
+        nvrtcResult res = nvrtc().CompileProgram(prog, (int)opts.size(), opts.data());
         size_t log_size = 0;
-        nvrtcGetProgramLogSize(prog, &log_size);
-        r->nvrtc_log.resize(log_size ? log_size - 1 : 0);
+        nvrtc().GetProgramLogSize(prog, &log_size);
+        r->nvrtc_log.clear();
         if (log_size > 1) {
             std::vector<char> log(log_size);
-            nvrtcGetProgramLog(prog, log.data());
+            nvrtc().GetProgramLog(prog, log.data());
             r->nvrtc_log.assign(log.data());
         }
+        {
+            int vmaj = 0, vmin = 0;
+            nvrtc().Version(&vmaj, &vmin);
+            r->nvrtc_log += "[NVRTC " + std::to_string(vmaj) + "." + std::to_string(vmin) + " from " + nvrtc().path + "]\n";
+        }
         if (res != NVRTC_SUCCESS) {
-            std::string msg = "NVRTC: " + std::string(nvrtcGetErrorString(res)) + "\n" + r->nvrtc_log;
-            nvrtcDestroyProgram(&prog);
+            std::string msg = "NVRTC: " + std::string(nvrtc().GetErrorString(res)) + "\n" + r->nvrtc_log;
+            nvrtc().DestroyProgram(&prog);
             delete r;
             return fail(SE_ERR_COMPILE, msg);
         }
         size_t cubin_size = 0;
-        if (nvrtcGetCUBINSize(prog, &cubin_size) != NVRTC_SUCCESS || cubin_size == 0) {
-            nvrtcDestroyProgram(&prog);
+        if (nvrtc().GetCUBINSize(prog, &cubin_size) != NVRTC_SUCCESS || cubin_size == 0) {
+            nvrtc().DestroyProgram(&prog);
             delete r;
             return fail(SE_ERR_COMPILE, "NVRTC produced no cubin");
         }
         r->cubin.resize(cubin_size);
-        nvrtcGetCUBIN(prog, r->cubin.data());
-        nvrtcDestroyProgram(&prog);
+        nvrtc().GetCUBIN(prog, r->cubin.data());
+        nvrtc().DestroyProgram(&prog);
         r->compiled = true;
     }
     *out = r;
@@ -494,8 +555,9 @@ int one_step(se_sim* s, bool use_mods, int n_mods) {
         lp.table_bytes = s->table_bytes; lp.pool_offset = s->pool_offset; lp.lut = s->d_lut;
         lp.pool = s->d_pool ? s->d_pool : s->d_lut + s->pool_offset / 4;      // mode 1: the pool sits behind the table in one image
         lp.tiles_x = s->lf_tiles_x; lp.tiles_y = s->lf_tiles_y; lp.buf_offset = s->lf_buf_offset;
+        lp.tiles_x_magic = s->lf_tiles_x > 1 ? (unsigned)((1ull << 32) / (unsigned long long)s->lf_tiles_x + 1ull) : 0u;
         void* fargs[] = {&s->tm_cells[s->cur], &s->tm_light[s->lcur], &lp};
-        int rcf = launch(s, s->f_step_lit, dim3(s->lf_grid), dim3(512), fargs, (unsigned)s->lf_smem);
+        int rcf = launch(s, s->f_step_lit, dim3(s->lf_grid), dim3(1024), fargs, (unsigned)s->lf_smem);
         if (rcf) return rcf;
         s->cur ^= 1;
         s->lcur ^= 1;
@@ -832,17 +894,19 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
         const int owned = s->row_end - s->row_begin;
         // ---- K3f: with lighting on, step + override + lighting in one TMA-fed kernel (se_step_lit) ----
         if (ok && s->lighting && !std::getenv("SE_NO_FUSED_LIT")) {     // env: A/B against the two-kernel path
-            s->lf_buf_offset = 0;                                        // the table is read from global memory: shared memory holds the two input buffers only
-            s->lf_smem = 2 * LF_BUF_BYTES + 128;                         // + 128: the kernel aligns its buffers itself
-            if (2 * (s->lf_smem + 13 * 1024) <= smem_optin) {            // two CTAs per SM (+ static: modification list, id bytes, fat table)
+            // one CTA of two halves per SM: the staged table (mode 1) + two input buffers per half (+ 128: the kernel aligns
+            // its buffers itself); static: modification lists, id bytes, fat table
+            s->lf_buf_offset = s->lut_mode == 1 ? (s->table_bytes + 127) / 128 * 128 : 0;
+            s->lf_smem = s->lf_buf_offset + 4 * LF_BUF_BYTES + 128;
+            if (s->lf_smem + 24 * 1024 <= smem_optin) {
                 SE_CU_S(driver().ModuleGetFunction(&s->f_step_lit, s->mod, "se_step_lit"));
                 SE_CU_S(driver().FuncSetAttribute(s->f_step_lit, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->lf_smem));
                 s->lf_tiles_x = (s->W + LF_TW - 1) / LF_TW;
                 s->lf_tiles_y = (s->Hl + LF_TH - 1) / LF_TH;
-                s->lf_grid = (int)std::min<long long>((long long)std::max(1, 2 * n_sm / s->device_share), (long long)s->lf_tiles_x * s->lf_tiles_y);
+                s->lf_grid = (int)std::min<long long>((long long)std::max(1, n_sm / s->device_share), ((long long)s->lf_tiles_x * s->lf_tiles_y + 1) / 2);
                 bool maps_ok = true;
                 for (int b = 0; b < 2 && maps_ok; ++b) {
-                    // ids: 3-D [Hl][W/4][4] u32 (groups of four cells = 16 bytes, like a float4), box 4 x 18 x 34: the box starts
+                    // ids: 3-D [Hl][W/4][4] u32 (groups of four cells = 16 bytes, like a float4), box 4 x 18 x (LF_TH + 2): the box starts
                     // four columns left of the tile; out-of-range elements read 0.  (A 2-D box with a 272-byte row is accepted
                     // by the encoder and then faults as an illegal instruction: box rows stay at 16 bytes.)
                     const cuuint64_t cdim[3] = {4, (cuuint64_t)s->W / 4, (cuuint64_t)s->Hl}, cstr[2] = {16, (cuuint64_t)s->W * 4};
@@ -850,7 +914,7 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
                     maps_ok = driver().TensorMapEncodeTiled(&s->tm_cells[b], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, s->cells[b], cdim, cstr, cbox, cel,
                                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-                    // light: 3-D [Hl][W][4] f32, box 4 x 66 x 34 (a float4 per cell)
+                    // light: 3-D [Hl][W][4] f32, box 4 x 66 x (LF_TH + 2) (a float4 per cell)
                     const cuuint64_t ldim[3] = {4, (cuuint64_t)s->W, (cuuint64_t)s->Hl}, lstr[2] = {16, (cuuint64_t)s->W * 16};
                     const cuuint32_t lbox[3] = {4, LF_TW + 2, LF_TH + 2}, lel[3] = {1, 1, 1};
                     maps_ok = maps_ok && driver().TensorMapEncodeTiled(&s->tm_light[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s->light[b], ldim, lstr, lbox, lel,

@@ -1321,30 +1321,39 @@ extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_
 // dispatch, falling_sand.glsl:737-799 + operations.glsl:99-171), for table-eligible rule sets.  HBM-bound by design:
 // 4 B old id + 16 B old light in, 4 B new id + 16 B new light out per cell = the 40 algorithmic bytes.
 //
-// Persistent CTAs (one per SM, 512 threads) walk 64 x 32 tiles.  The inputs of a tile -- light and ids of the tile and
-// its one-cell ring -- arrive by TMA (cp.async.bulk.tensor: one 3-D box of float4 light, one 3-D box of ids in groups of
-// four, out-of-grid elements zero-filled) into one of two shared-memory buffers, signalled by an mbarrier; the loads of tile i+1 are
-// issued before tile i is touched, so HBM latency is hidden by a whole tile of work without a single register staged.
-// Per tile, three phases:
-//   A  every ring + tile cell: old id -> one byte (unknown ids NULL, WALL outside the grid, MISSING inside the grid but
-//      outside a strip's buffer) and the reader-independent neighbour term (rgb * keep * a, a) written over the light
-//   B  the 2x2 blocks that cover the tile (they lie inside tile + ring: the block offset is 0 or 1) through the
-//      transition table, in place in the byte array; blocks cut by a tile edge are evaluated by both CTAs
-//      (deterministic: RAND depends on position and frame only)
-//   C  every tile cell: new id (table result, overridden by the culled modification list), stored; the eight
-//      neighbour terms combined in the shader's order with a sliding 3 x 3 window (as in se_light), stored
+// One persistent CTA of 1024 threads per SM, run as TWO INDEPENDENT HALVES of 16 warps (named barriers, like K1b) that
+// share one copy of the transition table in shared memory (mode 1; mode 2 reads it in place).  A half walks 64 x 16
+// tiles.  The inputs of a tile -- light and ids of the tile and its one-cell ring -- arrive by TMA
+// (cp.async.bulk.tensor: one 3-D box of float4 light, one 3-D box of ids in groups of four, out-of-grid elements
+// zero-filled) into one of the half's two buffers, signalled by an mbarrier.  Three jobs per tile:
+//   B  the 2x2 blocks that cover the tile (they lie inside tile + ring: the block offset is 0 or 1): old ids straight
+//      from the TMA buffer (unknown ids NULL, WALL outside the grid, MISSING inside the grid but outside a strip's
+//      buffer) through the transition table, one block per thread, new ids as bytes; blocks cut by a tile edge are
+//      evaluated by both neighbours (deterministic: RAND depends on position and frame only)
+//   A  every ring + tile cell: the reader-independent neighbour term (rgb * keep * a, a) written over the light
+//   C  every tile cell: new id (B's byte, overridden by the culled modification list), stored; the eight neighbour
+//      terms combined in the shader's order, stored.  Tiles whose ring lies inside the grid and the buffer take a
+//      branch-free version: packed adds (add.f32x2) for the sums, three-input maxima, the alpha rule (a zero alpha
+//      counts as the running maximum) as one predicated add.
+// A and B depend on the TMA data only, C on A and B of the same tile: the loop is software-pipelined -- an iteration is
+// C(k), then B(k+1) and A(k+1), then ONE barrier of the half; the loads of tile k+1 are issued at the start of the
+// iteration (their buffer was released by the barrier before) and land while C(k) runs.  Id bytes and the culled
+// modification list (indices) are double-buffered like the TMA buffers.
 // =============================================================================================
 #define SE_LF_TW 64
-#define SE_LF_TH 32
+#define SE_LF_TH 16
+#define SE_LF_RH (SE_LF_TH + 2)                      // ring rows
 #define SE_LF_LSTRIDE (SE_LF_TW + 2)                 // light / term row stride (float4)
 #define SE_LF_ISTRIDE (SE_LF_TW + 8)                 // id row stride (elements): the id box starts 4 columns left of the tile (16-byte groups)
 #define SE_LF_ICOL0 3                                // ring column j is element j + 3 of an id row
-#define SE_LF_LIGHT_BYTES ((SE_LF_TH + 2) * SE_LF_LSTRIDE * 16)
-#define SE_LF_IDS_BYTES ((SE_LF_TH + 2) * SE_LF_ISTRIDE * 4)
+#define SE_LF_LIGHT_BYTES (SE_LF_RH * SE_LF_LSTRIDE * 16)
+#define SE_LF_IDS_BYTES (SE_LF_RH * SE_LF_ISTRIDE * 4)
 #define SE_LF_IDS_OFFSET ((SE_LF_LIGHT_BYTES + 127) / 128 * 128)
 #define SE_LF_BUF_BYTES ((SE_LF_IDS_OFFSET + SE_LF_IDS_BYTES + 127) / 128 * 128)
 #define SE_LF_MISSING 0xFFu
-#define SE_LF_THREADS 512
+#define SE_LF_HALF 512
+#define SE_LF_THREADS 1024
+#define SE_LF_RING_CELLS (SE_LF_RH * SE_LF_LSTRIDE)
 
 struct alignas(64) SeTensorMap { unsigned long long opaque[16]; };   // CUtensorMap (cuda.h), encoded by the host
 
@@ -1359,7 +1368,8 @@ struct SeLitParams {
     const unsigned* lut;
     const unsigned* pool;
     int tiles_x, tiles_y;
-    int buf_offset;          // byte offset of the first input buffer in dynamic shared memory (128-aligned, behind the staged table)
+    int buf_offset;          // byte offset of the first input buffer in dynamic shared memory (behind the staged table)
+    unsigned tiles_x_magic;  // floor(2^32 / tiles_x) + 1: tile index -> (row, column) without a division
 };
 
 // can record m touch a cell of the rectangle?  (both shapes lie inside the square |dx|,|dy| <= size; negative sizes never
@@ -1382,24 +1392,41 @@ static __device__ __forceinline__ void se_mbar_wait(unsigned mbar_sa, unsigned p
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" :: "r"(mbar_sa), "r"(parity) : "memory");
 }
-static __device__ __forceinline__ void se_tma_load_2d(unsigned dst_sa, const SeTensorMap* tm, int c0, int c1, unsigned mbar_sa) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 :: "r"(dst_sa), "l"(reinterpret_cast<unsigned long long>(tm)), "r"(c0), "r"(c1), "r"(mbar_sa) : "memory");
-}
 static __device__ __forceinline__ void se_tma_load_3d(unsigned dst_sa, const SeTensorMap* tm, int c0, int c1, int c2, unsigned mbar_sa) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  :: "r"(dst_sa), "l"(reinterpret_cast<unsigned long long>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(mbar_sa) : "memory");
 }
 
-// phase A for one ring / tile cell c = i * SE_LF_LSTRIDE + j
-template <bool INTERIOR>
-static __device__ __forceinline__ void se_lit_stage_cell(const SeLitParams& p, const unsigned* fat_sm, unsigned light_sa, unsigned ids_sa, unsigned char* ids8,
+// a term / light value as two packed pairs: (x, y) and (z, w), the registers an LDS.128 delivers
+struct SeF4P { unsigned long long xy, zw; };
+static __device__ __forceinline__ SeF4P se_lds_f4p(unsigned a) {
+    SeF4P v;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v.xy), "=l"(v.zw) : "r"(a));
+    return v;
+}
+static __device__ __forceinline__ unsigned long long se_add2(unsigned long long a, unsigned long long b) {   // two IEEE f32 adds (FADD2)
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+static __device__ __forceinline__ float se_lo(unsigned long long v) { return __uint_as_float((unsigned)v); }
+static __device__ __forceinline__ float se_hi(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
+static __device__ __forceinline__ float se_max3(float a, float b, float c) {
+#if (__CUDACC_VER_MAJOR__ > 12) || (__CUDACC_VER_MAJOR__ == 12 && __CUDACC_VER_MINOR__ >= 9)
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));   // FMNMX3 (the ptxas of CUDA 12.8 and older rejects the three-input form)
+    return r;
+#else
+    return fmaxf(fmaxf(a, b), c);
+#endif
+}
+
+// phase A for one ring / tile cell c = i * SE_LF_LSTRIDE + j of a tile that touches the edge of the grid or of the buffer
+static __device__ __forceinline__ void se_lit_stage_cell(const SeLitParams& p, const unsigned* fat_sm, unsigned light_sa, unsigned ids_sa,
                                                          int x_org, int yl_org, int c, int i, int j) {
     const int x = x_org + j, yl = yl_org + i, y = p.gy0 + yl;
-    const bool in_grid = INTERIOR || (x >= 0 && x < p.W && y >= 0 && y < p.Hg);
-    const bool local = INTERIOR || (in_grid && yl >= 0 && yl < p.Hl);
+    const bool local = x >= 0 && x < p.W && y >= 0 && y < p.Hg && yl >= 0 && yl < p.Hl;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    unsigned idb = in_grid ? SE_LF_MISSING : 2u;                             // WALL outside the grid (operations.glsl:45-51)
     if (local) {
         const unsigned id = se_lds_u32(ids_sa + 4u * (unsigned)(i * SE_LF_ISTRIDE + j + SE_LF_ICOL0));
         float4 li;
@@ -1408,133 +1435,191 @@ static __device__ __forceinline__ void se_lit_stage_cell(const SeLitParams& p, c
         const float keep = (nf & SE_F_OBSTACLE) ? 0.0f : 1.0f;             // vec4(vec3(float(!obstacle)), 1.0), :498
         const float la = li.w;
         v = make_float4((li.x * keep) * la, (li.y * keep) * la, (li.z * keep) * la, la);
-        idb = se_clamp_id(id);
     }
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(light_sa + 16u * (unsigned)c), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-    ids8[i * SE_LF_ISTRIDE + j] = (unsigned char)idb;
 }
 
-extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 2) se_step_lit(const __grid_constant__ SeTensorMap tm_cells, const __grid_constant__ SeTensorMap tm_light,
+// per-cell modification scan over the culled list (indices into the frame's records, order kept): se_mod_lookup
+static __device__ __forceinline__ bool se_mod_lookup_culled(const SeMod* __restrict__ mods, const unsigned char* idx, int n, int x, int y, unsigned& mat_out) {
+    bool got = false;
+    int fin = 1;   // MAT_NULL
+    for (int i = 0; i < n; ++i) {
+        const SeMod m = mods[idx[i]];
+        const int dx = abs(m.px - x), dy = abs(m.py - y);
+        bool hit = false;
+        if (m.shape == 0) {
+            const float fx = (float)dx, fy = (float)dy;
+            const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)));
+            hit = dist <= (float)m.size;
+        } else if (m.shape == 1) {
+            hit = dx <= m.size && dy <= m.size;
+        }
+        if (hit) { got = true; fin = m.mat; }
+    }
+    mat_out = (unsigned)fin;
+    return got && fin != 1;
+}
+
+// one neighbour term of the branch-free phase C: sums as two packed adds; a zero alpha counts as the running maximum of
+// the alphas before it (math.glsl:168-176: adding the zero first is exact, so one predicated add corrects the sum), and the
+// running maximum itself is max(previous, alpha) in both cases (it is never negative)
+#define SE_LF_ACC(v)                                                                      \
+    {                                                                                     \
+        const float w_ = se_hi((v).zw);                                                   \
+        sxy = se_add2(sxy, (v).xy); szw = se_add2(szw, (v).zw);                           \
+        if (w_ == 0.0f) szw = ((unsigned long long)__float_as_uint(se_hi(szw) + mf) << 32) | (szw & 0xFFFFFFFFull); \
+        mf = fmaxf(mf, w_);                                                               \
+    }
+#define SE_LF_MAX2(v1, v2)                                                                \
+    {                                                                                     \
+        mxx = se_max3(mxx, se_lo((v1).xy), se_lo((v2).xy)); mxy = se_max3(mxy, se_hi((v1).xy), se_hi((v2).xy)); \
+        mxz = se_max3(mxz, se_lo((v1).zw), se_lo((v2).zw));                               \
+    }
+#define SE_LF_FINISH(out)                                                                 \
+    {                                                                                     \
+        const float ax = se_lo(sxy) * 0.125f, ay = se_hi(sxy) * 0.125f, az = se_lo(szw) * 0.125f, aw = se_hi(szw) * 0.125f;   /* num == 8: exact */ \
+        out = make_float4(ax * 0.5f + mxx * 0.5f, ay * 0.5f + mxy * 0.5f, az * 0.5f + mxz * 0.5f, aw);   /* mix(avg.rgb, max.rgb, 0.5), :521 */ \
+    }
+
+extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const __grid_constant__ SeTensorMap tm_cells, const __grid_constant__ SeTensorMap tm_light,
                                                                               const SeLitParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ unsigned fat_sm[256];
-    __shared__ SeMod mods_sm[256];
-    __shared__ int n_cull_sm;
-    __shared__ __align__(8) unsigned long long mbar[2];
-    __shared__ __align__(4) unsigned char ids8[(SE_LF_TH + 2) * SE_LF_ISTRIDE];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ unsigned char cull_sm[2][2][256];
+    __shared__ int n_cull_sm[2][2];
+    __shared__ __align__(8) unsigned long long mbar[4];
+    __shared__ __align__(16) unsigned char ids8[2][2][SE_LF_RH * SE_LF_ISTRIDE];
+    const int tid = threadIdx.x, lane = tid & 31, half = tid >> 9, ht = tid & (SE_LF_HALF - 1), hw = ht >> 5;
     unsigned smem_sa;
     asm volatile("mov.u32 %0, %1;" : "=r"(smem_sa) : "r"((unsigned)__cvta_generic_to_shared(smem)));
-    // the table is read where it lies in global memory (L1 / L2 resident: 561 blocks per tile against 2048 lit cells),
-    // which leaves the shared memory to two CTAs per SM: one stages / transitions while the other relaxes light
-    const SeTabG tab{p.lut, p.pool};
+#if SE_LUT_MODE == 1
+    {
+        const uint4* lut4 = reinterpret_cast<const uint4*>(p.lut);
+        const int n4 = (p.table_bytes + 15) >> 4;
+        for (int i = tid; i < n4; i += SE_LF_THREADS) {
+            const uint4 v = __ldg(lut4 + i);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(smem_sa + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        }
+    }
+    const SeTab tab{smem_sa, smem_sa + (unsigned)p.pool_offset};
+#else
+    const SeTab tab{p.lut, p.pool};
+#endif
     if (tid < 256) fat_sm[tid] = se_fat_table[tid];
-    const unsigned mbar_sa = (unsigned)__cvta_generic_to_shared(mbar);
+    const unsigned mbar_sa = (unsigned)__cvta_generic_to_shared(mbar) + 16u * (unsigned)half;   // this half's two barriers
     if (tid == 0) {
-        se_mbar_init(mbar_sa, 1u);
-        se_mbar_init(mbar_sa + 8u, 1u);
+        for (unsigned k = 0; k < 4u; ++k) se_mbar_init((unsigned)__cvta_generic_to_shared(mbar) + 8u * k, 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     const int n_tiles = p.tiles_x * p.tiles_y;
-    const unsigned buf0_sa = (smem_sa + 127u) & ~127u;       // TMA destinations are 128-byte aligned whatever the base of dynamic shared memory is
+    const int first = 2 * (int)blockIdx.x + half, stride = 2 * (int)gridDim.x;
+    // TMA destinations are 128-byte aligned whatever the base of dynamic shared memory is
+    const unsigned buf0_sa = ((smem_sa + (unsigned)p.buf_offset + 127u) & ~127u) + (unsigned)half * (2u * SE_LF_BUF_BYTES);
+    const unsigned ids8_base = (unsigned)__cvta_generic_to_shared(&ids8[half][0][0]);
+    auto tile_xy = [&](int t, int& bx, int& by) {          // t = by * tiles_x + bx
+        by = p.tiles_x > 1 ? (int)__umulhi((unsigned)t, p.tiles_x_magic) : t;
+        bx = t - by * p.tiles_x;
+        if (bx < 0) { --by; bx += p.tiles_x; }
+    };
     auto issue = [&](int t, int buf) {                       // one thread: both boxes of tile t into buffer `buf`
-        const int by = t / p.tiles_x, bx = t - by * p.tiles_x;
+        int bx, by;
+        tile_xy(t, bx, by);
         const unsigned dst = buf0_sa + (unsigned)buf * SE_LF_BUF_BYTES, mb = mbar_sa + 8u * (unsigned)buf;
         se_mbar_expect_tx(mb, SE_LF_LIGHT_BYTES + SE_LF_IDS_BYTES);
         se_tma_load_3d(dst, &tm_light, 0, bx * SE_LF_TW - 1, by * SE_LF_TH - 1, mb);
         se_tma_load_3d(dst + SE_LF_IDS_OFFSET, &tm_cells, 0, bx * (SE_LF_TW / 4) - 1, by * SE_LF_TH - 1, mb);
     };
-    if (tid == 0 && (int)blockIdx.x < n_tiles) issue((int)blockIdx.x, 0);
+    auto is_interior = [&](int bx, int by) {
+        const int x_org = bx * SE_LF_TW - 1, yl_org = by * SE_LF_TH - 1;
+        return x_org >= 0 && x_org + SE_LF_TW + 1 < p.W && yl_org >= 0 && yl_org + SE_LF_TH + 1 < p.Hl &&
+               p.gy0 + yl_org >= 0 && p.gy0 + yl_org + SE_LF_TH + 1 < p.Hg;
+    };
+    if (ht == 0 && first < n_tiles) issue(first, 0);
 
     int ox, oy;
     se_margolus_offset(p.frame, ox, oy);
-    int it = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const int by = t / p.tiles_x, bx = t - by * p.tiles_x;
-        const int x_org = bx * SE_LF_TW - 1, yl_org = by * SE_LF_TH - 1;      // ring cell (0, 0): column / local row
-        // the next tile's loads go out before this tile is touched (its buffer was released by the barrier that ended the
-        // previous iteration; the proxy fence orders that iteration's generic writes before the async ones)
-        if (tid == 0 && t + (int)gridDim.x < n_tiles) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(t + (int)gridDim.x, buf ^ 1);
-        }
-        // modification list culled against this tile by ONE warp, order kept (last match wins, falling_sand.glsl:764-773)
-        if (warp == 1) {
-            int n = 0;
-            const int x_lo = bx * SE_LF_TW, y_lo = p.gy0 + by * SE_LF_TH;
-            for (int m0 = 0; m0 < p.n_mods; m0 += 32) {
-                bool keep = false;
-                SeMod m;
-                if (m0 + lane < p.n_mods) { m = p.mods[m0 + lane]; keep = se_mod_touches(m, x_lo, x_lo + SE_LF_TW - 1, y_lo, y_lo + SE_LF_TH - 1); }
-                const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
-                if (keep) mods_sm[n + __popc(ballot & ((1u << lane) - 1u))] = m;
-                n += __popc(ballot);
+    for (int k = -1, t = first - stride;; ++k, t += stride) {
+        const bool has_next = t + stride < n_tiles;
+        if (k >= 0) {
+            const int buf = k & 1;
+            // every thread of the half is past phase C of tile k - 1: that tile's buffer takes the loads of tile k + 1
+            // (the proxy fence orders the generic writes of its phase A before the async ones)
+            if (ht == 0 && has_next) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(t + stride, buf ^ 1);
             }
-            if (lane == 0) n_cull_sm = n;
-        }
-        const bool interior = x_org >= 0 && x_org + SE_LF_TW + 1 < p.W && yl_org >= 0 && yl_org + SE_LF_TH + 1 < p.Hl &&
-                              p.gy0 + yl_org >= 0 && p.gy0 + yl_org + SE_LF_TH + 1 < p.Hg;
-        se_mbar_wait(mbar_sa + 8u * (unsigned)buf, (unsigned)(it >> 1) & 1u);
-        const unsigned light_sa = buf0_sa + (unsigned)buf * SE_LF_BUF_BYTES, ids_sa = light_sa + SE_LF_IDS_OFFSET;
-
-        // ---- phase A: id bytes and neighbour terms of every ring + tile cell ((i, j) stepped without a division) ----
-        {
-            int c = tid, i = tid / SE_LF_LSTRIDE, j = tid - i * SE_LF_LSTRIDE;
-            const int di = SE_LF_THREADS / SE_LF_LSTRIDE, dj = SE_LF_THREADS - di * SE_LF_LSTRIDE;
-            for (; c < (SE_LF_TH + 2) * SE_LF_LSTRIDE; c += SE_LF_THREADS) {
-                if (interior) se_lit_stage_cell<true>(p, fat_sm, light_sa, ids_sa, ids8, x_org, yl_org, c, i, j);
-                else se_lit_stage_cell<false>(p, fat_sm, light_sa, ids_sa, ids8, x_org, yl_org, c, i, j);
-                i += di; j += dj;
-                if (j >= SE_LF_LSTRIDE) { j -= SE_LF_LSTRIDE; ++i; }
-            }
-        }
-        __syncthreads();
-        const int n_cull = n_cull_sm;
-
-        // ---- phase B: the blocks that cover the tile, in place in ids8 ----
-        {
-            const int nbx = SE_LF_TW / 2 + ox, nby = SE_LF_TH / 2 + oy;
-            const unsigned fterm = (unsigned)p.frame * (2131u * 2131u);
-            for (int b = tid; b < nbx * nby; b += SE_LF_THREADS) {
-                const int bj = b / nbx, bi = b - bj * nbx;
-                const int cx = 2 * bi + 1 - ox, cy = 2 * bj + 1 - oy;      // ring coordinates of the block's top-left cell
-                unsigned char* q = ids8 + cy * SE_LF_ISTRIDE + cx;
-                const unsigned a = q[0], bb = q[1], c = q[SE_LF_ISTRIDE], d = q[SE_LF_ISTRIDE + 1];
-                if ((a | bb | c | d) & 0x80u) continue;                    // a row of the block is not in the local buffer: skipped (see K1a)
-                const unsigned v = a | (bb << 8) | (c << 16) | (d << 24);
-                const unsigned seed = (unsigned)(x_org + cx) * 461u + (unsigned)(p.gy0 + yl_org + cy) * 2131u + fterm;
-                const unsigned nv = se_block_lut(v, seed, 0, 0, 0, tab, fat_sm);
-                q[0] = (unsigned char)(nv & 0xFFu); q[1] = (unsigned char)((nv >> 8) & 0xFFu);
-                q[SE_LF_ISTRIDE] = (unsigned char)((nv >> 16) & 0xFFu); q[SE_LF_ISTRIDE + 1] = (unsigned char)(nv >> 24);
-            }
-        }
-        __syncthreads();
-
-        // ---- phase C: new id + light of every tile cell: column tid & 31 of half (warp & 1), rows 4 * (warp >> 1) .. + 3 ----
-        {
-            const int tx = lane + 32 * (warp & 1), row0 = (warp >> 1) * 4;
+            // ---- phase C of tile k: new id + light of every tile cell: column lane + 32 * (warp & 1), rows 2 * (warp >> 1), + 1 ----
+            int bx, by;
+            tile_xy(t, bx, by);
+            const unsigned light_sa = buf0_sa + (unsigned)buf * SE_LF_BUF_BYTES;
+            const unsigned ids8_sa = ids8_base + (unsigned)buf * (SE_LF_RH * SE_LF_ISTRIDE);
+            const int n_cull = n_cull_sm[half][buf];
+            const unsigned char* const cull = cull_sm[half][buf];
+            const int tx = lane + 32 * (hw & 1), row0 = (hw >> 1) * 2;
             const int x = bx * SE_LF_TW + tx;
-            if (x < p.W) {
-                const unsigned tp = light_sa + 16u * (unsigned)(row0 * SE_LF_LSTRIDE + tx);      // term (row0 - 1, tx - 1) of the tile
+            const unsigned tp = light_sa + 16u * (unsigned)(row0 * SE_LF_LSTRIDE + tx);      // term (row0 - 1, tx - 1) of the tile
+            const unsigned idp = ids8_sa + (unsigned)((row0 + 1) * SE_LF_ISTRIDE + tx + 1 + SE_LF_ICOL0);
+#define SE_LF_T(r, c) se_lds_f4p(tp + 16u * (unsigned)((r) * SE_LF_LSTRIDE + (c)))          /* ring row row0 + r, ring column tx + c */
+            if (is_interior(bx, by)) {
+                // rows R0..R3 = ring rows row0 .. row0 + 3; cell 1 sits in R1, cell 2 in R2.  Terms are loaded where the shader's
+                // order needs them; the four that both cells use (R1 and R2, left and right) stay in registers.
+                const int y1 = p.gy0 + by * SE_LF_TH + row0;
+                size_t idx = (size_t)(by * SE_LF_TH + row0) * p.W + x;
+                unsigned id1 = se_lds_u8(idp), id2 = se_lds_u8(idp + SE_LF_ISTRIDE);
+                if (n_cull) {
+                    unsigned m;
+                    if (se_mod_lookup_culled(p.mods, cull, n_cull, x, y1, m)) id1 = m;
+                    if (se_mod_lookup_culled(p.mods, cull, n_cull, x, y1 + 1, m)) id2 = m;
+                }
+                p.new_cells[idx] = id1;
+                p.new_cells[idx + (size_t)p.W] = id2;
+                const unsigned me1 = id1 < 255u ? id1 : 255u, me2 = id2 < 255u ? id2 : 255u;
+                const bool em1 = (fat_sm[me1] & SE_F_EMISSIVE) != 0u, em2 = (fat_sm[me2] & SE_F_EMISSIVE) != 0u;
+                float4 out1, out2;
+                SeF4P r1l, r1r, r2l, r2r;
+                {   // cell 1: DOWN, UP, DOWNLEFT, UPLEFT, DOWNRIGHT, UPRIGHT, RIGHT, LEFT (math.glsl:154-166)
+                    unsigned long long sxy = 0ull, szw = 0ull;
+                    float mf = 0.0f, mxx = 0.0f, mxy = 0.0f, mxz = 0.0f;
+                    { const SeF4P d = SE_LF_T(2, 1), u = SE_LF_T(0, 1); SE_LF_ACC(d) SE_LF_ACC(u) SE_LF_MAX2(d, u) }
+                    r2l = SE_LF_T(2, 0);
+                    { const SeF4P u = SE_LF_T(0, 0); SE_LF_ACC(r2l) SE_LF_ACC(u) SE_LF_MAX2(r2l, u) }
+                    r2r = SE_LF_T(2, 2);
+                    { const SeF4P u = SE_LF_T(0, 2); SE_LF_ACC(r2r) SE_LF_ACC(u) SE_LF_MAX2(r2r, u) }
+                    r1r = SE_LF_T(1, 2); r1l = SE_LF_T(1, 0);
+                    SE_LF_ACC(r1r) SE_LF_ACC(r1l) SE_LF_MAX2(r1r, r1l)
+                    SE_LF_FINISH(out1)
+                }
+                if (em1) out1 = make_float4(se_emission_table[me1 * 4 + 0], se_emission_table[me1 * 4 + 1], se_emission_table[me1 * 4 + 2], se_emission_table[me1 * 4 + 3]);   // operations.glsl:126-127
+                p.light_out[idx] = out1;
+                {   // cell 2
+                    unsigned long long sxy = 0ull, szw = 0ull;
+                    float mf = 0.0f, mxx = 0.0f, mxy = 0.0f, mxz = 0.0f;
+                    { const SeF4P d = SE_LF_T(3, 1), u = SE_LF_T(1, 1); SE_LF_ACC(d) SE_LF_ACC(u) SE_LF_MAX2(d, u) }
+                    { const SeF4P d = SE_LF_T(3, 0); SE_LF_ACC(d) SE_LF_ACC(r1l) SE_LF_MAX2(d, r1l) }
+                    { const SeF4P d = SE_LF_T(3, 2); SE_LF_ACC(d) SE_LF_ACC(r1r) SE_LF_MAX2(d, r1r) }
+                    SE_LF_ACC(r2r) SE_LF_ACC(r2l) SE_LF_MAX2(r2r, r2l)
+                    SE_LF_FINISH(out2)
+                }
+                if (em2) out2 = make_float4(se_emission_table[me2 * 4 + 0], se_emission_table[me2 * 4 + 1], se_emission_table[me2 * 4 + 2], se_emission_table[me2 * 4 + 3]);
+                p.light_out[idx + (size_t)p.W] = out2;
+            } else if (x < p.W) {
 #define SE_LF_LDT(dst, off) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dst.x), "=f"(dst.y), "=f"(dst.z), "=f"(dst.w) : "r"(tp + 16u * (unsigned)(off)))
                 float4 a0, a1, a2, b0, b1, b2;
                 SE_LF_LDT(a0, 0); SE_LF_LDT(a1, 1); SE_LF_LDT(a2, 2);
                 SE_LF_LDT(b0, SE_LF_LSTRIDE); SE_LF_LDT(b1, SE_LF_LSTRIDE + 1); SE_LF_LDT(b2, SE_LF_LSTRIDE + 2);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < 2; ++i) {
                     const int yl = by * SE_LF_TH + row0 + i;
                     if (yl >= p.Hl) break;
                     float4 c0, c1, c2;
                     SE_LF_LDT(c0, (i + 2) * SE_LF_LSTRIDE); SE_LF_LDT(c1, (i + 2) * SE_LF_LSTRIDE + 1); SE_LF_LDT(c2, (i + 2) * SE_LF_LSTRIDE + 2);
                     const int y = p.gy0 + yl;
                     const size_t idx = (size_t)yl * p.W + x;
-                    unsigned id = ids8[(row0 + i + 1) * SE_LF_ISTRIDE + tx + 1];
+                    unsigned id = se_lds_u8(idp + (unsigned)(i * SE_LF_ISTRIDE));
                     if (n_cull) {
                         unsigned m;
-                        if (se_mod_lookup(mods_sm, n_cull, x, y, m)) id = m;
+                        if (se_mod_lookup_culled(p.mods, cull, n_cull, x, y, m)) id = m;
                     }
                     p.new_cells[idx] = id;
                     const unsigned me = id < 255u ? id : 255u;
@@ -1546,27 +1631,20 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 2) se_step_lit(const
                     } else {
                         float4 avg = make_float4(0.f, 0.f, 0.f, 0.f), mx = make_float4(0.f, 0.f, 0.f, 0.f);
                         float max_falloff = 0.0f;
-                        if (interior) {
-                            // DOWN, UP, DOWNLEFT, UPLEFT, DOWNRIGHT, UPRIGHT, RIGHT, LEFT (math.glsl:154-166)
-                            SE_LIGHT_ACC(c1) SE_LIGHT_ACC(a1) SE_LIGHT_ACC(c0) SE_LIGHT_ACC(a0)
-                            SE_LIGHT_ACC(c2) SE_LIGHT_ACC(a2) SE_LIGHT_ACC(b2) SE_LIGHT_ACC(b0)
-                            avg.x *= 0.125f; avg.y *= 0.125f; avg.z *= 0.125f; avg.w *= 0.125f;    // num == 8: exact
-                        } else {
-                            const bool up = yl - 1 >= 0 && y - 1 >= 0, down = yl + 1 < p.Hl && y + 1 < p.Hg;
-                            const bool left = x - 1 >= 0, right = x + 1 < p.W;
-                            int num = 0;
-                            if (down) { SE_LIGHT_ACC(c1) ++num; }
-                            if (up) { SE_LIGHT_ACC(a1) ++num; }
-                            if (down && left) { SE_LIGHT_ACC(c0) ++num; }
-                            if (up && left) { SE_LIGHT_ACC(a0) ++num; }
-                            if (down && right) { SE_LIGHT_ACC(c2) ++num; }
-                            if (up && right) { SE_LIGHT_ACC(a2) ++num; }
-                            if (right) { SE_LIGHT_ACC(b2) ++num; }
-                            if (left) { SE_LIGHT_ACC(b0) ++num; }
-                            if (num > 0) {                                  // :516-518
-                                const float dn = (float)num;
-                                avg.x = __fdiv_rn(avg.x, dn); avg.y = __fdiv_rn(avg.y, dn); avg.z = __fdiv_rn(avg.z, dn); avg.w = __fdiv_rn(avg.w, dn);
-                            }
+                        const bool up = yl - 1 >= 0 && y - 1 >= 0, down = yl + 1 < p.Hl && y + 1 < p.Hg;
+                        const bool left = x - 1 >= 0, right = x + 1 < p.W;
+                        int num = 0;
+                        if (down) { SE_LIGHT_ACC(c1) ++num; }
+                        if (up) { SE_LIGHT_ACC(a1) ++num; }
+                        if (down && left) { SE_LIGHT_ACC(c0) ++num; }
+                        if (up && left) { SE_LIGHT_ACC(a0) ++num; }
+                        if (down && right) { SE_LIGHT_ACC(c2) ++num; }
+                        if (up && right) { SE_LIGHT_ACC(a2) ++num; }
+                        if (right) { SE_LIGHT_ACC(b2) ++num; }
+                        if (left) { SE_LIGHT_ACC(b0) ++num; }
+                        if (num > 0) {                                      // :516-518
+                            const float dn = (float)num;
+                            avg.x = __fdiv_rn(avg.x, dn); avg.y = __fdiv_rn(avg.y, dn); avg.z = __fdiv_rn(avg.z, dn); avg.w = __fdiv_rn(avg.w, dn);
                         }
                         light = make_float4(avg.x * 0.5f + mx.x * 0.5f, avg.y * 0.5f + mx.y * 0.5f, avg.z * 0.5f + mx.z * 0.5f, avg.w);   // mix(avg.rgb, max.rgb, 0.5), :521
                     }
@@ -1576,9 +1654,92 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 2) se_step_lit(const
                 }
 #undef SE_LF_LDT
             }
+#undef SE_LF_T
         }
-        __syncthreads();                                   // the buffers, ids8 and mods_sm are free for the next tile
+        if (!has_next) break;
+
+        // ---- tile k + 1: its loads have had phase C to land ----
+        {
+            const int buf = (k + 1) & 1;
+            int bx, by;
+            tile_xy(t + stride, bx, by);
+            const int x_org = bx * SE_LF_TW - 1, yl_org = by * SE_LF_TH - 1;      // ring cell (0, 0): column / local row
+            const bool interior = is_interior(bx, by);
+            const unsigned light_sa = buf0_sa + (unsigned)buf * SE_LF_BUF_BYTES, ids_sa = light_sa + SE_LF_IDS_OFFSET;
+            const unsigned ids8_sa = ids8_base + (unsigned)buf * (SE_LF_RH * SE_LF_ISTRIDE);
+            se_mbar_wait(mbar_sa + 8u * (unsigned)buf, (unsigned)((k + 1) >> 1) & 1u);
+
+            // ---- phase B: the blocks that cover the tile, old ids from the TMA buffer, new ids as bytes; the last warp
+            //      culls the modifications (order kept: last match wins, falling_sand.glsl:764-773) ----
+            const int nbx = SE_LF_TW / 2 + ox, nby = SE_LF_TH / 2 + oy;
+            if (ht < nbx * nby) {
+                const int bj = ox ? ht / (SE_LF_TW / 2 + 1) : ht / (SE_LF_TW / 2), bi = ht - bj * nbx;
+                const int cx = 2 * bi + 1 - ox, cy = 2 * bj + 1 - oy;      // ring coordinates of the block's top-left cell
+                const unsigned e0 = (unsigned)(cy * SE_LF_ISTRIDE + cx + SE_LF_ICOL0);
+                unsigned a = se_lds_u32(ids_sa + 4u * e0), bb = se_lds_u32(ids_sa + 4u * (e0 + 1u));
+                unsigned c = se_lds_u32(ids_sa + 4u * (e0 + SE_LF_ISTRIDE)), d = se_lds_u32(ids_sa + 4u * (e0 + SE_LF_ISTRIDE + 1u));
+                a = se_clamp_id(a); bb = se_clamp_id(bb); c = se_clamp_id(c); d = se_clamp_id(d);
+                if (!interior) {                                           // WALL outside the grid (operations.glsl:45-51), MISSING outside the buffer
+                    const int x0 = x_org + cx, yl0 = yl_org + cy, y0 = p.gy0 + yl0;
+                    const bool xin0 = x0 >= 0 && x0 < p.W, xin1 = x0 + 1 >= 0 && x0 + 1 < p.W;
+                    const bool yin0 = y0 >= 0 && y0 < p.Hg, yin1 = y0 + 1 >= 0 && y0 + 1 < p.Hg;
+                    const bool loc0 = yl0 >= 0 && yl0 < p.Hl, loc1 = yl0 + 1 >= 0 && yl0 + 1 < p.Hl;
+                    a = !(xin0 && yin0) ? 2u : (loc0 ? a : SE_LF_MISSING);
+                    bb = !(xin1 && yin0) ? 2u : (loc0 ? bb : SE_LF_MISSING);
+                    c = !(xin0 && yin1) ? 2u : (loc1 ? c : SE_LF_MISSING);
+                    d = !(xin1 && yin1) ? 2u : (loc1 ? d : SE_LF_MISSING);
+                }
+                unsigned nv = a | (bb << 8) | (c << 16) | (d << 24);
+                if (!((a | bb | c | d) & 0x80u)) {                         // else a row of the block is not in the local buffer: skipped (see K1a)
+                    const unsigned seed = (unsigned)(x_org + cx) * 461u + (unsigned)(p.gy0 + yl_org + cy) * 2131u + (unsigned)p.frame * (2131u * 2131u);
+                    nv = se_block_lut(nv, seed, 0, 0, 0, tab, fat_sm);
+                }
+                const unsigned q = ids8_sa + e0;
+                se_sts_u8(q, nv & 0xFFu); se_sts_u8(q + 1u, (nv >> 8) & 0xFFu);
+                se_sts_u8(q + SE_LF_ISTRIDE, (nv >> 16) & 0xFFu); se_sts_u8(q + SE_LF_ISTRIDE + 1u, nv >> 24);
+            } else if (hw == SE_LF_HALF / 32 - 1) {
+                int n = 0;
+                const int x_lo = bx * SE_LF_TW, y_lo = p.gy0 + by * SE_LF_TH;
+                for (int m0 = 0; m0 < p.n_mods; m0 += 32) {
+                    bool keep = false;
+                    if (m0 + lane < p.n_mods) keep = se_mod_touches(p.mods[m0 + lane], x_lo, x_lo + SE_LF_TW - 1, y_lo, y_lo + SE_LF_TH - 1);
+                    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
+                    if (keep) cull_sm[half][buf][n + __popc(ballot & ((1u << lane) - 1u))] = (unsigned char)(m0 + lane);
+                    n += __popc(ballot);
+                }
+                if (lane == 0) n_cull_sm[half][buf] = n;
+            }
+
+            // ---- phase A: the neighbour term of every ring + tile cell, in place; the short third pass goes to the warps
+            //      that had no block ----
+            if (interior) {
+#pragma unroll
+                for (int n = 0; n < 3; ++n) {
+                    const int c = n < 2 ? ht + n * SE_LF_HALF : ht + (SE_LF_RING_CELLS - SE_LF_HALF);
+                    if (n < 2 || c >= 2 * SE_LF_HALF) {
+                        const int i = c / SE_LF_LSTRIDE;
+                        const unsigned e = (unsigned)(c + i * (SE_LF_ISTRIDE - SE_LF_LSTRIDE) + SE_LF_ICOL0);   // i * ISTRIDE + j + ICOL0
+                        const unsigned id = se_lds_u32(ids_sa + 4u * e);
+                        const SeF4P li = se_lds_f4p(light_sa + 16u * (unsigned)c);
+                        const unsigned nf = fat_sm[id < 255u ? id : 255u];
+                        // (rgb * keep) * a with keep in {0, 1} is rgb * (keep ? a : 0) for finite light
+                        const float la = se_hi(li.zw), lk = (nf & SE_F_OBSTACLE) ? 0.0f : la;
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(light_sa + 16u * (unsigned)c),
+                                     "f"(se_lo(li.xy) * lk), "f"(se_hi(li.xy) * lk), "f"(se_lo(li.zw) * lk), "f"(la) : "memory");
+                    }
+                }
+            } else {
+                for (int c = ht; c < SE_LF_RING_CELLS; c += SE_LF_HALF) {
+                    const int i = c / SE_LF_LSTRIDE, j = c - i * SE_LF_LSTRIDE;
+                    se_lit_stage_cell(p, fat_sm, light_sa, ids_sa, x_org, yl_org, c, i, j);
+                }
+            }
+        }
+        se_half_sync(half);
     }
 }
+#undef SE_LF_ACC
+#undef SE_LF_MAX2
+#undef SE_LF_FINISH
 #endif  // SE_HOST_EMU
 #endif  // SE_LUT_ELIGIBLE
