@@ -1324,8 +1324,8 @@ extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_
 // One persistent CTA of 1024 threads per SM, run as TWO INDEPENDENT HALVES of 16 warps (named barriers, like K1b) that
 // share one copy of the transition table in shared memory (mode 1; mode 2 reads it in place).  A half walks 64 x 16
 // tiles.  The inputs of a tile -- light and ids of the tile and its one-cell ring -- arrive by TMA
-// (cp.async.bulk.tensor: one 3-D box of float4 light, one 3-D box of ids in groups of four, out-of-grid elements
-// zero-filled) into one of the half's two buffers, signalled by an mbarrier.  Three jobs per tile:
+// (cp.async.bulk.tensor: one 3-D box of light in groups of four float4, one 3-D box of ids in groups of 16, out-of-grid
+// elements zero-filled) into one of the half's two buffers, signalled by an mbarrier.  Three jobs per tile:
 //   B  the 2x2 blocks that cover the tile (they lie inside tile + ring: the block offset is 0 or 1): old ids straight
 //      from the TMA buffer (unknown ids NULL, WALL outside the grid, MISSING inside the grid but outside a strip's
 //      buffer) through the transition table, one block per thread, new ids as bytes; blocks cut by a tile edge are
@@ -1343,9 +1343,17 @@ extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_
 #define SE_LF_TW 64
 #define SE_LF_TH 16
 #define SE_LF_RH (SE_LF_TH + 2)                      // ring rows
-#define SE_LF_LSTRIDE (SE_LF_TW + 2)                 // light / term row stride (float4)
-#define SE_LF_ISTRIDE (SE_LF_TW + 8)                 // id row stride (elements): the id box starts 4 columns left of the tile (16-byte groups)
-#define SE_LF_ICOL0 3                                // ring column j is element j + 3 of an id row
+#define SE_LF_RW (SE_LF_TW + 2)                      // ring columns
+// TMA box rows are 64 bytes (16-byte rows -- a float4, four ids -- made the TMA unit the bottleneck: 1512 box rows per
+// tile): the light box is 18 groups of four float4 and starts 4 columns left of the tile, the id box is 6 groups of 16 ids
+// and starts 16 columns left of it.  Ring column j is element j + LCOL0 of a light row, j + ICOL0 of an id row and
+// j + BCOL0 of a row of id bytes.
+#define SE_LF_LSTRIDE (SE_LF_TW + 8)                 // light / term row stride (float4)
+#define SE_LF_LCOL0 3
+#define SE_LF_ISTRIDE (SE_LF_TW + 32)                // id row stride (u32)
+#define SE_LF_ICOL0 15
+#define SE_LF_BSTRIDE (SE_LF_TW + 8)                 // id byte row stride
+#define SE_LF_BCOL0 3
 #define SE_LF_LIGHT_BYTES (SE_LF_RH * SE_LF_LSTRIDE * 16)
 #define SE_LF_IDS_BYTES (SE_LF_RH * SE_LF_ISTRIDE * 4)
 #define SE_LF_IDS_OFFSET ((SE_LF_LIGHT_BYTES + 127) / 128 * 128)
@@ -1353,7 +1361,13 @@ extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_
 #define SE_LF_MISSING 0xFFu
 #define SE_LF_HALF 512
 #define SE_LF_THREADS 1024
-#define SE_LF_RING_CELLS (SE_LF_RH * SE_LF_LSTRIDE)
+#ifndef SE_LF_NBUF
+#define SE_LF_NBUF 3                                 // TMA buffers per half: the loads of tile k + NBUF - 1 are issued when tile k's phase C starts
+#endif
+#ifndef SE_LF_TABLE_SMEM
+#define SE_LF_TABLE_SMEM 0                           // 1: stage the transition table in shared memory (mode 1 only; leaves room for two buffers per half)
+#endif
+#define SE_LF_RING_CELLS (SE_LF_RH * SE_LF_RW)
 
 struct alignas(64) SeTensorMap { unsigned long long opaque[16]; };   // CUtensorMap (cuda.h), encoded by the host
 
@@ -1421,22 +1435,23 @@ static __device__ __forceinline__ float se_max3(float a, float b, float c) {
 #endif
 }
 
-// phase A for one ring / tile cell c = i * SE_LF_LSTRIDE + j of a tile that touches the edge of the grid or of the buffer
+// phase A for one ring / tile cell (row i, column j) of a tile that touches the edge of the grid or of the buffer
 static __device__ __forceinline__ void se_lit_stage_cell(const SeLitParams& p, const unsigned* fat_sm, unsigned light_sa, unsigned ids_sa,
-                                                         int x_org, int yl_org, int c, int i, int j) {
+                                                         int x_org, int yl_org, int i, int j) {
+    const unsigned c = (unsigned)(i * SE_LF_LSTRIDE + j + SE_LF_LCOL0);
     const int x = x_org + j, yl = yl_org + i, y = p.gy0 + yl;
     const bool local = x >= 0 && x < p.W && y >= 0 && y < p.Hg && yl >= 0 && yl < p.Hl;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (local) {
         const unsigned id = se_lds_u32(ids_sa + 4u * (unsigned)(i * SE_LF_ISTRIDE + j + SE_LF_ICOL0));
         float4 li;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(li.x), "=f"(li.y), "=f"(li.z), "=f"(li.w) : "r"(light_sa + 16u * (unsigned)c));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(li.x), "=f"(li.y), "=f"(li.z), "=f"(li.w) : "r"(light_sa + 16u * c));
         const unsigned nf = fat_sm[id < 255u ? id : 255u];
         const float keep = (nf & SE_F_OBSTACLE) ? 0.0f : 1.0f;             // vec4(vec3(float(!obstacle)), 1.0), :498
         const float la = li.w;
         v = make_float4((li.x * keep) * la, (li.y * keep) * la, (li.z * keep) * la, la);
     }
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(light_sa + 16u * (unsigned)c), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(light_sa + 16u * c), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 // per-cell modification scan over the culled list (indices into the frame's records, order kept): se_mod_lookup
@@ -1487,12 +1502,14 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
     __shared__ unsigned fat_sm[256];
     __shared__ unsigned char cull_sm[2][2][256];
     __shared__ int n_cull_sm[2][2];
-    __shared__ __align__(8) unsigned long long mbar[4];
-    __shared__ __align__(16) unsigned char ids8[2][2][SE_LF_RH * SE_LF_ISTRIDE];
+    __shared__ __align__(8) unsigned long long mbar[2 * SE_LF_NBUF];
+    __shared__ __align__(16) unsigned char ids8[2][2][SE_LF_RH * SE_LF_BSTRIDE];
     const int tid = threadIdx.x, lane = tid & 31, half = tid >> 9, ht = tid & (SE_LF_HALF - 1), hw = ht >> 5;
     unsigned smem_sa;
     asm volatile("mov.u32 %0, %1;" : "=r"(smem_sa) : "r"((unsigned)__cvta_generic_to_shared(smem)));
-#if SE_LUT_MODE == 1
+    // The table is read where it lies (L1 / L2): phase B is off the critical path (its results are needed behind the next
+    // barrier), and the shared memory buys a third TMA buffer per half instead -- the loads are what the kernel waits for.
+#if SE_LUT_MODE == 1 && SE_LF_TABLE_SMEM
     {
         const uint4* lut4 = reinterpret_cast<const uint4*>(p.lut);
         const int n4 = (p.table_bytes + 15) >> 4;
@@ -1501,14 +1518,14 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(smem_sa + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
         }
     }
-    const SeTab tab{smem_sa, smem_sa + (unsigned)p.pool_offset};
+    const SeTabS tab{smem_sa, smem_sa + (unsigned)p.pool_offset};
 #else
-    const SeTab tab{p.lut, p.pool};
+    const SeTabG tab{p.lut, p.pool};
 #endif
     if (tid < 256) fat_sm[tid] = se_fat_table[tid];
-    const unsigned mbar_sa = (unsigned)__cvta_generic_to_shared(mbar) + 16u * (unsigned)half;   // this half's two barriers
+    const unsigned mbar_sa = (unsigned)__cvta_generic_to_shared(mbar) + 8u * SE_LF_NBUF * (unsigned)half;   // this half's barriers
     if (tid == 0) {
-        for (unsigned k = 0; k < 4u; ++k) se_mbar_init((unsigned)__cvta_generic_to_shared(mbar) + 8u * k, 1u);
+        for (unsigned k = 0; k < 2u * SE_LF_NBUF; ++k) se_mbar_init((unsigned)__cvta_generic_to_shared(mbar) + 8u * k, 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -1516,7 +1533,7 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
     const int n_tiles = p.tiles_x * p.tiles_y;
     const int first = 2 * (int)blockIdx.x + half, stride = 2 * (int)gridDim.x;
     // TMA destinations are 128-byte aligned whatever the base of dynamic shared memory is
-    const unsigned buf0_sa = ((smem_sa + (unsigned)p.buf_offset + 127u) & ~127u) + (unsigned)half * (2u * SE_LF_BUF_BYTES);
+    const unsigned buf0_sa = ((smem_sa + (unsigned)p.buf_offset + 127u) & ~127u) + (unsigned)half * (SE_LF_NBUF * SE_LF_BUF_BYTES);
     const unsigned ids8_base = (unsigned)__cvta_generic_to_shared(&ids8[half][0][0]);
     auto tile_xy = [&](int t, int& bx, int& by) {          // t = by * tiles_x + bx
         by = p.tiles_x > 1 ? (int)__umulhi((unsigned)t, p.tiles_x_magic) : t;
@@ -1528,46 +1545,52 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
         tile_xy(t, bx, by);
         const unsigned dst = buf0_sa + (unsigned)buf * SE_LF_BUF_BYTES, mb = mbar_sa + 8u * (unsigned)buf;
         se_mbar_expect_tx(mb, SE_LF_LIGHT_BYTES + SE_LF_IDS_BYTES);
-        se_tma_load_3d(dst, &tm_light, 0, bx * SE_LF_TW - 1, by * SE_LF_TH - 1, mb);
-        se_tma_load_3d(dst + SE_LF_IDS_OFFSET, &tm_cells, 0, bx * (SE_LF_TW / 4) - 1, by * SE_LF_TH - 1, mb);
+        se_tma_load_3d(dst, &tm_light, 0, bx * (SE_LF_TW / 4) - 1, by * SE_LF_TH - 1, mb);
+        se_tma_load_3d(dst + SE_LF_IDS_OFFSET, &tm_cells, 0, bx * (SE_LF_TW / 16) - 1, by * SE_LF_TH - 1, mb);
     };
     auto is_interior = [&](int bx, int by) {
         const int x_org = bx * SE_LF_TW - 1, yl_org = by * SE_LF_TH - 1;
         return x_org >= 0 && x_org + SE_LF_TW + 1 < p.W && yl_org >= 0 && yl_org + SE_LF_TH + 1 < p.Hl &&
                p.gy0 + yl_org >= 0 && p.gy0 + yl_org + SE_LF_TH + 1 < p.Hg;
     };
-    if (ht == 0 && first < n_tiles) issue(first, 0);
+    if (ht == 0) {
+        for (int j = 0; j < SE_LF_NBUF - 1; ++j)
+            if (first + j * stride < n_tiles) issue(first + j * stride, j);
+    }
 
     int ox, oy;
     se_margolus_offset(p.frame, ox, oy);
+    // buffers: tile k sits in bufC, tile k + 1 is staged in bufS (mbarrier parity parS), tile k + NBUF - 1 is loaded into bufI
+    int bufI = 0, bufC = SE_LF_NBUF - 1, bufS = 0;
+    unsigned parS = 0u;
     for (int k = -1, t = first - stride;; ++k, t += stride) {
         const bool has_next = t + stride < n_tiles;
         if (k >= 0) {
-            const int buf = k & 1;
-            // every thread of the half is past phase C of tile k - 1: that tile's buffer takes the loads of tile k + 1
+            const int buf = bufC, par = k & 1;
+            // every thread of the half is past phase C of tile k - 1: that tile's buffer takes the loads of tile k + NBUF - 1
             // (the proxy fence orders the generic writes of its phase A before the async ones)
-            if (ht == 0 && has_next) {
+            if (ht == 0 && t + (SE_LF_NBUF - 1) * stride < n_tiles) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue(t + stride, buf ^ 1);
+                issue(t + (SE_LF_NBUF - 1) * stride, bufI);
             }
             // ---- phase C of tile k: new id + light of every tile cell: column lane + 32 * (warp & 1), rows 2 * (warp >> 1), + 1 ----
             int bx, by;
             tile_xy(t, bx, by);
             const unsigned light_sa = buf0_sa + (unsigned)buf * SE_LF_BUF_BYTES;
-            const unsigned ids8_sa = ids8_base + (unsigned)buf * (SE_LF_RH * SE_LF_ISTRIDE);
-            const int n_cull = n_cull_sm[half][buf];
-            const unsigned char* const cull = cull_sm[half][buf];
+            const unsigned ids8_sa = ids8_base + (unsigned)par * (SE_LF_RH * SE_LF_BSTRIDE);
+            const int n_cull = n_cull_sm[half][par];
+            const unsigned char* const cull = cull_sm[half][par];
             const int tx = lane + 32 * (hw & 1), row0 = (hw >> 1) * 2;
             const int x = bx * SE_LF_TW + tx;
-            const unsigned tp = light_sa + 16u * (unsigned)(row0 * SE_LF_LSTRIDE + tx);      // term (row0 - 1, tx - 1) of the tile
-            const unsigned idp = ids8_sa + (unsigned)((row0 + 1) * SE_LF_ISTRIDE + tx + 1 + SE_LF_ICOL0);
+            const unsigned tp = light_sa + 16u * (unsigned)(row0 * SE_LF_LSTRIDE + tx + SE_LF_LCOL0);      // term (row0 - 1, tx - 1) of the tile
+            const unsigned idp = ids8_sa + (unsigned)((row0 + 1) * SE_LF_BSTRIDE + tx + 1 + SE_LF_BCOL0);
 #define SE_LF_T(r, c) se_lds_f4p(tp + 16u * (unsigned)((r) * SE_LF_LSTRIDE + (c)))          /* ring row row0 + r, ring column tx + c */
             if (is_interior(bx, by)) {
                 // rows R0..R3 = ring rows row0 .. row0 + 3; cell 1 sits in R1, cell 2 in R2.  Terms are loaded where the shader's
                 // order needs them; the four that both cells use (R1 and R2, left and right) stay in registers.
                 const int y1 = p.gy0 + by * SE_LF_TH + row0;
                 size_t idx = (size_t)(by * SE_LF_TH + row0) * p.W + x;
-                unsigned id1 = se_lds_u8(idp), id2 = se_lds_u8(idp + SE_LF_ISTRIDE);
+                unsigned id1 = se_lds_u8(idp), id2 = se_lds_u8(idp + SE_LF_BSTRIDE);
                 if (n_cull) {
                     unsigned m;
                     if (se_mod_lookup_culled(p.mods, cull, n_cull, x, y1, m)) id1 = m;
@@ -1616,7 +1639,7 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
                     SE_LF_LDT(c0, (i + 2) * SE_LF_LSTRIDE); SE_LF_LDT(c1, (i + 2) * SE_LF_LSTRIDE + 1); SE_LF_LDT(c2, (i + 2) * SE_LF_LSTRIDE + 2);
                     const int y = p.gy0 + yl;
                     const size_t idx = (size_t)yl * p.W + x;
-                    unsigned id = se_lds_u8(idp + (unsigned)(i * SE_LF_ISTRIDE));
+                    unsigned id = se_lds_u8(idp + (unsigned)(i * SE_LF_BSTRIDE));
                     if (n_cull) {
                         unsigned m;
                         if (se_mod_lookup_culled(p.mods, cull, n_cull, x, y, m)) id = m;
@@ -1660,14 +1683,14 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
 
         // ---- tile k + 1: its loads have had phase C to land ----
         {
-            const int buf = (k + 1) & 1;
+            const int buf = bufS, par = (k + 1) & 1;
             int bx, by;
             tile_xy(t + stride, bx, by);
             const int x_org = bx * SE_LF_TW - 1, yl_org = by * SE_LF_TH - 1;      // ring cell (0, 0): column / local row
             const bool interior = is_interior(bx, by);
             const unsigned light_sa = buf0_sa + (unsigned)buf * SE_LF_BUF_BYTES, ids_sa = light_sa + SE_LF_IDS_OFFSET;
-            const unsigned ids8_sa = ids8_base + (unsigned)buf * (SE_LF_RH * SE_LF_ISTRIDE);
-            se_mbar_wait(mbar_sa + 8u * (unsigned)buf, (unsigned)((k + 1) >> 1) & 1u);
+            const unsigned ids8_sa = ids8_base + (unsigned)par * (SE_LF_RH * SE_LF_BSTRIDE);
+            se_mbar_wait(mbar_sa + 8u * (unsigned)buf, parS);
 
             // ---- phase B: the blocks that cover the tile, old ids from the TMA buffer, new ids as bytes; the last warp
             //      culls the modifications (order kept: last match wins, falling_sand.glsl:764-773) ----
@@ -1694,9 +1717,9 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
                     const unsigned seed = (unsigned)(x_org + cx) * 461u + (unsigned)(p.gy0 + yl_org + cy) * 2131u + (unsigned)p.frame * (2131u * 2131u);
                     nv = se_block_lut(nv, seed, 0, 0, 0, tab, fat_sm);
                 }
-                const unsigned q = ids8_sa + e0;
+                const unsigned q = ids8_sa + (unsigned)(cy * SE_LF_BSTRIDE + cx + SE_LF_BCOL0);
                 se_sts_u8(q, nv & 0xFFu); se_sts_u8(q + 1u, (nv >> 8) & 0xFFu);
-                se_sts_u8(q + SE_LF_ISTRIDE, (nv >> 16) & 0xFFu); se_sts_u8(q + SE_LF_ISTRIDE + 1u, nv >> 24);
+                se_sts_u8(q + SE_LF_BSTRIDE, (nv >> 16) & 0xFFu); se_sts_u8(q + SE_LF_BSTRIDE + 1u, nv >> 24);
             } else if (hw == SE_LF_HALF / 32 - 1) {
                 int n = 0;
                 const int x_lo = bx * SE_LF_TW, y_lo = p.gy0 + by * SE_LF_TH;
@@ -1704,10 +1727,10 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
                     bool keep = false;
                     if (m0 + lane < p.n_mods) keep = se_mod_touches(p.mods[m0 + lane], x_lo, x_lo + SE_LF_TW - 1, y_lo, y_lo + SE_LF_TH - 1);
                     const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
-                    if (keep) cull_sm[half][buf][n + __popc(ballot & ((1u << lane) - 1u))] = (unsigned char)(m0 + lane);
+                    if (keep) cull_sm[half][par][n + __popc(ballot & ((1u << lane) - 1u))] = (unsigned char)(m0 + lane);
                     n += __popc(ballot);
                 }
-                if (lane == 0) n_cull_sm[half][buf] = n;
+                if (lane == 0) n_cull_sm[half][par] = n;
             }
 
             // ---- phase A: the neighbour term of every ring + tile cell, in place; the short third pass goes to the warps
@@ -1717,25 +1740,28 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
                 for (int n = 0; n < 3; ++n) {
                     const int c = n < 2 ? ht + n * SE_LF_HALF : ht + (SE_LF_RING_CELLS - SE_LF_HALF);
                     if (n < 2 || c >= 2 * SE_LF_HALF) {
-                        const int i = c / SE_LF_LSTRIDE;
-                        const unsigned e = (unsigned)(c + i * (SE_LF_ISTRIDE - SE_LF_LSTRIDE) + SE_LF_ICOL0);   // i * ISTRIDE + j + ICOL0
+                        const int i = c / SE_LF_RW;                          // c = i * RW + j
+                        const unsigned e = (unsigned)(c + i * (SE_LF_ISTRIDE - SE_LF_RW) + SE_LF_ICOL0);   // i * ISTRIDE + j + ICOL0
+                        const unsigned la_sa = light_sa + 16u * (unsigned)(c + i * (SE_LF_LSTRIDE - SE_LF_RW) + SE_LF_LCOL0);
                         const unsigned id = se_lds_u32(ids_sa + 4u * e);
-                        const SeF4P li = se_lds_f4p(light_sa + 16u * (unsigned)c);
+                        const SeF4P li = se_lds_f4p(la_sa);
                         const unsigned nf = fat_sm[id < 255u ? id : 255u];
                         // (rgb * keep) * a with keep in {0, 1} is rgb * (keep ? a : 0) for finite light
                         const float la = se_hi(li.zw), lk = (nf & SE_F_OBSTACLE) ? 0.0f : la;
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(light_sa + 16u * (unsigned)c),
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(la_sa),
                                      "f"(se_lo(li.xy) * lk), "f"(se_hi(li.xy) * lk), "f"(se_lo(li.zw) * lk), "f"(la) : "memory");
                     }
                 }
             } else {
                 for (int c = ht; c < SE_LF_RING_CELLS; c += SE_LF_HALF) {
-                    const int i = c / SE_LF_LSTRIDE, j = c - i * SE_LF_LSTRIDE;
-                    se_lit_stage_cell(p, fat_sm, light_sa, ids_sa, x_org, yl_org, c, i, j);
+                    const int i = c / SE_LF_RW, j = c - i * SE_LF_RW;
+                    se_lit_stage_cell(p, fat_sm, light_sa, ids_sa, x_org, yl_org, i, j);
                 }
             }
         }
         se_half_sync(half);
+        bufI = bufC; bufC = bufS;
+        if (++bufS == SE_LF_NBUF) { bufS = 0; parS ^= 1u; }
     }
 }
 #undef SE_LF_ACC
