@@ -247,10 +247,21 @@ struct SeLitParams {
     int buf_offset;
     unsigned tiles_x_magic;
 };
-// geometry of se_step_lit (kernels/sand_kernels.cuh: SE_LF_*)
-constexpr int LF_TW = 64, LF_TH = 16, LF_NBUF = 3;   // SE_LF_NBUF of the kernel
-constexpr int LF_LIGHT_BYTES = (LF_TH + 2) * (LF_TW + 8) * 16, LF_IDS_BYTES = (LF_TH + 2) * (LF_TW + 32) * 4;
-constexpr int LF_IDS_OFFSET = (LF_LIGHT_BYTES + 127) / 128 * 128, LF_BUF_BYTES = (LF_IDS_OFFSET + LF_IDS_BYTES + 127) / 128 * 128;
+// geometry of se_step_lit (kernels/sand_kernels.cuh: SE_LF_*).  Tile height and buffer count can be overridden for experiments
+// (SE_LF_TH = 16 | 32, SE_LF_NBUF = 2 | 3 in the environment: passed to NVRTC and used for the tensor maps alike).
+constexpr int LF_TW = 64;
+int lf_env(const char* name, int dflt, int lo, int hi) {
+    const char* e = std::getenv(name);
+    if (!e) return dflt;
+    const int v = std::atoi(e);
+    return v >= lo && v <= hi ? v : dflt;
+}
+int lf_th() { const int v = lf_env("SE_LF_TH", 32, 16, 32); return v == 16 ? 16 : 32; }
+int lf_nbuf() { return lf_env("SE_LF_NBUF", 2, 2, 3); }
+int lf_buf_bytes() {
+    const int light = (lf_th() + 2) * (LF_TW + 8) * 16, ids = (lf_th() + 2) * (LF_TW + 16) * 4;
+    return ((light + 127) / 128 * 128 + ids + 127) / 128 * 128;
+}
 
 // words of the per-sim flag block that sits behind cells[0] in the same allocation (one IPC handle maps both)
 enum : int {
@@ -408,6 +419,8 @@ int compile_front(const char* yaml, size_t len, se_rules** out, bool with_nvrtc)
             const int v = std::atoi(mc);
             if (v >= 1 && v <= 8) extra.push_back("-DSE_LT_MINCTAS=" + std::to_string(v));
         }
+        extra.push_back("-DSE_LF_TH=" + std::to_string(lf_th()));
+        extra.push_back("-DSE_LF_NBUF=" + std::to_string(lf_nbuf()));
         if (const char* defs = std::getenv("SE_NVRTC_DEFS")) {
             std::string d(defs), tok;
             for (size_t i = 0; i <= d.size(); ++i) {
@@ -893,31 +906,31 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
         cudaFree(d_counter);
         const int owned = s->row_end - s->row_begin;
         // ---- K3f: with lighting on, step + override + lighting in one TMA-fed kernel (se_step_lit) ----
-        if (ok && s->lighting && (s->W % 16) == 0 && !std::getenv("SE_NO_FUSED_LIT")) {   // W % 16: the id box moves in groups of 16;     // env: A/B against the two-kernel path
+        if (ok && s->lighting && (s->W % 8) == 0 && !std::getenv("SE_NO_FUSED_LIT")) {   // W % 8: the id box moves in groups of 8;     // env: A/B against the two-kernel path
             // one CTA of two halves per SM, LF_NBUF input buffers per half (+ 128: the kernel aligns its buffers itself); the table
             // is read where it lies in global memory
             s->lf_buf_offset = 0;
-            s->lf_smem = 2 * LF_NBUF * LF_BUF_BYTES + 128;
-            if (s->lf_smem + 8 * 1024 <= smem_optin) {
+            s->lf_smem = 2 * lf_nbuf() * lf_buf_bytes() + 128;
+            if (s->lf_smem + 13 * 1024 <= smem_optin) {
                 SE_CU_S(driver().ModuleGetFunction(&s->f_step_lit, s->mod, "se_step_lit"));
                 SE_CU_S(driver().FuncSetAttribute(s->f_step_lit, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->lf_smem));
                 s->lf_tiles_x = (s->W + LF_TW - 1) / LF_TW;
-                s->lf_tiles_y = (s->Hl + LF_TH - 1) / LF_TH;
+                s->lf_tiles_y = (s->Hl + lf_th() - 1) / lf_th();
                 s->lf_grid = (int)std::min<long long>((long long)std::max(1, n_sm / s->device_share), ((long long)s->lf_tiles_x * s->lf_tiles_y + 1) / 2);
                 bool maps_ok = true;
                 for (int b = 0; b < 2 && maps_ok; ++b) {
-                    // Box rows are 64 bytes: 16-byte rows (a float4, four ids) made the TMA unit the bottleneck.  (A 2-D box with a
-                    // 272-byte row is accepted by the encoder and then faults as an illegal instruction.)
-                    // ids: 3-D [Hl][W/16][16] u32, box 16 x 6 x (LF_TH + 2): the box starts 16 columns left of the tile; out-of-range
+                    // Box rows are 64 bytes of light and 32 bytes of ids: 16-byte rows (a float4, four ids) made the TMA unit the
+                    // bottleneck.  (A 2-D box with a 272-byte row is accepted by the encoder and then faults as an illegal instruction.)
+                    // ids: 3-D [Hl][W/8][8] u32, box 8 x 10 x (TH + 2): the box starts 8 columns left of the tile; out-of-range
                     // elements read 0
-                    const cuuint64_t cdim[3] = {16, (cuuint64_t)s->W / 16, (cuuint64_t)s->Hl}, cstr[2] = {64, (cuuint64_t)s->W * 4};
-                    const cuuint32_t cbox[3] = {16, (LF_TW + 32) / 16, LF_TH + 2}, cel[3] = {1, 1, 1};
+                    const cuuint64_t cdim[3] = {8, (cuuint64_t)s->W / 8, (cuuint64_t)s->Hl}, cstr[2] = {32, (cuuint64_t)s->W * 4};
+                    const cuuint32_t cbox[3] = {8, (LF_TW + 16) / 8, (cuuint32_t)lf_th() + 2}, cel[3] = {1, 1, 1};
                     maps_ok = driver().TensorMapEncodeTiled(&s->tm_cells[b], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, s->cells[b], cdim, cstr, cbox, cel,
                                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-                    // light: 3-D [Hl][W/4][16] f32 (four cells), box 16 x 18 x (LF_TH + 2): starts 4 columns left of the tile
+                    // light: 3-D [Hl][W/4][16] f32 (four cells), box 16 x 18 x (TH + 2): starts 4 columns left of the tile
                     const cuuint64_t ldim[3] = {16, (cuuint64_t)s->W / 4, (cuuint64_t)s->Hl}, lstr[2] = {64, (cuuint64_t)s->W * 16};
-                    const cuuint32_t lbox[3] = {16, (LF_TW + 8) / 4, LF_TH + 2}, lel[3] = {1, 1, 1};
+                    const cuuint32_t lbox[3] = {16, (LF_TW + 8) / 4, (cuuint32_t)lf_th() + 2}, lel[3] = {1, 1, 1};
                     maps_ok = maps_ok && driver().TensorMapEncodeTiled(&s->tm_light[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s->light[b], ldim, lstr, lbox, lel,
                                                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;

@@ -1322,8 +1322,7 @@ extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_
 // 4 B old id + 16 B old light in, 4 B new id + 16 B new light out per cell = the 40 algorithmic bytes.
 //
 // One persistent CTA of 1024 threads per SM, run as TWO INDEPENDENT HALVES of 16 warps (named barriers, like K1b) that
-// share one copy of the transition table in shared memory (mode 1; mode 2 reads it in place).  A half walks 64 x 16
-// tiles.  The inputs of a tile -- light and ids of the tile and its one-cell ring -- arrive by TMA
+// read the transition table where it lies (L1 / L2).  A half walks 64 x 32 tiles.  The inputs of a tile -- light and ids of the tile and its one-cell ring -- arrive by TMA
 // (cp.async.bulk.tensor: one 3-D box of light in groups of four float4, one 3-D box of ids in groups of 16, out-of-grid
 // elements zero-filled) into one of the half's two buffers, signalled by an mbarrier.  Three jobs per tile:
 //   B  the 2x2 blocks that cover the tile (they lie inside tile + ring: the block offset is 0 or 1): old ids straight
@@ -1341,17 +1340,19 @@ extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_
 // modification list (indices) are double-buffered like the TMA buffers.
 // =============================================================================================
 #define SE_LF_TW 64
-#define SE_LF_TH 16
+#ifndef SE_LF_TH
+#define SE_LF_TH 32                                  // tile height: 16 or 32 (a thread relaxes SE_LF_TH / 8 cells of one column)
+#endif
 #define SE_LF_RH (SE_LF_TH + 2)                      // ring rows
 #define SE_LF_RW (SE_LF_TW + 2)                      // ring columns
-// TMA box rows are 64 bytes (16-byte rows -- a float4, four ids -- made the TMA unit the bottleneck: 1512 box rows per
-// tile): the light box is 18 groups of four float4 and starts 4 columns left of the tile, the id box is 6 groups of 16 ids
-// and starts 16 columns left of it.  Ring column j is element j + LCOL0 of a light row, j + ICOL0 of an id row and
-// j + BCOL0 of a row of id bytes.
+// TMA box rows are 64 bytes of light and 32 bytes of ids (16-byte rows -- a float4, four ids -- made the TMA unit the
+// bottleneck: 1512 box rows per 1024 cells): the light box is 18 groups of four float4 and starts 4 columns left of the
+// tile, the id box is 10 groups of 8 ids and starts 8 columns left of it.  Ring column j is element j + LCOL0 of a light
+// row, j + ICOL0 of an id row and j + BCOL0 of a row of id bytes.
 #define SE_LF_LSTRIDE (SE_LF_TW + 8)                 // light / term row stride (float4)
 #define SE_LF_LCOL0 3
-#define SE_LF_ISTRIDE (SE_LF_TW + 32)                // id row stride (u32)
-#define SE_LF_ICOL0 15
+#define SE_LF_ISTRIDE (SE_LF_TW + 16)                // id row stride (u32)
+#define SE_LF_ICOL0 7
 #define SE_LF_BSTRIDE (SE_LF_TW + 8)                 // id byte row stride
 #define SE_LF_BCOL0 3
 #define SE_LF_LIGHT_BYTES (SE_LF_RH * SE_LF_LSTRIDE * 16)
@@ -1362,12 +1363,10 @@ extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_
 #define SE_LF_HALF 512
 #define SE_LF_THREADS 1024
 #ifndef SE_LF_NBUF
-#define SE_LF_NBUF 3                                 // TMA buffers per half: the loads of tile k + NBUF - 1 are issued when tile k's phase C starts
-#endif
-#ifndef SE_LF_TABLE_SMEM
-#define SE_LF_TABLE_SMEM 0                           // 1: stage the transition table in shared memory (mode 1 only; leaves room for two buffers per half)
+#define SE_LF_NBUF 2                                 // TMA buffers per half: the loads of tile k + NBUF - 1 are issued when tile k's phase C starts
 #endif
 #define SE_LF_RING_CELLS (SE_LF_RH * SE_LF_RW)
+#define SE_LF_MAX_BLOCKS ((SE_LF_TW / 2 + 1) * (SE_LF_TH / 2 + 1))
 
 struct alignas(64) SeTensorMap { unsigned long long opaque[16]; };   // CUtensorMap (cuda.h), encoded by the host
 
@@ -1507,21 +1506,9 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
     const int tid = threadIdx.x, lane = tid & 31, half = tid >> 9, ht = tid & (SE_LF_HALF - 1), hw = ht >> 5;
     unsigned smem_sa;
     asm volatile("mov.u32 %0, %1;" : "=r"(smem_sa) : "r"((unsigned)__cvta_generic_to_shared(smem)));
-    // The table is read where it lies (L1 / L2): phase B is off the critical path (its results are needed behind the next
-    // barrier), and the shared memory buys a third TMA buffer per half instead -- the loads are what the kernel waits for.
-#if SE_LUT_MODE == 1 && SE_LF_TABLE_SMEM
-    {
-        const uint4* lut4 = reinterpret_cast<const uint4*>(p.lut);
-        const int n4 = (p.table_bytes + 15) >> 4;
-        for (int i = tid; i < n4; i += SE_LF_THREADS) {
-            const uint4 v = __ldg(lut4 + i);
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(smem_sa + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-        }
-    }
-    const SeTabS tab{smem_sa, smem_sa + (unsigned)p.pool_offset};
-#else
+    // The table is read where it lies (L1 / L2): phase B is off the critical path (its gather is in flight while phase A
+    // runs), and the shared memory holds the TMA buffers instead -- the loads are what the kernel waits for.
     const SeTabG tab{p.lut, p.pool};
-#endif
     if (tid < 256) fat_sm[tid] = se_fat_table[tid];
     const unsigned mbar_sa = (unsigned)__cvta_generic_to_shared(mbar) + 8u * SE_LF_NBUF * (unsigned)half;   // this half's barriers
     if (tid == 0) {
@@ -1546,12 +1533,7 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
         const unsigned dst = buf0_sa + (unsigned)buf * SE_LF_BUF_BYTES, mb = mbar_sa + 8u * (unsigned)buf;
         se_mbar_expect_tx(mb, SE_LF_LIGHT_BYTES + SE_LF_IDS_BYTES);
         se_tma_load_3d(dst, &tm_light, 0, bx * (SE_LF_TW / 4) - 1, by * SE_LF_TH - 1, mb);
-        se_tma_load_3d(dst + SE_LF_IDS_OFFSET, &tm_cells, 0, bx * (SE_LF_TW / 16) - 1, by * SE_LF_TH - 1, mb);
-    };
-    auto is_interior = [&](int bx, int by) {
-        const int x_org = bx * SE_LF_TW - 1, yl_org = by * SE_LF_TH - 1;
-        return x_org >= 0 && x_org + SE_LF_TW + 1 < p.W && yl_org >= 0 && yl_org + SE_LF_TH + 1 < p.Hl &&
-               p.gy0 + yl_org >= 0 && p.gy0 + yl_org + SE_LF_TH + 1 < p.Hg;
+        se_tma_load_3d(dst + SE_LF_IDS_OFFSET, &tm_cells, 0, bx * (SE_LF_TW / 8) - 1, by * SE_LF_TH - 1, mb);
     };
     if (ht == 0) {
         for (int j = 0; j < SE_LF_NBUF - 1; ++j)
@@ -1560,79 +1542,88 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
 
     int ox, oy;
     se_margolus_offset(p.frame, ox, oy);
+    const int nbx = SE_LF_TW / 2 + ox, n_blocks = nbx * (SE_LF_TH / 2 + oy);
     // buffers: tile k sits in bufC, tile k + 1 is staged in bufS (mbarrier parity parS), tile k + NBUF - 1 is loaded into bufI
     int bufI = 0, bufC = SE_LF_NBUF - 1, bufS = 0;
     unsigned parS = 0u;
+    unsigned tileC = 0u;                                     // tile k: bx | by << 10 | interior << 31 (set when it was staged)
     for (int k = -1, t = first - stride;; ++k, t += stride) {
         const bool has_next = t + stride < n_tiles;
         if (k >= 0) {
-            const int buf = bufC, par = k & 1;
+            const int par = k & 1;
             // every thread of the half is past phase C of tile k - 1: that tile's buffer takes the loads of tile k + NBUF - 1
             // (the proxy fence orders the generic writes of its phase A before the async ones)
             if (ht == 0 && t + (SE_LF_NBUF - 1) * stride < n_tiles) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 issue(t + (SE_LF_NBUF - 1) * stride, bufI);
             }
-            // ---- phase C of tile k: new id + light of every tile cell: column lane + 32 * (warp & 1), rows 2 * (warp >> 1), + 1 ----
-            int bx, by;
-            tile_xy(t, bx, by);
-            const unsigned light_sa = buf0_sa + (unsigned)buf * SE_LF_BUF_BYTES;
+            // ---- phase C of tile k: new id + light of every tile cell: column lane + 32 * (warp & 1), SE_LF_TH / 8 rows ----
+            const int bx = (int)(tileC & 0x3FFu), by = (int)((tileC >> 10) & 0x1FFFFFu);
+            const unsigned light_sa = buf0_sa + (unsigned)bufC * SE_LF_BUF_BYTES;
             const unsigned ids8_sa = ids8_base + (unsigned)par * (SE_LF_RH * SE_LF_BSTRIDE);
             const int n_cull = n_cull_sm[half][par];
             const unsigned char* const cull = cull_sm[half][par];
-            const int tx = lane + 32 * (hw & 1), row0 = (hw >> 1) * 2;
+            const int tx = lane + 32 * (hw & 1);
             const int x = bx * SE_LF_TW + tx;
-            const unsigned tp = light_sa + 16u * (unsigned)(row0 * SE_LF_LSTRIDE + tx + SE_LF_LCOL0);      // term (row0 - 1, tx - 1) of the tile
-            const unsigned idp = ids8_sa + (unsigned)((row0 + 1) * SE_LF_BSTRIDE + tx + 1 + SE_LF_BCOL0);
 #define SE_LF_T(r, c) se_lds_f4p(tp + 16u * (unsigned)((r) * SE_LF_LSTRIDE + (c)))          /* ring row row0 + r, ring column tx + c */
-            if (is_interior(bx, by)) {
-                // rows R0..R3 = ring rows row0 .. row0 + 3; cell 1 sits in R1, cell 2 in R2.  Terms are loaded where the shader's
-                // order needs them; the four that both cells use (R1 and R2, left and right) stay in registers.
-                const int y1 = p.gy0 + by * SE_LF_TH + row0;
-                size_t idx = (size_t)(by * SE_LF_TH + row0) * p.W + x;
-                unsigned id1 = se_lds_u8(idp), id2 = se_lds_u8(idp + SE_LF_BSTRIDE);
-                if (n_cull) {
-                    unsigned m;
-                    if (se_mod_lookup_culled(p.mods, cull, n_cull, x, y1, m)) id1 = m;
-                    if (se_mod_lookup_culled(p.mods, cull, n_cull, x, y1 + 1, m)) id2 = m;
+            if (tileC >> 31) {
+#pragma unroll 1
+                for (int pr = 0; pr < SE_LF_TH / 16; ++pr) {
+                    // rows R0..R3 = ring rows row0 .. row0 + 3; cell 1 sits in R1, cell 2 in R2.  Terms are loaded where the
+                    // shader's order needs them; the four that both cells use (R1 and R2, left and right) stay in registers.
+                    const int row0 = (hw >> 1) * (SE_LF_TH / 8) + 2 * pr;
+                    const unsigned tp = light_sa + 16u * (unsigned)(row0 * SE_LF_LSTRIDE + tx + SE_LF_LCOL0);   // term (row0 - 1, tx - 1) of the tile
+                    const unsigned idp = ids8_sa + (unsigned)((row0 + 1) * SE_LF_BSTRIDE + tx + 1 + SE_LF_BCOL0);
+                    const int y1 = p.gy0 + by * SE_LF_TH + row0;
+                    const size_t idx = (size_t)(by * SE_LF_TH + row0) * p.W + x;
+                    unsigned id1 = se_lds_u8(idp), id2 = se_lds_u8(idp + SE_LF_BSTRIDE);
+                    if (n_cull) {
+                        unsigned m;
+                        if (se_mod_lookup_culled(p.mods, cull, n_cull, x, y1, m)) id1 = m;
+                        if (se_mod_lookup_culled(p.mods, cull, n_cull, x, y1 + 1, m)) id2 = m;
+                    }
+                    p.new_cells[idx] = id1;
+                    p.new_cells[idx + (size_t)p.W] = id2;
+                    const unsigned me1 = id1 < 255u ? id1 : 255u, me2 = id2 < 255u ? id2 : 255u;
+                    const bool em1 = (fat_sm[me1] & SE_F_EMISSIVE) != 0u, em2 = (fat_sm[me2] & SE_F_EMISSIVE) != 0u;
+                    float4 out1, out2;
+                    SeF4P r1l, r1r, r2l, r2r;
+                    {   // cell 1: DOWN, UP, DOWNLEFT, UPLEFT, DOWNRIGHT, UPRIGHT, RIGHT, LEFT (math.glsl:154-166)
+                        unsigned long long sxy = 0ull, szw = 0ull;
+                        float mf = 0.0f, mxx = 0.0f, mxy = 0.0f, mxz = 0.0f;
+                        { const SeF4P d = SE_LF_T(2, 1), u = SE_LF_T(0, 1); SE_LF_ACC(d) SE_LF_ACC(u) SE_LF_MAX2(d, u) }
+                        r2l = SE_LF_T(2, 0);
+                        { const SeF4P u = SE_LF_T(0, 0); SE_LF_ACC(r2l) SE_LF_ACC(u) SE_LF_MAX2(r2l, u) }
+                        r2r = SE_LF_T(2, 2);
+                        { const SeF4P u = SE_LF_T(0, 2); SE_LF_ACC(r2r) SE_LF_ACC(u) SE_LF_MAX2(r2r, u) }
+                        r1r = SE_LF_T(1, 2); r1l = SE_LF_T(1, 0);
+                        SE_LF_ACC(r1r) SE_LF_ACC(r1l) SE_LF_MAX2(r1r, r1l)
+                        SE_LF_FINISH(out1)
+                    }
+                    if (em1) out1 = make_float4(se_emission_table[me1 * 4 + 0], se_emission_table[me1 * 4 + 1], se_emission_table[me1 * 4 + 2], se_emission_table[me1 * 4 + 3]);   // operations.glsl:126-127
+                    p.light_out[idx] = out1;
+                    {   // cell 2
+                        unsigned long long sxy = 0ull, szw = 0ull;
+                        float mf = 0.0f, mxx = 0.0f, mxy = 0.0f, mxz = 0.0f;
+                        { const SeF4P d = SE_LF_T(3, 1), u = SE_LF_T(1, 1); SE_LF_ACC(d) SE_LF_ACC(u) SE_LF_MAX2(d, u) }
+                        { const SeF4P d = SE_LF_T(3, 0); SE_LF_ACC(d) SE_LF_ACC(r1l) SE_LF_MAX2(d, r1l) }
+                        { const SeF4P d = SE_LF_T(3, 2); SE_LF_ACC(d) SE_LF_ACC(r1r) SE_LF_MAX2(d, r1r) }
+                        SE_LF_ACC(r2r) SE_LF_ACC(r2l) SE_LF_MAX2(r2r, r2l)
+                        SE_LF_FINISH(out2)
+                    }
+                    if (em2) out2 = make_float4(se_emission_table[me2 * 4 + 0], se_emission_table[me2 * 4 + 1], se_emission_table[me2 * 4 + 2], se_emission_table[me2 * 4 + 3]);
+                    p.light_out[idx + (size_t)p.W] = out2;
                 }
-                p.new_cells[idx] = id1;
-                p.new_cells[idx + (size_t)p.W] = id2;
-                const unsigned me1 = id1 < 255u ? id1 : 255u, me2 = id2 < 255u ? id2 : 255u;
-                const bool em1 = (fat_sm[me1] & SE_F_EMISSIVE) != 0u, em2 = (fat_sm[me2] & SE_F_EMISSIVE) != 0u;
-                float4 out1, out2;
-                SeF4P r1l, r1r, r2l, r2r;
-                {   // cell 1: DOWN, UP, DOWNLEFT, UPLEFT, DOWNRIGHT, UPRIGHT, RIGHT, LEFT (math.glsl:154-166)
-                    unsigned long long sxy = 0ull, szw = 0ull;
-                    float mf = 0.0f, mxx = 0.0f, mxy = 0.0f, mxz = 0.0f;
-                    { const SeF4P d = SE_LF_T(2, 1), u = SE_LF_T(0, 1); SE_LF_ACC(d) SE_LF_ACC(u) SE_LF_MAX2(d, u) }
-                    r2l = SE_LF_T(2, 0);
-                    { const SeF4P u = SE_LF_T(0, 0); SE_LF_ACC(r2l) SE_LF_ACC(u) SE_LF_MAX2(r2l, u) }
-                    r2r = SE_LF_T(2, 2);
-                    { const SeF4P u = SE_LF_T(0, 2); SE_LF_ACC(r2r) SE_LF_ACC(u) SE_LF_MAX2(r2r, u) }
-                    r1r = SE_LF_T(1, 2); r1l = SE_LF_T(1, 0);
-                    SE_LF_ACC(r1r) SE_LF_ACC(r1l) SE_LF_MAX2(r1r, r1l)
-                    SE_LF_FINISH(out1)
-                }
-                if (em1) out1 = make_float4(se_emission_table[me1 * 4 + 0], se_emission_table[me1 * 4 + 1], se_emission_table[me1 * 4 + 2], se_emission_table[me1 * 4 + 3]);   // operations.glsl:126-127
-                p.light_out[idx] = out1;
-                {   // cell 2
-                    unsigned long long sxy = 0ull, szw = 0ull;
-                    float mf = 0.0f, mxx = 0.0f, mxy = 0.0f, mxz = 0.0f;
-                    { const SeF4P d = SE_LF_T(3, 1), u = SE_LF_T(1, 1); SE_LF_ACC(d) SE_LF_ACC(u) SE_LF_MAX2(d, u) }
-                    { const SeF4P d = SE_LF_T(3, 0); SE_LF_ACC(d) SE_LF_ACC(r1l) SE_LF_MAX2(d, r1l) }
-                    { const SeF4P d = SE_LF_T(3, 2); SE_LF_ACC(d) SE_LF_ACC(r1r) SE_LF_MAX2(d, r1r) }
-                    SE_LF_ACC(r2r) SE_LF_ACC(r2l) SE_LF_MAX2(r2r, r2l)
-                    SE_LF_FINISH(out2)
-                }
-                if (em2) out2 = make_float4(se_emission_table[me2 * 4 + 0], se_emission_table[me2 * 4 + 1], se_emission_table[me2 * 4 + 2], se_emission_table[me2 * 4 + 3]);
-                p.light_out[idx + (size_t)p.W] = out2;
             } else if (x < p.W) {
+                const int row0 = (hw >> 1) * (SE_LF_TH / 8);
+                const unsigned tp = light_sa + 16u * (unsigned)(row0 * SE_LF_LSTRIDE + tx + SE_LF_LCOL0);
+                const unsigned idp = ids8_sa + (unsigned)((row0 + 1) * SE_LF_BSTRIDE + tx + 1 + SE_LF_BCOL0);
 #define SE_LF_LDT(dst, off) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dst.x), "=f"(dst.y), "=f"(dst.z), "=f"(dst.w) : "r"(tp + 16u * (unsigned)(off)))
                 float4 a0, a1, a2, b0, b1, b2;
                 SE_LF_LDT(a0, 0); SE_LF_LDT(a1, 1); SE_LF_LDT(a2, 2);
                 SE_LF_LDT(b0, SE_LF_LSTRIDE); SE_LF_LDT(b1, SE_LF_LSTRIDE + 1); SE_LF_LDT(b2, SE_LF_LSTRIDE + 2);
-                for (int i = 0; i < 2; ++i) {
+#pragma unroll 1
+                for (int i = 0; i < SE_LF_TH / 8; ++i) {
                     const int yl = by * SE_LF_TH + row0 + i;
                     if (yl >= p.Hl) break;
                     float4 c0, c1, c2;
@@ -1683,20 +1674,21 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
 
         // ---- tile k + 1: its loads have had phase C to land ----
         {
-            const int buf = bufS, par = (k + 1) & 1;
+            const int par = (k + 1) & 1;
             int bx, by;
             tile_xy(t + stride, bx, by);
             const int x_org = bx * SE_LF_TW - 1, yl_org = by * SE_LF_TH - 1;      // ring cell (0, 0): column / local row
-            const bool interior = is_interior(bx, by);
-            const unsigned light_sa = buf0_sa + (unsigned)buf * SE_LF_BUF_BYTES, ids_sa = light_sa + SE_LF_IDS_OFFSET;
+            const bool interior = x_org >= 0 && x_org + SE_LF_TW + 1 < p.W && yl_org >= 0 && yl_org + SE_LF_TH + 1 < p.Hl &&
+                                  p.gy0 + yl_org >= 0 && p.gy0 + yl_org + SE_LF_TH + 1 < p.Hg;
+            tileC = (unsigned)bx | ((unsigned)by << 10) | (interior ? 0x80000000u : 0u);
+            const unsigned light_sa = buf0_sa + (unsigned)bufS * SE_LF_BUF_BYTES, ids_sa = light_sa + SE_LF_IDS_OFFSET;
             const unsigned ids8_sa = ids8_base + (unsigned)par * (SE_LF_RH * SE_LF_BSTRIDE);
-            se_mbar_wait(mbar_sa + 8u * (unsigned)buf, parS);
+            se_mbar_wait(mbar_sa + 8u * (unsigned)bufS, parS);
 
-            // ---- phase B: the blocks that cover the tile, old ids from the TMA buffer, new ids as bytes; the last warp
-            //      culls the modifications (order kept: last match wins, falling_sand.glsl:764-773) ----
-            const int nbx = SE_LF_TW / 2 + ox, nby = SE_LF_TH / 2 + oy;
-            if (ht < nbx * nby) {
-                const int bj = ox ? ht / (SE_LF_TW / 2 + 1) : ht / (SE_LF_TW / 2), bi = ht - bj * nbx;
+            // ---- phase B, first part: the blocks that cover the tile, old ids from the TMA buffer, table read issued ----
+            // one block per thread per pass (a second pass only when both block offsets are 1: 49 blocks)
+            auto block_ids = [&](int b, unsigned& v, unsigned& seed, unsigned& q) {   // false: a row of the block is not in the local buffer
+                const int bj = ox ? b / (SE_LF_TW / 2 + 1) : b / (SE_LF_TW / 2), bi = b - bj * nbx;
                 const int cx = 2 * bi + 1 - ox, cy = 2 * bj + 1 - oy;      // ring coordinates of the block's top-left cell
                 const unsigned e0 = (unsigned)(cy * SE_LF_ISTRIDE + cx + SE_LF_ICOL0);
                 unsigned a = se_lds_u32(ids_sa + 4u * e0), bb = se_lds_u32(ids_sa + 4u * (e0 + 1u));
@@ -1712,34 +1704,38 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
                     c = !(xin0 && yin1) ? 2u : (loc1 ? c : SE_LF_MISSING);
                     d = !(xin1 && yin1) ? 2u : (loc1 ? d : SE_LF_MISSING);
                 }
-                unsigned nv = a | (bb << 8) | (c << 16) | (d << 24);
-                if (!((a | bb | c | d) & 0x80u)) {                         // else a row of the block is not in the local buffer: skipped (see K1a)
-                    const unsigned seed = (unsigned)(x_org + cx) * 461u + (unsigned)(p.gy0 + yl_org + cy) * 2131u + (unsigned)p.frame * (2131u * 2131u);
-                    nv = se_block_lut(nv, seed, 0, 0, 0, tab, fat_sm);
-                }
-                const unsigned q = ids8_sa + (unsigned)(cy * SE_LF_BSTRIDE + cx + SE_LF_BCOL0);
+                v = a | (bb << 8) | (c << 16) | (d << 24);
+                seed = (unsigned)(x_org + cx) * 461u + (unsigned)(p.gy0 + yl_org + cy) * 2131u + (unsigned)p.frame * (2131u * 2131u);
+                q = ids8_sa + (unsigned)(cy * SE_LF_BSTRIDE + cx + SE_LF_BCOL0);
+                return !((a | bb | c | d) & 0x80u);
+            };
+            auto block_store = [&](unsigned q, unsigned nv) {
                 se_sts_u8(q, nv & 0xFFu); se_sts_u8(q + 1u, (nv >> 8) & 0xFFu);
                 se_sts_u8(q + SE_LF_BSTRIDE, (nv >> 16) & 0xFFu); se_sts_u8(q + SE_LF_BSTRIDE + 1u, nv >> 24);
-            } else if (hw == SE_LF_HALF / 32 - 1) {
-                int n = 0;
-                const int x_lo = bx * SE_LF_TW, y_lo = p.gy0 + by * SE_LF_TH;
-                for (int m0 = 0; m0 < p.n_mods; m0 += 32) {
-                    bool keep = false;
-                    if (m0 + lane < p.n_mods) keep = se_mod_touches(p.mods[m0 + lane], x_lo, x_lo + SE_LF_TW - 1, y_lo, y_lo + SE_LF_TH - 1);
-                    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
-                    if (keep) cull_sm[half][par][n + __popc(ballot & ((1u << lane) - 1u))] = (unsigned char)(m0 + lane);
-                    n += __popc(ballot);
+            };
+            unsigned bv = 0u, bseed = 0u, bq = 0u, be = 0u, bsel = 0x3210u;
+            bool bok = false;
+            const bool has_block = ht < n_blocks;
+            if (has_block) {
+                bok = block_ids(ht, bv, bseed, bq);
+                if (bok) {
+                    const bool mirror = se_hashi(bseed * 213u) <= SE_MIRROR_UMAX;
+#if SE_LUT_TWO_TABLES
+                    be = se_tab_entry(tab, se_idx4(bv) + (mirror ? (unsigned)SE_N4 : 0u));
+#else
+                    bsel = mirror ? 0x2301u : 0x3210u;
+                    be = se_tab_entry(tab, se_idx4(__byte_perm(bv, 0u, bsel)));
+#endif
                 }
-                if (lane == 0) n_cull_sm[half][par] = n;
             }
 
-            // ---- phase A: the neighbour term of every ring + tile cell, in place; the short third pass goes to the warps
-            //      that had no block ----
+            // ---- phase A: the neighbour term of every ring + tile cell, in place; the short last pass goes to the upper threads ----
             if (interior) {
 #pragma unroll
-                for (int n = 0; n < 3; ++n) {
-                    const int c = n < 2 ? ht + n * SE_LF_HALF : ht + (SE_LF_RING_CELLS - SE_LF_HALF);
-                    if (n < 2 || c >= 2 * SE_LF_HALF) {
+                for (int n = 0; n <= SE_LF_RING_CELLS / SE_LF_HALF; ++n) {
+                    const bool last = n == SE_LF_RING_CELLS / SE_LF_HALF;
+                    const int c = last ? ht + (SE_LF_RING_CELLS - SE_LF_HALF) : ht + n * SE_LF_HALF;
+                    if (!last || c >= (SE_LF_RING_CELLS / SE_LF_HALF) * SE_LF_HALF) {
                         const int i = c / SE_LF_RW;                          // c = i * RW + j
                         const unsigned e = (unsigned)(c + i * (SE_LF_ISTRIDE - SE_LF_RW) + SE_LF_ICOL0);   // i * ISTRIDE + j + ICOL0
                         const unsigned la_sa = light_sa + 16u * (unsigned)(c + i * (SE_LF_LSTRIDE - SE_LF_RW) + SE_LF_LCOL0);
@@ -1757,6 +1753,34 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
                     const int i = c / SE_LF_RW, j = c - i * SE_LF_RW;
                     se_lit_stage_cell(p, fat_sm, light_sa, ids_sa, x_org, yl_org, i, j);
                 }
+            }
+
+            // ---- phase B, second part: the table entry has arrived; rand.y-dependent and slow states, new ids as bytes ----
+            if (has_block) {
+                unsigned nv = bv;
+                if (bok) {
+                    if (be & SE_E_SPECIAL) be = se_block_special(be, bv, bseed, bsel, 0, 0, 0, tab, fat_sm);
+                    nv = SE_LUT_TWO_TABLES ? be : __byte_perm(be, 0u, bsel);
+                }
+                block_store(bq, nv);
+            }
+            if (ht + SE_LF_HALF < n_blocks) {                              // the second pass
+                unsigned v, seed, q;
+                const bool ok = block_ids(ht + SE_LF_HALF, v, seed, q);
+                block_store(q, ok ? se_block_lut(v, seed, 0, 0, 0, tab, fat_sm) : v);
+            }
+            // the last warp culls the modifications against the tile (order kept: last match wins, falling_sand.glsl:764-773)
+            if (hw == SE_LF_HALF / 32 - 1) {
+                int n = 0;
+                const int x_lo = bx * SE_LF_TW, y_lo = p.gy0 + by * SE_LF_TH;
+                for (int m0 = 0; m0 < p.n_mods; m0 += 32) {
+                    bool keep = false;
+                    if (m0 + lane < p.n_mods) keep = se_mod_touches(p.mods[m0 + lane], x_lo, x_lo + SE_LF_TW - 1, y_lo, y_lo + SE_LF_TH - 1);
+                    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
+                    if (keep) cull_sm[half][par][n + __popc(ballot & ((1u << lane) - 1u))] = (unsigned char)(m0 + lane);
+                    n += __popc(ballot);
+                }
+                if (lane == 0) n_cull_sm[half][par] = n;
             }
         }
         se_half_sync(half);
