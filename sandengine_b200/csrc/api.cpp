@@ -247,8 +247,9 @@ struct SeLitParams {
     int buf_offset;
     unsigned tiles_x_magic;
 };
-// geometry of se_step_lit (kernels/sand_kernels.cuh: SE_LF_*).  Tile height and buffer count can be overridden for experiments
-// (SE_LF_TH = 16 | 32, SE_LF_NBUF = 2 | 3 in the environment: passed to NVRTC and used for the tensor maps alike).
+// geometry of se_step_lit (kernels/sand_kernels.cuh: SE_LF_*).  Threads per half, rows per thread and buffer count can be overridden
+// for experiments (SE_LF_HALF = 384 | 512, SE_LF_ROWS = 2 | 4, SE_LF_NBUF = 2 | 3 in the environment: passed to NVRTC and used for the
+// launch and the tensor maps alike).
 constexpr int LF_TW = 64;
 int lf_env(const char* name, int dflt, int lo, int hi) {
     const char* e = std::getenv(name);
@@ -256,7 +257,9 @@ int lf_env(const char* name, int dflt, int lo, int hi) {
     const int v = std::atoi(e);
     return v >= lo && v <= hi ? v : dflt;
 }
-int lf_th() { const int v = lf_env("SE_LF_TH", 32, 16, 32); return v == 16 ? 16 : 32; }
+int lf_half() { return lf_env("SE_LF_HALF", 384, 384, 512) == 512 ? 512 : 384; }
+int lf_rows() { return lf_env("SE_LF_ROWS", 4, 2, 4) == 2 ? 2 : 4; }
+int lf_th() { return lf_rows() * (lf_half() / 64); }
 int lf_nbuf() { return lf_env("SE_LF_NBUF", 2, 2, 3); }
 int lf_buf_bytes() {
     const int light = (lf_th() + 2) * (LF_TW + 8) * 16, ids = (lf_th() + 2) * (LF_TW + 16) * 4;
@@ -419,7 +422,8 @@ int compile_front(const char* yaml, size_t len, se_rules** out, bool with_nvrtc)
             const int v = std::atoi(mc);
             if (v >= 1 && v <= 8) extra.push_back("-DSE_LT_MINCTAS=" + std::to_string(v));
         }
-        extra.push_back("-DSE_LF_TH=" + std::to_string(lf_th()));
+        extra.push_back("-DSE_LF_HALF=" + std::to_string(lf_half()));
+        extra.push_back("-DSE_LF_ROWS=" + std::to_string(lf_rows()));
         extra.push_back("-DSE_LF_NBUF=" + std::to_string(lf_nbuf()));
         if (const char* defs = std::getenv("SE_NVRTC_DEFS")) {
             std::string d(defs), tok;
@@ -570,7 +574,7 @@ int one_step(se_sim* s, bool use_mods, int n_mods) {
         lp.tiles_x = s->lf_tiles_x; lp.tiles_y = s->lf_tiles_y; lp.buf_offset = s->lf_buf_offset;
         lp.tiles_x_magic = s->lf_tiles_x > 1 ? (unsigned)((1ull << 32) / (unsigned long long)s->lf_tiles_x + 1ull) : 0u;
         void* fargs[] = {&s->tm_cells[s->cur], &s->tm_light[s->lcur], &lp};
-        int rcf = launch(s, s->f_step_lit, dim3(s->lf_grid), dim3(1024), fargs, (unsigned)s->lf_smem);
+        int rcf = launch(s, s->f_step_lit, dim3(s->lf_grid), dim3(2 * lf_half()), fargs, (unsigned)s->lf_smem);
         if (rcf) return rcf;
         s->cur ^= 1;
         s->lcur ^= 1;

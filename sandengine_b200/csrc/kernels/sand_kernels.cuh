@@ -1321,8 +1321,8 @@ extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_
 // dispatch, falling_sand.glsl:737-799 + operations.glsl:99-171), for table-eligible rule sets.  HBM-bound by design:
 // 4 B old id + 16 B old light in, 4 B new id + 16 B new light out per cell = the 40 algorithmic bytes.
 //
-// One persistent CTA of 1024 threads per SM, run as TWO INDEPENDENT HALVES of 16 warps (named barriers, like K1b) that
-// read the transition table where it lies (L1 / L2).  A half walks 64 x 32 tiles.  The inputs of a tile -- light and ids of the tile and its one-cell ring -- arrive by TMA
+// One persistent CTA of 768 threads per SM, run as TWO INDEPENDENT HALVES of 12 warps (named barriers, like K1b) that
+// read the transition table where it lies (L1 / L2).  A half walks 64 x 24 tiles.  The inputs of a tile -- light and ids of the tile and its one-cell ring -- arrive by TMA
 // (cp.async.bulk.tensor: one 3-D box of light in groups of four float4, one 3-D box of ids in groups of 16, out-of-grid
 // elements zero-filled) into one of the half's two buffers, signalled by an mbarrier.  Three jobs per tile:
 //   B  the 2x2 blocks that cover the tile (they lie inside tile + ring: the block offset is 0 or 1): old ids straight
@@ -1340,9 +1340,13 @@ extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_
 // modification list (indices) are double-buffered like the TMA buffers.
 // =============================================================================================
 #define SE_LF_TW 64
-#ifndef SE_LF_TH
-#define SE_LF_TH 32                                  // tile height: 16 or 32 (a thread relaxes SE_LF_TH / 8 cells of one column)
+#ifndef SE_LF_HALF
+#define SE_LF_HALF 384                               // threads of a half: 384 (80 registers: the 3 x 3 window of phase C stays in registers) or 512
 #endif
+#ifndef SE_LF_ROWS
+#define SE_LF_ROWS 4                                 // cells of one column a thread relaxes: 2 or 4
+#endif
+#define SE_LF_TH (SE_LF_ROWS * (SE_LF_HALF / 64))    // tile height: 24 (12, 16, 32)
 #define SE_LF_RH (SE_LF_TH + 2)                      // ring rows
 #define SE_LF_RW (SE_LF_TW + 2)                      // ring columns
 // TMA box rows are 64 bytes of light and 32 bytes of ids (16-byte rows -- a float4, four ids -- made the TMA unit the
@@ -1360,8 +1364,7 @@ extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_
 #define SE_LF_IDS_OFFSET ((SE_LF_LIGHT_BYTES + 127) / 128 * 128)
 #define SE_LF_BUF_BYTES ((SE_LF_IDS_OFFSET + SE_LF_IDS_BYTES + 127) / 128 * 128)
 #define SE_LF_MISSING 0xFFu
-#define SE_LF_HALF 512
-#define SE_LF_THREADS 1024
+#define SE_LF_THREADS (2 * SE_LF_HALF)
 #ifndef SE_LF_NBUF
 #define SE_LF_NBUF 2                                 // TMA buffers per half: the loads of tile k + NBUF - 1 are issued when tile k's phase C starts
 #endif
@@ -1503,7 +1506,7 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
     __shared__ int n_cull_sm[2][2];
     __shared__ __align__(8) unsigned long long mbar[2 * SE_LF_NBUF];
     __shared__ __align__(16) unsigned char ids8[2][2][SE_LF_RH * SE_LF_BSTRIDE];
-    const int tid = threadIdx.x, lane = tid & 31, half = tid >> 9, ht = tid & (SE_LF_HALF - 1), hw = ht >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, half = tid >= SE_LF_HALF ? 1 : 0, ht = tid - half * SE_LF_HALF, hw = ht >> 5;
     unsigned smem_sa;
     asm volatile("mov.u32 %0, %1;" : "=r"(smem_sa) : "r"((unsigned)__cvta_generic_to_shared(smem)));
     // The table is read where it lies (L1 / L2): phase B is off the critical path (its gather is in flight while phase A
@@ -1557,7 +1560,7 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 issue(t + (SE_LF_NBUF - 1) * stride, bufI);
             }
-            // ---- phase C of tile k: new id + light of every tile cell: column lane + 32 * (warp & 1), SE_LF_TH / 8 rows ----
+            // ---- phase C of tile k: new id + light of every tile cell: column lane + 32 * (warp & 1), SE_LF_ROWS rows ----
             const int bx = (int)(tileC & 0x3FFu), by = (int)((tileC >> 10) & 0x1FFFFFu);
             const unsigned light_sa = buf0_sa + (unsigned)bufC * SE_LF_BUF_BYTES;
             const unsigned ids8_sa = ids8_base + (unsigned)par * (SE_LF_RH * SE_LF_BSTRIDE);
@@ -1567,55 +1570,43 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
             const int x = bx * SE_LF_TW + tx;
 #define SE_LF_T(r, c) se_lds_f4p(tp + 16u * (unsigned)((r) * SE_LF_LSTRIDE + (c)))          /* ring row row0 + r, ring column tx + c */
             if (tileC >> 31) {
-#pragma unroll 1
-                for (int pr = 0; pr < SE_LF_TH / 16; ++pr) {
-                    // rows R0..R3 = ring rows row0 .. row0 + 3; cell 1 sits in R1, cell 2 in R2.  Terms are loaded where the
-                    // shader's order needs them; the four that both cells use (R1 and R2, left and right) stay in registers.
-                    const int row0 = (hw >> 1) * (SE_LF_TH / 8) + 2 * pr;
-                    const unsigned tp = light_sa + 16u * (unsigned)(row0 * SE_LF_LSTRIDE + tx + SE_LF_LCOL0);   // term (row0 - 1, tx - 1) of the tile
-                    const unsigned idp = ids8_sa + (unsigned)((row0 + 1) * SE_LF_BSTRIDE + tx + 1 + SE_LF_BCOL0);
-                    const int y1 = p.gy0 + by * SE_LF_TH + row0;
-                    const size_t idx = (size_t)(by * SE_LF_TH + row0) * p.W + x;
-                    unsigned id1 = se_lds_u8(idp), id2 = se_lds_u8(idp + SE_LF_BSTRIDE);
+                // the 3 x 3 window slides down the thread's column: three terms are loaded per cell, six stay in registers
+                const int row0 = (hw >> 1) * SE_LF_ROWS;
+                const unsigned tp = light_sa + 16u * (unsigned)(row0 * SE_LF_LSTRIDE + tx + SE_LF_LCOL0);   // term (row0 - 1, tx - 1) of the tile
+                const unsigned idp = ids8_sa + (unsigned)((row0 + 1) * SE_LF_BSTRIDE + tx + 1 + SE_LF_BCOL0);
+                const int y0 = p.gy0 + by * SE_LF_TH + row0;
+                size_t idx = (size_t)(by * SE_LF_TH + row0) * p.W + x;
+                SeF4P a0 = SE_LF_T(0, 0), a1 = SE_LF_T(0, 1), a2 = SE_LF_T(0, 2);
+                SeF4P b0 = SE_LF_T(1, 0), b1 = SE_LF_T(1, 1), b2 = SE_LF_T(1, 2);
+#pragma unroll
+                for (int i = 0; i < SE_LF_ROWS; ++i) {
+                    const SeF4P c0 = SE_LF_T(i + 2, 0), c1 = SE_LF_T(i + 2, 1), c2 = SE_LF_T(i + 2, 2);
+                    unsigned id = se_lds_u8(idp + (unsigned)(i * SE_LF_BSTRIDE));
                     if (n_cull) {
                         unsigned m;
-                        if (se_mod_lookup_culled(p.mods, cull, n_cull, x, y1, m)) id1 = m;
-                        if (se_mod_lookup_culled(p.mods, cull, n_cull, x, y1 + 1, m)) id2 = m;
+                        if (se_mod_lookup_culled(p.mods, cull, n_cull, x, y0 + i, m)) id = m;
                     }
-                    p.new_cells[idx] = id1;
-                    p.new_cells[idx + (size_t)p.W] = id2;
-                    const unsigned me1 = id1 < 255u ? id1 : 255u, me2 = id2 < 255u ? id2 : 255u;
-                    const bool em1 = (fat_sm[me1] & SE_F_EMISSIVE) != 0u, em2 = (fat_sm[me2] & SE_F_EMISSIVE) != 0u;
-                    float4 out1, out2;
-                    SeF4P r1l, r1r, r2l, r2r;
-                    {   // cell 1: DOWN, UP, DOWNLEFT, UPLEFT, DOWNRIGHT, UPRIGHT, RIGHT, LEFT (math.glsl:154-166)
+                    p.new_cells[idx] = id;
+                    const unsigned me = id < 255u ? id : 255u;
+                    float4 out;
+                    {   // DOWN, UP, DOWNLEFT, UPLEFT, DOWNRIGHT, UPRIGHT, RIGHT, LEFT (math.glsl:154-166)
                         unsigned long long sxy = 0ull, szw = 0ull;
                         float mf = 0.0f, mxx = 0.0f, mxy = 0.0f, mxz = 0.0f;
-                        { const SeF4P d = SE_LF_T(2, 1), u = SE_LF_T(0, 1); SE_LF_ACC(d) SE_LF_ACC(u) SE_LF_MAX2(d, u) }
-                        r2l = SE_LF_T(2, 0);
-                        { const SeF4P u = SE_LF_T(0, 0); SE_LF_ACC(r2l) SE_LF_ACC(u) SE_LF_MAX2(r2l, u) }
-                        r2r = SE_LF_T(2, 2);
-                        { const SeF4P u = SE_LF_T(0, 2); SE_LF_ACC(r2r) SE_LF_ACC(u) SE_LF_MAX2(r2r, u) }
-                        r1r = SE_LF_T(1, 2); r1l = SE_LF_T(1, 0);
-                        SE_LF_ACC(r1r) SE_LF_ACC(r1l) SE_LF_MAX2(r1r, r1l)
-                        SE_LF_FINISH(out1)
+                        SE_LF_ACC(c1) SE_LF_ACC(a1) SE_LF_MAX2(c1, a1)
+                        SE_LF_ACC(c0) SE_LF_ACC(a0) SE_LF_MAX2(c0, a0)
+                        SE_LF_ACC(c2) SE_LF_ACC(a2) SE_LF_MAX2(c2, a2)
+                        SE_LF_ACC(b2) SE_LF_ACC(b0) SE_LF_MAX2(b2, b0)
+                        SE_LF_FINISH(out)
                     }
-                    if (em1) out1 = make_float4(se_emission_table[me1 * 4 + 0], se_emission_table[me1 * 4 + 1], se_emission_table[me1 * 4 + 2], se_emission_table[me1 * 4 + 3]);   // operations.glsl:126-127
-                    p.light_out[idx] = out1;
-                    {   // cell 2
-                        unsigned long long sxy = 0ull, szw = 0ull;
-                        float mf = 0.0f, mxx = 0.0f, mxy = 0.0f, mxz = 0.0f;
-                        { const SeF4P d = SE_LF_T(3, 1), u = SE_LF_T(1, 1); SE_LF_ACC(d) SE_LF_ACC(u) SE_LF_MAX2(d, u) }
-                        { const SeF4P d = SE_LF_T(3, 0); SE_LF_ACC(d) SE_LF_ACC(r1l) SE_LF_MAX2(d, r1l) }
-                        { const SeF4P d = SE_LF_T(3, 2); SE_LF_ACC(d) SE_LF_ACC(r1r) SE_LF_MAX2(d, r1r) }
-                        SE_LF_ACC(r2r) SE_LF_ACC(r2l) SE_LF_MAX2(r2r, r2l)
-                        SE_LF_FINISH(out2)
-                    }
-                    if (em2) out2 = make_float4(se_emission_table[me2 * 4 + 0], se_emission_table[me2 * 4 + 1], se_emission_table[me2 * 4 + 2], se_emission_table[me2 * 4 + 3]);
-                    p.light_out[idx + (size_t)p.W] = out2;
+                    if (fat_sm[me] & SE_F_EMISSIVE)                         // operations.glsl:126-127
+                        out = make_float4(se_emission_table[me * 4 + 0], se_emission_table[me * 4 + 1], se_emission_table[me * 4 + 2], se_emission_table[me * 4 + 3]);
+                    p.light_out[idx] = out;
+                    idx += (size_t)p.W;
+                    a0 = b0; a1 = b1; a2 = b2;
+                    b0 = c0; b1 = c1; b2 = c2;
                 }
             } else if (x < p.W) {
-                const int row0 = (hw >> 1) * (SE_LF_TH / 8);
+                const int row0 = (hw >> 1) * SE_LF_ROWS;
                 const unsigned tp = light_sa + 16u * (unsigned)(row0 * SE_LF_LSTRIDE + tx + SE_LF_LCOL0);
                 const unsigned idp = ids8_sa + (unsigned)((row0 + 1) * SE_LF_BSTRIDE + tx + 1 + SE_LF_BCOL0);
 #define SE_LF_LDT(dst, off) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dst.x), "=f"(dst.y), "=f"(dst.z), "=f"(dst.w) : "r"(tp + 16u * (unsigned)(off)))
@@ -1623,7 +1614,7 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
                 SE_LF_LDT(a0, 0); SE_LF_LDT(a1, 1); SE_LF_LDT(a2, 2);
                 SE_LF_LDT(b0, SE_LF_LSTRIDE); SE_LF_LDT(b1, SE_LF_LSTRIDE + 1); SE_LF_LDT(b2, SE_LF_LSTRIDE + 2);
 #pragma unroll 1
-                for (int i = 0; i < SE_LF_TH / 8; ++i) {
+                for (int i = 0; i < SE_LF_ROWS; ++i) {
                     const int yl = by * SE_LF_TH + row0 + i;
                     if (yl >= p.Hl) break;
                     float4 c0, c1, c2;
@@ -1783,7 +1774,7 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
                 if (lane == 0) n_cull_sm[half][par] = n;
             }
         }
-        se_half_sync(half);
+        asm volatile("bar.sync %0, %1;" :: "r"(half + 1), "n"(SE_LF_HALF) : "memory");
         bufI = bufC; bufC = bufS;
         if (++bufS == SE_LF_NBUF) { bufS = 0; parS ^= 1u; }
     }
