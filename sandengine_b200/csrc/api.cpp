@@ -248,7 +248,7 @@ struct SeLitParams {
     unsigned tiles_x_magic;
 };
 // geometry of se_step_lit (kernels/sand_kernels.cuh: SE_LF_*).  Threads per half, rows per thread and buffer count can be overridden
-// for experiments (SE_LF_HALF = 384 | 512, SE_LF_ROWS = 2 | 4, SE_LF_NBUF = 2 | 3 in the environment: passed to NVRTC and used for the
+// for experiments (SE_LF_NG = 2..4 groups, SE_LF_HALF = threads per group, SE_LF_ROWS = 2 | 4, SE_LF_NBUF = 2 | 3 in the environment: passed to NVRTC and used for the
 // launch and the tensor maps alike).
 constexpr int LF_TW = 64;
 int lf_env(const char* name, int dflt, int lo, int hi) {
@@ -257,7 +257,8 @@ int lf_env(const char* name, int dflt, int lo, int hi) {
     const int v = std::atoi(e);
     return v >= lo && v <= hi ? v : dflt;
 }
-int lf_half() { return lf_env("SE_LF_HALF", 384, 384, 512) == 512 ? 512 : 384; }
+int lf_ng() { return lf_env("SE_LF_NG", 3, 2, 4); }
+int lf_half() { const int v = lf_env("SE_LF_HALF", 256, 128, 512); return v / 64 * 64; }
 int lf_rows() { return lf_env("SE_LF_ROWS", 4, 2, 4) == 2 ? 2 : 4; }
 int lf_th() { return lf_rows() * (lf_half() / 64); }
 int lf_nbuf() { return lf_env("SE_LF_NBUF", 2, 2, 3); }
@@ -422,6 +423,7 @@ int compile_front(const char* yaml, size_t len, se_rules** out, bool with_nvrtc)
             const int v = std::atoi(mc);
             if (v >= 1 && v <= 8) extra.push_back("-DSE_LT_MINCTAS=" + std::to_string(v));
         }
+        extra.push_back("-DSE_LF_NG=" + std::to_string(lf_ng()));
         extra.push_back("-DSE_LF_HALF=" + std::to_string(lf_half()));
         extra.push_back("-DSE_LF_ROWS=" + std::to_string(lf_rows()));
         extra.push_back("-DSE_LF_NBUF=" + std::to_string(lf_nbuf()));
@@ -574,7 +576,7 @@ int one_step(se_sim* s, bool use_mods, int n_mods) {
         lp.tiles_x = s->lf_tiles_x; lp.tiles_y = s->lf_tiles_y; lp.buf_offset = s->lf_buf_offset;
         lp.tiles_x_magic = s->lf_tiles_x > 1 ? (unsigned)((1ull << 32) / (unsigned long long)s->lf_tiles_x + 1ull) : 0u;
         void* fargs[] = {&s->tm_cells[s->cur], &s->tm_light[s->lcur], &lp};
-        int rcf = launch(s, s->f_step_lit, dim3(s->lf_grid), dim3(2 * lf_half()), fargs, (unsigned)s->lf_smem);
+        int rcf = launch(s, s->f_step_lit, dim3(s->lf_grid), dim3(lf_ng() * lf_half()), fargs, (unsigned)s->lf_smem);
         if (rcf) return rcf;
         s->cur ^= 1;
         s->lcur ^= 1;
@@ -914,13 +916,13 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
             // one CTA of two halves per SM, LF_NBUF input buffers per half (+ 128: the kernel aligns its buffers itself); the table
             // is read where it lies in global memory
             s->lf_buf_offset = 0;
-            s->lf_smem = 2 * lf_nbuf() * lf_buf_bytes() + 128;
+            s->lf_smem = lf_ng() * lf_nbuf() * lf_buf_bytes() + 128;
             if (s->lf_smem + 13 * 1024 <= smem_optin) {
                 SE_CU_S(driver().ModuleGetFunction(&s->f_step_lit, s->mod, "se_step_lit"));
                 SE_CU_S(driver().FuncSetAttribute(s->f_step_lit, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->lf_smem));
                 s->lf_tiles_x = (s->W + LF_TW - 1) / LF_TW;
                 s->lf_tiles_y = (s->Hl + lf_th() - 1) / lf_th();
-                s->lf_grid = (int)std::min<long long>((long long)std::max(1, n_sm / s->device_share), ((long long)s->lf_tiles_x * s->lf_tiles_y + 1) / 2);
+                s->lf_grid = (int)std::min<long long>((long long)std::max(1, n_sm / s->device_share), ((long long)s->lf_tiles_x * s->lf_tiles_y + lf_ng() - 1) / lf_ng());
                 bool maps_ok = true;
                 for (int b = 0; b < 2 && maps_ok; ++b) {
                     // Box rows are 64 bytes of light and 32 bytes of ids: 16-byte rows (a float4, four ids) made the TMA unit the

@@ -1321,8 +1321,8 @@ extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_
 // dispatch, falling_sand.glsl:737-799 + operations.glsl:99-171), for table-eligible rule sets.  HBM-bound by design:
 // 4 B old id + 16 B old light in, 4 B new id + 16 B new light out per cell = the 40 algorithmic bytes.
 //
-// One persistent CTA of 768 threads per SM, run as TWO INDEPENDENT HALVES of 12 warps (named barriers, like K1b) that
-// read the transition table where it lies (L1 / L2).  A half walks 64 x 24 tiles.  The inputs of a tile -- light and ids of the tile and its one-cell ring -- arrive by TMA
+// One persistent CTA of 768 threads per SM, run as THREE INDEPENDENT GROUPS of 8 warps (named barriers, like K1b's halves; `half`
+// below is the group index) that read the transition table where it lies (L1 / L2).  A group walks 64 x 16 tiles.  The inputs of a tile -- light and ids of the tile and its one-cell ring -- arrive by TMA
 // (cp.async.bulk.tensor: one 3-D box of light in groups of four float4, one 3-D box of ids in groups of 16, out-of-grid
 // elements zero-filled) into one of the half's two buffers, signalled by an mbarrier.  Three jobs per tile:
 //   B  the 2x2 blocks that cover the tile (they lie inside tile + ring: the block offset is 0 or 1): old ids straight
@@ -1340,13 +1340,16 @@ extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_
 // modification list (indices) are double-buffered like the TMA buffers.
 // =============================================================================================
 #define SE_LF_TW 64
+#ifndef SE_LF_NG
+#define SE_LF_NG 3                                   // independent groups of warps per CTA (each with its own tiles, buffers and named barrier)
+#endif
 #ifndef SE_LF_HALF
-#define SE_LF_HALF 384                               // threads of a half: 384 (80 registers: the 3 x 3 window of phase C stays in registers) or 512
+#define SE_LF_HALF 256                               // threads of a group (NG x HALF = 768: 80 registers, the 3 x 3 window of phase C stays in registers)
 #endif
 #ifndef SE_LF_ROWS
 #define SE_LF_ROWS 4                                 // cells of one column a thread relaxes: 2 or 4
 #endif
-#define SE_LF_TH (SE_LF_ROWS * (SE_LF_HALF / 64))    // tile height: 24 (12, 16, 32)
+#define SE_LF_TH (SE_LF_ROWS * (SE_LF_HALF / 64))    // tile height: 16 (24 with groups of 384 threads)
 #define SE_LF_RH (SE_LF_TH + 2)                      // ring rows
 #define SE_LF_RW (SE_LF_TW + 2)                      // ring columns
 // TMA box rows are 64 bytes of light and 32 bytes of ids (16-byte rows -- a float4, four ids -- made the TMA unit the
@@ -1364,7 +1367,7 @@ extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_
 #define SE_LF_IDS_OFFSET ((SE_LF_LIGHT_BYTES + 127) / 128 * 128)
 #define SE_LF_BUF_BYTES ((SE_LF_IDS_OFFSET + SE_LF_IDS_BYTES + 127) / 128 * 128)
 #define SE_LF_MISSING 0xFFu
-#define SE_LF_THREADS (2 * SE_LF_HALF)
+#define SE_LF_THREADS (SE_LF_NG * SE_LF_HALF)
 #ifndef SE_LF_NBUF
 #define SE_LF_NBUF 2                                 // TMA buffers per half: the loads of tile k + NBUF - 1 are issued when tile k's phase C starts
 #endif
@@ -1502,11 +1505,11 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
                                                                               const SeLitParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ unsigned fat_sm[256];
-    __shared__ unsigned char cull_sm[2][2][256];
-    __shared__ int n_cull_sm[2][2];
-    __shared__ __align__(8) unsigned long long mbar[2 * SE_LF_NBUF];
-    __shared__ __align__(16) unsigned char ids8[2][2][SE_LF_RH * SE_LF_BSTRIDE];
-    const int tid = threadIdx.x, lane = tid & 31, half = tid >= SE_LF_HALF ? 1 : 0, ht = tid - half * SE_LF_HALF, hw = ht >> 5;
+    __shared__ unsigned char cull_sm[SE_LF_NG][2][256];
+    __shared__ int n_cull_sm[SE_LF_NG][2];
+    __shared__ __align__(8) unsigned long long mbar[SE_LF_NG * SE_LF_NBUF];
+    __shared__ __align__(16) unsigned char ids8[SE_LF_NG][2][SE_LF_RH * SE_LF_BSTRIDE];
+    const int tid = threadIdx.x, lane = tid & 31, half = tid / SE_LF_HALF, ht = tid - half * SE_LF_HALF, hw = ht >> 5;   // `half`: the thread's group
     unsigned smem_sa;
     asm volatile("mov.u32 %0, %1;" : "=r"(smem_sa) : "r"((unsigned)__cvta_generic_to_shared(smem)));
     // The table is read where it lies (L1 / L2): phase B is off the critical path (its gather is in flight while phase A
@@ -1515,13 +1518,13 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
     if (tid < 256) fat_sm[tid] = se_fat_table[tid];
     const unsigned mbar_sa = (unsigned)__cvta_generic_to_shared(mbar) + 8u * SE_LF_NBUF * (unsigned)half;   // this half's barriers
     if (tid == 0) {
-        for (unsigned k = 0; k < 2u * SE_LF_NBUF; ++k) se_mbar_init((unsigned)__cvta_generic_to_shared(mbar) + 8u * k, 1u);
+        for (unsigned k = 0; k < (unsigned)(SE_LF_NG * SE_LF_NBUF); ++k) se_mbar_init((unsigned)__cvta_generic_to_shared(mbar) + 8u * k, 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     const int n_tiles = p.tiles_x * p.tiles_y;
-    const int first = 2 * (int)blockIdx.x + half, stride = 2 * (int)gridDim.x;
+    const int first = SE_LF_NG * (int)blockIdx.x + half, stride = SE_LF_NG * (int)gridDim.x;
     // TMA destinations are 128-byte aligned whatever the base of dynamic shared memory is
     const unsigned buf0_sa = ((smem_sa + (unsigned)p.buf_offset + 127u) & ~127u) + (unsigned)half * (SE_LF_NBUF * SE_LF_BUF_BYTES);
     const unsigned ids8_base = (unsigned)__cvta_generic_to_shared(&ids8[half][0][0]);
@@ -1575,7 +1578,9 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
                 const unsigned tp = light_sa + 16u * (unsigned)(row0 * SE_LF_LSTRIDE + tx + SE_LF_LCOL0);   // term (row0 - 1, tx - 1) of the tile
                 const unsigned idp = ids8_sa + (unsigned)((row0 + 1) * SE_LF_BSTRIDE + tx + 1 + SE_LF_BCOL0);
                 const int y0 = p.gy0 + by * SE_LF_TH + row0;
-                size_t idx = (size_t)(by * SE_LF_TH + row0) * p.W + x;
+                const size_t idx0 = (size_t)(by * SE_LF_TH + row0) * p.W + x;
+                unsigned* cell_out = p.new_cells + idx0;
+                float4* light_out = p.light_out + idx0;
                 SeF4P a0 = SE_LF_T(0, 0), a1 = SE_LF_T(0, 1), a2 = SE_LF_T(0, 2);
                 SeF4P b0 = SE_LF_T(1, 0), b1 = SE_LF_T(1, 1), b2 = SE_LF_T(1, 2);
 #pragma unroll
@@ -1586,7 +1591,8 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
                         unsigned m;
                         if (se_mod_lookup_culled(p.mods, cull, n_cull, x, y0 + i, m)) id = m;
                     }
-                    p.new_cells[idx] = id;
+                    *cell_out = id;
+                    cell_out += p.W;
                     const unsigned me = id < 255u ? id : 255u;
                     float4 out;
                     {   // DOWN, UP, DOWNLEFT, UPLEFT, DOWNRIGHT, UPRIGHT, RIGHT, LEFT (math.glsl:154-166)
@@ -1598,10 +1604,12 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
                         SE_LF_ACC(b2) SE_LF_ACC(b0) SE_LF_MAX2(b2, b0)
                         SE_LF_FINISH(out)
                     }
-                    if (fat_sm[me] & SE_F_EMISSIVE)                         // operations.glsl:126-127
-                        out = make_float4(se_emission_table[me * 4 + 0], se_emission_table[me * 4 + 1], se_emission_table[me * 4 + 2], se_emission_table[me * 4 + 3]);
-                    p.light_out[idx] = out;
-                    idx += (size_t)p.W;
+                    const bool emissive = (fat_sm[me] & SE_F_EMISSIVE) != 0u;          // operations.glsl:126-127
+                    if (__any_sync(0xFFFFFFFFu, emissive)) {                           // rare: a branch of the warp, not eight predicated instructions
+                        if (emissive) out = make_float4(se_emission_table[me * 4 + 0], se_emission_table[me * 4 + 1], se_emission_table[me * 4 + 2], se_emission_table[me * 4 + 3]);
+                    }
+                    *light_out = out;
+                    light_out += p.W;
                     a0 = b0; a1 = b1; a2 = b2;
                     b0 = c0; b1 = c1; b2 = c2;
                 }
