@@ -258,7 +258,7 @@ int lf_env(const char* name, int dflt, int lo, int hi) {
     return v >= lo && v <= hi ? v : dflt;
 }
 int lf_ng() { return lf_env("SE_LF_NG", 3, 2, 4); }
-int lf_half() { const int v = lf_env("SE_LF_HALF", 256, 128, 512); return v / 64 * 64; }
+int lf_half() { const int v = lf_env("SE_LF_HALF", 256, 256, 512); return v / 64 * 64; }
 int lf_rows() { return lf_env("SE_LF_ROWS", 4, 2, 4) == 2 ? 2 : 4; }
 int lf_th() { return lf_rows() * (lf_half() / 64); }
 int lf_nbuf() { return lf_env("SE_LF_NBUF", 2, 2, 3); }

@@ -1373,6 +1373,7 @@ extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_
 #endif
 #define SE_LF_RING_CELLS (SE_LF_RH * SE_LF_RW)
 #define SE_LF_MAX_BLOCKS ((SE_LF_TW / 2 + 1) * (SE_LF_TH / 2 + 1))
+static_assert(SE_LF_MAX_BLOCKS - SE_LF_HALF <= 64 && SE_LF_HALF - SE_LF_RING_CELLS % SE_LF_HALF - 64 >= 0, "se_step_lit: work split of phases A and B");
 
 struct alignas(64) SeTensorMap { unsigned long long opaque[16]; };   // CUtensorMap (cuda.h), encoded by the host
 
@@ -1605,7 +1606,7 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
                         SE_LF_FINISH(out)
                     }
                     const bool emissive = (fat_sm[me] & SE_F_EMISSIVE) != 0u;          // operations.glsl:126-127
-                    if (__any_sync(0xFFFFFFFFu, emissive)) {                           // rare: a branch of the warp, not eight predicated instructions
+                    if (__any_sync(0xFFFFFFFFu, emissive)) {                           // rare
                         if (emissive) out = make_float4(se_emission_table[me * 4 + 0], se_emission_table[me * 4 + 1], se_emission_table[me * 4 + 2], se_emission_table[me * 4 + 3]);
                     }
                     *light_out = out;
@@ -1763,9 +1764,10 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
                 }
                 block_store(bq, nv);
             }
-            if (ht + SE_LF_HALF < n_blocks) {                              // the second pass
+            // the second pass (at most 41 blocks) goes to threads that had no cell in the short last pass of phase A
+            if (ht >= SE_LF_HALF - SE_LF_RING_CELLS % SE_LF_HALF - 64 && ht + 64 + SE_LF_RING_CELLS % SE_LF_HALF < n_blocks) {
                 unsigned v, seed, q;
-                const bool ok = block_ids(ht + SE_LF_HALF, v, seed, q);
+                const bool ok = block_ids(ht + 64 + SE_LF_RING_CELLS % SE_LF_HALF, v, seed, q);
                 block_store(q, ok ? se_block_lut(v, seed, 0, 0, 0, tab, fat_sm) : v);
             }
             // the last warp culls the modifications against the tile (order kept: last match wins, falling_sand.glsl:764-773)
