@@ -68,6 +68,12 @@ def _notrecog(unrecog, missing_in):
     return ParsingErr("NotRecognized", f"The expression '{unrecog}' (in '{missing_in}') was not recognized as valid syntax. Please check it is valid.")
 
 
+def _require_usable(rule):
+    """A rule that a type or a material refers to must be executable (module docstring: the Left-rule definition)."""
+    if rule.left_conflict is not None:
+        raise _notrecog(rule.left_conflict, f"rules/{rule.name} (LEFT in a mirrored rule, or LEFT mixed with RIGHT)")
+
+
 # ----------------------------------------------------------------------------------------------
 # YAML loading with serde_yaml-0.9-like (YAML 1.2 core schema) scalar resolution.  PyYAML is
 # YAML 1.1 (yes/no/on/off are bools, 1e3 is a string); override the implicit resolvers.
@@ -79,20 +85,24 @@ class _Loader(yaml.SafeLoader):
 _Loader.yaml_implicit_resolvers = {}
 _Loader.add_implicit_resolver("tag:yaml.org,2002:bool", re.compile(r"^(?:true|True|TRUE|false|False|FALSE)$"), list("tTfF"))
 _Loader.add_implicit_resolver("tag:yaml.org,2002:null", re.compile(r"^(?:~|null|Null|NULL|)$"), ["~", "n", "N", ""])
-_Loader.add_implicit_resolver("tag:yaml.org,2002:int", re.compile(r"^(?:[-+]?[0-9]+|0o[0-7]+|0x[0-9a-fA-F]+)$"), list("-+0123456789"))
+# serde_yaml 0.9.34 (the reference's Cargo.lock), de.rs parse_unsigned_int / parse_negative_int / digits_but_not_number: signed decimal,
+# hex, octal and binary integers; a decimal with a leading zero ("007", "-012") is a STRING (and not a float either)
+_Loader.add_implicit_resolver("tag:yaml.org,2002:int",
+                              re.compile(r"^[-+]?(?:0|[1-9][0-9]*|0o[0-7]+|0x[0-9a-fA-F]+|0b[01]+)$"), list("-+0123456789"))
 _Loader.add_implicit_resolver(
     "tag:yaml.org,2002:float",
-    re.compile(r"^(?:[-+]?(?:\.[0-9]+|[0-9]+(?:\.[0-9]*)?)(?:[eE][-+]?[0-9]+)?|[-+]?\.(?:inf|Inf|INF)|\.(?:nan|NaN|NAN))$"),
+    re.compile(r"^(?![-+]?0[0-9]+$)(?:[-+]?(?:\.[0-9]+|[0-9]+(?:\.[0-9]*)?)(?:[eE][-+]?[0-9]+)?|[-+]?\.(?:inf|Inf|INF)|\.(?:nan|NaN|NAN))$"),
     list("-+0123456789."),
 )
 
 
 def _construct_int(loader, node):
     s = loader.construct_scalar(node)
-    if s.startswith("0o"):
-        return int(s[2:], 8)
-    if s.startswith("0x"):
-        return int(s[2:], 16)
+    sign = -1 if s.startswith("-") else 1
+    body = s.lstrip("+-")
+    for prefix, radix in (("0o", 8), ("0x", 16), ("0b", 2)):
+        if body.startswith(prefix):
+            return sign * int(body[2:], radix)
     return int(s)
 
 
@@ -188,6 +198,7 @@ class SandRule:  # rules.rs:25-44
     used: bool = False
     mentions_left: bool = False   # oracle/product definition of a Left rule (module docstring)
     mentions_right: bool = False
+    left_conflict: Optional[str] = None   # raw text when LEFT sits in a mirrored rule or is mixed with RIGHT: an error once the rule is used
 
     @staticmethod
     def _func_logic(if_conds, do_actions, probabilities, indent_lvl):  # rules.rs:47-73
@@ -381,12 +392,14 @@ def _parse_rules(rules, type_names, material_names):  # rules.rs:105-203
         else:
             pre = DEFAULT_VAL_PRECONDITION
         joined = " ".join(raw_text)
-        mentions_left = "LEFT" in joined
-        mentions_right = "RIGHT" in joined
-        if mentions_left and (is_mirrored or mentions_right):
-            raise _notrecog(joined, f"rules/{name} (LEFT in a mirrored rule, or LEFT mixed with RIGHT)")
-        out.append(SandRule(name, ruletype, if_conds, do_actions, probs, is_mirrored, "" if pre else None,
-                            False, mentions_left, mentions_right))
+        idents = set(re.findall(r"[A-Za-z0-9_]+", joined))      # whole identifiers: a material LEFTOVER is not a cell name
+        mentions_left = bool(idents & {"LEFT", "DOWNLEFT"})
+        mentions_right = bool(idents & {"RIGHT", "DOWNRIGHT"})
+        rule = SandRule(name, ruletype, if_conds, do_actions, probs, is_mirrored, "" if pre else None,
+                        False, mentions_left, mentions_right)
+        # an error only once a type or a material uses the rule (the reference emits used rules only)
+        rule.left_conflict = joined if mentions_left and (is_mirrored or mentions_right) else None
+        out.append(rule)
     return out
 
 
@@ -450,6 +463,7 @@ def _parse_types(types, rules, rule_names, type_names):  # types.rs:51-182
                 if rn not in rule_names:
                     raise _notfound(rn, f"types/{name}/base_rules")
                 rule = next(r for r in rules if r.name == rn)
+                _require_usable(rule)
                 rule.used = True
                 _update_rule_precondition(rule, name)
                 base_rules.append(rn)
@@ -536,6 +550,7 @@ def _parse_materials(materials, rules, type_names):  # materials.rs:51-201
                     raise _invalid("extra_rules", f"materials/{name}", "string")
                 for r in rules:
                     if r.name == ern:
+                        _require_usable(r)
                         r.used = True
                         if r.precondition is not None:
                             if r.precondition == "":

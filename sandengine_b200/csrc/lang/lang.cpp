@@ -12,6 +12,21 @@ namespace {
 
 // parser.rs:27-34
 const char* const GLOBAL_CELLNAMES[6] = {"SELF", "LEFT", "RIGHT", "DOWN", "DOWNRIGHT", "DOWNLEFT"};
+
+// does the raw if/do text of a rule name the LEFT / RIGHT column as a cell (whole identifiers)?
+void mentions_cells(const std::string& text, bool& left, bool& right) {
+    left = right = false;
+    auto ident = [](char c) { return (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || (c >= '0' && c <= '9') || c == '_'; };
+    for (size_t i = 0; i < text.size();) {
+        if (!ident(text[i])) { ++i; continue; }
+        size_t j = i;
+        while (j < text.size() && ident(text[j])) ++j;
+        const std::string tok = text.substr(i, j - i);
+        if (tok == "LEFT" || tok == "DOWNLEFT") left = true;
+        if (tok == "RIGHT" || tok == "DOWNRIGHT") right = true;
+        i = j;
+    }
+}
 bool is_cellname(const std::string& s) {
     for (auto* c : GLOBAL_CELLNAMES)
         if (s == c) return true;
@@ -200,13 +215,19 @@ std::vector<SandRule> parse_rules(const YamlValue& rules, const std::vector<std:
         }
         rule.has_precondition = do_precondition;
 
-        rule.mentions_left = raw_text.find("LEFT") != std::string::npos;
-        rule.mentions_right = raw_text.find("RIGHT") != std::string::npos;
-        if (rule.mentions_left && (rule.mirror || rule.mentions_right))
-            throw not_recognized(trim_end(raw_text), "rules/" + rule.name + " (LEFT in a mirrored rule, or LEFT mixed with RIGHT)");
+        // whole identifiers only (a material LEFTOVER is not a cell name); a conflicting rule is an error only once a type or a
+        // material uses it -- the reference emits used rules only, so an unused draft rule must not reject the file
+        mentions_cells(raw_text, rule.mentions_left, rule.mentions_right);
+        if (rule.mentions_left && (rule.mirror || rule.mentions_right)) rule.left_conflict = trim_end(raw_text);
         out.push_back(std::move(rule));
     }
     return out;
+}
+
+// a rule that a type or a material refers to must be executable
+void require_usable(const SandRule& rule) {
+    if (!rule.left_conflict.empty())
+        throw not_recognized(rule.left_conflict, "rules/" + rule.name + " (LEFT in a mirrored rule, or LEFT mixed with RIGHT)");
 }
 
 // types.rs:78-88
@@ -276,6 +297,7 @@ std::vector<SandType> parse_types(const YamlValue& types, std::vector<SandRule>&
                 if (!item.is_str()) throw invalid_type("base_rules", "types/" + t.name, TYPE_HINT_STRING);
                 if (!contains(rule_names, item.s)) throw not_found(item.s, "types/" + t.name + "/base_rules");
                 SandRule* rule = find_rule(rules, item.s);
+                require_usable(*rule);
                 rule->used = true;
                 update_rule_precondition(*rule, "isType_" + t.name + "(self)");
                 t.base_rules.push_back(item.s);
@@ -353,6 +375,7 @@ std::vector<SandMaterial> parse_materials(const YamlValue& materials, std::vecto
                 if (!item.is_str()) throw invalid_type("extra_rules", "materials/" + m.name, TYPE_HINT_STRING);
                 for (auto& r : rules) {   // unknown names are silently ignored (materials.rs:153-165)
                     if (r.name == item.s) {
+                        require_usable(r);
                         r.used = true;
                         update_rule_precondition(r, "self.mat == MAT_" + m.name);
                         m.extra_rules.push_back(item.s);

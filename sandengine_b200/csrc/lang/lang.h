@@ -38,6 +38,7 @@ struct SandRule {
     bool used = false;
     bool mentions_left = false;                       // LEFT / DOWNLEFT appears in the raw if/do text
     bool mentions_right = false;
+    std::string left_conflict;                        // non-empty: LEFT in a mirrored rule or mixed with RIGHT (an error once the rule is used)
     // Classification this build actually executes: Left iff !mirror && mentions_left.
     SandRuleType effective_type() const {
         if (mirror) return SandRuleType::Mirrored;

@@ -25,7 +25,7 @@ bool all_digits(const std::string& s, size_t from, int base) {
     if (from >= s.size()) return false;
     for (size_t k = from; k < s.size(); ++k) {
         char c = s[k];
-        bool ok = base == 10 ? std::isdigit((unsigned char)c) : base == 8 ? (c >= '0' && c <= '7') : std::isxdigit((unsigned char)c);
+        bool ok = base == 10 ? std::isdigit((unsigned char)c) : base == 8 ? (c >= '0' && c <= '7') : base == 2 ? (c == '0' || c == '1') : std::isxdigit((unsigned char)c);
         if (!ok) return false;
     }
     return true;
@@ -65,15 +65,26 @@ YamlValue resolve_plain(const std::string& s) {
     if (s.empty() || s == "~" || s == "null" || s == "Null" || s == "NULL") { v.kind = YamlValue::Null; return v; }
     if (s == "true" || s == "True" || s == "TRUE") { v.kind = YamlValue::Bool; v.b = true; return v; }
     if (s == "false" || s == "False" || s == "FALSE") { v.kind = YamlValue::Bool; v.b = false; return v; }
+    // Integers as serde_yaml 0.9.34 resolves them (the reference's Cargo.lock; de.rs parse_unsigned_int / parse_negative_int /
+    // digits_but_not_number): optional sign, then decimal, 0x, 0o or 0b digits; a decimal with a leading zero ("007", "-012") is a
+    // string -- and stays one, it is not retried as a float.
     size_t sign = (s[0] == '-' || s[0] == '+') ? 1 : 0;
     if (all_digits(s, sign, 10)) {
+        if (s.size() - sign > 1 && s[sign] == '0') { v.kind = YamlValue::String; return v; }
         errno = 0;
         long long x = std::strtoll(s.c_str(), nullptr, 10);
         if (errno == 0) { v.kind = YamlValue::Int; v.i = x; return v; }
         v.kind = YamlValue::Float; v.f = std::strtod(s.c_str(), nullptr); return v;
     }
-    if (s.size() > 2 && s[0] == '0' && s[1] == 'x' && all_digits(s, 2, 16)) { v.kind = YamlValue::Int; v.i = (int64_t)std::strtoull(s.c_str() + 2, nullptr, 16); return v; }
-    if (s.size() > 2 && s[0] == '0' && s[1] == 'o' && all_digits(s, 2, 8)) { v.kind = YamlValue::Int; v.i = (int64_t)std::strtoull(s.c_str() + 2, nullptr, 8); return v; }
+    if (s.size() > sign + 2 && s[sign] == '0') {
+        const int radix = s[sign + 1] == 'x' ? 16 : s[sign + 1] == 'o' ? 8 : s[sign + 1] == 'b' ? 2 : 0;
+        if (radix && all_digits(s, sign + 2, radix)) {
+            const int64_t mag = (int64_t)std::strtoull(s.c_str() + sign + 2, nullptr, radix);
+            v.kind = YamlValue::Int;
+            v.i = s[0] == '-' ? -mag : mag;
+            return v;
+        }
+    }
     if (looks_float(s)) { v.kind = YamlValue::Float; v.f = std::strtod(s.c_str(), nullptr); return v; }
     {
         std::string t = s;

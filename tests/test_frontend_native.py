@@ -66,6 +66,42 @@ def test_error_classes_match_oracle_parser(native_lib, name, text, kind):
     assert f"({kind})" in str(ei.value)
 
 
+@pytest.mark.parametrize("text,want", [("0b11", 3.0), ("007", None), ("017", None), ("-012", None), ("-0x1F", -31.0), ("+0x10", 16.0), ("0o17", 15.0),
+                                       ("-0", 0.0), ("+12", 12.0), ("1e3", 1000.0), ("00.5", 0.5), ("0x", None), ("0b2", None), ("-.5", -0.5),
+                                       ("1.", 1.0), ("0", 0.0)])
+def test_plain_scalar_numbers_resolve_like_serde_yaml(native_lib, text, want):
+    """serde_yaml 0.9.34 (the reference's Cargo.lock) reads signed hex / octal / binary integers and treats a decimal
+    with a leading zero as a string (-> InvalidType for a density).  Product and oracle parser must agree case by case."""
+    import sandengine_b200 as se
+    doc = Y.BASE_OK.replace("density: 1.5", f"density: {text}")
+    if want is None:
+        with pytest.raises(se.SandEngineError) as ei:
+            se.parse_string(doc, compile=False)
+        assert ei.value.kind == "InvalidType"
+        with pytest.raises(L.ParsingErr) as eo:
+            L.parse_string(doc)
+        assert eo.value.kind == "InvalidType"
+    else:
+        assert se.parse_string(doc, compile=False).materials[-1].density == want
+        assert float(L.parse_string(doc).materials[-1].density) == want
+
+
+def test_unused_conflicting_rule_is_accepted(native_lib):
+    """the LEFT / RIGHT conflict is an error of a USED rule only (the reference emits used rules only)."""
+    import sandengine_b200 as se
+    r = se.parse_string(Y.UNUSED_LEFT_CONFLICT_OK, compile=False)
+    assert [x.name for x in r.rules if x.used] == ["gravity", "slide_diagonally"]
+    o = L.parse_string(Y.UNUSED_LEFT_CONFLICT_OK)
+    assert [x.name for x in o.rules if x.used] == ["gravity", "slide_diagonally"]
+    # ... and the same draft rule is rejected as soon as a type refers to it
+    with pytest.raises(se.SandEngineError) as ei:
+        se.parse_string(Y.UNUSED_LEFT_CONFLICT_OK.replace("base_rules: [gravity, slide_diagonally]", "base_rules: [gravity, draft_never_used]"), compile=False)
+    assert ei.value.kind == "NotRecognized"
+    with pytest.raises(L.ParsingErr) as eo:
+        L.parse_string(Y.UNUSED_LEFT_CONFLICT_OK.replace("base_rules: [gravity, slide_diagonally]", "base_rules: [gravity, draft_never_used]"))
+    assert eo.value.kind == "NotRecognized"
+
+
 @pytest.mark.parametrize("text", [Y.BASE_OK, Y.RICH_YAML], ids=["base", "rich"])
 def test_front_ends_agree_on_text(native_lib, text):
     """Two independent parsers (C++ product, Python oracle) must build the same rule text."""

@@ -110,6 +110,15 @@ materials:
                                               "if: LEFT.mat.density < RIGHT.mat.density\n    do: SWAP SELF LEFT\n    mirrored: false"), "NotRecognized"),
 ]
 
+# Accepted since round 2: a conflicting rule nobody uses does not reject the file (the reference emits used rules
+# only).  (LEFT / RIGHT are matched as whole identifiers for this check; the reference's own literal replaces -- rules.rs:338-351 --
+# still mangle any name that contains them, so such names stay unusable exactly as in the reference.)
+UNUSED_LEFT_CONFLICT_OK = BASE_OK.replace("types:", """  draft_never_used:
+    if: LEFT.mat.density < RIGHT.mat.density
+    do: SWAP SELF LEFT
+    mirrored: false
+types:""")
+
 # A rule set exercising most of the language: nested else chains, trailing else without `if`, lists of
 # actions, SET+SWAP in one string, deep inheritance, non-mirrored RIGHT and LEFT rules, density vs
 # literal, .mat.type / TYPE_ constants, != on materials, several probabilities.
