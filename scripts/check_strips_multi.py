@@ -92,6 +92,29 @@ def main():
         report(f"{W}x{H} lighting on, {steps} steps (light max-abs err {err:.1e})", bool(np.array_equal(full, ref)) and err <= 1e-6)
     strip.close()
     dist.barrier()
+    # ---- strip snapshots: save on every rank after 21 steps, restore with load_strip, 30 more steps ----
+    import tempfile
+    from sandengine_b200 import snapshot
+    W, H = 512, 1024
+    g = synthetic_grid(W, H, 31)
+    strip = StripSimulation(rules, (W, H), halo_rows=16, device=local)
+    strip.upload_cells(g[strip.row_begin:strip.row_end])
+    strip.params.frame = 1
+    strip.step(21)
+    tmp = Path(tempfile.gettempdir()) / f"se_strip_snapshot_{os.getpid()}_{rank}.npz"
+    snapshot.save(strip, tmp)
+    strip.close()
+    dist.barrier()
+    strip = snapshot.load_strip(rules, tmp, device=local)
+    tmp.unlink()
+    frame_ok = strip.params.frame == 22
+    strip.step(30)
+    full = gather_rows(strip, strip.download_cells(), world)
+    if rank == 0:
+        ref, _, _ = load_oracle().run(g, 1, 51, blocks=True)
+        report(f"{W}x{H} strip snapshot after 21 steps, restored with load_strip, 30 more steps", frame_ok and bool(np.array_equal(full, ref)))
+    strip.close()
+    dist.barrier()
     if rank == 0:
         out = REPO / "gpurun_out"
         out.mkdir(exist_ok=True)

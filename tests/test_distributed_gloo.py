@@ -93,3 +93,21 @@ def test_strip_plan_arithmetic():
         StripPlan(64, 64, 2, 3)
     with pytest.raises(ValueError):
         StripPlan(64, 16, 4, 8)
+
+
+def test_a_strip_snapshot_is_refused_by_the_single_device_loader(tmp_path, native_lib):
+    """a strip file holds owned rows only; `snapshot.load` must not build a strip without neighbours from it
+    (no GPU needed: the refusal comes before any device object is made).  `load_strip` is exercised on GPUs by
+    scripts/check_strips_multi.py."""
+    import json
+
+    import numpy as np
+
+    import sandengine_b200 as se
+    from sandengine_b200 import snapshot
+    rules = se.parse_path(REPO / "data" / "materials.yaml", compile=False)
+    meta = {"format": snapshot.FORMAT, "width": 64, "height": 128, "row_begin": 64, "row_end": 128, "halo_rows": 8, "frame": 5,
+            "lighting": False, "rules_sha256": snapshot.rules_digest(rules)}
+    np.savez_compressed(tmp_path / "strip.npz", meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), cells=np.zeros((64, 64), np.uint32))
+    with pytest.raises(ValueError, match="load_strip"):
+        snapshot.load(rules, tmp_path / "strip.npz")
