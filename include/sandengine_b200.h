@@ -64,8 +64,9 @@ typedef struct se_modification {
  * light field gets ghost rows too: attach the neighbours' light buffers (se_sim_ipc_export_light / _attach_light, or
  * se_sim_attach_local); the light stencil uses up one ghost row per step and se_sim_step exchanges when they run out. */
 #define SE_FLAG_LIT_STRIP_EXPERIMENTAL 4u
-/* With SE_FLAG_LIGHTING and a table-eligible rule set, run the Margolus step, the modification override and the
- * lighting relaxation as ONE kernel instead of two.  Same results.  Ignored where it does not apply. */
+/* Accepted for compatibility (round 1 gated the one-kernel lit path behind it): with SE_FLAG_LIGHTING, a table-eligible
+ * rule set and a width that is a multiple of 8, the Margolus step, the modification override and the lighting relaxation
+ * always run as ONE kernel (se_step_lit); elsewhere as two.  Same results either way. */
 #define SE_FLAG_FUSED_LIGHT_EXPERIMENTAL 8u
 
 typedef struct se_create_params {
@@ -157,7 +158,7 @@ int se_sim_ipc_export(se_sim* s, void* handles_2x64, uint64_t* local_rows, uint6
  * exported handles. */
 int se_sim_ipc_attach(se_sim* s, int which, const void* handles_2x64, uint64_t nb_local_rows,
                       uint64_t nb_ghost_top, uint64_t nb_ghost_bottom);
-/* Same pair for the two light buffers of a lit strip (SE_FLAG_LIT_STRIP_EXPERIMENTAL); call after se_sim_ipc_attach. */
+/* Same pair for the two light buffers of a lit strip; call after se_sim_ipc_attach. */
 int se_sim_ipc_export_light(se_sim* s, void* handles_2x64);
 int se_sim_ipc_attach_light(se_sim* s, int which, const void* handles_2x64);
 /* Attach a neighbour that lives in THIS process (one process driving several strips / devices, the

@@ -74,8 +74,9 @@ class StripPlan:
 
 
 class StripSimulation:
-    """One rank's strip of a sharded `Simulation`.  lighting=True is EXPERIMENTAL (SE_FLAG_LIT_STRIP_EXPERIMENTAL):
-    the light field gets ghost rows too and the exchange happens every `halo_rows` steps."""
+    """One rank's strip of a sharded `Simulation`.  `step(n)` is `Simulation.step(n)` on every rank: the library keeps the ghost
+    rows current (pushed by the boundary tiles of the tile kernel in runs of steps, exchanged on the stream when the per-step
+    kernels have used them up).  With lighting=True the light field gets ghost rows too (one is used up per step)."""
 
     def __init__(self, rules, size, halo_rows: int = 32, device=None, temporal_block: int = 0, device_sync: bool = True,
                  running_census: bool = False, lighting: bool = False, device_share: int = 1):

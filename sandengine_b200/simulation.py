@@ -66,7 +66,7 @@ class Simulation:
         self.params = Params()
         self.modifications: List[np.ndarray] = []
         flags = ((_capi.SE_FLAG_LIGHTING if lighting else 0) | (_capi.SE_FLAG_RUNNING_CENSUS if running_census else 0)
-                 | (_capi.SE_FLAG_LIT_STRIP_EXPERIMENTAL if lit_strip else 0) | (_capi.SE_FLAG_FUSED_LIGHT_EXPERIMENTAL if fused_light else 0))   # the last two: experimental, see the header
+                 | (_capi.SE_FLAG_LIT_STRIP_EXPERIMENTAL if lit_strip else 0) | (_capi.SE_FLAG_FUSED_LIGHT_EXPERIMENTAL if fused_light else 0))   # the last two: accepted for compatibility, see the header
         prm = _capi.se_create_params(self.size[0], self.size[1], flags, device,
                                      self.row_begin, self.row_end, int(halo_rows), int(temporal_block), int(device_share))
         h = C.c_void_p()
