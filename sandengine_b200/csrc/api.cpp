@@ -917,7 +917,7 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
             // is read where it lies in global memory
             s->lf_buf_offset = 0;
             s->lf_smem = lf_ng() * lf_nbuf() * lf_buf_bytes() + 128;
-            if (s->lf_smem + 13 * 1024 <= smem_optin) {
+            if (s->lf_smem + 16 * 1024 <= smem_optin) {
                 SE_CU_S(driver().ModuleGetFunction(&s->f_step_lit, s->mod, "se_step_lit"));
                 SE_CU_S(driver().FuncSetAttribute(s->f_step_lit, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->lf_smem));
                 s->lf_tiles_x = (s->W + LF_TW - 1) / LF_TW;

@@ -1505,7 +1505,7 @@ static __device__ __forceinline__ bool se_mod_lookup_culled(const SeMod* __restr
 extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const __grid_constant__ SeTensorMap tm_cells, const __grid_constant__ SeTensorMap tm_light,
                                                                               const SeLitParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ unsigned fat_sm[256];
+    __shared__ __align__(16) unsigned fat_sm[256 + 256 * 4];   // the fat-cell flags, then the emission (a float4 per material)
     __shared__ unsigned char cull_sm[SE_LF_NG][2][256];
     __shared__ int n_cull_sm[SE_LF_NG][2];
     __shared__ __align__(8) unsigned long long mbar[SE_LF_NG * SE_LF_NBUF];
@@ -1517,6 +1517,10 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
     // runs), and the shared memory holds the TMA buffers instead -- the loads are what the kernel waits for.
     const SeTabG tab{p.lut, p.pool};
     if (tid < 256) fat_sm[tid] = se_fat_table[tid];
+    for (int i = tid; i < 256 * 4; i += SE_LF_THREADS) fat_sm[256 + i] = __float_as_uint(se_emission_table[i]);
+    // both tables are read with plain shared-space addresses (a C array access costs four uniform instructions per look-up
+    // here: the kernel's shared memory is addressed through the cluster window)
+    const unsigned fat_sa = (unsigned)__cvta_generic_to_shared(fat_sm);
     const unsigned mbar_sa = (unsigned)__cvta_generic_to_shared(mbar) + 8u * SE_LF_NBUF * (unsigned)half;   // this half's barriers
     if (tid == 0) {
         for (unsigned k = 0; k < (unsigned)(SE_LF_NG * SE_LF_NBUF); ++k) se_mbar_init((unsigned)__cvta_generic_to_shared(mbar) + 8u * k, 1u);
@@ -1605,10 +1609,8 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
                         SE_LF_ACC(b2) SE_LF_ACC(b0) SE_LF_MAX2(b2, b0)
                         SE_LF_FINISH(out)
                     }
-                    const bool emissive = (fat_sm[me] & SE_F_EMISSIVE) != 0u;          // operations.glsl:126-127
-                    if (__any_sync(0xFFFFFFFFu, emissive)) {                           // rare
-                        if (emissive) out = make_float4(se_emission_table[me * 4 + 0], se_emission_table[me * 4 + 1], se_emission_table[me * 4 + 2], se_emission_table[me * 4 + 3]);
-                    }
+                    if (se_lds_u32(fat_sa + 4u * me) & SE_F_EMISSIVE)                  // operations.glsl:126-127
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(out.x), "=f"(out.y), "=f"(out.z), "=f"(out.w) : "r"(fat_sa + 1024u + 16u * me));
                     *light_out = out;
                     light_out += p.W;
                     a0 = b0; a1 = b1; a2 = b2;
@@ -1741,7 +1743,7 @@ extern "C" __global__ void __launch_bounds__(SE_LF_THREADS, 1) se_step_lit(const
                         const unsigned la_sa = light_sa + 16u * (unsigned)(c + i * (SE_LF_LSTRIDE - SE_LF_RW) + SE_LF_LCOL0);
                         const unsigned id = se_lds_u32(ids_sa + 4u * e);
                         const SeF4P li = se_lds_f4p(la_sa);
-                        const unsigned nf = fat_sm[id < 255u ? id : 255u];
+                        const unsigned nf = se_lds_u32(fat_sa + 4u * (id < 255u ? id : 255u));
                         // (rgb * keep) * a with keep in {0, 1} is rgb * (keep ? a : 0) for finite light
                         const float la = se_hi(li.zw), lk = (nf & SE_F_OBSTACLE) ? 0.0f : la;
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(la_sa),
