@@ -408,7 +408,18 @@ int compile_front(const char* yaml, size_t len, se_rules** out, bool with_nvrtc)
         nvrtcProgram prog;
         const char* hdr_src[1] = {r->cr.cuda_header.c_str()};
         const char* hdr_name[1] = {"rules_gen.cuh"};
-        if (nvrtc().CreateProgram(&prog, KERNEL_SOURCE, "sand_kernels.cu", 1, hdr_src, hdr_name) != NVRTC_SUCCESS) {
+        // experiments only: SE_KERNEL_SOURCE_FILE=<path> compiles that file instead of the embedded kernel source (A/B runs of two
+        // kernel versions on the same GPU box)
+        std::string source_override;
+        if (const char* sf = std::getenv("SE_KERNEL_SOURCE_FILE")) {
+            if (FILE* f = std::fopen(sf, "rb")) {
+                char buf[65536];
+                size_t n;
+                while ((n = std::fread(buf, 1, sizeof buf, f)) > 0) source_override.append(buf, n);
+                std::fclose(f);
+            }
+        }
+        if (nvrtc().CreateProgram(&prog, source_override.empty() ? KERNEL_SOURCE : source_override.c_str(), "sand_kernels.cu", 1, hdr_src, hdr_name) != NVRTC_SUCCESS) {
             delete r;
             return fail(SE_ERR_COMPILE, "nvrtcCreateProgram failed");
         }
