@@ -220,6 +220,8 @@ struct SeLutStepParams {
     int table_bytes, pool_offset;
     const unsigned* lut;
     const unsigned* pool;
+    int n_mods;
+    const SeMod* mods;
 };
 struct SeLutCensusParams {
     unsigned long long* census;
@@ -329,7 +331,7 @@ struct se_sim {
     unsigned census_slot = 0;
     // transition-table kernels (K1b tiles, K1c per frame)
     bool tiled = false;
-    CUfunction f_tiles = nullptr, f_build_lut = nullptr, f_lut_global = nullptr;
+    CUfunction f_tiles = nullptr, f_build_lut = nullptr, f_lut_global = nullptr, f_lut_global_mods = nullptr;
     unsigned* d_lut = nullptr;         // table image: N^4 * tables entries, then (mode 1, same allocation) the pool
     unsigned* d_pool = nullptr;        // mode 2: pool entries {thr, A, B} in global memory
     unsigned* d_tile_done = nullptr;   // per-tile sequence numbers (dataflow between the T-blocks of one launch)
@@ -357,7 +359,7 @@ struct se_sim {
     int lf_smem = 0, lf_grid = 0, lf_tiles_x = 0, lf_tiles_y = 0, lf_buf_offset = 0;
     // running census (SE_FLAG_RUNNING_CENSUS, experimental): d_running is valid only between K1c-census steps
     bool running = false, running_valid = false, running_copy_pending = false;
-    CUfunction f_lut_global_census = nullptr;
+    CUfunction f_lut_global_census = nullptr, f_lut_global_census_mods = nullptr;
     unsigned* d_lut_census = nullptr;      // copy of the table image whose outcomes carry SE_E_POPFLAG (kernels/sand_kernels.cuh)
     unsigned long long* d_running = nullptr;
     cudaEvent_t running_copy_done = nullptr;
@@ -870,6 +872,7 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
         SE_CU_S(driver().ModuleGetFunction(&s->f_tiles, s->mod, "se_step_tiles"));
         SE_CU_S(driver().ModuleGetFunction(&s->f_build_lut, s->mod, "se_build_lut"));
         SE_CU_S(driver().ModuleGetFunction(&s->f_lut_global, s->mod, "se_step_lut_global"));
+        SE_CU_S(driver().ModuleGetFunction(&s->f_lut_global_mods, s->mod, "se_step_lut_global_mods"));
         unsigned* d_counter = nullptr;
         SE_CUDA_S(cudaMalloc(&d_counter, sizeof(unsigned)));
         SE_CUDA_S(cudaMemsetAsync(d_counter, 0, sizeof(unsigned), s->stream));
@@ -970,6 +973,7 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
             const int tile_smem_max = s->tile_offset + 2 * 256 * PH_max;
             SE_CU_S(driver().FuncSetAttribute(s->f_tiles, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, tile_smem_max));
             if (s->k1c_smem > 0) SE_CU_S(driver().FuncSetAttribute(s->f_lut_global, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->k1c_smem));
+            if (s->k1c_smem > 0) SE_CU_S(driver().FuncSetAttribute(s->f_lut_global_mods, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->k1c_smem));
             int occ = 0;
             SE_CU_S(driver().OccupancyMaxActiveBlocks(&occ, s->f_tiles, 1024, (size_t)tile_smem_max));
             if (occ < 1) { fail(SE_ERR_CUDA, "se_step_tiles does not fit on an SM"); return bail(SE_ERR_CUDA); }
@@ -983,6 +987,7 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
             if ((prm->flags & SE_FLAG_RUNNING_CENSUS) && rules->cr.lut_tables == 1 && s->lut_mode == 1) {
                 // the census variant of K1c stages a second image of the table: same entries, population-changing outcomes flagged
                 SE_CU_S(driver().ModuleGetFunction(&s->f_lut_global_census, s->mod, "se_step_lut_global_census"));
+                SE_CU_S(driver().ModuleGetFunction(&s->f_lut_global_census_mods, s->mod, "se_step_lut_global_census_mods"));
                 const size_t image = (size_t)s->tile_offset + 16;
                 SE_CUDA_S(cudaMalloc(&s->d_lut_census, image));
                 SE_CUDA_S(cudaMemsetAsync(s->d_lut_census, 0, image, s->stream));
@@ -999,6 +1004,7 @@ int se_sim_create(const se_rules* rules, const se_create_params* prm, se_sim** o
                 SE_CUDA_S(cudaMalloc(&s->d_running, 256 * sizeof(unsigned long long)));
                 SE_CUDA_S(cudaEventCreateWithFlags(&s->running_copy_done, cudaEventDisableTiming));
                 SE_CU_S(driver().FuncSetAttribute(s->f_lut_global_census, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->k1c_smem));
+                SE_CU_S(driver().FuncSetAttribute(s->f_lut_global_census_mods, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, s->k1c_smem));
                 s->running = true;
             }
         }
@@ -1043,9 +1049,11 @@ int se_sim_step(se_sim* s, uint32_t n_steps) try {
     }
     for (uint32_t k = 0; k < n_steps;) {
         const bool mods_now = (k == 0 && n_mods > 0);
-        if (s->tiled && !mods_now && s->frame + 1 != 1) {
-            if (n_steps - k == 1) {
-                // a lone step (the per-frame path): K1c, table transitions straight from global memory, in place
+        if (s->tiled && s->frame + 1 != 1) {
+            if (n_steps - k == 1 || mods_now) {
+                // a lone step (the per-frame path) or the step that consumes the frame's modifications (a brush held down must
+                // not drop the per-frame path to the generated-code kernel): K1c, table transitions straight from global memory,
+                // in place, the override applied per cell where a record can touch the warp's work item
                 { int rc = guard_buffer_write(s, s->cur); if (rc) return rc; }
                 const int frame = s->frame + 1;
                 const int oy = ((frame & 3) == 1 || (frame & 3) == 2) ? 1 : 0;
@@ -1057,15 +1065,16 @@ int se_sim_step(se_sim* s, uint32_t n_steps) try {
                 lp.cells = s->cells[s->cur];
                 lp.W = s->W; lp.Hl = s->Hl; lp.gy0 = s->gy0; lp.Hg = s->Hg; lp.frame = frame;
                 lp.table_bytes = s->table_bytes; lp.pool_offset = s->pool_offset; lp.lut = s->d_lut; lp.pool = s->d_pool;
+                lp.n_mods = mods_now ? n_mods : 0; lp.mods = s->d_mods;
                 void* largs[] = {&lp};
                 int rc;
                 if (s->running && s->running_valid) {
                     SeLutCensusParams cx{s->d_running, s->row_begin, s->row_end};
                     lp.lut = s->d_lut_census;
                     void* cargs[] = {&lp, &cx};
-                    rc = launch(s, s->f_lut_global_census, dim3(s->k1c_grid), dim3(512), cargs, (unsigned)s->k1c_smem);
+                    rc = launch(s, mods_now ? s->f_lut_global_census_mods : s->f_lut_global_census, dim3(s->k1c_grid), dim3(512), cargs, (unsigned)s->k1c_smem);
                 } else {
-                    rc = launch(s, s->f_lut_global, dim3(s->k1c_grid), dim3(512), largs, (unsigned)s->k1c_smem);   // SE_K1C_THREADS
+                    rc = launch(s, mods_now ? s->f_lut_global_mods : s->f_lut_global, dim3(s->k1c_grid), dim3(512), largs, (unsigned)s->k1c_smem);   // SE_K1C_THREADS
                 }
                 if (rc) return rc;
                 s->frame += 1;

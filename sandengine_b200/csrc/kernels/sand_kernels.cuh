@@ -126,6 +126,13 @@ static __device__ __forceinline__ bool se_mod_lookup(const SeMod* __restrict__ m
     return got && fin != 1;
 }
 
+// can record m touch a cell of the rectangle?  (both shapes lie inside the square |dx|,|dy| <= size; negative sizes never
+// match; 64-bit sums: a position near INT_MAX must not wrap around)
+static __device__ __forceinline__ bool se_mod_touches(const SeMod& m, int x_lo, int x_hi, int y_lo, int y_hi) {
+    const long long px = m.px, py = m.py, sz = m.size;
+    return m.size >= 0 && px + sz >= x_lo && px - sz <= x_hi && py + sz >= y_lo && py - sz <= y_hi;
+}
+
 #ifndef SE_HOST_EMU   // kernels (the pure device functions above are also compiled on the host by tests/emu)
 // ---------------------------------------------------------------------------------------------
 // K1a: one Margolus step, one thread per 2x2 block, straight from/to global memory.
@@ -1121,6 +1128,8 @@ struct SeLutStepParams {
     int table_bytes, pool_offset;
     const unsigned* lut;
     const unsigned* pool;
+    int n_mods;             // the _mods kernels: already cut at the first mod_size == 0 (falling_sand.glsl:754-756)
+    const SeMod* mods;
 };
 
 #define SE_K1C_THREADS 512
@@ -1138,7 +1147,10 @@ struct SeLutCensusParams {
     int own_y0, own_y1;           // owned global rows [own_y0, own_y1)
 };
 
-template <bool CENSUS>
+// MODS: the frame's modification records override the cells they cover (falling_sand.glsl:749-794) -- a brush held down keeps the
+// per-frame path on the table kernel.  A warp tests the records against the bounding box of its work item once; only items a
+// record can touch scan the list per cell.
+template <bool CENSUS, bool MODS>
 static __device__ __forceinline__ void se_k1c_body(const SeLutStepParams& p, const SeLutCensusParams& cx, int* hist_sm) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ unsigned fat_sm[256];
@@ -1189,6 +1201,15 @@ static __device__ __forceinline__ void se_k1c_body(const SeLutStepParams& p, con
         // census: which of the two rows are counted (inside the grid and owned by this strip)
         const unsigned cm_rows = !CENSUS ? 0u : ((st0 == 0 && y0 >= cx.own_y0 && y0 < cx.own_y1) ? 3u : 0u) | ((st1 == 0 && y1 >= cx.own_y0 && y1 < cx.own_y1) ? 12u : 0u);
         const int c_begin = (int)sp * SE_K1C_SPAN, c_end = min((int)chunks_x, c_begin + SE_K1C_SPAN);
+        bool item_hit = false;                                             // can a modification record touch this item?
+        if (MODS) {
+            const int x_lo = 2 * (c_begin * 32) - ox, x_hi = 2 * (c_end * 32) - ox - 1;
+            for (int m0 = 0; m0 < p.n_mods; m0 += 32) {
+                bool touch = false;
+                if (m0 + lane < p.n_mods) touch = se_mod_touches(p.mods[m0 + lane], x_lo, x_hi, y0, y1);
+                item_hit = item_hit || __any_sync(0xFFFFFFFFu, touch);
+            }
+        }
         for (int cb = c_begin; cb < c_end; cb += SE_K1C_BATCH) {
             unsigned a[SE_K1C_BATCH], b[SE_K1C_BATCH], c[SE_K1C_BATCH], d[SE_K1C_BATCH];
 #pragma unroll
@@ -1262,12 +1283,21 @@ static __device__ __forceinline__ void se_k1c_body(const SeLutStepParams& p, con
                 const int x0 = 2 * bx - ox;
                 if (cb + u < c_end && bx < nbx) {
 #if !SE_LUT_TWO_TABLES
-                    const bool look = CENSUS && ((e[u] & SE_E_POPFLAG) || ((unknown >> u) & 1u));
+                    bool look = CENSUS && ((e[u] & SE_E_POPFLAG) || ((unknown >> u) & 1u));
                     if (CENSUS) e[u] &= ~SE_E_POPFLAG;
 #endif
-                    const unsigned nv = SE_LUT_TWO_TABLES ? e[u] : __byte_perm(e[u], 0u, ((mir >> u) & 1u) ? 0x2301u : 0x3210u);
+                    unsigned nv = SE_LUT_TWO_TABLES ? e[u] : __byte_perm(e[u], 0u, ((mir >> u) & 1u) ? 0x2301u : 0x3210u);
+                    bool overridden = false;
+                    if (MODS && item_hit) {
+                        unsigned m;
+                        if (se_mod_lookup(p.mods, p.n_mods, x0, y0, m)) { nv = (nv & 0xFFFFFF00u) | m; overridden = true; }
+                        if (se_mod_lookup(p.mods, p.n_mods, x0 + 1, y0, m)) { nv = (nv & 0xFFFF00FFu) | (m << 8); overridden = true; }
+                        if (se_mod_lookup(p.mods, p.n_mods, x0, y1, m)) { nv = (nv & 0xFF00FFFFu) | (m << 16); overridden = true; }
+                        if (se_mod_lookup(p.mods, p.n_mods, x0 + 1, y1, m)) { nv = (nv & 0x00FFFFFFu) | (m << 24); overridden = true; }
+                    }
 #if !SE_LUT_TWO_TABLES
                     // only flagged outcomes and blocks cut by the grid's / the strip's edge are looked at
+                    look = look || (CENSUS && overridden);
                     if (CENSUS && (look || cm_rows != 0xFu || x0 < 0 || x0 + 1 >= p.W)) {
                         const unsigned cm_cols = (x0 >= 0 ? 5u : 0u) | ((x0 + 1) < p.W ? 10u : 0u);
                         se_census_block(hist_sm, look, a[u], b[u], c[u], d[u], nv, cm_rows & cm_cols);
@@ -1305,13 +1335,20 @@ static __device__ __forceinline__ void se_k1c_body(const SeLutStepParams& p, con
 }
 
 extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_step_lut_global(const SeLutStepParams p) {
-    se_k1c_body<false>(p, SeLutCensusParams{}, nullptr);
+    se_k1c_body<false, false>(p, SeLutCensusParams{}, nullptr);
+}
+extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_step_lut_global_mods(const SeLutStepParams p) {
+    se_k1c_body<false, true>(p, SeLutCensusParams{}, nullptr);
 }
 
 #if !SE_LUT_TWO_TABLES
 extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_step_lut_global_census(const SeLutStepParams p, const SeLutCensusParams cx) {
     __shared__ int hist_sm[256];
-    se_k1c_body<true>(p, cx, hist_sm);
+    se_k1c_body<true, false>(p, cx, hist_sm);
+}
+extern "C" __global__ void __launch_bounds__(SE_K1C_THREADS, SE_K1C_MINCTAS) se_step_lut_global_census_mods(const SeLutStepParams p, const SeLutCensusParams cx) {
+    __shared__ int hist_sm[256];
+    se_k1c_body<true, true>(p, cx, hist_sm);
 }
 
 #endif
@@ -1391,13 +1428,6 @@ struct SeLitParams {
     int buf_offset;          // byte offset of the first input buffer in dynamic shared memory (behind the staged table)
     unsigned tiles_x_magic;  // floor(2^32 / tiles_x) + 1: tile index -> (row, column) without a division
 };
-
-// can record m touch a cell of the rectangle?  (both shapes lie inside the square |dx|,|dy| <= size; negative sizes never
-// match; 64-bit sums: a position near INT_MAX must not wrap around)
-static __device__ __forceinline__ bool se_mod_touches(const SeMod& m, int x_lo, int x_hi, int y_lo, int y_hi) {
-    const long long px = m.px, py = m.py, sz = m.size;
-    return m.size >= 0 && px + sz >= x_lo && px - sz <= x_hi && py + sz >= y_lo && py - sz <= y_hi;
-}
 
 static __device__ __forceinline__ void se_mbar_init(unsigned mbar_sa, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar_sa), "r"(count) : "memory"); }
 static __device__ __forceinline__ void se_mbar_expect_tx(unsigned mbar_sa, unsigned bytes) {

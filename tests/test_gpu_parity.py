@@ -528,6 +528,44 @@ def test_running_census(se, oracle, monkeypatch):
         sim.close()
 
 
+@pytest.mark.parametrize("running_census", [False, True])
+def test_brush_held_down_stays_on_the_per_frame_table_kernel(se, default_rules, oracle, running_census):
+    """A brush held down (modifications every frame, the reference's normal interactive use) runs on se_step_lut_global[_census]_mods:
+    cells bit-exact, the running census equal to a recount every frame, also with unknown ids, WALL / NULL cells, stamps that hang over
+    the grid's edge, more than 32 records, and frames with runs of steps behind the modified one."""
+    from sandengine_b200 import MOD_DTYPE
+    for (w, h, seed) in [(516, 130, 51), (1024, 512, 52)]:
+        rng = np.random.default_rng(seed)
+        g = synthetic_grid(w, h, seed)
+        g[rng.integers(0, h, 60), rng.integers(0, w, 60)] = 2
+        g[rng.integers(0, h, 20), rng.integers(0, w, 20)] = 1
+        g[7, 11] = 99; g[40, 300] = 3000000000
+        sim = se.Simulation(default_rules, (w, h), running_census=running_census)
+        sim.upload_cells(g); sim.params.frame = 1
+        frames = 36
+        mods = []
+        for k in range(frames):
+            m = make_mods(se, k, 11, w, h, rng)
+            if k == 5:                                   # 40 records: more than one warp-load of the list
+                m = np.zeros(40, MOD_DTYPE)
+                for i in range(40):
+                    m[i] = ((int(rng.integers(0, w)), int(rng.integers(0, h))), i % 2, 1 + i % 9, int(rng.integers(0, 11)), (0, 0, 0))
+            if k == 9:                                   # a stamp larger than the grid
+                m = np.zeros(1, MOD_DTYPE); m[0] = ((w // 2, h // 2), 1, 5000, 4, (0, 0, 0))
+            mods.append(m)
+        steps_per_frame = [1 if k % 6 else 3 for k in range(frames)]     # sometimes a run of steps behind the modified one
+        ref = g.copy(); frame = 1
+        for k in range(frames):
+            if len(mods[k]):
+                sim.push_modifications(mods[k])
+            sim.step(steps_per_frame[k])
+            ref, _, frame = oracle.run(ref, frame, steps_per_frame[k], mods_per_step=[mods[k]] + [np.zeros(0, MOD_DTYPE)] * (steps_per_frame[k] - 1))
+            want = np.bincount(np.minimum(ref, 255).ravel(), minlength=256)
+            assert np.array_equal(sim.census(), want), (w, h, k)
+        assert np.array_equal(sim.download_cells(), ref)
+        sim.close()
+
+
 @pytest.mark.parametrize("n_strips,halo,w,h", [(2, 4, 96, 64), (3, 6, 200, 150), (4, 2, 64, 64)])
 def test_lit_strips(se, default_rules, oracle, n_strips, halo, w, h):
     """Strips with lighting in one process (se_sim_attach_local): ids bit-exact, light bit-exact against the oracle's
