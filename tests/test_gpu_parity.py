@@ -528,6 +528,37 @@ def test_running_census(se, oracle, monkeypatch):
         sim.close()
 
 
+@pytest.mark.parametrize("lighting", [False, True])
+def test_push_brush_matches_the_oracle_circle_stamp(se, default_rules, oracle, lighting):
+    """`Simulation.push_brush()` (sandengine-core/src/lib.rs:59-67: one CIRCLE of brushSize / brushMaterial at mousePos * size) against the
+    oracle's stamp (falling_sand.glsl:749-794, the f32 distance test): every brush size 0..24 at positions inside, on the edge of and
+    outside the grid, one stamp per frame with the simulation running in between."""
+    from sandengine_b200 import MOD_DTYPE
+    w, h = 128, 96
+    g = synthetic_grid(w, h, 61)
+    L0 = np.zeros((h, w, 4), np.float32)
+    sim = se.Simulation(default_rules, (w, h), lighting=lighting)
+    sim.upload_cells(g); sim.params.frame = 1
+    if lighting: sim.upload_light(L0)
+    selectable = default_rules.selectable_materials
+    ref, refL, frame = g.copy(), (L0.copy() if lighting else None), 1
+    spots = [(0.5, 0.5), (0.0, 0.0), (0.999, 0.999), (0.25, 0.9), (1.2, 0.5), (-0.1, 0.3), (0.7, 0.01)]
+    for k in range(50):
+        size = k % 25
+        mouse = spots[k % len(spots)]
+        mat = selectable[k % len(selectable)]
+        sim.params.mousePos = list(mouse); sim.params.brushSize = size; sim.params.brushMaterial = mat
+        sim.push_brush()
+        sim.run()
+        m = np.zeros(1, MOD_DTYPE)
+        m[0] = ((int(mouse[0] * w), int(mouse[1] * h)), 0, size, mat.id, (0, 0, 0))
+        ref, refL, frame = oracle.run(ref, frame, 1, light=refL, mods_per_step=[m])
+        assert np.array_equal(sim.download_cells(), ref), (k, size, mouse)
+    if lighting:
+        assert np.abs(sim.download_light() - refL).max() <= LIGHT_ATOL
+    sim.close()
+
+
 @pytest.mark.parametrize("running_census", [False, True])
 def test_brush_held_down_stays_on_the_per_frame_table_kernel(se, default_rules, oracle, running_census):
     """A brush held down (modifications every frame, the reference's normal interactive use) runs on se_step_lut_global[_census]_mods:
