@@ -633,9 +633,14 @@ TileGeom choose_tile_geometry(const se_sim* s, int nblk, int tsteps, int owned) 
         const int last = owned - (ty - 1) * tho;
         if (last <= 0 || (ty > 1 && last < push_min)) continue;
         const long long items = (long long)nblk * tiles_x * ty;
-        const long long rounds = (items + workers - 1) / workers;
-        // + 24: per-tile fixed work (flag waits, barriers, exposed load/store) expressed in rows (fitted on B200)
-        const double cost = (double)rounds * (tho + 2 * HY + 24);
+        // Measured on B200 (scripts/geom_sweep.py, profiles/r2_geom_sweep.txt): a tile costs what its sub-steps cost, and a sub-step
+        // is ceil(PH / 32) block-row iterations of the half's 16 warps -- with a super-linear tail above six iterations (the two
+        // halves of an SM overlap each other's load / store phases less well with tall tiles).  kIter[i]: relative cost of a tile of
+        // i iterations; the work queue is dynamic, so the makespan is items / workers + about half a tile, not whole rounds.
+        static const double kIter[] = {0.030, 0.030, 0.035, 0.0437, 0.0559, 0.0685, 0.0800, 0.0992, 0.1131, 0.1270, 0.1410};
+        const int iters = (tho + 2 * HY + 31) / 32;
+        const double tile_cost = iters <= 10 ? kIter[iters] : kIter[10] + 0.014 * (iters - 10);
+        const double cost = ((double)items / workers + 0.5) * tile_cost;
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = TileGeom{ty, tho, tho + 2 * HY, HX, HY, tiles_x}; }
     }
     if (best.tiles_y == 0) {                                          // cannot happen for owned >= 2; keep a safe answer anyway

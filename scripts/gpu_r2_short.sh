@@ -1,8 +1,8 @@
 #!/bin/bash
+# what a short K1b launch costs on a strip-sized grid, over T-block lengths and tile heights
 cd "$(dirname "$0")/.."
-mkdir -p gpurun_out
 python scripts/short_probe.py 16384 2048
+for T in 20 10 7 5; do python scripts/short_probe.py 16384 2048 $T; done
+for PH in 218 184 240 282; do SE_TILE_PH=$PH python scripts/short_probe.py 16384 2048; done
 python scripts/short_probe.py 16384 4096
-python scripts/short_probe.py 16384 16384
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:se_step_tiles -c 12 --csv --log-file gpurun_out/short_launches.csv python scripts/short_probe.py 16384 2048 > /dev/null 2>&1
-grep se_step_tiles gpurun_out/short_launches.csv | awk -F, '{print $(NF)}' | tr '\n' ' '
+SE_TILE_PH=286 python scripts/short_probe.py 16384 4096

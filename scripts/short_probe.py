@@ -1,6 +1,6 @@
 """Fixed cost of one K1b launch on a strip-sized grid: time step(n) for n = 20, 40, 80 on W x H (default 16384 x 2048 = one of eight
 strips of the bench grid); 2 t(20) - t(40) is what a launch costs beyond its steps.
-  python scripts/short_probe.py [W] [H]"""
+  python scripts/short_probe.py [W] [H] [temporal_block]          (env SE_TILE_PH: tile height override)"""
 import json
 import sys
 from pathlib import Path
@@ -15,12 +15,13 @@ from sandengine_b200.grids import synthetic_grid  # noqa: E402
 
 W = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 H = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
+T = int(sys.argv[3]) if len(sys.argv) > 3 else 0        # temporal_block (0: the library's default)
 rules = se.parse_path(REPO / "data" / "materials.yaml")
-sim = se.Simulation(rules, (W, H))
+sim = se.Simulation(rules, (W, H), temporal_block=T)
 st = torch.cuda.Stream(); torch.cuda.set_stream(st); sim.set_stream(st.cuda_stream)
 sim.upload_cells(synthetic_grid(W, H, 3)); sim.params.frame = 1
 sim.step(5)
-out = {"W": W, "H": H}
+out = {"W": W, "H": H, "T": T, "SE_TILE_PH": __import__("os").environ.get("SE_TILE_PH")}
 for n in (10, 20, 40, 80, 20):
     ts = []
     for _ in range(7):
