@@ -1,3 +1,5 @@
-mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
-timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+#!/bin/bash
+# the whole GPU suite + smoke() on one B200 (gpurun -- 'bash scripts/gpu_final_check.sh')
+cd "$(dirname "$0")/.."
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4
+timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
